@@ -1,0 +1,440 @@
+// C-ABI of libdfit.so (include/dfit.h): handles, streams, chunked host<->device pipeline, dispatch.
+// Device code only -- there is deliberately no host implementation of the fit in this library.
+#include <cuda_runtime.h>
+
+#include <chrono>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <limits>
+#include <new>
+
+#include "../../include/dfit.h"
+#include "fit_kernel.cuh"
+
+using namespace dfit;
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+#define CUDA_TRY(expr)                                                                                      \
+  do {                                                                                                      \
+    cudaError_t _e = (expr);                                                                                \
+    if (_e != cudaSuccess)                                                                                  \
+      return fail(_e == cudaErrorMemoryAllocation ? DFIT_ERR_OOM : DFIT_ERR_CUDA, "%s: %s (%s:%d)", #expr, \
+                  cudaGetErrorString(_e), __FILE__, __LINE__);                                              \
+  } while (0)
+
+constexpr int kSlots = 3;  // pipeline depth of the host entry point
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+};
+
+struct Slot {
+  cudaStream_t stream = nullptr;
+  DevBuf y, mask, p0, popt, r2, status, niter;
+};
+
+int model_nparams(int model) {
+  switch (model) {
+    case DFIT_MODEL_MONOEXP: return 2;
+    case DFIT_MODEL_BIEXP: return 4;
+    case DFIT_MODEL_LINEAR: return 1;
+    default: return -1;
+  }
+}
+
+}  // namespace
+
+struct dfit_handle {
+  int device = 0;
+  int sm_count = 0;
+  cudaStream_t stream = nullptr;  // default stream for dfit_fit_device(stream = NULL)
+  Slot slots[kSlots];
+  unsigned long long* counters = nullptr;  // device, CNT_COUNT entries
+  cudaEvent_t ev_start = nullptr, ev_stop = nullptr;
+  bool ev_valid = false;
+  cudaStream_t ev_stream = nullptr;
+  int64_t last_n = 0;
+  int last_launches = 0;
+  float last_total_ms = 0.f;
+  float host_kernel_ms = -1.f;
+};
+
+namespace {
+
+int ensure(DevBuf& b, size_t bytes) {
+  if (bytes <= b.cap) return DFIT_OK;
+  if (b.p) cudaFree(b.p);
+  b.p = nullptr;
+  b.cap = 0;
+  const size_t want = bytes + (bytes >> 3) + 256;
+  CUDA_TRY(cudaMalloc(&b.p, want));
+  b.cap = want;
+  return DFIT_OK;
+}
+
+int validate(const dfit_opts* o, int n_echo, int64_t n_vox, const double* x, int y_dtype, int p0_dtype, int out_dtype,
+             bool have_p0v) {
+  if (!o) return fail(DFIT_ERR_BAD_ARG, "opts is NULL");
+  if (o->struct_size != (int32_t)sizeof(dfit_opts))
+    return fail(DFIT_ERR_BAD_ARG, "opts->struct_size=%d, expected %d (use dfit_default_opts)", o->struct_size,
+                (int)sizeof(dfit_opts));
+  const int P = model_nparams(o->model);
+  if (P < 0) return fail(DFIT_ERR_BAD_ARG, "unknown model %d", o->model);
+  if (n_echo < 1 || n_echo > DFIT_MAX_ECHOES)
+    return fail(DFIT_ERR_UNSUPPORTED, "n_echo=%d outside [1, %d]", n_echo, DFIT_MAX_ECHOES);
+  if (n_echo < P) return fail(DFIT_ERR_BAD_ARG, "n_echo=%d < number of parameters %d", n_echo, P);
+  if (n_vox < 0) return fail(DFIT_ERR_BAD_ARG, "n_vox < 0");
+  if (!x) return fail(DFIT_ERR_BAD_ARG, "x is NULL");
+  if (y_dtype < DFIT_F32 || y_dtype > DFIT_U8) return fail(DFIT_ERR_BAD_ARG, "bad y_dtype %d", y_dtype);
+  if (out_dtype != DFIT_F32 && out_dtype != DFIT_F64) return fail(DFIT_ERR_BAD_ARG, "bad out_dtype %d", out_dtype);
+  if (have_p0v && p0_dtype != DFIT_F32 && p0_dtype != DFIT_F64) return fail(DFIT_ERR_BAD_ARG, "bad p0_dtype");
+  if (o->compute_dtype != DFIT_F32 && o->compute_dtype != DFIT_F64)
+    return fail(DFIT_ERR_BAD_ARG, "bad compute_dtype %d", o->compute_dtype);
+  if (o->init_mode == DFIT_INIT_LOGLINEAR && o->model != DFIT_MODEL_MONOEXP)
+    return fail(DFIT_ERR_UNSUPPORTED, "log-linear initialisation is defined for the mono-exponential model only");
+  if (o->init_mode != DFIT_INIT_GIVEN && o->init_mode != DFIT_INIT_LOGLINEAR)
+    return fail(DFIT_ERR_BAD_ARG, "bad init_mode %d", o->init_mode);
+  for (int i = 0; i < P; ++i)
+    if (std::isnan(o->p0[i]) && !have_p0v && o->init_mode == DFIT_INIT_GIVEN)
+      return fail(DFIT_ERR_BAD_ARG, "p0[%d] is NaN (per-voxel) but p0_voxel is NULL", i);
+  if (o->maxfev < 1) return fail(DFIT_ERR_BAD_ARG, "maxfev < 1");
+  return DFIT_OK;
+}
+
+void make_desc(const dfit_opts* o, int n_echo, int64_t n_vox, const double* x, LaunchDesc& d) {
+  const int P = model_nparams(o->model);
+  const bool f32 = o->compute_dtype == DFIT_F32;
+  const double eps = f32 ? 1.1920929e-7 : 2.220446049250313e-16;
+  d.model = o->model;
+  d.compute_dtype = o->compute_dtype;
+  d.n_echo = n_echo;
+  d.n_vox = n_vox;
+  d.x = x;
+  d.p0_voxel_bits = 0;
+  for (int i = 0; i < 4; ++i) {
+    d.p0s[i] = i < P ? o->p0[i] : 0.0;
+    if (i < P && std::isnan(o->p0[i])) {
+      d.p0_voxel_bits |= 1u << i;
+      d.p0s[i] = 1.0;
+    }
+  }
+  // Engine tolerances: the reference's ftol bounds MINPACK's *last* relative cost decrease, which
+  // leaves its iterate up to ~1e-4 (relative) away from the minimiser on noisy data.  The engine
+  // iterates ftol_scale further so that it lands within rtol 1e-4 of wherever MINPACK stopped.
+  const double scale = o->ftol_scale > 0 ? o->ftol_scale : 1e-3;
+  double ftol = o->ftol * scale;
+  const double ftol_floor = f32 ? 1e-8 : 1e-14;
+  d.ftol = ftol < ftol_floor ? ftol_floor : ftol;
+  d.xtol = o->xtol > 0 ? o->xtol : (f32 ? 1e-6 : 1e-10);
+  d.lambda0 = o->lambda0 > 0 ? o->lambda0 : 1e-3;
+  d.floor_rel = (8 * eps) * (8 * eps);
+  d.r2_eps = o->r2_eps;
+  d.y_lo = o->y_lo;
+  d.y_hi = o->y_hi;
+  d.maxfev = o->maxfev;
+  d.init_mode = o->init_mode;
+  d.init_linear = o->init_linear < 0 ? (o->model == DFIT_MODEL_BIEXP ? 0 : 1) : o->init_linear;
+  d.po.enabled = o->post_enabled;
+  for (int i = 0; i < 4; ++i) {
+    d.po.ufunc[i] = o->ufunc[i];
+    d.po.lb[i] = o->lb[i];
+    d.po.ub[i] = o->ub[i];
+    d.po.decimals[i] = o->decimals[i];
+  }
+  d.po.has_r2_thresh = o->has_r2_threshold;
+  d.po.r2_thresh = o->r2_threshold;
+  d.po.has_fill = o->has_nan_fill;
+  d.po.fill = o->nan_fill;
+  d.mask_fill = o->has_nan_fill ? o->nan_fill : std::numeric_limits<double>::quiet_NaN();
+  d.use_tma = o->use_tma;
+}
+
+cudaError_t dispatch(const LaunchDesc& d) {
+  const bool f32 = d.compute_dtype == DFIT_F32;
+  switch (d.model) {
+    case DFIT_MODEL_MONOEXP: return f32 ? launch_mono_f32(d) : launch_mono_f64(d);
+    case DFIT_MODEL_BIEXP: return f32 ? launch_biexp_f32(d) : launch_biexp_f64(d);
+    default: return f32 ? launch_linear_f32(d) : launch_linear_f64(d);
+  }
+}
+
+bool is_pinned_or_device(const void* p) {
+  cudaPointerAttributes at;
+  if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return at.type == cudaMemoryTypeHost || at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged;
+}
+
+}  // namespace
+
+extern "C" {
+
+int dfit_version(void) { return DFIT_VERSION; }
+
+int dfit_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+
+const char* dfit_strerror(int code) {
+  switch (code) {
+    case DFIT_OK: return "ok";
+    case DFIT_ERR_BAD_ARG: return "bad argument";
+    case DFIT_ERR_NO_DEVICE: return "no CUDA device (this library has no CPU implementation)";
+    case DFIT_ERR_CUDA: return "CUDA error";
+    case DFIT_ERR_OOM: return "out of device memory";
+    case DFIT_ERR_UNSUPPORTED: return "unsupported configuration";
+    default: return "unknown error";
+  }
+}
+
+const char* dfit_last_error(void) { return g_err; }
+
+int dfit_model_nparams(int model) { return model_nparams(model); }
+
+int dfit_default_opts(dfit_opts* o, int model) {
+  if (!o) return fail(DFIT_ERR_BAD_ARG, "opts is NULL");
+  if (model_nparams(model) < 0) return fail(DFIT_ERR_BAD_ARG, "unknown model %d", model);
+  std::memset(o, 0, sizeof(*o));
+  o->struct_size = (int32_t)sizeof(dfit_opts);
+  o->model = model;
+  o->compute_dtype = DFIT_F32;
+  o->init_mode = DFIT_INIT_GIVEN;
+  o->init_linear = -1;
+  o->maxfev = 100;      // fitting.py:761
+  o->ftol = 1e-5;       // fitting.py:762
+  o->ftol_scale = 1e-3;
+  o->xtol = 0;
+  o->lambda0 = 0;
+  o->r2_eps = 1e-8;     // fitting.py:763
+  o->y_lo = -std::numeric_limits<double>::infinity();
+  o->y_hi = std::numeric_limits<double>::infinity();
+  for (int i = 0; i < DFIT_MAX_PARAMS; ++i) {
+    o->p0[i] = 1.0;  // SciPy's default when p0 is None (fitting.py:820-826)
+    o->ufunc[i] = DFIT_UFUNC_NONE;
+    o->lb[i] = -std::numeric_limits<double>::infinity();
+    o->ub[i] = std::numeric_limits<double>::infinity();
+    o->decimals[i] = -1;
+  }
+  o->lanes_per_voxel = 0;
+  o->use_tma = -1;
+  return DFIT_OK;
+}
+
+int dfit_create(int device, dfit_handle** out) {
+  if (!out) return fail(DFIT_ERR_BAD_ARG, "out is NULL");
+  *out = nullptr;
+  int n = dfit_device_count();
+  if (n <= 0) return fail(DFIT_ERR_NO_DEVICE, "no CUDA device visible; libdfit has no CPU path");
+  if (device < 0 || device >= n) return fail(DFIT_ERR_BAD_ARG, "device %d out of range [0, %d)", device, n);
+  CUDA_TRY(cudaSetDevice(device));
+  dfit_handle* h = new (std::nothrow) dfit_handle();
+  if (!h) return fail(DFIT_ERR_OOM, "host allocation failed");
+  h->device = device;
+  cudaDeviceProp prop;
+  CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+  if (prop.major < 10) {
+    delete h;
+    return fail(DFIT_ERR_UNSUPPORTED, "device %d is sm_%d%d; this library is built for sm_100a only", device,
+                prop.major, prop.minor);
+  }
+  h->sm_count = prop.multiProcessorCount;
+  CUDA_TRY(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  for (int s = 0; s < kSlots; ++s) CUDA_TRY(cudaStreamCreateWithFlags(&h->slots[s].stream, cudaStreamNonBlocking));
+  CUDA_TRY(cudaMalloc(&h->counters, CNT_COUNT * sizeof(unsigned long long)));
+  CUDA_TRY(cudaMemset(h->counters, 0, CNT_COUNT * sizeof(unsigned long long)));
+  CUDA_TRY(cudaEventCreate(&h->ev_start));
+  CUDA_TRY(cudaEventCreate(&h->ev_stop));
+  *out = h;
+  return DFIT_OK;
+}
+
+int dfit_destroy(dfit_handle* h) {
+  if (!h) return DFIT_OK;
+  cudaSetDevice(h->device);
+  cudaDeviceSynchronize();
+  for (int s = 0; s < kSlots; ++s) {
+    Slot& sl = h->slots[s];
+    DevBuf* bufs[] = {&sl.y, &sl.mask, &sl.p0, &sl.popt, &sl.r2, &sl.status, &sl.niter};
+    for (DevBuf* b : bufs)
+      if (b->p) cudaFree(b->p);
+    if (sl.stream) cudaStreamDestroy(sl.stream);
+  }
+  if (h->stream) cudaStreamDestroy(h->stream);
+  if (h->counters) cudaFree(h->counters);
+  if (h->ev_start) cudaEventDestroy(h->ev_start);
+  if (h->ev_stop) cudaEventDestroy(h->ev_stop);
+  delete h;
+  return DFIT_OK;
+}
+
+int dfit_fit_device(dfit_handle* h, const dfit_opts* opts, int n_echo, int64_t n_vox, const double* x, const void* y,
+                    int y_dtype, int y_layout, int64_t ld, const uint8_t* mask, const void* p0_voxel, int p0_dtype,
+                    void* popt, void* r2, int out_dtype, uint8_t* status, uint8_t* niter, void* stream) {
+  if (!h) return fail(DFIT_ERR_BAD_ARG, "handle is NULL");
+  int rc = validate(opts, n_echo, n_vox, x, y_dtype, p0_dtype, out_dtype, p0_voxel != nullptr);
+  if (rc != DFIT_OK) return rc;
+  if (y_layout != DFIT_PLANAR && y_layout != DFIT_ECHO_FASTEST) return fail(DFIT_ERR_BAD_ARG, "bad layout");
+  if (n_vox > 0 && (!y || !popt || !r2)) return fail(DFIT_ERR_BAD_ARG, "y/popt/r2 must not be NULL");
+  if (ld < (y_layout == DFIT_PLANAR ? n_vox : (int64_t)n_echo)) return fail(DFIT_ERR_BAD_ARG, "ld too small");
+  CUDA_TRY(cudaSetDevice(h->device));
+  cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
+  LaunchDesc d;
+  make_desc(opts, n_echo, n_vox, x, d);
+  d.y = y;
+  d.y_dtype = y_dtype;
+  d.layout = y_layout;
+  d.ld = ld;
+  d.mask = mask;
+  d.p0v = p0_voxel;
+  d.p0_dtype = p0_dtype;
+  if (!p0_voxel) d.p0_voxel_bits = 0;
+  d.popt = popt;
+  d.r2 = r2;
+  d.out_dtype = out_dtype;
+  d.status = status;
+  d.niter = niter;
+  d.counters = h->counters;
+  d.stream = st;
+  CUDA_TRY(cudaMemsetAsync(h->counters, 0, CNT_COUNT * sizeof(unsigned long long), st));
+  CUDA_TRY(cudaEventRecord(h->ev_start, st));
+  h->last_launches = 0;
+  if (n_vox > 0) {
+    CUDA_TRY(dispatch(d));
+    h->last_launches = 1;
+  }
+  CUDA_TRY(cudaEventRecord(h->ev_stop, st));
+  h->ev_valid = true;
+  h->ev_stream = st;
+  h->last_n = n_vox;
+  h->last_total_ms = -1.f;
+  h->host_kernel_ms = -1.f;
+  return DFIT_OK;
+}
+
+int dfit_fit_host(dfit_handle* h, const dfit_opts* opts, int n_echo, int64_t n_vox, const double* x,
+                  const void* const* y_planes, int y_dtype, const uint8_t* mask, const void* p0_voxel, int p0_dtype,
+                  void* popt, void* r2, int out_dtype, uint8_t* status, uint8_t* niter) {
+  if (!h) return fail(DFIT_ERR_BAD_ARG, "handle is NULL");
+  int rc = validate(opts, n_echo, n_vox, x, y_dtype, p0_dtype, out_dtype, p0_voxel != nullptr);
+  if (rc != DFIT_OK) return rc;
+  if (n_vox > 0 && (!y_planes || !popt || !r2)) return fail(DFIT_ERR_BAD_ARG, "y_planes/popt/r2 must not be NULL");
+  for (int e = 0; e < n_echo && n_vox > 0; ++e)
+    if (!y_planes[e]) return fail(DFIT_ERR_BAD_ARG, "y_planes[%d] is NULL", e);
+  CUDA_TRY(cudaSetDevice(h->device));
+  const auto t0 = std::chrono::steady_clock::now();
+  const int P = model_nparams(opts->model);
+  const size_t ysz = dtype_size(y_dtype), osz = out_dtype == DFIT_F32 ? 4 : 8, psz = p0_dtype == DFIT_F32 ? 4 : 8;
+
+  // Chunks of voxels flow through kSlots stream slots: H2D(chunk i+1) overlaps fit(chunk i) and
+  // D2H(chunk i-1).  Chunk size keeps every copy large enough to run PCIe at full rate.
+  int64_t chunk = 1 << 21;
+  if (n_vox < chunk * 2) chunk = (n_vox + 1) / 2;
+  chunk = (chunk + 127) / 128 * 128;  // 512 B row alignment for vector/TMA access
+  if (chunk <= 0) chunk = 128;
+
+  CUDA_TRY(cudaMemsetAsync(h->counters, 0, CNT_COUNT * sizeof(unsigned long long), h->slots[0].stream));
+  CUDA_TRY(cudaStreamSynchronize(h->slots[0].stream));
+  h->last_launches = 0;
+
+  LaunchDesc d;
+  make_desc(opts, n_echo, n_vox, x, d);
+  if (!p0_voxel) d.p0_voxel_bits = 0;
+  d.y_dtype = y_dtype;
+  d.layout = DFIT_PLANAR;
+  d.ld = chunk;
+  d.p0_dtype = p0_dtype;
+  d.out_dtype = out_dtype;
+  d.counters = h->counters;
+
+  int64_t idx = 0;
+  for (int64_t v0 = 0; v0 < n_vox; v0 += chunk, ++idx) {
+    const int64_t n = n_vox - v0 < chunk ? n_vox - v0 : chunk;
+    Slot& sl = h->slots[idx % kSlots];
+    if ((rc = ensure(sl.y, (size_t)n_echo * chunk * ysz)) != DFIT_OK) return rc;
+    if ((rc = ensure(sl.popt, (size_t)chunk * P * osz)) != DFIT_OK) return rc;
+    if ((rc = ensure(sl.r2, (size_t)chunk * osz)) != DFIT_OK) return rc;
+    if (mask && (rc = ensure(sl.mask, (size_t)chunk)) != DFIT_OK) return rc;
+    if (p0_voxel && (rc = ensure(sl.p0, (size_t)chunk * P * psz)) != DFIT_OK) return rc;
+    if (status && (rc = ensure(sl.status, (size_t)chunk)) != DFIT_OK) return rc;
+    if (niter && (rc = ensure(sl.niter, (size_t)chunk)) != DFIT_OK) return rc;
+    cudaStream_t st = sl.stream;
+    for (int e = 0; e < n_echo; ++e)
+      CUDA_TRY(cudaMemcpyAsync((char*)sl.y.p + (size_t)e * chunk * ysz, (const char*)y_planes[e] + (size_t)v0 * ysz,
+                               (size_t)n * ysz, cudaMemcpyHostToDevice, st));
+    if (mask) CUDA_TRY(cudaMemcpyAsync(sl.mask.p, mask + v0, (size_t)n, cudaMemcpyHostToDevice, st));
+    if (p0_voxel)
+      CUDA_TRY(cudaMemcpyAsync(sl.p0.p, (const char*)p0_voxel + (size_t)v0 * P * psz, (size_t)n * P * psz,
+                               cudaMemcpyHostToDevice, st));
+    d.n_vox = n;
+    d.y = sl.y.p;
+    d.mask = mask ? (const uint8_t*)sl.mask.p : nullptr;
+    d.p0v = p0_voxel ? sl.p0.p : nullptr;
+    d.popt = sl.popt.p;
+    d.r2 = sl.r2.p;
+    d.status = status ? (uint8_t*)sl.status.p : nullptr;
+    d.niter = niter ? (uint8_t*)sl.niter.p : nullptr;
+    d.stream = st;
+    CUDA_TRY(dispatch(d));
+    ++h->last_launches;
+    CUDA_TRY(cudaMemcpyAsync((char*)popt + (size_t)v0 * P * osz, sl.popt.p, (size_t)n * P * osz, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync((char*)r2 + (size_t)v0 * osz, sl.r2.p, (size_t)n * osz, cudaMemcpyDeviceToHost, st));
+    if (status) CUDA_TRY(cudaMemcpyAsync(status + v0, sl.status.p, (size_t)n, cudaMemcpyDeviceToHost, st));
+    if (niter) CUDA_TRY(cudaMemcpyAsync(niter + v0, sl.niter.p, (size_t)n, cudaMemcpyDeviceToHost, st));
+  }
+  for (int s = 0; s < kSlots; ++s) CUDA_TRY(cudaStreamSynchronize(h->slots[s].stream));
+  const auto t1 = std::chrono::steady_clock::now();
+  h->last_total_ms = std::chrono::duration<float, std::milli>(t1 - t0).count();
+  h->ev_valid = false;
+  h->last_n = n_vox;
+  (void)is_pinned_or_device;
+  return DFIT_OK;
+}
+
+int dfit_get_stats(dfit_handle* h, dfit_stats* out) {
+  if (!h || !out) return fail(DFIT_ERR_BAD_ARG, "NULL argument");
+  CUDA_TRY(cudaSetDevice(h->device));
+  std::memset(out, 0, sizeof(*out));
+  float kms = -1.f;
+  if (h->ev_valid) {
+    CUDA_TRY(cudaEventSynchronize(h->ev_stop));
+    CUDA_TRY(cudaEventElapsedTime(&kms, h->ev_start, h->ev_stop));
+  } else {
+    for (int s = 0; s < kSlots; ++s) CUDA_TRY(cudaStreamSynchronize(h->slots[s].stream));
+  }
+  unsigned long long c[CNT_COUNT];
+  CUDA_TRY(cudaMemcpy(c, h->counters, sizeof(c), cudaMemcpyDeviceToHost));
+  out->n_voxels = h->last_n;
+  out->n_fitted = (int64_t)c[CNT_FITTED];
+  out->n_failed = (int64_t)c[CNT_FAILED];
+  out->n_nonfinite = (int64_t)c[CNT_NONFINITE];
+  out->n_oob = (int64_t)c[CNT_OOB];
+  out->sum_iters = (int64_t)c[CNT_ITERS];
+  out->max_iters = (int32_t)c[CNT_MAXITER];
+  out->n_launches = h->last_launches;
+  out->kernel_ms = kms;
+  out->total_ms = h->last_total_ms;
+  return DFIT_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,300 @@
+// Fit kernels: one voxel per lane, samples and the whole LM state in registers.
+//
+//   fit_kernel      -- coalesced/vectorised global loads straight into registers
+//   fit_kernel_tma  -- persistent CTAs, sample tiles staged through shared memory by TMA
+//                      (cp.async.bulk.tensor) in a double-buffered mbarrier pipeline
+//
+// Both replace the N-voxel loop of dosma/core/fitting.py:855-868 and fuse what the reference does
+// around it: dtype up-cast (:711, SciPy's asarray(float)), mask select/scatter (:199-215), the
+// log-linear initial guess (:701-718), `_process_params` (:109-146) and rounding (:734-737).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "lm_core.cuh"
+
+namespace dfit {
+
+constexpr int kBlock = 128;
+
+enum DType : int { DT_F32 = 0, DT_F64 = 1, DT_I16 = 2, DT_U16 = 3, DT_I32 = 4, DT_U8 = 5 };
+enum Layout : int { LAYOUT_PLANAR = 0, LAYOUT_ECHO_FASTEST = 1 };
+enum Counter : int { CNT_FITTED = 0, CNT_FAILED, CNT_NONFINITE, CNT_OOB, CNT_ITERS, CNT_MAXITER, CNT_COUNT };
+
+template <typename T, int EMAX>
+struct KernelArgs {
+  XTab<T, EMAX> xt;
+  VoxelOpts<T> vo;
+  PostOpts po;
+  const void* y;
+  int64_t ld;
+  int64_t n;
+  int y_dtype, layout, E;
+  const uint8_t* mask;
+  const void* p0v;  // [N, P] per-voxel initial guess or null
+  int p0_dtype;
+  unsigned p0_voxel_bits;  // bit i set: parameter i comes from p0v
+  T p0s[4];
+  void* popt;
+  void* r2;
+  int out_dtype;
+  uint8_t* status;
+  uint8_t* niter;
+  double mask_fill;  // value written outside the mask: NaN or nan_to_num (fitting.py:207-212)
+  unsigned long long* counters;
+};
+
+static inline size_t dtype_size(int dt) {
+  switch (dt) {
+    case DT_F32: case DT_I32: return 4;
+    case DT_F64: return 8;
+    case DT_I16: case DT_U16: return 2;
+    default: return 1;
+  }
+}
+
+#if defined(__CUDACC__)
+
+template <typename T>
+__device__ __forceinline__ T load_as(const void* __restrict__ base, int dtype, int64_t idx) {
+  switch (dtype) {
+    case DT_F32: return (T)__ldcs(reinterpret_cast<const float*>(base) + idx);
+    case DT_F64: return (T)__ldcs(reinterpret_cast<const double*>(base) + idx);
+    case DT_I16: return (T)__ldcs(reinterpret_cast<const short*>(base) + idx);
+    case DT_U16: return (T)__ldcs(reinterpret_cast<const unsigned short*>(base) + idx);
+    case DT_I32: return (T)__ldcs(reinterpret_cast<const int*>(base) + idx);
+    default: return (T)__ldcs(reinterpret_cast<const unsigned char*>(base) + idx);
+  }
+}
+
+template <typename T, int EMAX, bool EXACT>
+__device__ __forceinline__ void load_samples(const KernelArgs<T, EMAX>& a, int64_t v, T (&y)[EMAX]) {
+  if (a.layout == LAYOUT_PLANAR) {
+    // lane l of a warp reads voxel v0 + l of every echo plane: one fully coalesced 128 B line per echo
+#pragma unroll
+    for (int e = 0; e < EMAX; ++e) y[e] = (EXACT || e < a.E) ? load_as<T>(a.y, a.y_dtype, (int64_t)e * a.ld + v) : (T)0;
+  } else {
+    const int64_t base = v * a.ld;
+    if (a.y_dtype == DT_F32 && (EMAX % 4 == 0) && (a.ld % 4 == 0) && (EXACT || a.E == EMAX) &&
+        ((reinterpret_cast<uintptr_t>(a.y) & 15) == 0)) {
+      const float4* src = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(a.y) + base);
+#pragma unroll
+      for (int q = 0; q < EMAX / 4; ++q) {
+        const float4 t = __ldcs(src + q);
+        y[4 * q + 0] = (T)t.x;
+        y[4 * q + 1] = (T)t.y;
+        y[4 * q + 2] = (T)t.z;
+        y[4 * q + 3] = (T)t.w;
+      }
+    } else {
+#pragma unroll
+      for (int e = 0; e < EMAX; ++e) y[e] = (EXACT || e < a.E) ? load_as<T>(a.y, a.y_dtype, base + e) : (T)0;
+    }
+  }
+}
+
+template <int P, typename T, int EMAX>
+__device__ __forceinline__ void load_p0(const KernelArgs<T, EMAX>& a, int64_t v, T (&p)[P]) {
+#pragma unroll
+  for (int i = 0; i < P; ++i) {
+    p[i] = a.p0s[i];
+    if ((a.p0_voxel_bits >> i) & 1u) p[i] = load_as<T>(a.p0v, a.p0_dtype, v * P + i);
+  }
+}
+
+template <int P, typename TO>
+__device__ __forceinline__ void store_vec(TO* __restrict__ dst, const double (&q)[P]) {
+  if constexpr (sizeof(TO) == 4 && P == 2) {
+    __stcs(reinterpret_cast<float2*>(dst), make_float2((float)q[0], (float)q[1]));
+  } else if constexpr (sizeof(TO) == 4 && P == 4) {
+    __stcs(reinterpret_cast<float4*>(dst), make_float4((float)q[0], (float)q[1], (float)q[2], (float)q[3]));
+  } else if constexpr (sizeof(TO) == 8 && P == 2) {
+    __stcs(reinterpret_cast<double2*>(dst), make_double2(q[0], q[1]));
+  } else if constexpr (sizeof(TO) == 8 && P == 4) {
+    __stcs(reinterpret_cast<double2*>(dst), make_double2(q[0], q[1]));
+    __stcs(reinterpret_cast<double2*>(dst) + 1, make_double2(q[2], q[3]));
+  } else {
+#pragma unroll
+    for (int i = 0; i < P; ++i) dst[i] = (TO)q[i];
+  }
+}
+
+// Epilogue + stores for one voxel.  `fitted` false: voxel outside the mask.
+template <int P, typename T, int EMAX>
+__device__ __forceinline__ void store_voxel(const KernelArgs<T, EMAX>& a, int64_t v, const T (&p)[P], T r2, bool fitted,
+                                            int st, int iters) {
+  double q[P];
+  double r2o;
+  if (fitted) {
+    r2o = (double)r2;
+#pragma unroll
+    for (int i = 0; i < P; ++i) q[i] = post_param(a.po, i, (double)p[i], r2o);
+  } else {
+    r2o = a.mask_fill;
+#pragma unroll
+    for (int i = 0; i < P; ++i) {
+      q[i] = a.mask_fill;
+      if (a.po.enabled && a.po.decimals[i] >= 0) {
+        const double s = pow10i(a.po.decimals[i]);
+        q[i] = rint(q[i] * s) / s;
+      }
+    }
+  }
+  if (a.out_dtype == DT_F32) {
+    store_vec<P, float>(reinterpret_cast<float*>(a.popt) + v * P, q);
+    __stcs(reinterpret_cast<float*>(a.r2) + v, (float)r2o);
+  } else {
+    store_vec<P, double>(reinterpret_cast<double*>(a.popt) + v * P, q);
+    __stcs(reinterpret_cast<double*>(a.r2) + v, r2o);
+  }
+  if (a.status) a.status[v] = (uint8_t)st;
+  if (a.niter) a.niter[v] = (uint8_t)(iters > 255 ? 255 : iters);
+}
+
+// Warp-aggregated statistics: one atomic per warp and counter.
+__device__ __forceinline__ void warp_stats(unsigned long long* cnt, int st, int iters, unsigned flags) {
+  const unsigned full = 0xffffffffu;
+  const unsigned n_fit = __popc(__ballot_sync(full, st >= ST_CONV_F));
+  const unsigned n_fail = __popc(__ballot_sync(full, st >= ST_MAXITER));
+  const unsigned n_nf = __popc(__ballot_sync(full, (flags & FLAG_NONFINITE) != 0));
+  const unsigned n_oob = __popc(__ballot_sync(full, (flags & FLAG_OOB) != 0));
+  const unsigned s_it = __reduce_add_sync(full, (unsigned)iters);
+  const unsigned m_it = __reduce_max_sync(full, (unsigned)iters);
+  if ((threadIdx.x & 31) == 0) {
+    if (n_fit) atomicAdd(cnt + CNT_FITTED, (unsigned long long)n_fit);
+    if (n_fail) atomicAdd(cnt + CNT_FAILED, (unsigned long long)n_fail);
+    if (n_nf) atomicAdd(cnt + CNT_NONFINITE, (unsigned long long)n_nf);
+    if (n_oob) atomicAdd(cnt + CNT_OOB, (unsigned long long)n_oob);
+    if (s_it) atomicAdd(cnt + CNT_ITERS, (unsigned long long)s_it);
+    if (m_it) atomicMax(cnt + CNT_MAXITER, (unsigned long long)m_it);
+  }
+}
+
+template <class M, typename T, int EMAX, bool EXACT>
+__global__ void __launch_bounds__(kBlock) fit_kernel(const __grid_constant__ KernelArgs<T, EMAX> a) {
+  constexpr int P = M::P;
+  const int64_t v = (int64_t)blockIdx.x * kBlock + threadIdx.x;
+  int st = -1, iters = 0;
+  unsigned flags = 0;
+  if (v < a.n) {
+    const bool active = a.mask == nullptr || a.mask[v] != 0;
+    T p[P], r2 = 0;
+    st = ST_SKIPPED;
+    if (active) {
+      T y[EMAX];
+      load_samples<T, EMAX, EXACT>(a, v, y);
+      load_p0<P, T, EMAX>(a, v, p);
+      st = fit_voxel<M, T, T, EMAX, EXACT>(y, a.xt, a.E, a.vo, p, r2, iters, flags);
+    }
+    store_voxel<P, T, EMAX>(a, v, p, r2, active, st, iters);
+  }
+  warp_stats(a.counters, st, iters, flags);
+}
+
+#endif  // __CUDACC__
+
+// Type-erased launch description filled by the C-ABI layer and consumed by the per-model
+// translation units (inst_*.cu).
+struct LaunchDesc {
+  int model, compute_dtype, n_echo;
+  int64_t n_vox;
+  const double* x;  // host
+  const void* y;
+  int y_dtype, layout;
+  int64_t ld;
+  const uint8_t* mask;
+  const void* p0v;
+  int p0_dtype;
+  unsigned p0_voxel_bits;
+  double p0s[4];
+  void* popt;
+  void* r2;
+  int out_dtype;
+  uint8_t* status;
+  uint8_t* niter;
+  unsigned long long* counters;
+  // solver
+  double ftol, xtol, lambda0, floor_rel, r2_eps, y_lo, y_hi;
+  int maxfev, init_mode, init_linear;
+  PostOpts po;
+  double mask_fill;
+  int use_tma;
+  cudaStream_t stream;
+};
+
+template <typename T, int EMAX>
+inline void fill_args(const LaunchDesc& d, KernelArgs<T, EMAX>& a) {
+  double xbar = 0, sxx = 0;
+  for (int e = 0; e < d.n_echo; ++e) xbar += d.x[e];
+  xbar /= d.n_echo;
+  for (int e = 0; e < EMAX; ++e) {
+    const double xe = e < d.n_echo ? d.x[e] : 0.0;
+    a.xt.x[e] = (T)xe;
+    a.xt.xs[e] = (T)(xe * 1.4426950408889634074);
+    a.xt.xc[e] = (T)(e < d.n_echo ? xe - xbar : 0.0);
+    if (e < d.n_echo) sxx += (xe - xbar) * (xe - xbar);
+  }
+  a.xt.xbar = (T)xbar;
+  a.xt.inv_sxx = (T)(sxx > 0 ? 1.0 / sxx : 0.0);
+  a.vo.s.ftol = (T)d.ftol;
+  a.vo.s.xtol = (T)d.xtol;
+  a.vo.s.lambda0 = (T)d.lambda0;
+  a.vo.s.floor_rel = (T)d.floor_rel;
+  a.vo.s.maxfev = d.maxfev;
+  a.vo.s.init_linear = d.init_linear;
+  a.vo.y_lo = (T)d.y_lo;
+  a.vo.y_hi = (T)d.y_hi;
+  a.vo.r2_eps = (T)d.r2_eps;
+  a.vo.init_mode = d.init_mode;
+  a.po = d.po;
+  a.y = d.y;
+  a.ld = d.ld;
+  a.n = d.n_vox;
+  a.y_dtype = d.y_dtype;
+  a.layout = d.layout;
+  a.E = d.n_echo;
+  a.mask = d.mask;
+  a.p0v = d.p0v;
+  a.p0_dtype = d.p0_dtype;
+  a.p0_voxel_bits = d.p0_voxel_bits;
+  for (int i = 0; i < 4; ++i) a.p0s[i] = (T)d.p0s[i];
+  a.popt = d.popt;
+  a.r2 = d.r2;
+  a.out_dtype = d.out_dtype;
+  a.status = d.status;
+  a.niter = d.niter;
+  a.mask_fill = d.mask_fill;
+  a.counters = d.counters;
+}
+
+#if defined(__CUDACC__)
+template <class M, typename T, int EMAX, bool EXACT>
+inline cudaError_t launch_one(const LaunchDesc& d) {
+  KernelArgs<T, EMAX> a;
+  fill_args<T, EMAX>(d, a);
+  const int64_t blocks = (d.n_vox + kBlock - 1) / kBlock;
+  fit_kernel<M, T, EMAX, EXACT><<<(unsigned)blocks, kBlock, 0, d.stream>>>(a);
+  return cudaGetLastError();
+}
+
+// Echo-count buckets: samples live in EMAX registers; exact-size instances drop the predicates.
+template <class M, typename T>
+inline cudaError_t launch_model(const LaunchDesc& d) {
+  const int E = d.n_echo;
+  if (E <= 4) return E == 4 ? launch_one<M, T, 4, true>(d) : launch_one<M, T, 4, false>(d);
+  if (E <= 8) return E == 8 ? launch_one<M, T, 8, true>(d) : launch_one<M, T, 8, false>(d);
+  if (E <= 16) return E == 16 ? launch_one<M, T, 16, true>(d) : launch_one<M, T, 16, false>(d);
+  return launch_one<M, T, 32, false>(d);
+}
+#endif
+
+// Implemented one per translation unit so the (large, fully unrolled) instances compile in parallel.
+cudaError_t launch_mono_f32(const LaunchDesc& d);
+cudaError_t launch_mono_f64(const LaunchDesc& d);
+cudaError_t launch_biexp_f32(const LaunchDesc& d);
+cudaError_t launch_biexp_f64(const LaunchDesc& d);
+cudaError_t launch_linear_f32(const LaunchDesc& d);
+cudaError_t launch_linear_f64(const LaunchDesc& d);
+
+}  // namespace dfit

@@ -1,0 +1,93 @@
+// TEST-ONLY harness: compiles the device solver header (dosma_b200/csrc/lm_core.cuh) with g++ so the
+// CPU test-suite (-m "not gpu") can exercise the exact per-voxel arithmetic the CUDA kernels run.
+// It is NOT part of the product: dosma_b200/ never loads it and the shipped library (libdfit.so)
+// contains no host implementation of the fit (no CPU fallback).
+#include <cstdint>
+#include <cstring>
+
+#include "../../dosma_b200/csrc/lm_core.cuh"
+
+using namespace dfit;
+
+template <class M, typename T, typename TA, int EMAX>
+static void run(int E, int64_t N, const double* x, const double* y, const double* p0, int64_t n_p0, int init_mode,
+                int init_linear, double ftol, double xtol, double lambda0, double floor_rel, int max_iter,
+                double r2_eps, double y_lo, double y_hi, double* popt, double* r2, int32_t* status, int32_t* iters) {
+  constexpr int P = M::P;
+  XTab<T, EMAX> xt;
+  double xbar = 0, sxx = 0;
+  for (int e = 0; e < E; ++e) xbar += x[e];
+  xbar /= E;
+  for (int e = 0; e < EMAX; ++e) {
+    double xe = e < E ? x[e] : 0.0;
+    xt.x[e] = (T)xe;
+    xt.xs[e] = (T)(xe * 1.4426950408889634);
+    xt.xc[e] = (T)(e < E ? xe - xbar : 0.0);
+    if (e < E) sxx += (xe - xbar) * (xe - xbar);
+  }
+  xt.xbar = (T)xbar;
+  xt.inv_sxx = (T)(1.0 / sxx);
+  VoxelOpts<T> vo;
+  vo.s.ftol = (T)ftol;
+  vo.s.xtol = (T)xtol;
+  vo.s.lambda0 = (T)lambda0;
+  vo.s.floor_rel = (T)floor_rel;
+  vo.s.maxfev = max_iter;
+  vo.s.init_linear = init_linear;
+  vo.y_lo = (T)y_lo;
+  vo.y_hi = (T)y_hi;
+  vo.r2_eps = (T)r2_eps;
+  vo.init_mode = init_mode;
+  for (int64_t v = 0; v < N; ++v) {
+    T yy[EMAX];
+    for (int e = 0; e < EMAX; ++e) yy[e] = e < E ? (T)y[(size_t)e * N + v] : (T)0;
+    T p[P];
+    const double* pv = p0 + (n_p0 > 1 ? (size_t)v * P : 0);
+    for (int i = 0; i < P; ++i) p[i] = (T)pv[i];
+    T r2v;
+    int it;
+    unsigned flags;
+    int st = fit_voxel<M, T, TA, EMAX, false>(yy, xt, E, vo, p, r2v, it, flags);
+    for (int i = 0; i < P; ++i) popt[(size_t)v * P + i] = (double)p[i];
+    r2[v] = (double)r2v;
+    status[v] = st;
+    iters[v] = it;
+  }
+}
+
+extern "C" int hostsim_fit(int model, int dtype, int acc64, int E, int64_t N, const double* x, const double* y,
+                           const double* p0, int64_t n_p0, int init_mode, int init_linear, double ftol, double xtol,
+                           double lambda0, double floor_rel, int max_iter, double r2_eps, double y_lo, double y_hi,
+                           double* popt, double* r2, int32_t* status, int32_t* iters) {
+  if (E > 32) return -1;
+#define ARGS E, N, x, y, p0, n_p0, init_mode, init_linear, ftol, xtol, lambda0, floor_rel, max_iter, r2_eps, y_lo, y_hi, popt, r2, status, iters
+#define DISPATCH(M)                                         \
+  if (dtype == 0 && !acc64) run<M, float, float, 32>(ARGS); \
+  else if (dtype == 0) run<M, float, double, 32>(ARGS);     \
+  else run<M, double, double, 32>(ARGS);
+  switch (model) {
+    case 0: DISPATCH(MonoExp); break;
+    case 1: DISPATCH(BiExp); break;
+    case 2: DISPATCH(Linear1); break;
+    default: return -2;
+  }
+  return 0;
+}
+
+extern "C" double hostsim_post_param(int enabled, const int* ufunc, const double* lb, const double* ub, int has_thr,
+                                     double thr, int has_fill, double fill, const int* decimals, int i, double v,
+                                     double r2) {
+  PostOpts po;
+  po.enabled = enabled;
+  for (int k = 0; k < 4; ++k) {
+    po.ufunc[k] = ufunc[k];
+    po.lb[k] = lb[k];
+    po.ub[k] = ub[k];
+    po.decimals[k] = decimals[k];
+  }
+  po.has_r2_thresh = has_thr;
+  po.r2_thresh = thr;
+  po.has_fill = has_fill;
+  po.fill = fill;
+  return post_param(po, i, v, r2);
+}
