@@ -298,7 +298,7 @@ int dfit_fit_device(dfit_handle* h, const dfit_opts* opts, int n_echo, int64_t n
   if (n_vox > 0 && (!y || !popt || !r2)) return fail(DFIT_ERR_BAD_ARG, "y/popt/r2 must not be NULL");
   if (ld < (y_layout == DFIT_PLANAR ? n_vox : (int64_t)n_echo)) return fail(DFIT_ERR_BAD_ARG, "ld too small");
   CUDA_TRY(cudaSetDevice(h->device));
-  cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
+  cudaStream_t st = (cudaStream_t)stream;  // NULL is the legacy default stream (what torch calls its default stream)
   LaunchDesc d;
   make_desc(opts, n_echo, n_vox, x, d);
   d.y = y;

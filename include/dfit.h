@@ -153,7 +153,7 @@ int dfit_destroy(dfit_handle* h);
  *   p0_voxel device, p0_dtype (F32|F64) [N, P] or NULL (fitting.py:849-851)
  *   popt     device, out_dtype (F32|F64) [N, P];  r2 device, out_dtype [N]
  *   status   device uint8[N] or NULL;  niter device uint8[N] or NULL
- *   stream   cudaStream_t (as void*) to launch on; NULL = the handle's own stream
+ *   stream   cudaStream_t (as void*) to launch on; NULL = the legacy default stream
  * Asynchronous with respect to the host; outputs are valid once `stream` has drained. */
 int dfit_fit_device(dfit_handle* h, const dfit_opts* opts, int n_echo, int64_t n_vox, const double* x, const void* y,
                     int y_dtype, int y_layout, int64_t ld, const uint8_t* mask, const void* p0_voxel, int p0_dtype,
