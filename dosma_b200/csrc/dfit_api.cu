@@ -261,8 +261,8 @@ int dfit_create(int device, dfit_handle** out) {
   h->sm_count = prop.multiProcessorCount;
   CUDA_TRY(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
   for (int s = 0; s < kSlots; ++s) CUDA_TRY(cudaStreamCreateWithFlags(&h->slots[s].stream, cudaStreamNonBlocking));
-  CUDA_TRY(cudaMalloc(&h->counters, CNT_COUNT * sizeof(unsigned long long)));
-  CUDA_TRY(cudaMemset(h->counters, 0, CNT_COUNT * sizeof(unsigned long long)));
+  CUDA_TRY(cudaMalloc(&h->counters, kStatSlots * CNT_COUNT * sizeof(unsigned long long)));
+  CUDA_TRY(cudaMemset(h->counters, 0, kStatSlots * CNT_COUNT * sizeof(unsigned long long)));
   CUDA_TRY(cudaEventCreate(&h->ev_start));
   CUDA_TRY(cudaEventCreate(&h->ev_stop));
   *out = h;
@@ -316,7 +316,7 @@ int dfit_fit_device(dfit_handle* h, const dfit_opts* opts, int n_echo, int64_t n
   d.niter = niter;
   d.counters = h->counters;
   d.stream = st;
-  CUDA_TRY(cudaMemsetAsync(h->counters, 0, CNT_COUNT * sizeof(unsigned long long), st));
+  CUDA_TRY(cudaMemsetAsync(h->counters, 0, kStatSlots * CNT_COUNT * sizeof(unsigned long long), st));
   CUDA_TRY(cudaEventRecord(h->ev_start, st));
   h->last_launches = 0;
   if (n_vox > 0) {
@@ -353,7 +353,7 @@ int dfit_fit_host(dfit_handle* h, const dfit_opts* opts, int n_echo, int64_t n_v
   chunk = (chunk + 127) / 128 * 128;  // 512 B row alignment for vector/TMA access
   if (chunk <= 0) chunk = 128;
 
-  CUDA_TRY(cudaMemsetAsync(h->counters, 0, CNT_COUNT * sizeof(unsigned long long), h->slots[0].stream));
+  CUDA_TRY(cudaMemsetAsync(h->counters, 0, kStatSlots * CNT_COUNT * sizeof(unsigned long long), h->slots[0].stream));
   CUDA_TRY(cudaStreamSynchronize(h->slots[0].stream));
   h->last_launches = 0;
 
@@ -422,8 +422,15 @@ int dfit_get_stats(dfit_handle* h, dfit_stats* out) {
   } else {
     for (int s = 0; s < kSlots; ++s) CUDA_TRY(cudaStreamSynchronize(h->slots[s].stream));
   }
-  unsigned long long c[CNT_COUNT];
-  CUDA_TRY(cudaMemcpy(c, h->counters, sizeof(c), cudaMemcpyDeviceToHost));
+  static thread_local unsigned long long slots[kStatSlots * CNT_COUNT];
+  CUDA_TRY(cudaMemcpy(slots, h->counters, sizeof(slots), cudaMemcpyDeviceToHost));
+  unsigned long long c[CNT_COUNT] = {0};
+  for (int s = 0; s < kStatSlots; ++s)
+    for (int k = 0; k < CNT_COUNT; ++k) {
+      const unsigned long long v = slots[s * CNT_COUNT + k];
+      if (k == CNT_MAXITER) c[k] = v > c[k] ? v : c[k];
+      else c[k] += v;
+    }
   out->n_voxels = h->last_n;
   out->n_fitted = (int64_t)c[CNT_FITTED];
   out->n_failed = (int64_t)c[CNT_FAILED];

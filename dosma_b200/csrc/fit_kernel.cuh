@@ -21,6 +21,7 @@ constexpr int kBlock = 128;
 enum DType : int { DT_F32 = 0, DT_F64 = 1, DT_I16 = 2, DT_U16 = 3, DT_I32 = 4, DT_U8 = 5 };
 enum Layout : int { LAYOUT_PLANAR = 0, LAYOUT_ECHO_FASTEST = 1 };
 enum Counter : int { CNT_FITTED = 0, CNT_FAILED, CNT_NONFINITE, CNT_OOB, CNT_ITERS, CNT_MAXITER, CNT_COUNT };
+constexpr int kStatSlots = 256;  // power of two
 
 template <typename T, int EMAX>
 struct KernelArgs {
@@ -152,8 +153,14 @@ __device__ __forceinline__ void store_voxel(const KernelArgs<T, EMAX>& a, int64_
   if (a.niter) a.niter[v] = (uint8_t)(iters > 255 ? 255 : iters);
 }
 
-// Warp-aggregated statistics: one atomic per warp and counter.
-__device__ __forceinline__ void warp_stats(unsigned long long* cnt, int st, int iters, unsigned flags) {
+// Statistics: warp ballots/reductions -> shared-memory block totals -> ONE global atomic per block
+// and counter, spread over kStatSlots address slots (same-address atomics serialise in the L2
+// atomic unit; 1.8 M warps hammering six addresses cost more than the fit itself).  The host sums
+// the slots in dfit_get_stats.
+__device__ __forceinline__ void block_stats(unsigned long long* cnt, int st, int iters, unsigned flags) {
+  __shared__ unsigned s_cnt[CNT_COUNT];
+  if (threadIdx.x < CNT_COUNT) s_cnt[threadIdx.x] = 0;
+  __syncthreads();
   const unsigned full = 0xffffffffu;
   const unsigned n_fit = __popc(__ballot_sync(full, st >= ST_CONV_F));
   const unsigned n_fail = __popc(__ballot_sync(full, st >= ST_MAXITER));
@@ -162,12 +169,21 @@ __device__ __forceinline__ void warp_stats(unsigned long long* cnt, int st, int 
   const unsigned s_it = __reduce_add_sync(full, (unsigned)iters);
   const unsigned m_it = __reduce_max_sync(full, (unsigned)iters);
   if ((threadIdx.x & 31) == 0) {
-    if (n_fit) atomicAdd(cnt + CNT_FITTED, (unsigned long long)n_fit);
-    if (n_fail) atomicAdd(cnt + CNT_FAILED, (unsigned long long)n_fail);
-    if (n_nf) atomicAdd(cnt + CNT_NONFINITE, (unsigned long long)n_nf);
-    if (n_oob) atomicAdd(cnt + CNT_OOB, (unsigned long long)n_oob);
-    if (s_it) atomicAdd(cnt + CNT_ITERS, (unsigned long long)s_it);
-    if (m_it) atomicMax(cnt + CNT_MAXITER, (unsigned long long)m_it);
+    if (n_fit) atomicAdd(&s_cnt[CNT_FITTED], n_fit);
+    if (n_fail) atomicAdd(&s_cnt[CNT_FAILED], n_fail);
+    if (n_nf) atomicAdd(&s_cnt[CNT_NONFINITE], n_nf);
+    if (n_oob) atomicAdd(&s_cnt[CNT_OOB], n_oob);
+    if (s_it) atomicAdd(&s_cnt[CNT_ITERS], s_it);
+    if (m_it) atomicMax(&s_cnt[CNT_MAXITER], m_it);
+  }
+  __syncthreads();
+  if (threadIdx.x < CNT_COUNT) {
+    const unsigned v = s_cnt[threadIdx.x];
+    unsigned long long* dst = cnt + (size_t)(blockIdx.x & (kStatSlots - 1)) * CNT_COUNT + threadIdx.x;
+    if (v) {
+      if (threadIdx.x == CNT_MAXITER) atomicMax(dst, (unsigned long long)v);
+      else atomicAdd(dst, (unsigned long long)v);
+    }
   }
 }
 
@@ -189,7 +205,7 @@ __global__ void __launch_bounds__(kBlock) fit_kernel(const __grid_constant__ Ker
     }
     store_voxel<P, T, EMAX>(a, v, p, r2, active, st, iters);
   }
-  warp_stats(a.counters, st, iters, flags);
+  block_stats(a.counters, st, iters, flags);
 }
 
 #endif  // __CUDACC__
@@ -278,14 +294,39 @@ inline cudaError_t launch_one(const LaunchDesc& d) {
   return cudaGetLastError();
 }
 
-// Echo-count buckets: samples live in EMAX registers; exact-size instances drop the predicates.
+// Samples live in registers, so the echo count is a template parameter: exact instances for
+// E <= 16 (fully unrolled, no predicates, paired FP32 arithmetic), one predicated 32-register
+// instance above that.
+template <class M, typename T, int E>
+inline cudaError_t launch_exact(const LaunchDesc& d) {
+  if constexpr (E < M::P) {
+    return cudaErrorInvalidValue;
+  } else {
+    return launch_one<M, T, E, true>(d);
+  }
+}
+
 template <class M, typename T>
 inline cudaError_t launch_model(const LaunchDesc& d) {
-  const int E = d.n_echo;
-  if (E <= 4) return E == 4 ? launch_one<M, T, 4, true>(d) : launch_one<M, T, 4, false>(d);
-  if (E <= 8) return E == 8 ? launch_one<M, T, 8, true>(d) : launch_one<M, T, 8, false>(d);
-  if (E <= 16) return E == 16 ? launch_one<M, T, 16, true>(d) : launch_one<M, T, 16, false>(d);
-  return launch_one<M, T, 32, false>(d);
+  switch (d.n_echo) {
+    case 1: return launch_exact<M, T, 1>(d);
+    case 2: return launch_exact<M, T, 2>(d);
+    case 3: return launch_exact<M, T, 3>(d);
+    case 4: return launch_exact<M, T, 4>(d);
+    case 5: return launch_exact<M, T, 5>(d);
+    case 6: return launch_exact<M, T, 6>(d);
+    case 7: return launch_exact<M, T, 7>(d);
+    case 8: return launch_exact<M, T, 8>(d);
+    case 9: return launch_exact<M, T, 9>(d);
+    case 10: return launch_exact<M, T, 10>(d);
+    case 11: return launch_exact<M, T, 11>(d);
+    case 12: return launch_exact<M, T, 12>(d);
+    case 13: return launch_exact<M, T, 13>(d);
+    case 14: return launch_exact<M, T, 14>(d);
+    case 15: return launch_exact<M, T, 15>(d);
+    case 16: return launch_exact<M, T, 16>(d);
+    default: return launch_one<M, T, 32, false>(d);
+  }
 }
 #endif
 

@@ -54,6 +54,27 @@ struct num<float> {
     return exp2f(b * xs);
 #endif
   }
+  // Approximate reciprocal / rsqrt (MUFU, ~1 ulp): used only inside the solver (scaling, damping,
+  // step computation), where an inexact step is corrected by the next iteration.  The model
+  // evaluation and r2 use exact arithmetic.
+  static DFIT_HD float rcp_(float v) {
+#if defined(__CUDA_ARCH__)
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v));
+    return r;
+#else
+    return 1.0f / v;
+#endif
+  }
+  static DFIT_HD float rsqrt_(float v) {
+#if defined(__CUDA_ARCH__)
+    float r;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v));
+    return r;
+#else
+    return 1.0f / sqrtf(v);
+#endif
+  }
   static DFIT_HD float exp_(float v) { return expf(v); }
   static DFIT_HD float log_(float v) { return logf(v); }
   static DFIT_HD float sqrt_(float v) { return sqrtf(v); }
@@ -71,6 +92,8 @@ struct num<double> {
   static DFIT_HD double tiny() { return 1.0e-290; }
   static DFIT_HD double huge() { return 1.0e300; }
   static DFIT_HD double expbx(double b, double x, double /*xs*/) { return exp(b * x); }
+  static DFIT_HD double rcp_(double v) { return 1.0 / v; }
+  static DFIT_HD double rsqrt_(double v) { return 1.0 / sqrt(v); }
   static DFIT_HD double exp_(double v) { return exp(v); }
   static DFIT_HD double log_(double v) { return log(v); }
   static DFIT_HD double sqrt_(double v) { return sqrt(v); }
@@ -81,20 +104,104 @@ struct num<double> {
   static DFIT_HD bool finite(double v) { return fabs(v) <= 1.7976931348623157e308; }
 };
 
+// ------------------------------------------------------------------------------------ pair2
+// Two samples processed per instruction.  For float on sm_100a the arithmetic maps onto Blackwell's
+// packed FP32 instructions (PTX fma/mul/add.rn.f32x2 -> SASS FFMA2/FMUL2/FADD2): the FMA pipe does
+// the same 128 FMA/clk/SM either way (profiles/microbench/pipe_rates.cu), but a packed instruction
+// takes ONE issue slot for two FMAs, and this kernel is issue-bound.  Elsewhere (double, host) the
+// pair is two scalar operations.
+template <typename T>
+struct pair2 {
+  T lo, hi;
+};
+
+template <typename T>
+DFIT_HD pair2<T> p2_make(T lo, T hi) {
+  pair2<T> r;
+  r.lo = lo;
+  r.hi = hi;
+  return r;
+}
+template <typename T>
+DFIT_HD pair2<T> p2_bcast(T v) {
+  return p2_make<T>(v, v);
+}
+template <typename T>
+DFIT_HD pair2<T> p2_fma(pair2<T> a, pair2<T> b, pair2<T> c) {
+  return p2_make<T>(num<T>::fma_(a.lo, b.lo, c.lo), num<T>::fma_(a.hi, b.hi, c.hi));
+}
+template <typename T>
+DFIT_HD pair2<T> p2_mul(pair2<T> a, pair2<T> b) {
+  return p2_make<T>(a.lo * b.lo, a.hi * b.hi);
+}
+template <typename T>
+DFIT_HD pair2<T> p2_add(pair2<T> a, pair2<T> b) {
+  return p2_make<T>(a.lo + b.lo, a.hi + b.hi);
+}
+#if defined(__CUDA_ARCH__)
+template <>
+__device__ __forceinline__ pair2<float> p2_fma<float>(pair2<float> a, pair2<float> b, pair2<float> c) {
+  pair2<float> d;
+  asm("{.reg .b64 ra, rb, rc, rd;\n\t"
+      "mov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tmov.b64 rc, {%6, %7};\n\t"
+      "fma.rn.f32x2 rd, ra, rb, rc;\n\tmov.b64 {%0, %1}, rd;}"
+      : "=f"(d.lo), "=f"(d.hi)
+      : "f"(a.lo), "f"(a.hi), "f"(b.lo), "f"(b.hi), "f"(c.lo), "f"(c.hi));
+  return d;
+}
+template <>
+__device__ __forceinline__ pair2<float> p2_mul<float>(pair2<float> a, pair2<float> b) {
+  pair2<float> d;
+  asm("{.reg .b64 ra, rb, rd;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\t"
+      "mul.rn.f32x2 rd, ra, rb;\n\tmov.b64 {%0, %1}, rd;}"
+      : "=f"(d.lo), "=f"(d.hi)
+      : "f"(a.lo), "f"(a.hi), "f"(b.lo), "f"(b.hi));
+  return d;
+}
+template <>
+__device__ __forceinline__ pair2<float> p2_add<float>(pair2<float> a, pair2<float> b) {
+  pair2<float> d;
+  asm("{.reg .b64 ra, rb, rd;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\t"
+      "add.rn.f32x2 rd, ra, rb;\n\tmov.b64 {%0, %1}, rd;}"
+      : "=f"(d.lo), "=f"(d.hi)
+      : "f"(a.lo), "f"(a.hi), "f"(b.lo), "f"(b.hi));
+  return d;
+}
+#endif
+template <typename T>
+DFIT_HD pair2<T> p2_expbx(T b, pair2<T> x, pair2<T> xs) {
+  return p2_make<T>(num<T>::expbx(b, x.lo, xs.lo), num<T>::expbx(b, x.hi, xs.hi));
+}
+
 // ------------------------------------------------------------------------------------ models
-// Each model provides the value f and the analytic Jacobian row J[P] for one sample, and LIN, the
-// bit-mask of parameters the model is linear in (used for the variable-projection start).
+// Each model provides, for one sample, the value f and an UNSCALED Jacobian row Jh[P]; the true
+// Jacobian is J_i = cs_i * Jh_i with per-parameter column scales cs (colscale()) that do not depend
+// on the sample.  Accumulating Jh^T Jh and applying cs once per pass saves a multiply per sample and
+// column (d/db of a*exp(b x) is a * [x exp(b x)]).  LIN is the bit-mask of parameters the model is
+// linear in (used for the variable-projection start).
 
 // fitting.py:1016-1018  f = a * exp(b x)
 struct MonoExp {
   static constexpr int P = 2;
   static constexpr unsigned LIN = 0x1u;
   template <typename T>
-  static DFIT_HD void eval(const T (&p)[2], T x, T xs, T& f, T (&J)[2]) {
+  static DFIT_HD void eval(const T (&p)[2], T x, T xs, T& f, T (&Jh)[2]) {
     T e = num<T>::expbx(p[1], x, xs);
-    J[0] = e;
+    Jh[0] = e;
+    Jh[1] = x * e;
     f = p[0] * e;
-    J[1] = x * f;
+  }
+  template <typename T>
+  static DFIT_HD void eval2(const T (&p)[2], pair2<T> x, pair2<T> xs, pair2<T> yneg, pair2<T>& r, pair2<T> (&Jh)[2]) {
+    const pair2<T> e = p2_expbx<T>(p[1], x, xs);
+    Jh[0] = e;
+    Jh[1] = p2_mul<T>(x, e);
+    r = p2_fma<T>(p2_bcast<T>(p[0]), e, yneg);
+  }
+  template <typename T>
+  static DFIT_HD void colscale(const T (&p)[2], T (&cs)[2]) {
+    cs[0] = (T)1;
+    cs[1] = p[0];
   }
 };
 
@@ -103,15 +210,31 @@ struct BiExp {
   static constexpr int P = 4;
   static constexpr unsigned LIN = 0x5u;
   template <typename T>
-  static DFIT_HD void eval(const T (&p)[4], T x, T xs, T& f, T (&J)[4]) {
+  static DFIT_HD void eval(const T (&p)[4], T x, T xs, T& f, T (&Jh)[4]) {
     T e1 = num<T>::expbx(p[1], x, xs);
     T e2 = num<T>::expbx(p[3], x, xs);
-    T f1 = p[0] * e1, f2 = p[2] * e2;
-    J[0] = e1;
-    J[1] = x * f1;
-    J[2] = e2;
-    J[3] = x * f2;
-    f = f1 + f2;
+    Jh[0] = e1;
+    Jh[1] = x * e1;
+    Jh[2] = e2;
+    Jh[3] = x * e2;
+    f = num<T>::fma_(p[0], e1, p[2] * e2);
+  }
+  template <typename T>
+  static DFIT_HD void eval2(const T (&p)[4], pair2<T> x, pair2<T> xs, pair2<T> yneg, pair2<T>& r, pair2<T> (&Jh)[4]) {
+    const pair2<T> e1 = p2_expbx<T>(p[1], x, xs);
+    const pair2<T> e2 = p2_expbx<T>(p[3], x, xs);
+    Jh[0] = e1;
+    Jh[1] = p2_mul<T>(x, e1);
+    Jh[2] = e2;
+    Jh[3] = p2_mul<T>(x, e2);
+    r = p2_fma<T>(p2_bcast<T>(p[0]), e1, p2_fma<T>(p2_bcast<T>(p[2]), e2, yneg));
+  }
+  template <typename T>
+  static DFIT_HD void colscale(const T (&p)[4], T (&cs)[4]) {
+    cs[0] = (T)1;
+    cs[1] = p[0];
+    cs[2] = (T)1;
+    cs[3] = p[2];
   }
 };
 
@@ -120,9 +243,18 @@ struct Linear1 {
   static constexpr int P = 1;
   static constexpr unsigned LIN = 0x1u;
   template <typename T>
-  static DFIT_HD void eval(const T (&p)[1], T x, T /*xs*/, T& f, T (&J)[1]) {
-    J[0] = x;
+  static DFIT_HD void eval(const T (&p)[1], T x, T /*xs*/, T& f, T (&Jh)[1]) {
+    Jh[0] = x;
     f = p[0] * x;
+  }
+  template <typename T>
+  static DFIT_HD void eval2(const T (&p)[1], pair2<T> x, pair2<T> /*xs*/, pair2<T> yneg, pair2<T>& r, pair2<T> (&Jh)[1]) {
+    Jh[0] = x;
+    r = p2_fma<T>(p2_bcast<T>(p[0]), x, yneg);
+  }
+  template <typename T>
+  static DFIT_HD void colscale(const T (&)[1], T (&cs)[1]) {
+    cs[0] = (T)1;
   }
 };
 
@@ -141,25 +273,44 @@ struct SolverOpts {
 // Packed lower-triangular index, i >= j.
 DFIT_HD constexpr int tri(int i, int j) { return i * (i + 1) / 2 + j; }
 
-// One pass over the echoes: residuals r = f - y, cost F = sum r^2, A = J^T J (packed), g = J^T r.
-// TA is the accumulator type (float, or double for the ill-conditioned 4-parameter model).
+// One pass over the echoes: cost F = sum (f - y)^2, A = J^T J (packed lower), g = J^T r.
+// With an exact echo count and matching accumulator type the echoes are processed two at a time
+// (pair2 -> packed FP32 instructions on sm_100a); partial sums of even and odd echoes are kept in
+// the two halves and added at the end.
 template <class M, typename T, typename TA, int EMAX, bool EXACT>
 DFIT_HD void eval_all(const T (&p)[M::P], const T (&y)[EMAX], const T* __restrict__ x,
-                      const T* __restrict__ xs, int E, T (&r)[EMAX], TA& F, TA (&A)[M::P * (M::P + 1) / 2],
-                      TA (&g)[M::P]) {
+                      const T* __restrict__ xs, int E, TA& F, TA (&A)[M::P * (M::P + 1) / 2], TA (&g)[M::P]) {
   constexpr int P = M::P;
-  F = 0;
+  constexpr int NA = P * (P + 1) / 2;
+  constexpr bool PAIRED = EXACT && sizeof(T) == sizeof(TA) && EMAX >= 2;
+  if constexpr (PAIRED) {
+    pair2<T> F2 = p2_bcast<T>((T)0), A2[NA], g2[P];
 #pragma unroll
-  for (int k = 0; k < P * (P + 1) / 2; ++k) A[k] = 0;
+    for (int k = 0; k < NA; ++k) A2[k] = p2_bcast<T>((T)0);
 #pragma unroll
-  for (int k = 0; k < P; ++k) g[k] = 0;
+    for (int k = 0; k < P; ++k) g2[k] = p2_bcast<T>((T)0);
 #pragma unroll
-  for (int e = 0; e < EMAX; ++e) {
-    if (EXACT || e < E) {
+    for (int e = 0; e + 1 < EMAX; e += 2) {
+      pair2<T> r, J[P];
+      M::template eval2<T>(p, p2_make<T>(x[e], x[e + 1]), p2_make<T>(xs[e], xs[e + 1]), p2_make<T>(-y[e], -y[e + 1]), r,
+                           J);
+      F2 = p2_fma<T>(r, r, F2);
+#pragma unroll
+      for (int i = 0; i < P; ++i) {
+        g2[i] = p2_fma<T>(J[i], r, g2[i]);
+#pragma unroll
+        for (int j = 0; j <= i; ++j) A2[tri(i, j)] = p2_fma<T>(J[i], J[j], A2[tri(i, j)]);
+      }
+    }
+    F = (TA)(F2.lo + F2.hi);
+#pragma unroll
+    for (int k = 0; k < NA; ++k) A[k] = (TA)(A2[k].lo + A2[k].hi);
+#pragma unroll
+    for (int k = 0; k < P; ++k) g[k] = (TA)(g2[k].lo + g2[k].hi);
+    if constexpr (EMAX & 1) {
       T f, J[P];
-      M::template eval<T>(p, x[e], xs[e], f, J);
-      T re = f - y[e];
-      r[e] = re;
+      M::template eval<T>(p, x[EMAX - 1], xs[EMAX - 1], f, J);
+      const T re = f - y[EMAX - 1];
       F = num<TA>::fma_((TA)re, (TA)re, F);
 #pragma unroll
       for (int i = 0; i < P; ++i) {
@@ -168,49 +319,95 @@ DFIT_HD void eval_all(const T (&p)[M::P], const T (&y)[EMAX], const T* __restric
         for (int j = 0; j <= i; ++j) A[tri(i, j)] = num<TA>::fma_((TA)J[i], (TA)J[j], A[tri(i, j)]);
       }
     }
+  } else {
+    F = 0;
+#pragma unroll
+    for (int k = 0; k < NA; ++k) A[k] = 0;
+#pragma unroll
+    for (int k = 0; k < P; ++k) g[k] = 0;
+#pragma unroll
+    for (int e = 0; e < EMAX; ++e) {
+      if (EXACT || e < E) {
+        T f, J[P];
+        M::template eval<T>(p, x[e], xs[e], f, J);
+        const T re = f - y[e];
+        F = num<TA>::fma_((TA)re, (TA)re, F);
+#pragma unroll
+        for (int i = 0; i < P; ++i) {
+          g[i] = num<TA>::fma_((TA)J[i], (TA)re, g[i]);
+#pragma unroll
+          for (int j = 0; j <= i; ++j) A[tri(i, j)] = num<TA>::fma_((TA)J[i], (TA)J[j], A[tri(i, j)]);
+        }
+      }
+    }
+  }
+  T cs[P];
+  M::template colscale<T>(p, cs);
+#pragma unroll
+  for (int i = 0; i < P; ++i) {
+    g[i] *= (TA)cs[i];
+#pragma unroll
+    for (int j = 0; j <= i; ++j) A[tri(i, j)] *= (TA)cs[i] * (TA)cs[j];
   }
 }
 
-// Solve (C + lam I) z = -gs for symmetric C (packed lower) by Cholesky, all in registers.
-// Rows/columns whose bit is cleared in `active` are frozen (z_i = 0).
+// Solve (C + lam I) z = -gs for symmetric C (packed lower), all in registers.  Rows/columns whose
+// bit is cleared in `active` are frozen (z_i = 0).  P <= 2 uses the closed form, larger systems an
+// unrolled Cholesky.  Reciprocals are approximate (see num<>::rcp_).
 template <int P, typename TA>
 DFIT_HD bool chol_solve(const TA (&C)[P * (P + 1) / 2], TA lam, const TA (&gs)[P], unsigned active, TA (&z)[P]) {
-  TA L[P * (P + 1) / 2];
+  const TA tiny = num<TA>::eps() * (TA)4;
+  if constexpr (P == 1) {
+    const TA d = C[0] + lam;
+    z[0] = (active & 1u) ? -gs[0] * num<TA>::rcp_(d) : (TA)0;
+    return d > tiny || !(active & 1u);
+  } else if constexpr (P == 2) {
+    const bool a0 = active & 1u, a1 = (active >> 1) & 1u;
+    const TA d0 = a0 ? C[0] + lam : (TA)1, d1 = a1 ? C[2] + lam : (TA)1;
+    const TA c = (a0 && a1) ? C[1] : (TA)0;
+    const TA g0 = a0 ? gs[0] : (TA)0, g1 = a1 ? gs[1] : (TA)0;
+    const TA det = d0 * d1 - c * c;
+    const TA inv = num<TA>::rcp_(det);
+    z[0] = (c * g1 - d1 * g0) * inv;
+    z[1] = (c * g0 - d0 * g1) * inv;
+    return det > tiny * d0 * d1 && d0 > tiny && d1 > tiny;
+  } else {
+    TA L[P * (P + 1) / 2], Dinv[P];
 #pragma unroll
-  for (int j = 0; j < P; ++j) {
-    const bool aj = (active >> j) & 1u;
-    TA s = aj ? C[tri(j, j)] + lam : (TA)1;
+    for (int j = 0; j < P; ++j) {
+      const bool aj = (active >> j) & 1u;
+      TA s = aj ? C[tri(j, j)] + lam : (TA)1;
 #pragma unroll
-    for (int k = 0; k < j; ++k) s -= L[tri(j, k)] * L[tri(j, k)];
-    if (!(s > num<TA>::eps() * (TA)4)) return false;
-    TA d = num<TA>::sqrt_(s);
-    L[tri(j, j)] = d;
-    TA inv = (TA)1 / d;
+      for (int k = 0; k < j; ++k) s -= L[tri(j, k)] * L[tri(j, k)];
+      if (!(s > tiny)) return false;
+      const TA inv = num<TA>::rsqrt_(s);
+      Dinv[j] = inv;
 #pragma unroll
-    for (int i = j + 1; i < P; ++i) {
-      const bool ai = (active >> i) & 1u;
-      TA t = (aj && ai) ? C[tri(i, j)] : (TA)0;
+      for (int i = j + 1; i < P; ++i) {
+        const bool ai = (active >> i) & 1u;
+        TA t = (aj && ai) ? C[tri(i, j)] : (TA)0;
 #pragma unroll
-      for (int k = 0; k < j; ++k) t -= L[tri(i, k)] * L[tri(j, k)];
-      L[tri(i, j)] = t * inv;
+        for (int k = 0; k < j; ++k) t -= L[tri(i, k)] * L[tri(j, k)];
+        L[tri(i, j)] = t * inv;
+      }
     }
+    TA w[P];
+#pragma unroll
+    for (int i = 0; i < P; ++i) {
+      TA t = ((active >> i) & 1u) ? -gs[i] : (TA)0;
+#pragma unroll
+      for (int k = 0; k < i; ++k) t -= L[tri(i, k)] * w[k];
+      w[i] = t * Dinv[i];
+    }
+#pragma unroll
+    for (int i = P - 1; i >= 0; --i) {
+      TA t = w[i];
+#pragma unroll
+      for (int k = i + 1; k < P; ++k) t -= L[tri(k, i)] * z[k];
+      z[i] = t * Dinv[i];
+    }
+    return true;
   }
-  TA w[P];
-#pragma unroll
-  for (int i = 0; i < P; ++i) {
-    TA t = ((active >> i) & 1u) ? -gs[i] : (TA)0;
-#pragma unroll
-    for (int k = 0; k < i; ++k) t -= L[tri(i, k)] * w[k];
-    w[i] = t / L[tri(i, i)];
-  }
-#pragma unroll
-  for (int i = P - 1; i >= 0; --i) {
-    TA t = w[i];
-#pragma unroll
-    for (int k = i + 1; k < P; ++k) t -= L[tri(k, i)] * z[k];
-    z[i] = t / L[tri(i, i)];
-  }
-  return true;
 }
 
 // Log-linear (degree-1 polyfit of ln y) initial guess for the mono-exponential model:
@@ -241,16 +438,57 @@ DFIT_HD void loglinear_init(const T (&y)[EMAX], const T* __restrict__ xc, T xbar
   }
 }
 
+// Marquardt-scaled step from the current normal equations.  Returns false if the (restricted)
+// system is not positive definite.  Outputs the trial point pt, |z|^2, the scaled norm of pt and the
+// predicted reduction z^T C z + 2 lam z^T z (all terms >= 0) of the linearised model.
+template <int P, typename T, typename TA>
+DFIT_HD bool lm_step(const T (&p)[P], const TA (&A)[P * (P + 1) / 2], const TA (&g)[P], TA (&D2)[P], TA lam,
+                     unsigned active, T (&pt)[P], TA& zz, TA& pnorm2, TA& pred) {
+  constexpr int NA = P * (P + 1) / 2;
+  TA Di[P], C[NA], gs[P], z[P];
+#pragma unroll
+  for (int i = 0; i < P; ++i) {
+    D2[i] = num<TA>::max_(D2[i], A[tri(i, i)]);  // running maximum: MINPACK's diag rule
+    Di[i] = D2[i] > 0 ? num<TA>::rsqrt_(D2[i]) : (TA)1;
+  }
+#pragma unroll
+  for (int i = 0; i < P; ++i) {
+    gs[i] = g[i] * Di[i];
+#pragma unroll
+    for (int j = 0; j <= i; ++j) C[tri(i, j)] = A[tri(i, j)] * Di[i] * Di[j];
+  }
+  if (!chol_solve<P, TA>(C, lam, gs, active, z)) return false;
+  zz = 0;
+  pnorm2 = 0;
+  TA zCz = 0;
+#pragma unroll
+  for (int i = 0; i < P; ++i) {
+    pt[i] = p[i] + (T)(z[i] * Di[i]);
+    zz = num<TA>::fma_(z[i], z[i], zz);
+    zCz = num<TA>::fma_(C[tri(i, i)] * z[i], z[i], zCz);
+#pragma unroll
+    for (int j = 0; j < i; ++j) zCz = num<TA>::fma_((TA)2 * C[tri(i, j)] * z[i], z[j], zCz);
+    pnorm2 = num<TA>::fma_(D2[i] * (TA)pt[i], (TA)pt[i], pnorm2);
+  }
+  pred = zCz + (TA)2 * lam * zz;
+  return true;
+}
+
 // The solver.  On entry p holds the initial guess; on exit the accepted parameters.
-// Returns a Status; F_out is the final sum of squared residuals, iters the trial steps taken.
+// Returns a Status; F_out is the sum of squared residuals at the returned point, iters the number
+// of passes over the echoes (model + Jacobian evaluations) spent.
+//
+// Every pass (eval_all) yields the cost for the gain ratio AND the normal equations for the next
+// step.  Two passes are saved relative to a textbook LM:
+//   * the variable-projection start is a first step restricted to the linear parameters with zero
+//     damping, taken from the linear parameters set to zero (its trial pass IS the first pass);
+//   * a step whose predicted reduction is already below ftol*F is taken without evaluating it.
 template <class M, typename T, typename TA, int EMAX, bool EXACT>
 DFIT_HD int lm_solve(T (&p)[M::P], const T (&y)[EMAX], const T* __restrict__ x, const T* __restrict__ xs, int E,
                      const SolverOpts<T>& o, T& F_out, int& iters) {
   constexpr int P = M::P;
   constexpr int NA = P * (P + 1) / 2;
   constexpr unsigned ALL = (1u << P) - 1u;
-  T r[EMAX];
-  TA F, A[NA], g[P];
   iters = 0;
 
   TA ysq = 0;
@@ -258,143 +496,126 @@ DFIT_HD int lm_solve(T (&p)[M::P], const T (&y)[EMAX], const T* __restrict__ x, 
   for (int e = 0; e < EMAX; ++e)
     if (EXACT || e < E) ysq = num<TA>::fma_((TA)y[e], (TA)y[e], ysq);
   const TA floorF = (TA)o.floor_rel * ysq;
+  const TA ftol = (TA)o.ftol, xtol2 = (TA)o.xtol * (TA)o.xtol;
+  const TA eps16 = (TA)16 * (TA)num<T>::eps();
 
-  if (o.init_linear) {
-    // Variable-projection start: with the non-linear parameters fixed, the optimum of the linear
-    // ones is a linear least-squares problem -- one Gauss-Newton step from zero, restricted to them.
-    T q[P];
+  TA F = 0, A[NA], g[P], D2[P];
 #pragma unroll
-    for (int i = 0; i < P; ++i) q[i] = ((M::LIN >> i) & 1u) ? (T)0 : p[i];
-    eval_all<M, T, TA, EMAX, EXACT>(q, y, x, xs, E, r, F, A, g);
-    TA D[P], C[NA], gs[P], z[P];
-    bool ok = true;
-#pragma unroll
-    for (int i = 0; i < P; ++i) {
-      D[i] = num<TA>::sqrt_(A[tri(i, i)]);
-      if (!(D[i] > 0)) D[i] = 1;
-      D[i] = (TA)1 / D[i];
-    }
+  for (int i = 0; i < P; ++i) D2[i] = 0;
+  TA zz = 0, pnorm2 = 0, pred = 0;
+  int fev = 0;
+
+  // ---- start: at most three passes with one evaluation site --------------------------------
+  // stage 0: the point with the linear parameters zeroed (cost = sum y^2, J of the linear columns)
+  // stage 1: the projected point; stage 2: p0 exactly as given (projection off or not usable)
+  {
+    T plin[P], pt[P];
+    int stage = o.init_linear != 0 ? 0 : 2;
 #pragma unroll
     for (int i = 0; i < P; ++i) {
-      gs[i] = g[i] * D[i];
-#pragma unroll
-      for (int j = 0; j <= i; ++j) C[tri(i, j)] = A[tri(i, j)] * D[i] * D[j];
+      plin[i] = p[i];
+      pt[i] = (stage == 0 && ((M::LIN >> i) & 1u)) ? (T)0 : p[i];
     }
-    ok = chol_solve<P, TA>(C, (TA)0, gs, M::LIN, z);
+    for (;;) {
+      TA Fn, An[NA], gn[P];
+      eval_all<M, T, TA, EMAX, EXACT>(pt, y, x, xs, E, Fn, An, gn);
+      ++iters;
+      fev += 1 + P;
+      const bool good = num<TA>::finite(Fn);
+      if (stage == 1 && !(good && Fn <= F)) {  // projection did not help: start from p0 as given
+        stage = 2;
 #pragma unroll
-    for (int i = 0; i < P; ++i) {
-      q[i] = ((M::LIN >> i) & 1u) ? (T)(z[i] * D[i]) : p[i];
-      ok = ok && num<T>::finite(q[i]);
-    }
-    if (ok) {
+        for (int i = 0; i < P; ++i) pt[i] = plin[i];
+        continue;
+      }
+      if (!good) {
+        F_out = (T)Fn;
+        return ST_NUMERIC;
+      }
 #pragma unroll
-      for (int i = 0; i < P; ++i) p[i] = q[i];
+      for (int i = 0; i < P; ++i) {
+        p[i] = pt[i];
+        g[i] = gn[i];
+      }
+#pragma unroll
+      for (int k = 0; k < NA; ++k) A[k] = An[k];
+      F = Fn;
+      if (stage != 0) break;
+      TA D2p[P];
+#pragma unroll
+      for (int i = 0; i < P; ++i) D2p[i] = 0;
+      if (lm_step<P, T, TA>(p, A, g, D2p, (TA)0, M::LIN, pt, zz, pnorm2, pred)) {
+        stage = 1;
+      } else {
+        stage = 2;
+#pragma unroll
+        for (int i = 0; i < P; ++i) pt[i] = plin[i];
+      }
     }
   }
 
-  eval_all<M, T, TA, EMAX, EXACT>(p, y, x, xs, E, r, F, A, g);
-  if (!num<TA>::finite(F)) {
-    F_out = (T)F;
-    return ST_NUMERIC;
-  }
-
-  TA D[P];
-#pragma unroll
-  for (int i = 0; i < P; ++i) D[i] = 0;
+  // ---- Levenberg-Marquardt iterations -----------------------------------------------------------
   TA lam = (TA)o.lambda0, nu = 2;
   int status = ST_MAXITER;
-  const TA ftol = (TA)o.ftol, xtol2 = (TA)o.xtol * (TA)o.xtol;
-
-  int fev = 1 + P;
   while (fev < o.maxfev) {
     if (F <= floorF) {
       status = ST_EXACT;
       break;
     }
+    T pt[P];
+    bool solved = lm_step<P, T, TA>(p, A, g, D2, lam, ALL, pt, zz, pnorm2, pred);
+    for (int tries = 0; tries < 12 && !solved; ++tries) {
+      lam = num<TA>::max_(lam * (TA)10, (TA)1e-3);
+      solved = lm_step<P, T, TA>(p, A, g, D2, lam, ALL, pt, zz, pnorm2, pred);
+    }
+    if (!solved) break;
+    if (pred <= ftol * F && lam <= (TA)1) {
+      // the step is below the tolerance before it is even evaluated: take it and stop
+#pragma unroll
+      for (int i = 0; i < P; ++i) p[i] = pt[i];
+      status = zz <= xtol2 * pnorm2 ? ST_CONV_FX : ST_CONV_F;
+      break;
+    }
+    TA Fn, An[NA], gn[P];
+    eval_all<M, T, TA, EMAX, EXACT>(pt, y, x, xs, E, Fn, An, gn);
     ++iters;
     ++fev;
-    // Marquardt scaling with MINPACK's running-maximum rule: D_i = max(D_i, ||J_i||), 1 if zero.
-    TA Di[P], C[NA], gs[P], z[P];
-#pragma unroll
-    for (int i = 0; i < P; ++i) {
-      D[i] = num<TA>::max_(D[i], num<TA>::sqrt_(A[tri(i, i)]));
-      Di[i] = (TA)1 / (D[i] > 0 ? D[i] : (TA)1);
-    }
-#pragma unroll
-    for (int i = 0; i < P; ++i) {
-      gs[i] = g[i] * Di[i];
-#pragma unroll
-      for (int j = 0; j <= i; ++j) C[tri(i, j)] = A[tri(i, j)] * Di[i] * Di[j];
-    }
-    if (!chol_solve<P, TA>(C, lam, gs, ALL, z)) {
-      lam = num<TA>::max_(lam * (TA)10, (TA)1e-3);
-      continue;
-    }
-    T pn[P];
-#pragma unroll
-    for (int i = 0; i < P; ++i) pn[i] = p[i] + (T)(z[i] * Di[i]);
-
-    T rn[EMAX];
-    TA Fn, An[NA], gn[P];
-    eval_all<M, T, TA, EMAX, EXACT>(pn, y, x, xs, E, rn, Fn, An, gn);
-
-    // predicted reduction of the linearised model: z^T C z + 2 lam z^T z  (all terms >= 0)
-    TA zz = 0, zCz = 0;
-#pragma unroll
-    for (int i = 0; i < P; ++i) {
-      zz = num<TA>::fma_(z[i], z[i], zz);
-      zCz = num<TA>::fma_(C[tri(i, i)] * z[i], z[i], zCz);
-#pragma unroll
-      for (int j = 0; j < i; ++j) zCz = num<TA>::fma_((TA)2 * C[tri(i, j)] * z[i], z[j], zCz);
-    }
-    const TA pred = zCz + (TA)2 * lam * zz;
-    // actual reduction F - Fn, accumulated as sum (r - rn)(r + rn) so that it stays accurate when
-    // the two costs agree to more digits than T resolves.
-    TA act = 0;
-#pragma unroll
-    for (int e = 0; e < EMAX; ++e)
-      if (EXACT || e < E) act = num<TA>::fma_((TA)(r[e] - rn[e]), (TA)(r[e] + rn[e]), act);
-
     const bool good = num<TA>::finite(Fn);
-    // `act` is a difference of model evaluations each carrying ~eps*|y| of rounding, so it cannot
-    // resolve reductions below tau ~ eps*sqrt(sum y^2 * F).  Below that level the gain ratio is
-    // noise: trust the (accurately computed) predicted reduction instead of rejecting at random.
-    const TA tau = (TA)8 * (TA)num<T>::eps() * num<TA>::sqrt_(ysq * F);
-    const bool reliable = pred > tau;
-    const TA rho = (good && pred > 0) ? (reliable ? act / pred : (TA)1) : (TA)-1;
-    const bool accept = good && (reliable ? rho > (TA)1e-4 : act > -tau);
-    const TA relact = reliable ? num<TA>::abs_(act) / F : (TA)0, relpred = pred / F;
+    const TA act = F - Fn;
+    // F and Fn are sums of squares of model evaluations that each carry ~eps*|y| of rounding, so
+    // their difference cannot resolve reductions below tau ~ eps*sqrt(sum y^2 * F).  Below that
+    // level the gain ratio is noise: trust the (accurately computed) predicted reduction instead
+    // of rejecting at random.  (Compared squared to avoid the square root.)
+    const TA tau2 = eps16 * eps16 * ysq * F;
+    const bool reliable = pred * pred > tau2;
+    const bool accept = good && (reliable ? act > (TA)1e-4 * pred : act * num<TA>::abs_(act) > -tau2);
+    const TA rho = reliable ? act * num<TA>::rcp_(pred) : (TA)1;
+    const bool small_f =
+        good && pred <= ftol * F && (!reliable || (num<TA>::abs_(act) <= ftol * F && act <= (TA)2 * pred));
+    const bool conv_x = accept && zz <= xtol2 * pnorm2;
     if (accept) {
 #pragma unroll
       for (int i = 0; i < P; ++i) {
-        p[i] = pn[i];
+        p[i] = pt[i];
         g[i] = gn[i];
       }
 #pragma unroll
       for (int k = 0; k < NA; ++k) A[k] = An[k];
-#pragma unroll
-      for (int e = 0; e < EMAX; ++e)
-        if (EXACT || e < E) r[e] = rn[e];
       F = Fn;
       const TA t = (TA)2 * rho - (TA)1;
-      lam *= num<TA>::max_((TA)(1.0 / 3.0), (TA)1 - t * t * t);
-      lam = num<TA>::max_(lam, (TA)1e-9);
+      lam = num<TA>::max_(lam * num<TA>::max_((TA)(1.0 / 3.0), (TA)1 - t * t * t), (TA)1e-9);
       nu = 2;
-      fev += P;
+      fev += P;  // MINPACK re-differences its Jacobian here: P more evaluations of its budget
     } else {
       lam *= nu;
       nu *= 2;
     }
-    TA pnorm2 = 0;
-#pragma unroll
-    for (int i = 0; i < P; ++i) pnorm2 = num<TA>::fma_(D[i] * (TA)p[i], D[i] * (TA)p[i], pnorm2);
-    const bool conv_f = good && relact <= ftol && relpred <= ftol && rho <= (TA)2;
-    const bool conv_x = accept && zz <= xtol2 * pnorm2;
-    if (conv_f || conv_x) {
-      status = conv_f ? (conv_x ? ST_CONV_FX : ST_CONV_F) : ST_CONV_X;
+    if (small_f || conv_x) {
+      status = small_f ? (conv_x ? ST_CONV_FX : ST_CONV_F) : ST_CONV_X;
       break;
     }
   }
+  if (status == ST_MAXITER && F <= floorF) status = ST_EXACT;
   F_out = (T)F;
   return status;
 }

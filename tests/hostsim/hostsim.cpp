@@ -9,7 +9,7 @@
 
 using namespace dfit;
 
-template <class M, typename T, typename TA, int EMAX>
+template <class M, typename T, typename TA, int EMAX, bool EXACT>
 static void run(int E, int64_t N, const double* x, const double* y, const double* p0, int64_t n_p0, int init_mode,
                 int init_linear, double ftol, double xtol, double lambda0, double floor_rel, int max_iter,
                 double r2_eps, double y_lo, double y_hi, double* popt, double* r2, int32_t* status, int32_t* iters) {
@@ -47,7 +47,7 @@ static void run(int E, int64_t N, const double* x, const double* y, const double
     T r2v;
     int it;
     unsigned flags;
-    int st = fit_voxel<M, T, TA, EMAX, false>(yy, xt, E, vo, p, r2v, it, flags);
+    int st = fit_voxel<M, T, TA, EMAX, EXACT>(yy, xt, E, vo, p, r2v, it, flags);
     for (int i = 0; i < P; ++i) popt[(size_t)v * P + i] = (double)p[i];
     r2[v] = (double)r2v;
     status[v] = st;
@@ -61,10 +61,18 @@ extern "C" int hostsim_fit(int model, int dtype, int acc64, int E, int64_t N, co
                            double* popt, double* r2, int32_t* status, int32_t* iters) {
   if (E > 32) return -1;
 #define ARGS E, N, x, y, p0, n_p0, init_mode, init_linear, ftol, xtol, lambda0, floor_rel, max_iter, r2_eps, y_lo, y_hi, popt, r2, status, iters
-#define DISPATCH(M)                                         \
-  if (dtype == 0 && !acc64) run<M, float, float, 32>(ARGS); \
-  else if (dtype == 0) run<M, float, double, 32>(ARGS);     \
-  else run<M, double, double, 32>(ARGS);
+#define RUN_E(M, T, TA)                                                                     \
+  switch (E) {                                                                                \
+    case 4: if (4 >= M::P) { run<M, T, TA, 4, true>(ARGS); break; }                           \
+    case 7: if (E == 7 && 7 >= M::P) { run<M, T, TA, 7, true>(ARGS); break; }                 \
+    case 8: if (E == 8) { run<M, T, TA, 8, true>(ARGS); break; }                              \
+    case 16: if (E == 16) { run<M, T, TA, 16, true>(ARGS); break; }                           \
+    default: run<M, T, TA, 32, false>(ARGS);                                                  \
+  }
+#define DISPATCH(M)                                  \
+  if (dtype == 0 && !acc64) { RUN_E(M, float, float) } \
+  else if (dtype == 0) { run<M, float, double, 32, false>(ARGS); } \
+  else { RUN_E(M, double, double) }
   switch (model) {
     case 0: DISPATCH(MonoExp); break;
     case 1: DISPATCH(BiExp); break;
