@@ -231,12 +231,40 @@ def run_gpu(args):
     r2 = torch.empty((n,), dtype=torch.float32, device=dev)
     counts = [n] * world
 
+    # N > 1: the reassembly of the parameter map is fused into the fit kernel's epilogue -- each voxel's
+    # [a, b, r2] row is stored straight into every rank's map over NVLink (dosma_b200.sharding.PeerMaps).
+    # If peer mapping is unavailable the same result is produced by a plain NCCL all-gather.
+    peer = None
+    gather_mode = "none"
+    if world > 1:
+        try:
+            peer = sharding.PeerMaps(n, P + 1, dev)
+            gather_mode = "fused peer stores over NVLink (in-kernel all-gather)"
+        except Exception as e:  # pragma: no cover
+            peer = None
+            gather_mode = f"nccl all_gather_into_tensor (peer mapping unavailable: {type(e).__name__})"
+        flag = torch.tensor([1 if peer is not None else 0], device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if int(flag.item()) == 0 and peer is not None:
+            peer.close()
+            peer = None
+            gather_mode = "nccl all_gather_into_tensor (peer mapping unavailable on some rank)"
+
     def step():
         A.fit_device(opts, P, X_MS, y, popt=popt, r2=r2, handle=handle)
-        if world > 1:
+        if world > 1 and peer is None:
             packed = torch.cat([popt, r2[:, None]], dim=1)
             return sharding.gather_maps(packed, counts)
         return popt
+
+    if peer is not None:  # one-off check of the fused gather against NCCL
+        step()
+        peer.synchronize()
+        ref = sharding.gather_maps(torch.cat([popt, r2[:, None]], dim=1), counts)
+        same = torch.equal(peer.local.nan_to_num(-1.0), ref.nan_to_num(-1.0))
+        del ref
+        if not same:
+            raise SystemExit("fused all-gather disagrees with NCCL all-gather")
 
     def sync():
         if world > 1:
@@ -257,7 +285,7 @@ def run_gpu(args):
         kev[k][0].record()
         A.fit_device(opts, P, X_MS, y, popt=popt, r2=r2, handle=handle)
         kev[k][1].record()
-        if world > 1:
+        if world > 1 and peer is None:
             packed = torch.cat([popt, r2[:, None]], dim=1)
             sharding.gather_maps(packed, counts)
         ev[k + 1].record()
@@ -266,6 +294,8 @@ def run_gpu(args):
     kernel_ms = float(np.mean([s.elapsed_time(e) for s, e in kev]))
     stats = handle.stats()
     clocks = sampler.stop() if rank == 0 else None
+    if peer is not None:
+        peer.close()
 
     # ---- end-to-end through the host entry point (pinned host buffers) -------------------------
     yh = torch.empty((ECHOES, n), dtype=torch.float32).pin_memory()
@@ -308,7 +338,8 @@ def run_gpu(args):
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(world),
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": dict(workload_config(world), gather=gather_mode),
             "clocks": clocks,
             "e2e": {"value": world * n * e2e_steps / (e2e_ms * 1e-3), "unit": UNIT,
                     "h2d_bytes_per_step": 4 * ECHOES * n, "d2h_bytes_per_step": 4 * (P + 1) * n,

@@ -30,6 +30,7 @@ NP_TO_DTYPE = {
 EXPORTED_SYMBOLS = (
     "dfit_version", "dfit_device_count", "dfit_strerror", "dfit_last_error", "dfit_default_opts",
     "dfit_model_nparams", "dfit_create", "dfit_destroy", "dfit_fit_device", "dfit_fit_host", "dfit_get_stats",
+    "dfit_set_gather", "dfit_ipc_alloc", "dfit_ipc_open", "dfit_ipc_close", "dfit_ipc_free",
 )
 
 
@@ -118,6 +119,11 @@ def load():
         lib.dfit_fit_host.argtypes = [vp, ctypes.POINTER(DfitOpts), i32, i64, vp, vp, i32, vp, vp, i32, vp, vp, i32,
                                       vp, vp]
         lib.dfit_get_stats.argtypes = [vp, ctypes.POINTER(DfitStats)]
+        lib.dfit_set_gather.argtypes = [vp, i32, i32, vp, i64]
+        lib.dfit_ipc_alloc.argtypes = [vp, ctypes.c_size_t, ctypes.POINTER(vp), ctypes.c_char_p]
+        lib.dfit_ipc_open.argtypes = [vp, ctypes.c_char_p, ctypes.POINTER(vp)]
+        lib.dfit_ipc_close.argtypes = [vp, vp]
+        lib.dfit_ipc_free.argtypes = [vp, vp]
         _lib = lib
         return lib
 

@@ -71,6 +71,9 @@ struct dfit_handle {
   int last_launches = 0;
   float last_total_ms = 0.f;
   float host_kernel_ms = -1.f;
+  float* gather[kMaxPeers] = {nullptr};
+  int gather_world = 0, gather_rank = 0;
+  int64_t gather_rows_per_rank = 0;
 };
 
 namespace {
@@ -161,6 +164,9 @@ void make_desc(const dfit_opts* o, int n_echo, int64_t n_vox, const double* x, L
   d.po.fill = o->nan_fill;
   d.mask_fill = o->has_nan_fill ? o->nan_fill : std::numeric_limits<double>::quiet_NaN();
   d.use_tma = o->use_tma;
+  for (int r = 0; r < kMaxPeers; ++r) d.gather[r] = nullptr;
+  d.gather_world = 0;
+  d.gather_row0 = 0;
 }
 
 cudaError_t dispatch(const LaunchDesc& d) {
@@ -295,7 +301,11 @@ int dfit_fit_device(dfit_handle* h, const dfit_opts* opts, int n_echo, int64_t n
   int rc = validate(opts, n_echo, n_vox, x, y_dtype, p0_dtype, out_dtype, p0_voxel != nullptr);
   if (rc != DFIT_OK) return rc;
   if (y_layout != DFIT_PLANAR && y_layout != DFIT_ECHO_FASTEST) return fail(DFIT_ERR_BAD_ARG, "bad layout");
-  if (n_vox > 0 && (!y || !popt || !r2)) return fail(DFIT_ERR_BAD_ARG, "y/popt/r2 must not be NULL");
+  const bool gathering = h->gather_world > 0;
+  if (n_vox > 0 && !y) return fail(DFIT_ERR_BAD_ARG, "y must not be NULL");
+  if (n_vox > 0 && (!popt != !r2)) return fail(DFIT_ERR_BAD_ARG, "popt and r2 must both be given or both be NULL");
+  if (n_vox > 0 && !popt && !gathering) return fail(DFIT_ERR_BAD_ARG, "popt/r2 may only be NULL with dfit_set_gather");
+  if (gathering && n_vox > h->gather_rows_per_rank) return fail(DFIT_ERR_BAD_ARG, "n_vox exceeds gather rows_per_rank");
   if (ld < (y_layout == DFIT_PLANAR ? n_vox : (int64_t)n_echo)) return fail(DFIT_ERR_BAD_ARG, "ld too small");
   CUDA_TRY(cudaSetDevice(h->device));
   cudaStream_t st = (cudaStream_t)stream;  // NULL is the legacy default stream (what torch calls its default stream)
@@ -316,6 +326,11 @@ int dfit_fit_device(dfit_handle* h, const dfit_opts* opts, int n_echo, int64_t n
   d.niter = niter;
   d.counters = h->counters;
   d.stream = st;
+  if (gathering) {
+    for (int r = 0; r < h->gather_world; ++r) d.gather[r] = h->gather[r];
+    d.gather_world = h->gather_world;
+    d.gather_row0 = (int64_t)h->gather_rank * h->gather_rows_per_rank;
+  }
   CUDA_TRY(cudaMemsetAsync(h->counters, 0, kStatSlots * CNT_COUNT * sizeof(unsigned long long), st));
   CUDA_TRY(cudaEventRecord(h->ev_start, st));
   h->last_launches = 0;
@@ -408,6 +423,78 @@ int dfit_fit_host(dfit_handle* h, const dfit_opts* opts, int n_echo, int64_t n_v
   h->ev_valid = false;
   h->last_n = n_vox;
   (void)is_pinned_or_device;
+  return DFIT_OK;
+}
+
+int dfit_set_gather(dfit_handle* h, int world, int rank, void* const* maps, int64_t rows_per_rank) {
+  if (!h) return fail(DFIT_ERR_BAD_ARG, "handle is NULL");
+  if (world == 0) {
+    h->gather_world = 0;
+    return DFIT_OK;
+  }
+  if (world < 1 || world > kMaxPeers || rank < 0 || rank >= world || !maps || rows_per_rank < 0)
+    return fail(DFIT_ERR_BAD_ARG, "bad gather specification (world=%d rank=%d, at most %d peers)", world, rank, kMaxPeers);
+  CUDA_TRY(cudaSetDevice(h->device));
+  for (int r = 0; r < world; ++r) {
+    if (!maps[r]) return fail(DFIT_ERR_BAD_ARG, "maps[%d] is NULL", r);
+    cudaPointerAttributes at;
+    CUDA_TRY(cudaPointerGetAttributes(&at, maps[r]));
+    if (at.type != cudaMemoryTypeDevice) return fail(DFIT_ERR_BAD_ARG, "maps[%d] is not device memory", r);
+    if (at.device != h->device) {  // a peer's map: this device must be allowed to store into it
+      int can = 0;
+      CUDA_TRY(cudaDeviceCanAccessPeer(&can, h->device, at.device));
+      if (!can) return fail(DFIT_ERR_UNSUPPORTED, "device %d cannot access peer device %d", h->device, at.device);
+    }
+    h->gather[r] = static_cast<float*>(maps[r]);
+  }
+  h->gather_world = world;
+  h->gather_rank = rank;
+  h->gather_rows_per_rank = rows_per_rank;
+  return DFIT_OK;
+}
+
+int dfit_ipc_alloc(dfit_handle* h, size_t bytes, void** dev_ptr, unsigned char* handle_out) {
+  if (!h || !dev_ptr || !handle_out || bytes == 0) return fail(DFIT_ERR_BAD_ARG, "bad argument");
+  static_assert(sizeof(cudaIpcMemHandle_t) == DFIT_IPC_HANDLE_BYTES, "IPC handle size");
+  CUDA_TRY(cudaSetDevice(h->device));
+  void* p = nullptr;
+  CUDA_TRY(cudaMalloc(&p, bytes));
+  CUDA_TRY(cudaMemset(p, 0, bytes));
+  cudaIpcMemHandle_t hd;
+  cudaError_t e = cudaIpcGetMemHandle(&hd, p);
+  if (e != cudaSuccess) {
+    cudaFree(p);
+    return fail(DFIT_ERR_CUDA, "cudaIpcGetMemHandle: %s", cudaGetErrorString(e));
+  }
+  std::memcpy(handle_out, &hd, sizeof(hd));
+  *dev_ptr = p;
+  return DFIT_OK;
+}
+
+int dfit_ipc_open(dfit_handle* h, const unsigned char* handle, void** dev_ptr) {
+  if (!h || !handle || !dev_ptr) return fail(DFIT_ERR_BAD_ARG, "bad argument");
+  // Opened with THIS rank's device current so that the mapping is made for the device whose kernels
+  // will store through it (lazy peer access over NVLink).
+  CUDA_TRY(cudaSetDevice(h->device));
+  cudaIpcMemHandle_t hd;
+  std::memcpy(&hd, handle, sizeof(hd));
+  void* p = nullptr;
+  CUDA_TRY(cudaIpcOpenMemHandle(&p, hd, cudaIpcMemLazyEnablePeerAccess));
+  *dev_ptr = p;
+  return DFIT_OK;
+}
+
+int dfit_ipc_close(dfit_handle* h, void* dev_ptr) {
+  if (!h || !dev_ptr) return fail(DFIT_ERR_BAD_ARG, "bad argument");
+  CUDA_TRY(cudaSetDevice(h->device));
+  CUDA_TRY(cudaIpcCloseMemHandle(dev_ptr));
+  return DFIT_OK;
+}
+
+int dfit_ipc_free(dfit_handle* h, void* dev_ptr) {
+  if (!h || !dev_ptr) return fail(DFIT_ERR_BAD_ARG, "bad argument");
+  CUDA_TRY(cudaSetDevice(h->device));
+  CUDA_TRY(cudaFree(dev_ptr));
   return DFIT_OK;
 }
 

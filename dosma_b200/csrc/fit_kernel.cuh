@@ -22,6 +22,7 @@ enum DType : int { DT_F32 = 0, DT_F64 = 1, DT_I16 = 2, DT_U16 = 3, DT_I32 = 4, D
 enum Layout : int { LAYOUT_PLANAR = 0, LAYOUT_ECHO_FASTEST = 1 };
 enum Counter : int { CNT_FITTED = 0, CNT_FAILED, CNT_NONFINITE, CNT_OOB, CNT_ITERS, CNT_MAXITER, CNT_COUNT };
 constexpr int kStatSlots = 256;  // power of two
+constexpr int kMaxPeers = 8;
 
 template <typename T, int EMAX>
 struct KernelArgs {
@@ -44,6 +45,12 @@ struct KernelArgs {
   uint8_t* niter;
   double mask_fill;  // value written outside the mask: NaN or nan_to_num (fitting.py:207-212)
   unsigned long long* counters;
+  // Fused all-gather epilogue: when gather_world > 0 every voxel's packed row [popt..., r2] (fp32) is
+  // also stored straight into the reassembled map of EVERY rank (peer-mapped over NVLink) at row
+  // gather_row0 + v -- the collective overlaps the fit instead of following it.
+  float* gather[kMaxPeers];
+  int gather_world;
+  int64_t gather_row0;
 };
 
 static inline size_t dtype_size(int dt) {
@@ -142,12 +149,26 @@ __device__ __forceinline__ void store_voxel(const KernelArgs<T, EMAX>& a, int64_
       }
     }
   }
-  if (a.out_dtype == DT_F32) {
-    store_vec<P, float>(reinterpret_cast<float*>(a.popt) + v * P, q);
-    __stcs(reinterpret_cast<float*>(a.r2) + v, (float)r2o);
-  } else {
-    store_vec<P, double>(reinterpret_cast<double*>(a.popt) + v * P, q);
-    __stcs(reinterpret_cast<double*>(a.r2) + v, r2o);
+  if (a.popt != nullptr) {
+    if (a.out_dtype == DT_F32) {
+      store_vec<P, float>(reinterpret_cast<float*>(a.popt) + v * P, q);
+      __stcs(reinterpret_cast<float*>(a.r2) + v, (float)r2o);
+    } else {
+      store_vec<P, double>(reinterpret_cast<double*>(a.popt) + v * P, q);
+      __stcs(reinterpret_cast<double*>(a.r2) + v, r2o);
+    }
+  }
+  if (a.gather_world > 0) {
+    const int64_t off = (a.gather_row0 + v) * (P + 1);
+#pragma unroll
+    for (int r = 0; r < kMaxPeers; ++r) {
+      if (r < a.gather_world) {
+        float* dst = a.gather[r] + off;  // local HBM for r == own rank, a peer's HBM over NVLink otherwise
+#pragma unroll
+        for (int i = 0; i < P; ++i) dst[i] = (float)q[i];
+        dst[P] = (float)r2o;
+      }
+    }
   }
   if (a.status) a.status[v] = (uint8_t)st;
   if (a.niter) a.niter[v] = (uint8_t)(iters > 255 ? 255 : iters);
@@ -237,6 +258,9 @@ struct LaunchDesc {
   double mask_fill;
   int use_tma;
   cudaStream_t stream;
+  float* gather[kMaxPeers];
+  int gather_world;
+  int64_t gather_row0;
 };
 
 template <typename T, int EMAX>
@@ -282,6 +306,9 @@ inline void fill_args(const LaunchDesc& d, KernelArgs<T, EMAX>& a) {
   a.niter = d.niter;
   a.mask_fill = d.mask_fill;
   a.counters = d.counters;
+  for (int r = 0; r < kMaxPeers; ++r) a.gather[r] = d.gather[r];
+  a.gather_world = d.gather_world;
+  a.gather_row0 = d.gather_row0;
 }
 
 #if defined(__CUDACC__)

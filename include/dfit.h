@@ -22,6 +22,7 @@
 #ifndef DFIT_H_
 #define DFIT_H_
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -158,6 +159,26 @@ int dfit_destroy(dfit_handle* h);
 int dfit_fit_device(dfit_handle* h, const dfit_opts* opts, int n_echo, int64_t n_vox, const double* x, const void* y,
                     int y_dtype, int y_layout, int64_t ld, const uint8_t* mask, const void* p0_voxel, int p0_dtype,
                     void* popt, void* r2, int out_dtype, uint8_t* status, uint8_t* niter, void* stream);
+
+/* Fused all-gather epilogue for multi-GPU runs (one process per GPU).  maps[r], r = 0..world-1, is a
+ * device pointer THIS process can store to that addresses rank r's reassembled fp32 map of shape
+ * [world * rows_per_rank, P + 1] (its own allocation for r == rank, a CUDA-IPC / peer mapping of
+ * rank r's allocation otherwise).  While set, every dfit_fit_device call on this handle additionally
+ * stores each voxel's packed row [popt..., r2] into all `world` maps at row rank * rows_per_rank + v,
+ * so the reassembly of the parameter map travels over NVLink while the fit is
+ * still running; popt / r2 may then be NULL.  Peer stores are complete when the launching stream has
+ * drained; ranks synchronise with each other before reading their maps.  world = 0 clears. */
+int dfit_set_gather(dfit_handle* h, int world, int rank, void* const* maps, int64_t rows_per_rank);
+
+/* Plumbing for the maps above: allocate a zeroed device buffer and export its CUDA IPC handle
+ * (DFIT_IPC_HANDLE_BYTES bytes, to be sent to the peer processes by any means), and map a peer's
+ * buffer into this process for stores from THIS handle's device (peer access over NVLink is enabled
+ * lazily by the mapping). */
+#define DFIT_IPC_HANDLE_BYTES 64
+int dfit_ipc_alloc(dfit_handle* h, size_t bytes, void** dev_ptr, unsigned char* handle_out);
+int dfit_ipc_open(dfit_handle* h, const unsigned char* handle, void** dev_ptr);
+int dfit_ipc_close(dfit_handle* h, void* dev_ptr);
+int dfit_ipc_free(dfit_handle* h, void* dev_ptr);
 
 /* Fit N voxels whose samples are in HOST memory: the reference-facing call.
  *   y_planes  host, n_echo pointers, one contiguous [N] plane per echo (the list of volumes the
