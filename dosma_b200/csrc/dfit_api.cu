@@ -164,9 +164,52 @@ void make_desc(const dfit_opts* o, int n_echo, int64_t n_vox, const double* x, L
   d.po.fill = o->nan_fill;
   d.mask_fill = o->has_nan_fill ? o->nan_fill : std::numeric_limits<double>::quiet_NaN();
   d.use_tma = o->use_tma;
+  d.tmap = nullptr;
+  d.sm_count = 148;
   for (int r = 0; r < kMaxPeers; ++r) d.gather[r] = nullptr;
   d.gather_world = 0;
   d.gather_row0 = 0;
+}
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time dependency on libcuda).
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qr;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qr) == cudaSuccess &&
+        qr == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+    cudaGetLastError();
+  }
+  return fn;
+}
+
+// 2-D tensor map over planar fp32 samples: dim0 = voxels (contiguous), dim1 = echoes (pitch ld).
+// Box = kTmaTile voxels x E echoes; out-of-range voxels of the last tile are zero-filled.
+bool make_sample_tmap(CUtensorMap* map, const void* y, int n_echo, int64_t n_vox, int64_t ld) {
+  EncodeTiledFn fn = encode_tiled_fn();
+  if (!fn) return false;
+  if ((reinterpret_cast<uintptr_t>(y) & 15) != 0 || (ld * 4) % 16 != 0) return false;
+  cuuint64_t dims[2] = {(cuuint64_t)n_vox, (cuuint64_t)n_echo};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
+  cuuint32_t box[2] = {(cuuint32_t)kTmaTile, (cuuint32_t)n_echo};
+  cuuint32_t estr[2] = {1, 1};
+  return fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(y), dims, strides, box, estr,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+// The TMA-staged kernel is used when asked for (use_tma = 1) and the samples qualify.
+bool tma_eligible(const LaunchDesc& d) {
+  return d.use_tma == 1 && d.compute_dtype == DFIT_F32 && d.y_dtype == DFIT_F32 && d.layout == DFIT_PLANAR &&
+         d.n_echo <= 16 && d.n_vox < (int64_t)1 << 31;
 }
 
 cudaError_t dispatch(const LaunchDesc& d) {
@@ -334,6 +377,15 @@ int dfit_fit_device(dfit_handle* h, const dfit_opts* opts, int n_echo, int64_t n
   CUDA_TRY(cudaMemsetAsync(h->counters, 0, kStatSlots * CNT_COUNT * sizeof(unsigned long long), st));
   CUDA_TRY(cudaEventRecord(h->ev_start, st));
   h->last_launches = 0;
+  CUtensorMap tmap;
+  d.sm_count = h->sm_count;
+  if (n_vox > 0 && tma_eligible(d)) {
+    if (!make_sample_tmap(&tmap, y, n_echo, n_vox, ld))
+      return fail(DFIT_ERR_UNSUPPORTED, "use_tma=1 but the samples do not qualify (16-byte aligned base and pitch)");
+    d.tmap = &tmap;
+  } else if (opts->use_tma == 1) {
+    return fail(DFIT_ERR_UNSUPPORTED, "use_tma=1 needs fp32 planar samples, fp32 arithmetic and <= 16 echoes");
+  }
   if (n_vox > 0) {
     CUDA_TRY(dispatch(d));
     h->last_launches = 1;
@@ -410,6 +462,10 @@ int dfit_fit_host(dfit_handle* h, const dfit_opts* opts, int n_echo, int64_t n_v
     d.status = status ? (uint8_t*)sl.status.p : nullptr;
     d.niter = niter ? (uint8_t*)sl.niter.p : nullptr;
     d.stream = st;
+    CUtensorMap tmap;
+    d.sm_count = h->sm_count;
+    d.tmap = nullptr;
+    if (tma_eligible(d) && make_sample_tmap(&tmap, d.y, n_echo, n, chunk)) d.tmap = &tmap;
     CUDA_TRY(dispatch(d));
     ++h->last_launches;
     CUDA_TRY(cudaMemcpyAsync((char*)popt + (size_t)v0 * P * osz, sl.popt.p, (size_t)n * P * osz, cudaMemcpyDeviceToHost, st));

@@ -9,6 +9,7 @@
 // log-linear initial guess (:701-718), `_process_params` (:109-146) and rounding (:734-737).
 #pragma once
 
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -229,6 +230,139 @@ __global__ void __launch_bounds__(kBlock) fit_kernel(const __grid_constant__ Ker
   block_stats(a.counters, st, iters, flags);
 }
 
+// ------------------------------------------------------------------------------------------------
+// TMA-staged variant.  Persistent warps: every warp owns a 2-stage shared-memory ring of
+// [E][32-voxel] sample tiles that the Tensor Memory Accelerator fills (cp.async.bulk.tensor.2d over a
+// 2-D tensor map of the planar (E, ld) array, box = 32 voxels x E echoes) while the warp is busy
+// fitting the previous tile; completion is signalled on a per-stage mbarrier (complete_tx::bytes).
+// There is no block-level synchronisation -- warps run their own pipelines, so a slow voxel only
+// holds its own warp.  Used for fp32 planar samples whose row pitch is a multiple of 16 bytes.
+constexpr int kTmaWarps = 8;          // warps per CTA
+constexpr int kTmaStages = 2;
+constexpr int kTmaTile = 32;          // voxels per warp tile (one per lane)
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t}" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+          smem_u32(dst)),
+      "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+      : "memory");
+}
+
+template <class M, typename T, int EMAX>
+__global__ void __launch_bounds__(kTmaWarps * 32)
+    fit_kernel_tma(const __grid_constant__ KernelArgs<T, EMAX> a, const __grid_constant__ CUtensorMap tmap) {
+  constexpr int P = M::P;
+  constexpr unsigned kTileBytes = EMAX * kTmaTile * sizeof(float);
+  __shared__ __align__(128) float tiles[kTmaWarps][kTmaStages][EMAX][kTmaTile];
+  __shared__ __align__(8) uint64_t full[kTmaWarps][kTmaStages];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t n_tiles = (a.n + kTmaTile - 1) / kTmaTile;
+  const int64_t warp_global = (int64_t)blockIdx.x * kTmaWarps + warp;
+  const int64_t warp_stride = (int64_t)gridDim.x * kTmaWarps;
+
+  if (lane == 0) {
+#pragma unroll
+    for (int s = 0; s < kTmaStages; ++s) mbar_init(&full[warp][s], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    // prologue: fill the ring
+#pragma unroll
+    for (int s = 0; s < kTmaStages; ++s) {
+      const int64_t t = warp_global + (int64_t)s * warp_stride;
+      if (t < n_tiles) {
+        mbar_expect_tx(&full[warp][s], kTileBytes);
+        tma_load_2d(&tiles[warp][s][0][0], &tmap, (int)(t * kTmaTile), 0, &full[warp][s]);
+      }
+    }
+  }
+  __syncwarp();
+
+  int st_acc_fit = 0, st_acc_fail = 0, st_acc_nf = 0, st_acc_oob = 0, it_sum = 0, it_max = 0;
+  int k = 0;
+  for (int64_t t = warp_global; t < n_tiles; t += warp_stride, ++k) {
+    const int s = k % kTmaStages;
+    const unsigned parity = (unsigned)(k / kTmaStages) & 1u;
+    mbar_wait(&full[warp][s], parity);
+    T y[EMAX];
+#pragma unroll
+    for (int e = 0; e < EMAX; ++e) y[e] = (T)tiles[warp][s][e][lane];  // conflict-free: lane == bank
+    __syncwarp();
+    if (lane == 0) {  // the stage is drained: refill it with the tile two trips ahead
+      const int64_t tn = t + (int64_t)kTmaStages * warp_stride;
+      if (tn < n_tiles) {
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        mbar_expect_tx(&full[warp][s], kTileBytes);
+        tma_load_2d(&tiles[warp][s][0][0], &tmap, (int)(tn * kTmaTile), 0, &full[warp][s]);
+      }
+    }
+    const int64_t v = t * kTmaTile + lane;
+    int st = -1, iters = 0;
+    unsigned flags = 0;
+    if (v < a.n) {
+      const bool active = a.mask == nullptr || a.mask[v] != 0;
+      T p[P], r2 = 0;
+      st = ST_SKIPPED;
+      if (active) {
+        load_p0<P, T, EMAX>(a, v, p);
+        st = fit_voxel<M, T, T, EMAX, true>(y, a.xt, a.E, a.vo, p, r2, iters, flags);
+      }
+      store_voxel<P, T, EMAX>(a, v, p, r2, active, st, iters);
+    }
+    st_acc_fit += st >= ST_CONV_F;
+    st_acc_fail += st >= ST_MAXITER;
+    st_acc_nf += (flags & FLAG_NONFINITE) != 0;
+    st_acc_oob += (flags & FLAG_OOB) != 0;
+    it_sum += iters;
+    it_max = iters > it_max ? iters : it_max;
+  }
+  // statistics: per-thread accumulators -> one reduction per CTA
+  {
+    __shared__ unsigned s_cnt[CNT_COUNT];
+    if (threadIdx.x < CNT_COUNT) s_cnt[threadIdx.x] = 0;
+    __syncthreads();
+    const unsigned full_mask = 0xffffffffu;
+    const unsigned v0 = __reduce_add_sync(full_mask, (unsigned)st_acc_fit), v1 = __reduce_add_sync(full_mask, (unsigned)st_acc_fail);
+    const unsigned v2 = __reduce_add_sync(full_mask, (unsigned)st_acc_nf), v3 = __reduce_add_sync(full_mask, (unsigned)st_acc_oob);
+    const unsigned v4 = __reduce_add_sync(full_mask, (unsigned)it_sum), v5 = __reduce_max_sync(full_mask, (unsigned)it_max);
+    if (lane == 0) {
+      atomicAdd(&s_cnt[CNT_FITTED], v0);
+      atomicAdd(&s_cnt[CNT_FAILED], v1);
+      atomicAdd(&s_cnt[CNT_NONFINITE], v2);
+      atomicAdd(&s_cnt[CNT_OOB], v3);
+      atomicAdd(&s_cnt[CNT_ITERS], v4);
+      atomicMax(&s_cnt[CNT_MAXITER], v5);
+    }
+    __syncthreads();
+    if (threadIdx.x < CNT_COUNT) {
+      const unsigned val = s_cnt[threadIdx.x];
+      unsigned long long* dst = a.counters + (size_t)(blockIdx.x & (kStatSlots - 1)) * CNT_COUNT + threadIdx.x;
+      if (val) {
+        if (threadIdx.x == CNT_MAXITER) atomicMax(dst, (unsigned long long)val);
+        else atomicAdd(dst, (unsigned long long)val);
+      }
+    }
+  }
+}
+
 #endif  // __CUDACC__
 
 // Type-erased launch description filled by the C-ABI layer and consumed by the per-model
@@ -261,6 +395,8 @@ struct LaunchDesc {
   float* gather[kMaxPeers];
   int gather_world;
   int64_t gather_row0;
+  const CUtensorMap* tmap;  // host pointer to an encoded 2-D map of the planar fp32 samples, or null
+  int sm_count;
 };
 
 template <typename T, int EMAX>
@@ -316,6 +452,21 @@ template <class M, typename T, int EMAX, bool EXACT>
 inline cudaError_t launch_one(const LaunchDesc& d) {
   KernelArgs<T, EMAX> a;
   fill_args<T, EMAX>(d, a);
+  if constexpr (EXACT && sizeof(T) == 4) {
+    if (d.tmap != nullptr) {  // TMA-staged persistent variant (the C-ABI layer checked eligibility)
+      int per_sm = 0;
+      cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fit_kernel_tma<M, T, EMAX>,
+                                                                    kTmaWarps * 32, 0);
+      if (e != cudaSuccess) return e;
+      if (per_sm < 1) per_sm = 1;
+      const int64_t n_tiles = (d.n_vox + kTmaTile - 1) / kTmaTile;
+      int64_t blocks = (int64_t)d.sm_count * per_sm;
+      const int64_t needed = (n_tiles + kTmaWarps - 1) / kTmaWarps;
+      if (blocks > needed) blocks = needed;
+      fit_kernel_tma<M, T, EMAX><<<(unsigned)blocks, kTmaWarps * 32, 0, d.stream>>>(a, *d.tmap);
+      return cudaGetLastError();
+    }
+  }
   const int64_t blocks = (d.n_vox + kBlock - 1) / kBlock;
   fit_kernel<M, T, EMAX, EXACT><<<(unsigned)blocks, kBlock, 0, d.stream>>>(a);
   return cudaGetLastError();

@@ -2,7 +2,7 @@
 NVLink, dosma_b200.sharding.PeerMaps) must equal a plain NCCL all-gather of the per-rank results.
 
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 \
-        --master-port 29512 tests/multigpu/check_fused_gather.py [n_voxels]
+        --master-port 29512 tests/gpu_scripts/check_fused_gather.py [n_voxels]
 """
 import os
 import sys

@@ -236,6 +236,35 @@ def test_device_layouts_and_determinism(D):
     assert torch.equal(p1.nan_to_num(-1), p2.nan_to_num(-1)) and torch.equal(r1, r2)
 
 
+def test_tma_staged_variant_is_bitwise_identical(D):
+    """The TMA-staged persistent kernel (cp.async.bulk.tensor + mbarrier ring, use_tma=1) and the plain
+    coalesced-load kernel run the same per-voxel arithmetic: results must be bit-identical, including a
+    ragged last tile."""
+    import torch
+
+    from dosma_b200 import device_api as A
+
+    g = torch.Generator(device="cuda").manual_seed(9)
+    x = np.arange(1, 9) * 10.0
+    xt = torch.tensor(x, device="cuda", dtype=torch.float32)[:, None]
+    for n in (40, 100_004, 1_000_000):
+        y = (500 + 1000 * torch.rand(n, device="cuda", generator=g)) * torch.exp(
+            -xt / (10 + 70 * torch.rand(n, device="cuda", generator=g))) + 10 * torch.randn(8, n, device="cuda", generator=g)
+        mask = torch.rand(n, device="cuda", generator=g) > 0.3
+        for init in ("given", "loglinear"):
+            o0, P = A.make_opts(D.monoexponential, p0=(1.0, -1 / 30), init=init, use_tma=0)
+            o1, _ = A.make_opts(D.monoexponential, p0=(1.0, -1 / 30), init=init, use_tma=1)
+            p0_, r0_ = A.fit_device(o0, P, x, y, mask=mask)
+            p1_, r1_ = A.fit_device(o1, P, x, y, mask=mask)
+            torch.cuda.synchronize()
+            assert torch.equal(p0_.nan_to_num(-1), p1_.nan_to_num(-1))
+            assert torch.equal(r0_.nan_to_num(-1), r1_.nan_to_num(-1))
+    # ineligible inputs must be refused loudly, not silently rerouted
+    o1, P = A.make_opts(D.monoexponential, p0=(1.0, -1 / 30), use_tma=1)
+    with pytest.raises(Exception):
+        A.fit_device(o1, P, x, y.t().contiguous(), layout="echo_fastest")
+
+
 def test_scaling_and_permutation_properties(D):
     """Size-independent properties at a BASELINE-sized workload (384 x 384 x 16 slab, 8 echoes):
     scaling y by 2 scales a by 2 and leaves b (to rounding); permuting voxels permutes results exactly."""
