@@ -137,8 +137,9 @@ void make_desc(const dfit_opts* o, int n_echo, int64_t n_vox, const double* x, L
   }
   // Engine tolerances: the reference's ftol bounds MINPACK's *last* relative cost decrease, which
   // leaves its iterate up to ~1e-4 (relative) away from the minimiser on noisy data.  The engine
-  // iterates ftol_scale further so that it lands within rtol 1e-4 of wherever MINPACK stopped.
-  const double scale = o->ftol_scale > 0 ? o->ftol_scale : 1e-3;
+  // iterates ftol_scale (two decades by default) further so that it lands within rtol 1e-4 of wherever
+  // MINPACK stopped.
+  const double scale = o->ftol_scale > 0 ? o->ftol_scale : 1e-2;
   double ftol = o->ftol * scale;
   const double ftol_floor = f32 ? 1e-8 : 1e-14;
   d.ftol = ftol < ftol_floor ? ftol_floor : ftol;
@@ -272,7 +273,7 @@ int dfit_default_opts(dfit_opts* o, int model) {
   o->init_linear = -1;
   o->maxfev = 100;      // fitting.py:761
   o->ftol = 1e-5;       // fitting.py:762
-  o->ftol_scale = 1e-3;
+  o->ftol_scale = 1e-2;
   o->xtol = 0;
   o->lambda0 = 0;
   o->r2_eps = 1e-8;     // fitting.py:763

@@ -17,7 +17,7 @@
 
 namespace dfit {
 
-constexpr int kBlock = 128;
+constexpr int kBlock = 128;  // block_stats packs 8-bit counters: keep <= 255
 
 enum DType : int { DT_F32 = 0, DT_F64 = 1, DT_I16 = 2, DT_U16 = 3, DT_I32 = 4, DT_U8 = 5 };
 enum Layout : int { LAYOUT_PLANAR = 0, LAYOUT_ECHO_FASTEST = 1 };
@@ -77,29 +77,42 @@ __device__ __forceinline__ T load_as(const void* __restrict__ base, int dtype, i
   }
 }
 
+template <typename T, typename S, int EMAX, bool EXACT>
+__device__ __forceinline__ void load_strided(const S* __restrict__ src, int64_t stride, int E, T (&y)[EMAX]) {
+#pragma unroll
+  for (int e = 0; e < EMAX; ++e) y[e] = (EXACT || e < E) ? (T)__ldcs(src + (int64_t)e * stride) : (T)0;
+}
+
 template <typename T, int EMAX, bool EXACT>
 __device__ __forceinline__ void load_samples(const KernelArgs<T, EMAX>& a, int64_t v, T (&y)[EMAX]) {
-  if (a.layout == LAYOUT_PLANAR) {
-    // lane l of a warp reads voxel v0 + l of every echo plane: one fully coalesced 128 B line per echo
+  if (a.layout == LAYOUT_ECHO_FASTEST && a.y_dtype == DT_F32 && (EMAX % 4 == 0) && (a.ld % 4 == 0) &&
+      (EXACT || a.E == EMAX) && ((reinterpret_cast<uintptr_t>(a.y) & 15) == 0)) {
+    const float4* src = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(a.y) + v * a.ld);
 #pragma unroll
-    for (int e = 0; e < EMAX; ++e) y[e] = (EXACT || e < a.E) ? load_as<T>(a.y, a.y_dtype, (int64_t)e * a.ld + v) : (T)0;
-  } else {
-    const int64_t base = v * a.ld;
-    if (a.y_dtype == DT_F32 && (EMAX % 4 == 0) && (a.ld % 4 == 0) && (EXACT || a.E == EMAX) &&
-        ((reinterpret_cast<uintptr_t>(a.y) & 15) == 0)) {
-      const float4* src = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(a.y) + base);
-#pragma unroll
-      for (int q = 0; q < EMAX / 4; ++q) {
-        const float4 t = __ldcs(src + q);
-        y[4 * q + 0] = (T)t.x;
-        y[4 * q + 1] = (T)t.y;
-        y[4 * q + 2] = (T)t.z;
-        y[4 * q + 3] = (T)t.w;
-      }
-    } else {
-#pragma unroll
-      for (int e = 0; e < EMAX; ++e) y[e] = (EXACT || e < a.E) ? load_as<T>(a.y, a.y_dtype, base + e) : (T)0;
+    for (int q = 0; q < EMAX / 4; ++q) {
+      const float4 t = __ldcs(src + q);
+      y[4 * q + 0] = (T)t.x;
+      y[4 * q + 1] = (T)t.y;
+      y[4 * q + 2] = (T)t.z;
+      y[4 * q + 3] = (T)t.w;
     }
+    return;
+  }
+  // Planar: lane l of a warp reads voxel v0 + l of every echo plane -- one fully coalesced line per
+  // echo.  The element type is switched once, outside the echo loop.
+  const bool planar = a.layout == LAYOUT_PLANAR;
+  const int64_t first = planar ? v : v * a.ld, stride = planar ? a.ld : 1;
+  switch (a.y_dtype) {
+    case DT_F32: load_strided<T, float, EMAX, EXACT>(reinterpret_cast<const float*>(a.y) + first, stride, a.E, y); break;
+    case DT_F64: load_strided<T, double, EMAX, EXACT>(reinterpret_cast<const double*>(a.y) + first, stride, a.E, y); break;
+    case DT_I16: load_strided<T, short, EMAX, EXACT>(reinterpret_cast<const short*>(a.y) + first, stride, a.E, y); break;
+    case DT_U16:
+      load_strided<T, unsigned short, EMAX, EXACT>(reinterpret_cast<const unsigned short*>(a.y) + first, stride, a.E, y);
+      break;
+    case DT_I32: load_strided<T, int, EMAX, EXACT>(reinterpret_cast<const int*>(a.y) + first, stride, a.E, y); break;
+    default:
+      load_strided<T, unsigned char, EMAX, EXACT>(reinterpret_cast<const unsigned char*>(a.y) + first, stride, a.E, y);
+      break;
   }
 }
 
@@ -180,32 +193,36 @@ __device__ __forceinline__ void store_voxel(const KernelArgs<T, EMAX>& a, int64_
 // atomic unit; 1.8 M warps hammering six addresses cost more than the fit itself).  The host sums
 // the slots in dfit_get_stats.
 __device__ __forceinline__ void block_stats(unsigned long long* cnt, int st, int iters, unsigned flags) {
-  __shared__ unsigned s_cnt[CNT_COUNT];
-  if (threadIdx.x < CNT_COUNT) s_cnt[threadIdx.x] = 0;
+  // four 8-bit counters (fitted, failed, non-finite, out-of-bounds) ride in one word: a 128-thread
+  // CTA cannot overflow a byte, so one warp reduction and one shared atomic cover all four
+  __shared__ unsigned s_pack, s_iters, s_max;
+  if (threadIdx.x == 0) {
+    s_pack = 0;
+    s_iters = 0;
+    s_max = 0;
+  }
   __syncthreads();
   const unsigned full = 0xffffffffu;
-  const unsigned n_fit = __popc(__ballot_sync(full, st >= ST_CONV_F));
-  const unsigned n_fail = __popc(__ballot_sync(full, st >= ST_MAXITER));
-  const unsigned n_nf = __popc(__ballot_sync(full, (flags & FLAG_NONFINITE) != 0));
-  const unsigned n_oob = __popc(__ballot_sync(full, (flags & FLAG_OOB) != 0));
+  const unsigned mine = (unsigned)(st >= ST_CONV_F) | ((unsigned)(st >= ST_MAXITER) << 8) |
+                        ((unsigned)((flags & FLAG_NONFINITE) != 0) << 16) | ((unsigned)((flags & FLAG_OOB) != 0) << 24);
+  const unsigned pack = __reduce_add_sync(full, mine);
   const unsigned s_it = __reduce_add_sync(full, (unsigned)iters);
   const unsigned m_it = __reduce_max_sync(full, (unsigned)iters);
   if ((threadIdx.x & 31) == 0) {
-    if (n_fit) atomicAdd(&s_cnt[CNT_FITTED], n_fit);
-    if (n_fail) atomicAdd(&s_cnt[CNT_FAILED], n_fail);
-    if (n_nf) atomicAdd(&s_cnt[CNT_NONFINITE], n_nf);
-    if (n_oob) atomicAdd(&s_cnt[CNT_OOB], n_oob);
-    if (s_it) atomicAdd(&s_cnt[CNT_ITERS], s_it);
-    if (m_it) atomicMax(&s_cnt[CNT_MAXITER], m_it);
+    atomicAdd(&s_pack, pack);
+    atomicAdd(&s_iters, s_it);
+    atomicMax(&s_max, m_it);
   }
   __syncthreads();
-  if (threadIdx.x < CNT_COUNT) {
-    const unsigned v = s_cnt[threadIdx.x];
-    unsigned long long* dst = cnt + (size_t)(blockIdx.x & (kStatSlots - 1)) * CNT_COUNT + threadIdx.x;
-    if (v) {
-      if (threadIdx.x == CNT_MAXITER) atomicMax(dst, (unsigned long long)v);
-      else atomicAdd(dst, (unsigned long long)v);
-    }
+  if (threadIdx.x == 0) {
+    unsigned long long* dst = cnt + (size_t)(blockIdx.x & (kStatSlots - 1)) * CNT_COUNT;
+    const unsigned pk = s_pack;
+    if (pk & 0xffu) atomicAdd(dst + CNT_FITTED, (unsigned long long)(pk & 0xffu));
+    if ((pk >> 8) & 0xffu) atomicAdd(dst + CNT_FAILED, (unsigned long long)((pk >> 8) & 0xffu));
+    if ((pk >> 16) & 0xffu) atomicAdd(dst + CNT_NONFINITE, (unsigned long long)((pk >> 16) & 0xffu));
+    if (pk >> 24) atomicAdd(dst + CNT_OOB, (unsigned long long)(pk >> 24));
+    if (s_iters) atomicAdd(dst + CNT_ITERS, (unsigned long long)s_iters);
+    if (s_max) atomicMax(dst + CNT_MAXITER, (unsigned long long)s_max);
   }
 }
 

@@ -172,6 +172,16 @@ template <typename T>
 DFIT_HD pair2<T> p2_expbx(T b, pair2<T> x, pair2<T> xs) {
   return p2_make<T>(num<T>::expbx(b, x.lo, xs.lo), num<T>::expbx(b, x.hi, xs.hi));
 }
+#if defined(__CUDA_ARCH__)
+template <>
+__device__ __forceinline__ pair2<float> p2_expbx<float>(float b, pair2<float> /*x*/, pair2<float> xs) {
+  const pair2<float> t = p2_mul<float>(p2_bcast<float>(b), xs);  // one FMUL2 for both arguments
+  pair2<float> e;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e.lo) : "f"(t.lo));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e.hi) : "f"(t.hi));
+  return e;
+}
+#endif
 
 // ------------------------------------------------------------------------------------ models
 // Each model provides, for one sample, the value f and an UNSCALED Jacobian row Jh[P]; the true
@@ -277,11 +287,14 @@ DFIT_HD constexpr int tri(int i, int j) { return i * (i + 1) / 2 + j; }
 // With an exact echo count and matching accumulator type the echoes are processed two at a time
 // (pair2 -> packed FP32 instructions on sm_100a); partial sums of even and odd echoes are kept in
 // the two halves and added at the end.
-template <class M, typename T, typename TA, int EMAX, bool EXACT>
+// MASK selects the parameters whose rows/columns are accumulated (all of them for an LM pass, only
+// the linear ones for the projection pass, where the rest of the system is never read).
+template <class M, typename T, typename TA, int EMAX, bool EXACT, unsigned MASK = 0xffu>
 DFIT_HD void eval_all(const T (&p)[M::P], const T (&y)[EMAX], const T* __restrict__ x,
                       const T* __restrict__ xs, int E, TA& F, TA (&A)[M::P * (M::P + 1) / 2], TA (&g)[M::P]) {
   constexpr int P = M::P;
   constexpr int NA = P * (P + 1) / 2;
+#define DFIT_ON(i) (((MASK) >> (i)) & 1u)
   constexpr bool PAIRED = EXACT && sizeof(T) == sizeof(TA) && EMAX >= 2;
   if constexpr (PAIRED) {
     pair2<T> F2 = p2_bcast<T>((T)0), A2[NA], g2[P];
@@ -297,9 +310,10 @@ DFIT_HD void eval_all(const T (&p)[M::P], const T (&y)[EMAX], const T* __restric
       F2 = p2_fma<T>(r, r, F2);
 #pragma unroll
       for (int i = 0; i < P; ++i) {
-        g2[i] = p2_fma<T>(J[i], r, g2[i]);
+        if (DFIT_ON(i)) g2[i] = p2_fma<T>(J[i], r, g2[i]);
 #pragma unroll
-        for (int j = 0; j <= i; ++j) A2[tri(i, j)] = p2_fma<T>(J[i], J[j], A2[tri(i, j)]);
+        for (int j = 0; j <= i; ++j)
+          if (DFIT_ON(i) && DFIT_ON(j)) A2[tri(i, j)] = p2_fma<T>(J[i], J[j], A2[tri(i, j)]);
       }
     }
     F = (TA)(F2.lo + F2.hi);
@@ -314,9 +328,10 @@ DFIT_HD void eval_all(const T (&p)[M::P], const T (&y)[EMAX], const T* __restric
       F = num<TA>::fma_((TA)re, (TA)re, F);
 #pragma unroll
       for (int i = 0; i < P; ++i) {
-        g[i] = num<TA>::fma_((TA)J[i], (TA)re, g[i]);
+        if (DFIT_ON(i)) g[i] = num<TA>::fma_((TA)J[i], (TA)re, g[i]);
 #pragma unroll
-        for (int j = 0; j <= i; ++j) A[tri(i, j)] = num<TA>::fma_((TA)J[i], (TA)J[j], A[tri(i, j)]);
+        for (int j = 0; j <= i; ++j)
+          if (DFIT_ON(i) && DFIT_ON(j)) A[tri(i, j)] = num<TA>::fma_((TA)J[i], (TA)J[j], A[tri(i, j)]);
       }
     }
   } else {
@@ -334,9 +349,10 @@ DFIT_HD void eval_all(const T (&p)[M::P], const T (&y)[EMAX], const T* __restric
         F = num<TA>::fma_((TA)re, (TA)re, F);
 #pragma unroll
         for (int i = 0; i < P; ++i) {
-          g[i] = num<TA>::fma_((TA)J[i], (TA)re, g[i]);
+          if (DFIT_ON(i)) g[i] = num<TA>::fma_((TA)J[i], (TA)re, g[i]);
 #pragma unroll
-          for (int j = 0; j <= i; ++j) A[tri(i, j)] = num<TA>::fma_((TA)J[i], (TA)J[j], A[tri(i, j)]);
+          for (int j = 0; j <= i; ++j)
+            if (DFIT_ON(i) && DFIT_ON(j)) A[tri(i, j)] = num<TA>::fma_((TA)J[i], (TA)J[j], A[tri(i, j)]);
         }
       }
     }
@@ -345,10 +361,12 @@ DFIT_HD void eval_all(const T (&p)[M::P], const T (&y)[EMAX], const T* __restric
   M::template colscale<T>(p, cs);
 #pragma unroll
   for (int i = 0; i < P; ++i) {
-    g[i] *= (TA)cs[i];
+    if (DFIT_ON(i)) g[i] *= (TA)cs[i];
 #pragma unroll
-    for (int j = 0; j <= i; ++j) A[tri(i, j)] *= (TA)cs[i] * (TA)cs[j];
+    for (int j = 0; j <= i; ++j)
+      if (DFIT_ON(i) && DFIT_ON(j)) A[tri(i, j)] *= (TA)cs[i] * (TA)cs[j];
   }
+#undef DFIT_ON
 }
 
 // Solve (C + lam I) z = -gs for symmetric C (packed lower), all in registers.  Rows/columns whose
@@ -505,53 +523,61 @@ DFIT_HD int lm_solve(T (&p)[M::P], const T (&y)[EMAX], const T* __restrict__ x, 
   TA zz = 0, pnorm2 = 0, pred = 0;
   int fev = 0;
 
-  // ---- start: at most three passes with one evaluation site --------------------------------
-  // stage 0: the point with the linear parameters zeroed (cost = sum y^2, J of the linear columns)
-  // stage 1: the projected point; stage 2: p0 exactly as given (projection off or not usable)
+  // ---- start ---------------------------------------------------------------------------------------
+  // Projection: with the linear parameters at zero the residual is -y and only the linear block of
+  // the normal equations is needed (a cheap pass); its unregularised solution is the least-squares
+  // optimum of the linear parameters for the given non-linear ones.  The projected point is then
+  // evaluated in full; if that is not an improvement over sum y^2 (degenerate linear sub-problem),
+  // or projection is off, the fit starts from p0 exactly as given.
   {
     T plin[P], pt[P];
-    int stage = o.init_linear != 0 ? 0 : 2;
+    bool projected = false;
 #pragma unroll
-    for (int i = 0; i < P; ++i) {
-      plin[i] = p[i];
-      pt[i] = (stage == 0 && ((M::LIN >> i) & 1u)) ? (T)0 : p[i];
-    }
-    for (;;) {
-      TA Fn, An[NA], gn[P];
-      eval_all<M, T, TA, EMAX, EXACT>(pt, y, x, xs, E, Fn, An, gn);
+    for (int i = 0; i < P; ++i) plin[i] = pt[i] = p[i];
+    if (o.init_linear != 0) {
+#pragma unroll
+      for (int i = 0; i < P; ++i)
+        if ((M::LIN >> i) & 1u) pt[i] = (T)0;
+      TA F0, A0[NA], g0[P], D2p[P];
+#pragma unroll
+      for (int k = 0; k < NA; ++k) A0[k] = 0;
+#pragma unroll
+      for (int i = 0; i < P; ++i) {
+        g0[i] = 0;
+        D2p[i] = 0;
+      }
+      eval_all<M, T, TA, EMAX, EXACT, M::LIN>(pt, y, x, xs, E, F0, A0, g0);
       ++iters;
-      fev += 1 + P;
-      const bool good = num<TA>::finite(Fn);
-      if (stage == 1 && !(good && Fn <= F)) {  // projection did not help: start from p0 as given
-        stage = 2;
+      fev += 1;
+      T pp[P];
+      projected = lm_step<P, T, TA>(pt, A0, g0, D2p, (TA)0, M::LIN, pp, zz, pnorm2, pred);
+#pragma unroll
+      for (int i = 0; i < P; ++i) {
+        projected = projected && num<T>::finite(pp[i]);
+        pt[i] = pp[i];
+      }
+    }
+    for (int trip = 0; trip < 2; ++trip) {
+      if (!projected) {
 #pragma unroll
         for (int i = 0; i < P; ++i) pt[i] = plin[i];
+      }
+      eval_all<M, T, TA, EMAX, EXACT>(pt, y, x, xs, E, F, A, g);
+      ++iters;
+      fev += 1 + P;
+      const bool good = num<TA>::finite(F);
+      if (projected && !(good && F <= ysq)) {
+        projected = false;
         continue;
       }
       if (!good) {
-        F_out = (T)Fn;
+        F_out = (T)F;
         return ST_NUMERIC;
       }
-#pragma unroll
-      for (int i = 0; i < P; ++i) {
-        p[i] = pt[i];
-        g[i] = gn[i];
-      }
-#pragma unroll
-      for (int k = 0; k < NA; ++k) A[k] = An[k];
-      F = Fn;
-      if (stage != 0) break;
-      TA D2p[P];
-#pragma unroll
-      for (int i = 0; i < P; ++i) D2p[i] = 0;
-      if (lm_step<P, T, TA>(p, A, g, D2p, (TA)0, M::LIN, pt, zz, pnorm2, pred)) {
-        stage = 1;
-      } else {
-        stage = 2;
-#pragma unroll
-        for (int i = 0; i < P; ++i) pt[i] = plin[i];
-      }
+      break;
     }
+#pragma unroll
+    for (int i = 0; i < P; ++i) p[i] = pt[i];
   }
 
   // ---- Levenberg-Marquardt iterations -----------------------------------------------------------

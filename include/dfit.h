@@ -101,7 +101,7 @@ typedef struct dfit_opts {
   int32_t maxfev;        /* reference budget (fitting.py:761, default 100), counted like MINPACK:
                             1 per trial step + P per accepted step */
   double ftol;           /* reference tolerance (fitting.py:762, default 1e-5) */
-  double ftol_scale;     /* engine stops at ftol*ftol_scale (default 1e-3): see DESIGN.md "Parity definition" */
+  double ftol_scale;     /* engine stops at ftol*ftol_scale (default 1e-2): see DESIGN.md "Parity definition" */
   double xtol;           /* relative scaled-step tolerance; <= 0 selects the dtype default */
   double lambda0;        /* initial Marquardt damping; <= 0 selects the default 1e-3 */
   double r2_eps;         /* fitting.py:763, default 1e-8 */

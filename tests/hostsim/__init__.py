@@ -34,7 +34,7 @@ def fit(model, x, y, p0=None, dtype="f32", acc64=False, init_mode=0, init_linear
     p0 = np.ones((1, P)) if p0 is None else np.ascontiguousarray(np.atleast_2d(np.asarray(p0, dtype=np.float64)))
     f32 = dtype == "f32"
     eps = 1.19e-7 if f32 else 2.2e-16
-    ftol = (1e-8 if f32 else 1e-12) if ftol is None else ftol
+    ftol = (1e-7 if f32 else 1e-12) if ftol is None else ftol
     xtol = (1e-6 if f32 else 1e-10) if xtol is None else xtol
     floor_rel = (32 * eps) ** 2 if floor_rel is None else floor_rel
     lo, hi = (-np.inf, np.inf) if y_bounds is None else y_bounds
