@@ -31,6 +31,7 @@ EXPORTED_SYMBOLS = (
     "dfit_version", "dfit_device_count", "dfit_strerror", "dfit_last_error", "dfit_default_opts",
     "dfit_model_nparams", "dfit_create", "dfit_destroy", "dfit_fit_device", "dfit_fit_host", "dfit_get_stats",
     "dfit_set_gather", "dfit_ipc_alloc", "dfit_ipc_open", "dfit_ipc_close", "dfit_ipc_free",
+    "dfit_default_qdess_opts", "dfit_qdess_t2_device", "dfit_qdess_t2_host",
 )
 
 
@@ -61,6 +62,25 @@ class DfitOpts(ctypes.Structure):
         ("decimals", ctypes.c_int32 * MAX_PARAMS),
         ("lanes_per_voxel", ctypes.c_int32),
         ("use_tma", ctypes.c_int32),
+    ]
+
+
+class DfitQdessOpts(ctypes.Structure):
+    _fields_ = [
+        ("struct_size", ctypes.c_int32),
+        ("k", ctypes.c_double),
+        ("c1", ctypes.c_double),
+        ("tr_minus_te", ctypes.c_double),
+        ("has_bounds", ctypes.c_int32),
+        ("lb", ctypes.c_double),
+        ("ub", ctypes.c_double),
+        ("has_nan_fill", ctypes.c_int32),
+        ("nan_fill", ctypes.c_double),
+        ("decimals", ctypes.c_int32),
+        ("suppress_fat", ctypes.c_int32),
+        ("suppress_fluid", ctypes.c_int32),
+        ("beta", ctypes.c_double),
+        ("compute_dtype", ctypes.c_int32),
     ]
 
 
@@ -124,6 +144,9 @@ def load():
         lib.dfit_ipc_open.argtypes = [vp, ctypes.c_char_p, ctypes.POINTER(vp)]
         lib.dfit_ipc_close.argtypes = [vp, vp]
         lib.dfit_ipc_free.argtypes = [vp, vp]
+        lib.dfit_default_qdess_opts.argtypes = [ctypes.POINTER(DfitQdessOpts)]
+        lib.dfit_qdess_t2_device.argtypes = [vp, ctypes.POINTER(DfitQdessOpts), i64, vp, vp, i32, vp, i32, vp]
+        lib.dfit_qdess_t2_host.argtypes = [vp, ctypes.POINTER(DfitQdessOpts), i64, vp, vp, i32, vp, i32]
         _lib = lib
         return lib
 

@@ -10,12 +10,11 @@
 #include <limits>
 #include <new>
 
-#include "../../include/dfit.h"
-#include "fit_kernel.cuh"
+#include "dfit_internal.h"
 
 using namespace dfit;
 
-namespace {
+namespace dfit {
 
 thread_local char g_err[512] = "";
 
@@ -27,25 +26,22 @@ int fail(int code, const char* fmt, ...) {
   return code;
 }
 
-#define CUDA_TRY(expr)                                                                                      \
-  do {                                                                                                      \
-    cudaError_t _e = (expr);                                                                                \
-    if (_e != cudaSuccess)                                                                                  \
-      return fail(_e == cudaErrorMemoryAllocation ? DFIT_ERR_OOM : DFIT_ERR_CUDA, "%s: %s (%s:%d)", #expr, \
-                  cudaGetErrorString(_e), __FILE__, __LINE__);                                              \
-  } while (0)
+const char* last_error() { return g_err; }
 
-constexpr int kSlots = 3;  // pipeline depth of the host entry point
+int ensure(DevBuf& b, size_t bytes) {
+  if (bytes <= b.cap) return DFIT_OK;
+  if (b.p) cudaFree(b.p);
+  b.p = nullptr;
+  b.cap = 0;
+  const size_t want = bytes + (bytes >> 3) + 256;
+  CUDA_TRY(cudaMalloc(&b.p, want));
+  b.cap = want;
+  return DFIT_OK;
+}
 
-struct DevBuf {
-  void* p = nullptr;
-  size_t cap = 0;
-};
+}  // namespace dfit
 
-struct Slot {
-  cudaStream_t stream = nullptr;
-  DevBuf y, mask, p0, popt, r2, status, niter;
-};
+namespace {
 
 int model_nparams(int model) {
   switch (model) {
@@ -58,36 +54,7 @@ int model_nparams(int model) {
 
 }  // namespace
 
-struct dfit_handle {
-  int device = 0;
-  int sm_count = 0;
-  cudaStream_t stream = nullptr;  // default stream for dfit_fit_device(stream = NULL)
-  Slot slots[kSlots];
-  unsigned long long* counters = nullptr;  // device, CNT_COUNT entries
-  cudaEvent_t ev_start = nullptr, ev_stop = nullptr;
-  bool ev_valid = false;
-  cudaStream_t ev_stream = nullptr;
-  int64_t last_n = 0;
-  int last_launches = 0;
-  float last_total_ms = 0.f;
-  float host_kernel_ms = -1.f;
-  float* gather[kMaxPeers] = {nullptr};
-  int gather_world = 0, gather_rank = 0;
-  int64_t gather_rows_per_rank = 0;
-};
-
 namespace {
-
-int ensure(DevBuf& b, size_t bytes) {
-  if (bytes <= b.cap) return DFIT_OK;
-  if (b.p) cudaFree(b.p);
-  b.p = nullptr;
-  b.cap = 0;
-  const size_t want = bytes + (bytes >> 3) + 256;
-  CUDA_TRY(cudaMalloc(&b.p, want));
-  b.cap = want;
-  return DFIT_OK;
-}
 
 int validate(const dfit_opts* o, int n_echo, int64_t n_vox, const double* x, int y_dtype, int p0_dtype, int out_dtype,
              bool have_p0v) {
@@ -258,7 +225,7 @@ const char* dfit_strerror(int code) {
   }
 }
 
-const char* dfit_last_error(void) { return g_err; }
+const char* dfit_last_error(void) { return dfit::last_error(); }
 
 int dfit_model_nparams(int model) { return model_nparams(model); }
 
@@ -332,6 +299,7 @@ int dfit_destroy(dfit_handle* h) {
   }
   if (h->stream) cudaStreamDestroy(h->stream);
   if (h->counters) cudaFree(h->counters);
+  if (h->scratch.p) cudaFree(h->scratch.p);
   if (h->ev_start) cudaEventDestroy(h->ev_start);
   if (h->ev_stop) cudaEventDestroy(h->ev_stop);
   delete h;

@@ -1,0 +1,59 @@
+// Private to the library: handle layout and error helpers shared by the translation units that
+// implement the C-ABI (dfit_api.cu, qdess.cu, metrics.cu).
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdio>
+
+#include "../../include/dfit.h"
+#include "fit_kernel.cuh"
+
+namespace dfit {
+
+int fail(int code, const char* fmt, ...);
+const char* last_error();
+
+#define CUDA_TRY(expr)                                                                                            \
+  do {                                                                                                            \
+    cudaError_t _e = (expr);                                                                                      \
+    if (_e != cudaSuccess)                                                                                        \
+      return dfit::fail(_e == cudaErrorMemoryAllocation ? DFIT_ERR_OOM : DFIT_ERR_CUDA, "%s: %s (%s:%d)", #expr, \
+                        cudaGetErrorString(_e), __FILE__, __LINE__);                                              \
+  } while (0)
+
+constexpr int kSlots = 3;  // pipeline depth of the host entry points
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+};
+
+int ensure(DevBuf& b, size_t bytes);
+
+struct Slot {
+  cudaStream_t stream = nullptr;
+  DevBuf y, mask, p0, popt, r2, status, niter;
+};
+
+}  // namespace dfit
+
+struct dfit_handle {
+  int device = 0;
+  int sm_count = 0;
+  cudaStream_t stream = nullptr;
+  dfit::Slot slots[dfit::kSlots];
+  unsigned long long* counters = nullptr;  // device, kStatSlots x CNT_COUNT entries
+  cudaEvent_t ev_start = nullptr, ev_stop = nullptr;
+  bool ev_valid = false;
+  cudaStream_t ev_stream = nullptr;
+  int64_t last_n = 0;
+  int last_launches = 0;
+  float last_total_ms = 0.f;
+  float host_kernel_ms = -1.f;
+  float* gather[dfit::kMaxPeers] = {nullptr};
+  int gather_world = 0, gather_rank = 0;
+  int64_t gather_rows_per_rank = 0;
+  dfit::DevBuf scratch;  // small device scratch (qDESS maxima, metrics partials)
+};

@@ -193,6 +193,32 @@ int dfit_fit_host(dfit_handle* h, const dfit_opts* opts, int n_echo, int64_t n_v
 /* Counters of the most recent dfit_fit_* call on this handle (synchronises the handle's stream). */
 int dfit_get_stats(dfit_handle* h, dfit_stats* out);
 
+/* ---- qDESS analytic T2 map --------------------------------------------------
+ * Element-wise restatement of dosma/scan_sequences/mri/qdess.py:225-255:
+ *   t2 = nan_to_num(-2000 (TR - TE) / (log(|nan_to_num(S2 / S1)| / k) + c1)), then bounds -> NaN (:237-239),
+ *   NaN -> fill (:240-245), around(decimals) (:247-248), optional fat / fluid suppression (:250-255).
+ * k and c1 are the scalars of qdess.py:204-223, computed by the caller from the sequence parameters. */
+typedef struct dfit_qdess_opts {
+  int32_t struct_size;
+  double k, c1;
+  double tr_minus_te; /* seconds */
+  int32_t has_bounds;
+  double lb, ub;
+  int32_t has_nan_fill;
+  double nan_fill;
+  int32_t decimals; /* < 0: none */
+  int32_t suppress_fat, suppress_fluid;
+  double beta;
+  int32_t compute_dtype; /* -1 / DFIT_F64: the reference's float64 arithmetic (exact parity, default);
+                            DFIT_F32: fp32 + MUFU fast path (HBM-bound, ~2e-6 relative before rounding) */
+} dfit_qdess_opts;
+
+int dfit_default_qdess_opts(dfit_qdess_opts* opts);
+int dfit_qdess_t2_device(dfit_handle* h, const dfit_qdess_opts* opts, int64_t n_vox, const void* echo1, const void* echo2,
+                         int in_dtype, void* t2, int out_dtype, void* stream);
+int dfit_qdess_t2_host(dfit_handle* h, const dfit_qdess_opts* opts, int64_t n_vox, const void* echo1, const void* echo2,
+                       int in_dtype, void* t2, int out_dtype);
+
 #ifdef __cplusplus
 }
 #endif
