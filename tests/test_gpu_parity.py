@@ -318,6 +318,82 @@ def test_full_size_round_trip(D):
     assert st["n_fitted"] == n and st["n_failed"] == 0
 
 
+def test_config3_masked_t1rho_full_size(D):
+    """BASELINE config 3 (512 x 512 x 256, 7 MAPSS-like spin-lock times, ~10 % tissue mask): fitting with the
+    mask equals fitting everything and selecting (bitwise), outside the mask reads NaN / fill, and the
+    statistics count exactly the masked voxels."""
+    import torch
+
+    from dosma_b200 import _cabi, device_api as A
+
+    dev = torch.device("cuda", 0)
+    g = torch.Generator(device=dev).manual_seed(2)
+    x7 = [0.0, 10.0, 12.847, 25.695, 40.0, 51.39, 80.0]  # tests/scan_sequences/mri/test_mapss.py:43
+    shape = (512, 512, 256)
+    n = int(np.prod(shape))
+    xt = torch.tensor(x7, device=dev, dtype=torch.float32)[:, None]
+    y = (500 + 1000 * torch.rand(n, device=dev, generator=g)) * torch.exp(-xt / (20 + 100 * torch.rand(n, device=dev, generator=g)))
+    y += 10 * torch.randn(7, n, device=dev, generator=g)
+    zz, yy, xx = torch.meshgrid(*[torch.linspace(-1, 1, s, device=dev) for s in shape], indexing="ij")
+    rad = (zz ** 2 + yy ** 2 + (xx * 1.6) ** 2).sqrt()
+    mask = ((rad > 0.55) & (rad < 0.62)).reshape(-1)
+    del zz, yy, xx, rad
+    o, P = A.make_opts(D.monoexponential, p0=(1.0, -1 / 30))
+    p_all, r_all = A.fit_device(o, P, x7, y)
+    p_m, r_m = A.fit_device(o, P, x7, y, mask=mask)
+    torch.cuda.synchronize()
+    st = _cabi.get_handle(0).stats()
+    assert st["n_fitted"] == int(mask.sum())
+    assert torch.equal(p_m[mask].nan_to_num(-1), p_all[mask].nan_to_num(-1)) and torch.equal(r_m[mask], r_all[mask])
+    assert torch.isnan(p_m[~mask]).all() and torch.isnan(r_m[~mask]).all()
+    post = {"ufunc": [0, 1], "lb": [-np.inf, 0.0], "ub": [np.inf, 500.0], "decimals": [-1, 3], "r2_threshold": 0.9,
+            "nan_to_num": 0.0}
+    o2, _ = A.make_opts(D.monoexponential, p0=(1.0, -1 / 30), post=post)
+    p_f, r_f = A.fit_device(o2, P, x7, y, mask=mask)
+    torch.cuda.synchronize()
+    assert (p_f[~mask] == 0).all() and (r_f[~mask] == 0).all()  # MonoExponentialFit convention (fitting.py:731)
+    keep = mask & (r_m >= 0.9) & (p_m[:, 1] != 0)
+    tc = (1 / p_m[keep, 1].abs().double())
+    inb = tc <= 500
+    assert torch.allclose(p_f[keep, 1][inb].double(), torch.round(tc[inb] * 1e3) / 1e3, atol=2e-3)
+
+
+def test_config4_biexp_full_size_round_trip(D):
+    """BASELINE config 4 (256 x 256 x 128, 16 echoes, bi-exponential), noise-free: fp64 arithmetic recovers the
+    generating parameters; fp32 arithmetic converges on the same voxels with the accuracy fp32 allows for this
+    ill-conditioned model."""
+    import torch
+
+    from dosma_b200 import device_api as A
+
+    dev = torch.device("cuda", 0)
+    g = torch.Generator(device=dev).manual_seed(3)
+    x16 = [5.0 * i for i in range(1, 17)]
+    n = 256 * 256 * 128
+    xt = torch.tensor(x16, device=dev, dtype=torch.float64)[:, None]
+    amp = 500 + 1000 * torch.rand(n, device=dev, generator=g, dtype=torch.float64)
+    fs = 0.3 + 0.4 * torch.rand(n, device=dev, generator=g, dtype=torch.float64)
+    ts = 8 + 12 * torch.rand(n, device=dev, generator=g, dtype=torch.float64)
+    tl = 50 + 50 * torch.rand(n, device=dev, generator=g, dtype=torch.float64)
+    y = amp * fs * torch.exp(-xt / ts) + amp * (1 - fs) * torch.exp(-xt / tl)
+    o, P = A.make_opts(D.biexponential, p0=(500.0, -1 / 10, 500.0, -1 / 60), compute_dtype="f64")
+    p, r = A.fit_device(o, P, x16, y, out_dtype=torch.float64)
+    torch.cuda.synchronize()
+    ok = ~torch.isnan(p[:, 0])
+    assert ok.double().mean() > 0.99
+    truth = torch.stack([amp * fs, -1 / ts, amp * (1 - fs), -1 / tl], dim=1)
+    rel = ((p[ok] - truth[ok]).abs() / truth[ok].abs()).max(dim=1).values
+    assert (rel < 1e-6).double().mean() > 0.99, float((rel < 1e-6).double().mean())
+    assert (r[ok] > 1 - 1e-9).all()
+    o32, _ = A.make_opts(D.biexponential, p0=(500.0, -1 / 10, 500.0, -1 / 60), compute_dtype="f32")
+    p32, r32 = A.fit_device(o32, P, x16, y.float())
+    torch.cuda.synchronize()
+    ok32 = ~torch.isnan(p32[:, 0])
+    assert ok32.float().mean() > 0.99
+    rel32 = ((p32[ok32].double() - truth[ok32]).abs() / truth[ok32].abs()).max(dim=1).values
+    assert rel32.median() < 1e-3 and (r32[ok32] > 1 - 1e-5).all()
+
+
 def test_nonfinite_input_raises(D):
     x = np.arange(1, 5) * 10.0
     y = np.ones((4, 100), dtype=np.float32)
