@@ -31,7 +31,7 @@ EXPORTED_SYMBOLS = (
     "dfit_version", "dfit_device_count", "dfit_strerror", "dfit_last_error", "dfit_default_opts",
     "dfit_model_nparams", "dfit_create", "dfit_destroy", "dfit_fit_device", "dfit_fit_host", "dfit_get_stats",
     "dfit_set_gather", "dfit_ipc_alloc", "dfit_ipc_open", "dfit_ipc_close", "dfit_ipc_free",
-    "dfit_default_qdess_opts", "dfit_qdess_t2_device", "dfit_qdess_t2_host",
+    "dfit_default_qdess_opts", "dfit_qdess_t2_device", "dfit_qdess_t2_host", "dfit_region_metrics_host",
 )
 
 
@@ -147,6 +147,8 @@ def load():
         lib.dfit_default_qdess_opts.argtypes = [ctypes.POINTER(DfitQdessOpts)]
         lib.dfit_qdess_t2_device.argtypes = [vp, ctypes.POINTER(DfitQdessOpts), i64, vp, vp, i32, vp, i32, vp]
         lib.dfit_qdess_t2_host.argtypes = [vp, ctypes.POINTER(DfitQdessOpts), i64, vp, vp, i32, vp, i32]
+        lib.dfit_region_metrics_host.argtypes = [vp, i64, vp, i32, vp, i32, i32, vp, i32, ctypes.c_double,
+                                                 ctypes.c_double, i32, i32, vp]
         _lib = lib
         return lib
 

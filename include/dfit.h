@@ -219,6 +219,18 @@ int dfit_qdess_t2_device(dfit_handle* h, const dfit_qdess_opts* opts, int64_t n_
 int dfit_qdess_t2_host(dfit_handle* h, const dfit_qdess_opts* opts, int64_t n_vox, const void* echo1, const void* echo2,
                        int in_dtype, void* t2, int out_dtype);
 
+/* ---- region statistics of a fitted map -------------------------------------
+ * `QuantitativeValue.to_metrics`, dosma/core/quant_vals.py:145-229: for each region, over the valid voxels
+ * (finite, and inside `bounds` with the given closedness, :182-190): number of voxels, np.nanmean,
+ * np.nanstd (population) and np.nanmedian, in float64.
+ *   map            host, f32 or f64 [N];  labels: host label mask [N] (any dfit_dtype) or NULL
+ *   region_labels  n_regions entries: L > 0 selects label L (:218), -1 any positive label ("total" with a
+ *                  mask, :216), -2 every voxel ("total" without a mask, :214)
+ *   out            n_regions x 4 doubles: count, mean, std, median (NaN where the region is empty) */
+int dfit_region_metrics_host(dfit_handle* h, int64_t n_vox, const void* map, int map_dtype, const void* labels,
+                             int labels_dtype, int n_regions, const int32_t* region_labels, int has_bounds, double lb,
+                             double ub, int closed_left, int closed_right, double* out);
+
 #ifdef __cplusplus
 }
 #endif
