@@ -134,6 +134,8 @@ void make_desc(const dfit_opts* o, int n_echo, int64_t n_vox, const double* x, L
   d.use_tma = o->use_tma;
   d.tmap = nullptr;
   d.sm_count = 148;
+  d.index = nullptr;
+  d.index_count = nullptr;
   for (int r = 0; r < kMaxPeers; ++r) d.gather[r] = nullptr;
   d.gather_world = 0;
   d.gather_row0 = 0;
@@ -292,7 +294,7 @@ int dfit_destroy(dfit_handle* h) {
   cudaDeviceSynchronize();
   for (int s = 0; s < kSlots; ++s) {
     Slot& sl = h->slots[s];
-    DevBuf* bufs[] = {&sl.y, &sl.mask, &sl.p0, &sl.popt, &sl.r2, &sl.status, &sl.niter};
+    DevBuf* bufs[] = {&sl.y, &sl.mask, &sl.p0, &sl.popt, &sl.r2, &sl.status, &sl.niter, &sl.index};
     for (DevBuf* b : bufs)
       if (b->p) cudaFree(b->p);
     if (sl.stream) cudaStreamDestroy(sl.stream);
@@ -300,6 +302,7 @@ int dfit_destroy(dfit_handle* h) {
   if (h->stream) cudaStreamDestroy(h->stream);
   if (h->counters) cudaFree(h->counters);
   if (h->scratch.p) cudaFree(h->scratch.p);
+  if (h->index_buf.p) cudaFree(h->index_buf.p);
   if (h->ev_start) cudaEventDestroy(h->ev_start);
   if (h->ev_stop) cudaEventDestroy(h->ev_stop);
   delete h;
@@ -348,6 +351,12 @@ int dfit_fit_device(dfit_handle* h, const dfit_opts* opts, int n_echo, int64_t n
   h->last_launches = 0;
   CUtensorMap tmap;
   d.sm_count = h->sm_count;
+  if (mask != nullptr && n_vox > 0) {
+    if (n_vox >= ((int64_t)1 << 32)) return fail(DFIT_ERR_UNSUPPORTED, "masked fits are limited to 2^32 voxels per call");
+    if ((rc = ensure(h->index_buf, (size_t)n_vox * sizeof(unsigned) + 16)) != DFIT_OK) return rc;
+    d.index_count = reinterpret_cast<unsigned*>(h->index_buf.p);
+    d.index = d.index_count + 4;
+  }
   if (n_vox > 0 && tma_eligible(d)) {
     if (!make_sample_tmap(&tmap, y, n_echo, n_vox, ld))
       return fail(DFIT_ERR_UNSUPPORTED, "use_tma=1 but the samples do not qualify (16-byte aligned base and pitch)");
@@ -357,7 +366,7 @@ int dfit_fit_device(dfit_handle* h, const dfit_opts* opts, int n_echo, int64_t n
   }
   if (n_vox > 0) {
     CUDA_TRY(dispatch(d));
-    h->last_launches = 1;
+    h->last_launches = mask != nullptr && d.tmap == nullptr ? 2 : 1;
   }
   CUDA_TRY(cudaEventRecord(h->ev_stop, st));
   h->ev_valid = true;
@@ -411,6 +420,7 @@ int dfit_fit_host(dfit_handle* h, const dfit_opts* opts, int n_echo, int64_t n_v
     if ((rc = ensure(sl.popt, (size_t)chunk * P * osz)) != DFIT_OK) return rc;
     if ((rc = ensure(sl.r2, (size_t)chunk * osz)) != DFIT_OK) return rc;
     if (mask && (rc = ensure(sl.mask, (size_t)chunk)) != DFIT_OK) return rc;
+    if (mask && (rc = ensure(sl.index, (size_t)chunk * sizeof(unsigned) + 16)) != DFIT_OK) return rc;
     if (p0_voxel && (rc = ensure(sl.p0, (size_t)chunk * P * psz)) != DFIT_OK) return rc;
     if (status && (rc = ensure(sl.status, (size_t)chunk)) != DFIT_OK) return rc;
     if (niter && (rc = ensure(sl.niter, (size_t)chunk)) != DFIT_OK) return rc;
@@ -425,6 +435,8 @@ int dfit_fit_host(dfit_handle* h, const dfit_opts* opts, int n_echo, int64_t n_v
     d.n_vox = n;
     d.y = sl.y.p;
     d.mask = mask ? (const uint8_t*)sl.mask.p : nullptr;
+    d.index_count = mask ? reinterpret_cast<unsigned*>(sl.index.p) : nullptr;
+    d.index = mask ? d.index_count + 4 : nullptr;
     d.p0v = p0_voxel ? sl.p0.p : nullptr;
     d.popt = sl.popt.p;
     d.r2 = sl.r2.p;
@@ -436,7 +448,7 @@ int dfit_fit_host(dfit_handle* h, const dfit_opts* opts, int n_echo, int64_t n_v
     d.tmap = nullptr;
     if (tma_eligible(d) && make_sample_tmap(&tmap, d.y, n_echo, n, chunk)) d.tmap = &tmap;
     CUDA_TRY(dispatch(d));
-    ++h->last_launches;
+    h->last_launches += mask && d.tmap == nullptr ? 2 : 1;
     CUDA_TRY(cudaMemcpyAsync((char*)popt + (size_t)v0 * P * osz, sl.popt.p, (size_t)n * P * osz, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaMemcpyAsync((char*)r2 + (size_t)v0 * osz, sl.r2.p, (size_t)n * osz, cudaMemcpyDeviceToHost, st));
     if (status) CUDA_TRY(cudaMemcpyAsync(status + v0, sl.status.p, (size_t)n, cudaMemcpyDeviceToHost, st));

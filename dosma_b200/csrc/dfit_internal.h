@@ -34,7 +34,7 @@ int ensure(DevBuf& b, size_t bytes);
 
 struct Slot {
   cudaStream_t stream = nullptr;
-  DevBuf y, mask, p0, popt, r2, status, niter;
+  DevBuf y, mask, p0, popt, r2, status, niter, index;
 };
 
 }  // namespace dfit
@@ -55,5 +55,6 @@ struct dfit_handle {
   float* gather[dfit::kMaxPeers] = {nullptr};
   int gather_world = 0, gather_rank = 0;
   int64_t gather_rows_per_rank = 0;
-  dfit::DevBuf scratch;  // small device scratch (qDESS maxima, metrics partials)
+  dfit::DevBuf scratch;    // small device scratch (qDESS maxima, metrics partials)
+  dfit::DevBuf index_buf;  // compacted voxel list of the masked device path
 };

@@ -35,6 +35,8 @@ struct KernelArgs {
   int64_t n;
   int y_dtype, layout, E;
   const uint8_t* mask;
+  const unsigned* index;        // compacted list of voxels to fit (mask path), or null: fit voxel v = thread id
+  const unsigned* index_count;  // device counter: number of entries in `index`
   const void* p0v;  // [N, P] per-voxel initial guess or null
   int p0_dtype;
   unsigned p0_voxel_bits;  // bit i set: parameter i comes from p0v
@@ -226,23 +228,111 @@ __device__ __forceinline__ void block_stats(unsigned long long* cnt, int st, int
   }
 }
 
+// Mask path, step 1: one streaming pass over the mask that (a) appends the voxels to fit to a compact
+// index list -- each warp claims a contiguous run with one atomic, so neighbours stay neighbours -- and
+// (b) writes the fill value for every voxel outside the mask (fitting.py:205-215).  Step 2 is the fit
+// kernel over the list: all 32 lanes of a warp fit, however thin the tissue mask is.
+__device__ __forceinline__ void block_stats_packed(unsigned long long* cnt, unsigned pack, int it_sum, int it_max) {
+  __shared__ unsigned s_c[4], s_iters, s_max;
+  if (threadIdx.x < 4) s_c[threadIdx.x] = 0;
+  if (threadIdx.x == 0) {
+    s_iters = 0;
+    s_max = 0;
+  }
+  __syncthreads();
+  const unsigned full = 0xffffffffu;
+  unsigned c[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) c[k] = __reduce_add_sync(full, (pack >> (8 * k)) & 0xffu);
+  const unsigned s_it = __reduce_add_sync(full, (unsigned)it_sum);
+  const unsigned m_it = __reduce_max_sync(full, (unsigned)it_max);
+  if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      if (c[k]) atomicAdd(&s_c[k], c[k]);
+    atomicAdd(&s_iters, s_it);
+    atomicMax(&s_max, m_it);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned long long* dst = cnt + (size_t)(blockIdx.x & (kStatSlots - 1)) * CNT_COUNT;
+    if (s_c[0]) atomicAdd(dst + CNT_FITTED, (unsigned long long)s_c[0]);
+    if (s_c[1]) atomicAdd(dst + CNT_FAILED, (unsigned long long)s_c[1]);
+    if (s_c[2]) atomicAdd(dst + CNT_NONFINITE, (unsigned long long)s_c[2]);
+    if (s_c[3]) atomicAdd(dst + CNT_OOB, (unsigned long long)s_c[3]);
+    if (s_iters) atomicAdd(dst + CNT_ITERS, (unsigned long long)s_iters);
+    if (s_max) atomicMax(dst + CNT_MAXITER, (unsigned long long)s_max);
+  }
+}
+
+constexpr int kCompactPerThread = 8;  // voxels per thread in the compaction pass (2048 per CTA)
+
+template <int P, typename T, int EMAX>
+__global__ void __launch_bounds__(256) mask_compact_kernel(const __grid_constant__ KernelArgs<T, EMAX> a, unsigned* index,
+                                                           unsigned* count) {
+  __shared__ unsigned s_list[256 * kCompactPerThread];
+  __shared__ unsigned s_n, s_base;
+  if (threadIdx.x == 0) s_n = 0;
+  __syncthreads();
+  const int64_t v0 = (int64_t)blockIdx.x * (256 * kCompactPerThread);
+  const int lane = threadIdx.x & 31;
+#pragma unroll
+  for (int k = 0; k < kCompactPerThread; ++k) {
+    const int64_t v = v0 + k * 256 + threadIdx.x;
+    const bool in = v < a.n;
+    const bool active = in && a.mask[v] != 0;
+    const unsigned ballot = __ballot_sync(0xffffffffu, active);
+    unsigned base = 0;
+    if (lane == 0 && ballot) base = atomicAdd(&s_n, (unsigned)__popc(ballot));  // shared-memory atomic
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (active) s_list[base + __popc(ballot & ((1u << lane) - 1u))] = (unsigned)v;
+    if (in && !active) {
+      T p[P];
+      store_voxel<P, T, EMAX>(a, v, p, (T)0, false, ST_SKIPPED, 0);
+    }
+  }
+  __syncthreads();
+  const unsigned n = s_n;
+  if (threadIdx.x == 0 && n) s_base = atomicAdd(count, n);  // ONE global atomic per 2048 voxels
+  __syncthreads();
+  for (unsigned i = threadIdx.x; i < n; i += 256) index[s_base + i] = s_list[i];
+}
+
 template <class M, typename T, int EMAX, bool EXACT>
 __global__ void __launch_bounds__(kBlock) fit_kernel(const __grid_constant__ KernelArgs<T, EMAX> a) {
   constexpr int P = M::P;
-  const int64_t v = (int64_t)blockIdx.x * kBlock + threadIdx.x;
   int st = -1, iters = 0;
   unsigned flags = 0;
-  if (v < a.n) {
-    const bool active = a.mask == nullptr || a.mask[v] != 0;
-    T p[P], r2 = 0;
-    st = ST_SKIPPED;
-    if (active) {
-      T y[EMAX];
+  if (a.index == nullptr) {
+    const int64_t v = (int64_t)blockIdx.x * kBlock + threadIdx.x;
+    if (v < a.n) {
+      T p[P], r2 = 0, y[EMAX];
       load_samples<T, EMAX, EXACT>(a, v, y);
       load_p0<P, T, EMAX>(a, v, p);
       st = fit_voxel<M, T, T, EMAX, EXACT>(y, a.xt, a.E, a.vo, p, r2, iters, flags);
+      store_voxel<P, T, EMAX>(a, v, p, r2, true, st, iters);
     }
-    store_voxel<P, T, EMAX>(a, v, p, r2, active, st, iters);
+  } else {
+    // compacted mask path: grid-stride over the index list (its length is only known on the device)
+    const unsigned count = *a.index_count;
+    int it_sum = 0;
+    unsigned pack = 0;
+    for (unsigned i = blockIdx.x * kBlock + threadIdx.x; i < count; i += gridDim.x * kBlock) {
+      const int64_t v = (int64_t)a.index[i];
+      T p[P], r2 = 0, y[EMAX];
+      int it = 0;
+      unsigned fl = 0;
+      load_samples<T, EMAX, EXACT>(a, v, y);
+      load_p0<P, T, EMAX>(a, v, p);
+      const int s = fit_voxel<M, T, T, EMAX, EXACT>(y, a.xt, a.E, a.vo, p, r2, it, fl);
+      store_voxel<P, T, EMAX>(a, v, p, r2, true, s, it);
+      it_sum += it;
+      iters = it > iters ? it : iters;
+      pack += (unsigned)(s >= ST_CONV_F) | ((unsigned)(s >= ST_MAXITER) << 8) |
+              ((unsigned)((fl & FLAG_NONFINITE) != 0) << 16) | ((unsigned)((fl & FLAG_OOB) != 0) << 24);
+    }
+    block_stats_packed(a.counters, pack, it_sum, iters);
+    return;
   }
   block_stats(a.counters, st, iters, flags);
 }
@@ -392,6 +482,8 @@ struct LaunchDesc {
   int y_dtype, layout;
   int64_t ld;
   const uint8_t* mask;
+  unsigned* index;        // device scratch for the compacted mask path (n_vox entries) or null
+  unsigned* index_count;  // device counter
   const void* p0v;
   int p0_dtype;
   unsigned p0_voxel_bits;
@@ -448,6 +540,8 @@ inline void fill_args(const LaunchDesc& d, KernelArgs<T, EMAX>& a) {
   a.layout = d.layout;
   a.E = d.n_echo;
   a.mask = d.mask;
+  a.index = nullptr;
+  a.index_count = nullptr;
   a.p0v = d.p0v;
   a.p0_dtype = d.p0_dtype;
   a.p0_voxel_bits = d.p0_voxel_bits;
@@ -485,6 +579,19 @@ inline cudaError_t launch_one(const LaunchDesc& d) {
     }
   }
   const int64_t blocks = (d.n_vox + kBlock - 1) / kBlock;
+  if (d.mask != nullptr && d.index != nullptr) {
+    // mask path: compact + fill, then fit the list with a grid sized for the SMs (grid-stride)
+    cudaError_t e = cudaMemsetAsync(d.index_count, 0, sizeof(unsigned), d.stream);
+    if (e != cudaSuccess) return e;
+    const int64_t per_cta = 256 * kCompactPerThread;
+    mask_compact_kernel<M::P, T, EMAX><<<(unsigned)((d.n_vox + per_cta - 1) / per_cta), 256, 0, d.stream>>>(a, d.index, d.index_count);
+    a.index = d.index;
+    a.index_count = d.index_count;
+    int64_t g = (int64_t)d.sm_count * 16;
+    if (g > blocks) g = blocks;
+    fit_kernel<M, T, EMAX, EXACT><<<(unsigned)g, kBlock, 0, d.stream>>>(a);
+    return cudaGetLastError();
+  }
   fit_kernel<M, T, EMAX, EXACT><<<(unsigned)blocks, kBlock, 0, d.stream>>>(a);
   return cudaGetLastError();
 }

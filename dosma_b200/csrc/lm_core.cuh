@@ -77,6 +77,14 @@ struct num<float> {
   }
   static DFIT_HD float exp_(float v) { return expf(v); }
   static DFIT_HD float log_(float v) { return logf(v); }
+  // natural log for the log-linear INITIAL GUESS only (MUFU.LG2 + FMUL on the device)
+  static DFIT_HD float log_fast(float v) {
+#if defined(__CUDA_ARCH__)
+    return __logf(v);
+#else
+    return logf(v);
+#endif
+  }
   static DFIT_HD float sqrt_(float v) { return sqrtf(v); }
   static DFIT_HD float abs_(float v) { return fabsf(v); }
   static DFIT_HD float max_(float a, float b) { return fmaxf(a, b); }
@@ -96,6 +104,7 @@ struct num<double> {
   static DFIT_HD double rsqrt_(double v) { return 1.0 / sqrt(v); }
   static DFIT_HD double exp_(double v) { return exp(v); }
   static DFIT_HD double log_(double v) { return log(v); }
+  static DFIT_HD double log_fast(double v) { return log(v); }
   static DFIT_HD double sqrt_(double v) { return sqrt(v); }
   static DFIT_HD double abs_(double v) { return fabs(v); }
   static DFIT_HD double max_(double a, double b) { return fmax(a, b); }
@@ -439,7 +448,7 @@ DFIT_HD void loglinear_init(const T (&y)[EMAX], const T* __restrict__ xc, T xbar
   for (int e = 0; e < EMAX; ++e) {
     if (EXACT || e < E) {
       T v = y[e] == (T)0 ? (T)1e-10 : y[e];
-      T l = num<T>::log_(v);  // NaN for v < 0
+      T l = num<T>::log_fast(v);  // NaN for v < 0
       sl += l;
       sxl = num<T>::fma_(xc[e], l, sxl);
     }
@@ -447,7 +456,7 @@ DFIT_HD void loglinear_init(const T (&y)[EMAX], const T* __restrict__ xc, T xbar
   T slope = sxl * inv_sxx;
   T icpt = sl / (T)E - slope * xbar;
   T a = num<T>::exp_(icpt);
-  if (num<T>::finite(slope) && num<T>::finite(a)) {
+  if (num<T>::finite(slope) && num<T>::finite(a) && num<T>::finite(sl)) {
     p[0] = a;
     p[1] = slope;
   } else {

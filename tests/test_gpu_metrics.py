@@ -5,10 +5,11 @@ import pytest
 pytestmark = pytest.mark.gpu
 
 
-def _check(got, ref):
-    assert got["Category"] == ref["Category"] and got["# Voxels"] == ref["# Voxels"]
+def _check(got, ref, rtol=1e-11):
+    assert got["Category"] == ref["Category"], (got["Category"], ref["Category"])
+    assert got["# Voxels"] == ref["# Voxels"], (got["# Voxels"], ref["# Voxels"])
     for k in ("Mean", "Std"):
-        np.testing.assert_allclose(got[k], ref[k], rtol=1e-11, equal_nan=True)
+        np.testing.assert_allclose(got[k], ref[k], rtol=rtol, equal_nan=True)
     np.testing.assert_array_equal(np.asarray(got["Median"]), np.asarray(ref["Median"]))  # exact selection
 
 
@@ -24,6 +25,14 @@ def test_metrics_match_oracle(dtype):
     vol[rng.random(shape) < 0.01] = np.inf
     vol[rng.random(shape) < 0.2] = 0.0
     lab = rng.integers(0, 5, shape).astype(np.uint8)
+    # numpy reduces a float32 map in float32 (pairwise), the kernel always accumulates in float64: for float32
+    # maps the oracle itself is only good to ~1e-6; fitted maps are float64 (fitting.py:870), the exact case
+    rtol = 1e-11 if dtype == np.float64 else 2e-6
+    _check_ = _check
+
+    def _check(got, ref):  # noqa: F811
+        _check_(got, ref, rtol)
+
     for kw in (dict(), dict(bounds=(0, 100)), dict(bounds=(0, 100), closed="both"), dict(bounds=(10, 90), closed="neither")):
         _check(region_metrics(vol, as_frame=False, **kw), M.to_metrics(vol, **kw))
         _check(region_metrics(vol, mask=lab, as_frame=False, **kw), M.to_metrics(vol, mask=lab, **kw))
