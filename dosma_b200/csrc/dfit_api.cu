@@ -321,6 +321,8 @@ int dfit_fit_device(dfit_handle* h, const dfit_opts* opts, int n_echo, int64_t n
   if (n_vox > 0 && (!popt != !r2)) return fail(DFIT_ERR_BAD_ARG, "popt and r2 must both be given or both be NULL");
   if (n_vox > 0 && !popt && !gathering) return fail(DFIT_ERR_BAD_ARG, "popt/r2 may only be NULL with dfit_set_gather");
   if (gathering && n_vox > h->gather_rows_per_rank) return fail(DFIT_ERR_BAD_ARG, "n_vox exceeds gather rows_per_rank");
+  if (gathering && opts->compute_dtype != DFIT_F32)
+    return fail(DFIT_ERR_UNSUPPORTED, "the fused all-gather map is fp32: use compute_dtype = DFIT_F32 with dfit_set_gather");
   if (ld < (y_layout == DFIT_PLANAR ? n_vox : (int64_t)n_echo)) return fail(DFIT_ERR_BAD_ARG, "ld too small");
   CUDA_TRY(cudaSetDevice(h->device));
   cudaStream_t st = (cudaStream_t)stream;  // NULL is the legacy default stream (what torch calls its default stream)

@@ -145,9 +145,9 @@ __device__ __forceinline__ void store_vec(TO* __restrict__ dst, const double (&q
 }
 
 // Epilogue + stores for one voxel.  `fitted` false: voxel outside the mask.
-template <int P, typename T, int EMAX>
+template <int P, typename T, int EMAX, bool GATHER = true>
 __device__ __forceinline__ void store_voxel(const KernelArgs<T, EMAX>& a, int64_t v, const T (&p)[P], T r2, bool fitted,
-                                            int st, int iters) {
+                                            int st, int iters, bool warp_rows = false) {
   double q[P];
   double r2o;
   if (fitted) {
@@ -174,15 +174,48 @@ __device__ __forceinline__ void store_voxel(const KernelArgs<T, EMAX>& a, int64_
       __stcs(reinterpret_cast<double*>(a.r2) + v, r2o);
     }
   }
-  if (a.gather_world > 0) {
-    const int64_t off = (a.gather_row0 + v) * (P + 1);
+  if (GATHER && a.gather_world > 0) {
+    constexpr int C = P + 1;
+    float row[C];
 #pragma unroll
-    for (int r = 0; r < kMaxPeers; ++r) {
-      if (r < a.gather_world) {
-        float* dst = a.gather[r] + off;  // local HBM for r == own rank, a peer's HBM over NVLink otherwise
+    for (int i = 0; i < P; ++i) row[i] = (float)q[i];
+    row[P] = (float)r2o;
+    if (warp_rows) {
+      // The warp's 32 rows are one contiguous block of 32*C floats in every map.  Transpose it through
+      // shuffles so that each of the C store instructions writes 128 contiguous bytes per warp: NVLink
+      // carries full write packets instead of 4-byte fragments at a 4*C-byte stride.
+      const int lane = threadIdx.x & 31;
+      float word[C];
 #pragma unroll
-        for (int i = 0; i < P; ++i) dst[i] = (float)q[i];
-        dst[P] = (float)r2o;
+      for (int k = 0; k < C; ++k) {
+        const int w = k * 32 + lane;  // word of the block this lane stores in round k
+        const int src = w / C, col = w - src * C;
+        float val = 0.f;
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+          const float t = __shfl_sync(0xffffffffu, row[c], src);
+          if (c == col) val = t;
+        }
+        word[k] = val;
+      }
+      const int64_t block0 = (a.gather_row0 + (v - lane)) * C;
+#pragma unroll
+      for (int r = 0; r < kMaxPeers; ++r) {
+        if (r < a.gather_world) {
+          float* dst = a.gather[r] + block0 + lane;  // local HBM for r == own rank, a peer's over NVLink otherwise
+#pragma unroll
+          for (int k = 0; k < C; ++k) dst[k * 32] = word[k];
+        }
+      }
+    } else {
+      const int64_t off = (a.gather_row0 + v) * C;
+#pragma unroll
+      for (int r = 0; r < kMaxPeers; ++r) {
+        if (r < a.gather_world) {
+          float* dst = a.gather[r] + off;
+#pragma unroll
+          for (int i = 0; i < C; ++i) dst[i] = row[i];
+        }
       }
     }
   }
@@ -298,19 +331,21 @@ __global__ void __launch_bounds__(256) mask_compact_kernel(const __grid_constant
   for (unsigned i = threadIdx.x; i < n; i += 256) index[s_base + i] = s_list[i];
 }
 
-template <class M, typename T, int EMAX, bool EXACT>
-__global__ void __launch_bounds__(kBlock) fit_kernel(const __grid_constant__ KernelArgs<T, EMAX> a) {
+template <class M, typename T, int EMAX, bool EXACT, bool GATHER>
+__global__ void __launch_bounds__(kBlock, EMAX <= 8 ? 8 : 1) fit_kernel(const __grid_constant__ KernelArgs<T, EMAX> a) {
   constexpr int P = M::P;
   int st = -1, iters = 0;
   unsigned flags = 0;
   if (a.index == nullptr) {
     const int64_t v = (int64_t)blockIdx.x * kBlock + threadIdx.x;
+    const bool whole_warp = (v | 31) < a.n;  // all 32 voxels of this warp exist: cooperative stores are legal
     if (v < a.n) {
       T p[P], r2 = 0, y[EMAX];
       load_samples<T, EMAX, EXACT>(a, v, y);
       load_p0<P, T, EMAX>(a, v, p);
       st = fit_voxel<M, T, T, EMAX, EXACT>(y, a.xt, a.E, a.vo, p, r2, iters, flags);
-      store_voxel<P, T, EMAX>(a, v, p, r2, true, st, iters);
+      if (whole_warp) __syncwarp();
+      store_voxel<P, T, EMAX, GATHER>(a, v, p, r2, true, st, iters, whole_warp);
     }
   } else {
     // compacted mask path: grid-stride over the index list (its length is only known on the device)
@@ -325,7 +360,7 @@ __global__ void __launch_bounds__(kBlock) fit_kernel(const __grid_constant__ Ker
       load_samples<T, EMAX, EXACT>(a, v, y);
       load_p0<P, T, EMAX>(a, v, p);
       const int s = fit_voxel<M, T, T, EMAX, EXACT>(y, a.xt, a.E, a.vo, p, r2, it, fl);
-      store_voxel<P, T, EMAX>(a, v, p, r2, true, s, it);
+      store_voxel<P, T, EMAX, GATHER>(a, v, p, r2, true, s, it);
       it_sum += it;
       iters = it > iters ? it : iters;
       pack += (unsigned)(s >= ST_CONV_F) | ((unsigned)(s >= ST_MAXITER) << 8) |
@@ -589,10 +624,21 @@ inline cudaError_t launch_one(const LaunchDesc& d) {
     a.index_count = d.index_count;
     int64_t g = (int64_t)d.sm_count * 16;
     if (g > blocks) g = blocks;
-    fit_kernel<M, T, EMAX, EXACT><<<(unsigned)g, kBlock, 0, d.stream>>>(a);
+    if (d.gather_world > 0) {
+      if constexpr (sizeof(T) == 4) fit_kernel<M, T, EMAX, EXACT, true><<<(unsigned)g, kBlock, 0, d.stream>>>(a);
+      else return cudaErrorNotSupported;
+    } else {
+      fit_kernel<M, T, EMAX, EXACT, false><<<(unsigned)g, kBlock, 0, d.stream>>>(a);
+    }
     return cudaGetLastError();
   }
-  fit_kernel<M, T, EMAX, EXACT><<<(unsigned)blocks, kBlock, 0, d.stream>>>(a);
+  // the fused all-gather epilogue is a separate instance so that single-GPU launches do not pay its registers
+  if (d.gather_world > 0) {
+    if constexpr (sizeof(T) == 4) fit_kernel<M, T, EMAX, EXACT, true><<<(unsigned)blocks, kBlock, 0, d.stream>>>(a);
+    else return cudaErrorNotSupported;  // the gathered map is fp32 (the C-ABI layer rejects this earlier)
+  } else {
+    fit_kernel<M, T, EMAX, EXACT, false><<<(unsigned)blocks, kBlock, 0, d.stream>>>(a);
+  }
   return cudaGetLastError();
 }
 
@@ -608,8 +654,9 @@ inline cudaError_t launch_exact(const LaunchDesc& d) {
   }
 }
 
+// Split in two halves so that each model/dtype compiles as two translation units in parallel.
 template <class M, typename T>
-inline cudaError_t launch_model(const LaunchDesc& d) {
+inline cudaError_t launch_model_lo(const LaunchDesc& d) {  // 1..8 echoes
   switch (d.n_echo) {
     case 1: return launch_exact<M, T, 1>(d);
     case 2: return launch_exact<M, T, 2>(d);
@@ -618,7 +665,13 @@ inline cudaError_t launch_model(const LaunchDesc& d) {
     case 5: return launch_exact<M, T, 5>(d);
     case 6: return launch_exact<M, T, 6>(d);
     case 7: return launch_exact<M, T, 7>(d);
-    case 8: return launch_exact<M, T, 8>(d);
+    default: return launch_exact<M, T, 8>(d);
+  }
+}
+
+template <class M, typename T>
+inline cudaError_t launch_model_hi(const LaunchDesc& d) {  // 9..32 echoes
+  switch (d.n_echo) {
     case 9: return launch_exact<M, T, 9>(d);
     case 10: return launch_exact<M, T, 10>(d);
     case 11: return launch_exact<M, T, 11>(d);
@@ -633,11 +686,16 @@ inline cudaError_t launch_model(const LaunchDesc& d) {
 #endif
 
 // Implemented one per translation unit so the (large, fully unrolled) instances compile in parallel.
-cudaError_t launch_mono_f32(const LaunchDesc& d);
-cudaError_t launch_mono_f64(const LaunchDesc& d);
-cudaError_t launch_biexp_f32(const LaunchDesc& d);
-cudaError_t launch_biexp_f64(const LaunchDesc& d);
-cudaError_t launch_linear_f32(const LaunchDesc& d);
-cudaError_t launch_linear_f64(const LaunchDesc& d);
+#define DFIT_DECLARE_LAUNCH(name)                    \
+  cudaError_t launch_##name##_lo(const LaunchDesc& d); \
+  cudaError_t launch_##name##_hi(const LaunchDesc& d); \
+  inline cudaError_t launch_##name(const LaunchDesc& d) { return d.n_echo <= 8 ? launch_##name##_lo(d) : launch_##name##_hi(d); }
+DFIT_DECLARE_LAUNCH(mono_f32)
+DFIT_DECLARE_LAUNCH(mono_f64)
+DFIT_DECLARE_LAUNCH(biexp_f32)
+DFIT_DECLARE_LAUNCH(biexp_f64)
+DFIT_DECLARE_LAUNCH(linear_f32)
+DFIT_DECLARE_LAUNCH(linear_f64)
+#undef DFIT_DECLARE_LAUNCH
 
 }  // namespace dfit
