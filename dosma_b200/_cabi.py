@@ -60,7 +60,7 @@ class DfitOpts(ctypes.Structure):
         ("has_nan_fill", ctypes.c_int32),
         ("nan_fill", ctypes.c_double),
         ("decimals", ctypes.c_int32 * MAX_PARAMS),
-        ("lanes_per_voxel", ctypes.c_int32),
+        ("fast_path", ctypes.c_int32),
         ("use_tma", ctypes.c_int32),
     ]
 

@@ -119,6 +119,9 @@ void make_desc(const dfit_opts* o, int n_echo, int64_t n_vox, const double* x, L
   d.maxfev = o->maxfev;
   d.init_mode = o->init_mode;
   d.init_linear = o->init_linear < 0 ? (o->model == DFIT_MODEL_BIEXP ? 0 : 1) : o->init_linear;
+  // The fast path spends at most kMonoFastPasses passes; a budget too small for that means the caller is
+  // probing maxfev behaviour (fitting.py:761), which only the LM reproduces.
+  d.fast_path = (o->model == DFIT_MODEL_MONOEXP && o->fast_path != 0 && o->maxfev >= 3 * (kMonoFastPasses + 1)) ? 1 : 0;
   d.po.enabled = o->post_enabled;
   for (int i = 0; i < 4; ++i) {
     d.po.ufunc[i] = o->ufunc[i];
@@ -255,7 +258,7 @@ int dfit_default_opts(dfit_opts* o, int model) {
     o->ub[i] = std::numeric_limits<double>::infinity();
     o->decimals[i] = -1;
   }
-  o->lanes_per_voxel = 0;
+  o->fast_path = -1;
   o->use_tma = -1;
   return DFIT_OK;
 }

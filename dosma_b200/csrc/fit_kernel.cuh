@@ -148,6 +148,22 @@ __device__ __forceinline__ void store_vec(TO* __restrict__ dst, const double (&q
 template <int P, typename T, int EMAX, bool GATHER = true>
 __device__ __forceinline__ void store_voxel(const KernelArgs<T, EMAX>& a, int64_t v, const T (&p)[P], T r2, bool fitted,
                                             int st, int iters, bool warp_rows = false) {
+  if constexpr (sizeof(T) == 4) {
+    // Raw fp32 parameters into fp32 maps (curve_fit without an epilogue): no trip through double.
+    if (fitted && !a.po.enabled && a.out_dtype == DT_F32 && a.popt != nullptr && !(GATHER && a.gather_world > 0)) {
+      float* dst = reinterpret_cast<float*>(a.popt) + v * P;
+      if constexpr (P == 2) __stcs(reinterpret_cast<float2*>(dst), make_float2(p[0], p[1]));
+      else if constexpr (P == 4) __stcs(reinterpret_cast<float4*>(dst), make_float4(p[0], p[1], p[2], p[3]));
+      else {
+#pragma unroll
+        for (int i = 0; i < P; ++i) __stcs(dst + i, p[i]);
+      }
+      __stcs(reinterpret_cast<float*>(a.r2) + v, r2);
+      if (a.status) a.status[v] = (uint8_t)st;
+      if (a.niter) a.niter[v] = (uint8_t)(iters > 255 ? 255 : iters);
+      return;
+    }
+  }
   double q[P];
   double r2o;
   if (fitted) {
@@ -380,7 +396,7 @@ __global__ void __launch_bounds__(kBlock, EMAX <= 8 ? 8 : 1) fit_kernel(const __
 // There is no block-level synchronisation -- warps run their own pipelines, so a slow voxel only
 // holds its own warp.  Used for fp32 planar samples whose row pitch is a multiple of 16 bytes.
 constexpr int kTmaWarps = 8;          // warps per CTA
-constexpr int kTmaStages = 2;
+constexpr int tma_stages(int E) { return E <= 8 ? 4 : 2; }  // ring depth: 32 KB of tiles per CTA at 8 echoes
 constexpr int kTmaTile = 32;          // voxels per warp tile (one per lane)
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -415,6 +431,7 @@ __global__ void __launch_bounds__(kTmaWarps * 32)
     fit_kernel_tma(const __grid_constant__ KernelArgs<T, EMAX> a, const __grid_constant__ CUtensorMap tmap) {
   constexpr int P = M::P;
   constexpr unsigned kTileBytes = EMAX * kTmaTile * sizeof(float);
+  constexpr int kTmaStages = tma_stages(EMAX);
   __shared__ __align__(128) float tiles[kTmaWarps][kTmaStages][EMAX][kTmaTile];
   __shared__ __align__(8) uint64_t full[kTmaWarps][kTmaStages];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -531,7 +548,7 @@ struct LaunchDesc {
   unsigned long long* counters;
   // solver
   double ftol, xtol, lambda0, floor_rel, r2_eps, y_lo, y_hi;
-  int maxfev, init_mode, init_linear;
+  int maxfev, init_mode, init_linear, fast_path;
   PostOpts po;
   double mask_fill;
   int use_tma;
@@ -545,18 +562,7 @@ struct LaunchDesc {
 
 template <typename T, int EMAX>
 inline void fill_args(const LaunchDesc& d, KernelArgs<T, EMAX>& a) {
-  double xbar = 0, sxx = 0;
-  for (int e = 0; e < d.n_echo; ++e) xbar += d.x[e];
-  xbar /= d.n_echo;
-  for (int e = 0; e < EMAX; ++e) {
-    const double xe = e < d.n_echo ? d.x[e] : 0.0;
-    a.xt.x[e] = (T)xe;
-    a.xt.xs[e] = (T)(xe * 1.4426950408889634074);
-    a.xt.xc[e] = (T)(e < d.n_echo ? xe - xbar : 0.0);
-    if (e < d.n_echo) sxx += (xe - xbar) * (xe - xbar);
-  }
-  a.xt.xbar = (T)xbar;
-  a.xt.inv_sxx = (T)(sxx > 0 ? 1.0 / sxx : 0.0);
+  fill_xtab<T, EMAX>(a.xt, d.x, d.n_echo);
   a.vo.s.ftol = (T)d.ftol;
   a.vo.s.xtol = (T)d.xtol;
   a.vo.s.lambda0 = (T)d.lambda0;
@@ -567,6 +573,8 @@ inline void fill_args(const LaunchDesc& d, KernelArgs<T, EMAX>& a) {
   a.vo.y_hi = (T)d.y_hi;
   a.vo.r2_eps = (T)d.r2_eps;
   a.vo.init_mode = d.init_mode;
+  a.vo.has_bounds = (d.y_lo > -1.7e308 || d.y_hi < 1.7e308) ? 1 : 0;
+  a.vo.fast = d.fast_path;
   a.po = d.po;
   a.y = d.y;
   a.ld = d.ld;

@@ -203,6 +203,7 @@ __device__ __forceinline__ pair2<float> p2_expbx<float>(float b, pair2<float> /*
 struct MonoExp {
   static constexpr int P = 2;
   static constexpr unsigned LIN = 0x1u;
+  static constexpr bool MONO = true;  // eligible for the variable-projection Newton fast path
   template <typename T>
   static DFIT_HD void eval(const T (&p)[2], T x, T xs, T& f, T (&Jh)[2]) {
     T e = num<T>::expbx(p[1], x, xs);
@@ -228,6 +229,7 @@ struct MonoExp {
 struct BiExp {
   static constexpr int P = 4;
   static constexpr unsigned LIN = 0x5u;
+  static constexpr bool MONO = false;
   template <typename T>
   static DFIT_HD void eval(const T (&p)[4], T x, T xs, T& f, T (&Jh)[4]) {
     T e1 = num<T>::expbx(p[1], x, xs);
@@ -261,6 +263,7 @@ struct BiExp {
 struct Linear1 {
   static constexpr int P = 1;
   static constexpr unsigned LIN = 0x1u;
+  static constexpr bool MONO = false;
   template <typename T>
   static DFIT_HD void eval(const T (&p)[1], T x, T /*xs*/, T& f, T (&Jh)[1]) {
     Jh[0] = x;
@@ -655,7 +658,7 @@ DFIT_HD int lm_solve(T (&p)[M::P], const T (&y)[EMAX], const T* __restrict__ x, 
   return status;
 }
 
-// ------------------------------------------------------------------------------------ one voxel
+// ------------------------------------------------------------------------------------ echo table
 // Echo-time table shared by all voxels of a launch (lives in the kernel parameter / constant bank).
 template <typename T, int EMAX>
 struct XTab {
@@ -663,8 +666,181 @@ struct XTab {
   T xs[EMAX];  // x * log2(e), so exp(b x) = ex2(b * xs)
   T xc[EMAX];  // x - mean(x), for the log-linear initial guess
   T xbar, inv_sxx;
+  // Uniform spacing x_k = x0 + k dx (multi-echo spin echo, cones, ...): exp(b x_k) = e0 q^k with
+  // q = exp(b dx), so the mono-exponential model is a POLYNOMIAL in q (mono_uniform_newton).
+  int uniform;   // 1: spacing is uniform to within the arithmetic's resolution (host decides)
+  T x0, x0s;     // first echo time and x0 * log2(e)
+  T inv_dx;      // 1 / dx
+  T q_lo, q_hi;  // admissible range of q: q^(2E-2) must stay finite
 };
 
+// Host-side fill of the echo table (shared by the C-ABI layer and the test-only host build).
+template <typename T, int EMAX>
+inline void fill_xtab(XTab<T, EMAX>& xt, const double* x, int n_echo) {
+  double xbar = 0, sxx = 0;
+  for (int e = 0; e < n_echo; ++e) xbar += x[e];
+  xbar /= n_echo;
+  for (int e = 0; e < EMAX; ++e) {
+    const double xe = e < n_echo ? x[e] : 0.0;
+    xt.x[e] = (T)xe;
+    xt.xs[e] = (T)(xe * 1.4426950408889634074);
+    xt.xc[e] = (T)(e < n_echo ? xe - xbar : 0.0);
+    if (e < n_echo) sxx += (xe - xbar) * (xe - xbar);
+  }
+  xt.xbar = (T)xbar;
+  xt.inv_sxx = (T)(sxx > 0 ? 1.0 / sxx : 0.0);
+  const double dx = n_echo >= 2 ? (x[n_echo - 1] - x[0]) / (n_echo - 1) : 0.0;
+  bool uni = n_echo >= 3 && dx != 0.0 && dx == dx;
+  double xmax = 0;
+  for (int e = 0; e < n_echo; ++e) xmax = fmax(xmax, fabs(x[e]));
+  // "uniform" must not change the model: deviations from the grid have to be below what the
+  // arithmetic type resolves in b * x (one ulp of the largest echo time)
+  const double tol = (double)num<T>::eps() * xmax;
+  for (int e = 0; e < n_echo && uni; ++e) uni = fabs(x[e] - (x[0] + e * dx)) <= tol;
+  xt.uniform = uni ? 1 : 0;
+  xt.x0 = (T)(n_echo ? x[0] : 0.0);
+  xt.x0s = (T)(n_echo ? x[0] * 1.4426950408889634074 : 0.0);
+  xt.inv_dx = (T)(uni ? 1.0 / dx : 0.0);
+  const double decades = sizeof(T) == 4 ? 30.0 : 280.0;
+  xt.q_hi = (T)pow(10.0, decades / (2.0 * (n_echo > 1 ? n_echo : 2) - 2.0));
+  xt.q_lo = (T)(sizeof(T) == 4 ? 1e-30 : 1e-280);
+}
+
+// ------------------------------------------------------------------------------------ fast path
+// Mono-exponential fit on UNIFORMLY spaced echoes x_k = x0 + k dx, by variable projection.
+//
+// With q = exp(b dx) and a' = a exp(b x0) the model is a' q^k: a polynomial in q.  For a given q the
+// optimal amplitude is a'(q) = N(q) / D(q) with N = sum_k y_k q^k and D = sum_k q^2k, and the projected
+// cost is phi(q) = sum y^2 - N^2 / D.  Its stationary points are exactly those of the two-parameter
+// least-squares problem the reference hands to MINPACK (fitting.py:1044-1062), so an exact Newton
+// iteration on phi converges (quadratically) to the same minimiser -- with no exponentials at all in the
+// loop: N, N', N'' and D, D', D'' come from one packed Horner recurrence (lo half: coefficients y_k,
+// multiplier q; hi half: coefficients 1, multiplier q^2), 3E - 6 packed FMAs per pass.
+//
+// The start is the linear-prediction (Prony) estimate q0 = sum y_k y_k+1 / sum y_k^2, which is within a
+// few per cent of the minimiser on decaying signals, so two to three passes suffice; the user's p0 only
+// selects the basin MINPACK would start in and is not needed (the general LM below, which honours it,
+// takes over whenever this path declines).  Convergence is judged like the LM's "predicted reduction
+// <= ftol * F" test, applied to the error expected AFTER the step about to be taken: with the observed
+// contraction kappa = |dq_k| / |dq_k-1| (clamped to [1e-2, 1]) that is kappa^2 * pred <= ftol * F.
+//
+// Returns a Status (ST_CONV_F / ST_EXACT) or -1 when the path declines (no admissible start, curvature
+// not positive, not converged in kMonoFastPasses, non-finite data): the caller then runs the general path.
+constexpr int kMonoFastPasses = 6;
+
+template <typename T, int E>
+DFIT_HD int mono_uniform_newton(const T (&y)[E], const XTab<T, E>& xt, const SolverOpts<T>& o, T (&p)[2], T& F_out,
+                                int& iters) {
+  static_assert(E >= 3, "needs at least three echoes");
+  typedef num<T> nm;
+  // Prony start; sum y^2 falls out of the same recurrence
+  pair2<T> nd = p2_mul<T>(p2_bcast<T>(y[0]), p2_make<T>(y[1], y[0]));
+#pragma unroll
+  for (int k = 1; k + 1 < E; ++k) nd = p2_fma<T>(p2_bcast<T>(y[k]), p2_make<T>(y[k + 1], y[k]), nd);
+  const T ysq = nm::fma_(y[E - 1], y[E - 1], nd.hi);
+  T q = nd.lo * nm::rcp_(nd.hi);
+  if (!(q > xt.q_lo && q < xt.q_hi && nm::finite(ysq))) return -1;  // also catches NaN and all-zero voxels
+
+  const T floorF = o.floor_rel * ysq;
+  T dprev2 = 0, qf = 0, af = 0;
+  int k = 0;
+  bool done = false;
+#pragma unroll 1
+  for (; k < kMonoFastPasses; ++k) {
+    const T s = q * q;
+    const pair2<T> m = p2_make<T>(q, s);
+    // Horner with first and (half) second derivative: lo = N(q) chain, hi = D(s) chain
+    pair2<T> P0 = p2_make<T>(y[E - 1], (T)1), P1, P2;
+    P1 = P0;
+    P0 = p2_fma<T>(P0, m, p2_make<T>(y[E - 2], (T)1));
+    P2 = P1;
+    P1 = p2_fma<T>(P1, m, P0);
+    P0 = p2_fma<T>(P0, m, p2_make<T>(y[E - 3], (T)1));
+#pragma unroll
+    for (int j = E - 4; j >= 0; --j) {
+      P2 = p2_fma<T>(P2, m, P1);
+      P1 = p2_fma<T>(P1, m, P0);
+      P0 = p2_fma<T>(P0, m, p2_make<T>(y[j], (T)1));
+    }
+    const T N = P0.lo, N1 = P1.lo, N2h = P2.lo;  // N, dN/dq, (d2N/dq2) / 2
+    const T D = P0.hi;                           // D(s), s = q^2
+    const T D1 = (T)2 * q * P1.hi;               // dD/dq
+    const T D2 = nm::fma_((T)8 * s, P2.hi, (T)2 * P1.hi);  // d2D/dq2
+    const T rD = nm::rcp_(D);
+    const T a = N * rD;                    // projected amplitude a'(q)
+    const T u = nm::fma_(a, D1, -N1);      // = -D da'/dq
+    const T ap = -u * rD;                  // da'/dq
+    const T g = a * (u - N1);              // dphi/dq
+    const T h = nm::fma_(a, nm::fma_(a, D2, (T)-4 * N2h), (T)2 * u * ap);  // d2phi/dq2
+    if (!(h > (T)0)) return -1;            // not in the convex basin (or NaN): decline
+    T dq = -g * nm::rcp_(h);
+    const T pred = (T)-0.5 * g * dq;       // Newton decrement: predicted reduction of phi
+    const T Fest = nm::max_(nm::fma_(-N, a, ysq), (T)0);
+    const T step2 = dq * dq;
+    const T dref2 = k == 0 ? step2 : dprev2;
+    const T kap2 = nm::min_(nm::max_(step2, (T)1e-4 * dref2), dref2);  // kappa^2 * dref2
+    done = pred * kap2 <= nm::fma_(o.ftol, Fest, floorF) * dref2;
+    dq = nm::min_(nm::max_(dq, (T)-0.5 * q), q);  // keep q positive whatever happens
+    if (done) {
+      qf = q + dq;
+      af = nm::fma_(ap, dq, a);
+      ++k;
+      break;
+    }
+    q += dq;
+    dprev2 = step2;
+  }
+  iters = k;
+  if (!done || !(qf > xt.q_lo && qf < xt.q_hi) || !nm::finite(af)) return -1;
+
+  // cost at the returned point: r_k = y_k - a' q^k, powers two at a time
+  T F;
+  {
+    pair2<T> ee = p2_make<T>((T)1, qf);
+    const pair2<T> ss = p2_bcast<T>(qf * qf), na = p2_bcast<T>(-af);
+    pair2<T> F2 = p2_bcast<T>((T)0);
+#pragma unroll
+    for (int e = 0; e + 1 < E; e += 2) {
+      const pair2<T> r = p2_fma<T>(na, ee, p2_make<T>(y[e], y[e + 1]));
+      F2 = p2_fma<T>(r, r, F2);
+      if (e + 2 < E) ee = p2_mul<T>(ee, ss);
+    }
+    F = F2.lo + F2.hi;
+    if constexpr (E & 1) {
+      const T r = nm::fma_(-af, ee.lo, y[E - 1]);
+      F = nm::fma_(r, r, F);
+    }
+  }
+  // back to the reference's parameters: b = ln(q) / dx, a = a' exp(-b x0)
+  const T b = nm::log_(qf) * xt.inv_dx;
+  p[1] = b;
+  p[0] = xt.x0 != (T)0 ? af * nm::expbx(-b, xt.x0, xt.x0s) : af;
+  F_out = F;
+  return F <= floorF ? ST_EXACT : ST_CONV_F;
+}
+
+// sum (y - mean)^2 for the r2 of fitting.py:1032-1035, two samples per instruction
+template <typename T, int E>
+DFIT_HD T ss_total(const T (&y)[E]) {
+  pair2<T> s2 = p2_bcast<T>((T)0);
+#pragma unroll
+  for (int e = 0; e + 1 < E; e += 2) s2 = p2_add<T>(s2, p2_make<T>(y[e], y[e + 1]));
+  T s = s2.lo + s2.hi;
+  if constexpr (E & 1) s += y[E - 1];
+  const T mean = s / (T)E;
+  const pair2<T> nm2 = p2_bcast<T>(-mean);
+  pair2<T> t2 = p2_bcast<T>((T)0);
+#pragma unroll
+  for (int e = 0; e + 1 < E; e += 2) {
+    const pair2<T> d = p2_add<T>(p2_make<T>(y[e], y[e + 1]), nm2);
+    t2 = p2_fma<T>(d, d, t2);
+  }
+  T t = t2.lo + t2.hi;
+  if constexpr (E & 1) t = num<T>::fma_(y[E - 1] - mean, y[E - 1] - mean, t);
+  return t;
+}
+
+// ------------------------------------------------------------------------------------ one voxel
 enum InitMode : int { INIT_GIVEN = 0, INIT_LOGLINEAR = 1 };
 enum VoxelFlags : unsigned { FLAG_NONFINITE = 1u, FLAG_OOB = 2u };
 
@@ -674,6 +850,8 @@ struct VoxelOpts {
   T y_lo, y_hi;   // y_bounds (fitting.py:1065): any sample outside -> voxel skipped
   T r2_eps;       // fitting.py:763
   int init_mode;  // InitMode
+  int has_bounds; // y_lo / y_hi are finite somewhere (otherwise the bounds test is skipped)
+  int fast;       // 1: try the variable-projection Newton fast path first (mono-exponential only)
 };
 
 // Everything the reference does for one voxel (`_curve_fit`, fitting.py:1026-1073), on samples that
@@ -682,6 +860,19 @@ template <class M, typename T, typename TA, int EMAX, bool EXACT>
 DFIT_HD int fit_voxel(const T (&y)[EMAX], const XTab<T, EMAX>& xt, int E, const VoxelOpts<T>& vo, T (&p)[M::P],
                       T& r2, int& iters, unsigned& flags) {
   constexpr int P = M::P;
+  if constexpr (M::MONO && EXACT && EMAX >= 3 && sizeof(T) == sizeof(TA)) {
+    // Fast path first (uniform echo spacing, no y_bounds): it declines (-1) on anything unusual -- zero,
+    // non-finite or non-decaying-looking voxels included -- and those take the general path below.
+    if (vo.fast != 0 && xt.uniform != 0 && vo.has_bounds == 0) {
+      T F;
+      const int st = mono_uniform_newton<T, EMAX>(y, xt, vo.s, p, F, iters);
+      if (st > 0) {
+        flags = 0;
+        r2 = (T)1 - F * num<T>::rcp_(ss_total<T, EMAX>(y) + vo.r2_eps);  // fitting.py:1032-1035
+        return st;
+      }
+    }
+  }
   bool all_zero = true, oob = false, nonfinite = false;
   T ysum = 0;
 #pragma unroll

@@ -28,7 +28,7 @@ __all__ = ["CurveFitter", "MonoExponentialFit", "curve_fit", "monoexponential", 
 _R2_THRESHOLD_TEMPLATE = 0.9  # dosma/resources/templates/.preferences.yml:3-4 (fitting/r2.threshold)
 _AFFINE_DECIMAL_PRECISION = 4  # dosma/defaults.py AFFINE_DECIMAL_PRECISION, used at fitting.py:104
 _ENGINE_KWARGS = ("compute_dtype", "device", "xtol", "lambda0", "ftol_scale", "init_linear", "use_tma",
-                  "lanes_per_voxel", "return_stats")
+                  "fast_path", "return_stats")
 
 _default_compute_dtype = "auto"
 
@@ -116,7 +116,7 @@ def _engine_fit(model_id, nparams, x, planes, mask, p0_cols, *, init_mode=_cabi.
     for k in ("xtol", "lambda0", "ftol_scale"):
         if engine.get(k) is not None:
             setattr(o, k, float(engine[k]))
-    for k in ("init_linear", "use_tma", "lanes_per_voxel"):
+    for k in ("init_linear", "use_tma", "fast_path"):
         if engine.get(k) is not None:
             setattr(o, k, int(engine[k]))
     if y_bounds is not None:

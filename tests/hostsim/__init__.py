@@ -25,7 +25,7 @@ def _load():
 
 
 def fit(model, x, y, p0=None, dtype="f32", acc64=False, init_mode=0, init_linear=1, ftol=None, xtol=None,
-        lambda0=1e-3, floor_rel=None, maxfev=100, r2_eps=1e-8, y_bounds=None):
+        lambda0=1e-3, floor_rel=None, maxfev=100, r2_eps=1e-8, y_bounds=None, fast=1):
     lib = _load()
     mid, P = MODELS[model]
     x = np.ascontiguousarray(x, dtype=np.float64)
@@ -46,7 +46,7 @@ def fit(model, x, y, p0=None, dtype="f32", acc64=False, init_mode=0, init_linear
     ip = ctypes.POINTER(ctypes.c_int32)
     rc = lib.hostsim_fit(ctypes.c_int(mid), ctypes.c_int(0 if f32 else 1), ctypes.c_int(int(acc64)), ctypes.c_int(E),
                          ctypes.c_int64(N), x.ctypes.data_as(dp), y.ctypes.data_as(dp), p0.ctypes.data_as(dp),
-                         ctypes.c_int64(p0.shape[0]), ctypes.c_int(init_mode), ctypes.c_int(init_linear),
+                         ctypes.c_int64(p0.shape[0]), ctypes.c_int(init_mode), ctypes.c_int(init_linear), ctypes.c_int(int(fast)),
                          ctypes.c_double(ftol), ctypes.c_double(xtol), ctypes.c_double(lambda0),
                          ctypes.c_double(floor_rel), ctypes.c_int(maxfev), ctypes.c_double(r2_eps),
                          ctypes.c_double(lo), ctypes.c_double(hi), popt.ctypes.data_as(dp), r2.ctypes.data_as(dp),

@@ -11,22 +11,11 @@ using namespace dfit;
 
 template <class M, typename T, typename TA, int EMAX, bool EXACT>
 static void run(int E, int64_t N, const double* x, const double* y, const double* p0, int64_t n_p0, int init_mode,
-                int init_linear, double ftol, double xtol, double lambda0, double floor_rel, int max_iter,
+                int init_linear, int fast, double ftol, double xtol, double lambda0, double floor_rel, int max_iter,
                 double r2_eps, double y_lo, double y_hi, double* popt, double* r2, int32_t* status, int32_t* iters) {
   constexpr int P = M::P;
   XTab<T, EMAX> xt;
-  double xbar = 0, sxx = 0;
-  for (int e = 0; e < E; ++e) xbar += x[e];
-  xbar /= E;
-  for (int e = 0; e < EMAX; ++e) {
-    double xe = e < E ? x[e] : 0.0;
-    xt.x[e] = (T)xe;
-    xt.xs[e] = (T)(xe * 1.4426950408889634);
-    xt.xc[e] = (T)(e < E ? xe - xbar : 0.0);
-    if (e < E) sxx += (xe - xbar) * (xe - xbar);
-  }
-  xt.xbar = (T)xbar;
-  xt.inv_sxx = (T)(1.0 / sxx);
+  fill_xtab<T, EMAX>(xt, x, E);
   VoxelOpts<T> vo;
   vo.s.ftol = (T)ftol;
   vo.s.xtol = (T)xtol;
@@ -38,6 +27,8 @@ static void run(int E, int64_t N, const double* x, const double* y, const double
   vo.y_hi = (T)y_hi;
   vo.r2_eps = (T)r2_eps;
   vo.init_mode = init_mode;
+  vo.has_bounds = (y_lo > -1.7e308 || y_hi < 1.7e308) ? 1 : 0;
+  vo.fast = fast;
   for (int64_t v = 0; v < N; ++v) {
     T yy[EMAX];
     for (int e = 0; e < EMAX; ++e) yy[e] = e < E ? (T)y[(size_t)e * N + v] : (T)0;
@@ -56,11 +47,11 @@ static void run(int E, int64_t N, const double* x, const double* y, const double
 }
 
 extern "C" int hostsim_fit(int model, int dtype, int acc64, int E, int64_t N, const double* x, const double* y,
-                           const double* p0, int64_t n_p0, int init_mode, int init_linear, double ftol, double xtol,
+                           const double* p0, int64_t n_p0, int init_mode, int init_linear, int fast, double ftol, double xtol,
                            double lambda0, double floor_rel, int max_iter, double r2_eps, double y_lo, double y_hi,
                            double* popt, double* r2, int32_t* status, int32_t* iters) {
   if (E > 32) return -1;
-#define ARGS E, N, x, y, p0, n_p0, init_mode, init_linear, ftol, xtol, lambda0, floor_rel, max_iter, r2_eps, y_lo, y_hi, popt, r2, status, iters
+#define ARGS E, N, x, y, p0, n_p0, init_mode, init_linear, fast, ftol, xtol, lambda0, floor_rel, max_iter, r2_eps, y_lo, y_hi, popt, r2, status, iters
 #define RUN_E(M, T, TA)                                                                     \
   switch (E) {                                                                                \
     case 4: if (4 >= M::P) { run<M, T, TA, 4, true>(ARGS); break; }                           \
