@@ -22,7 +22,7 @@ constexpr int kBlock = 128;  // block_stats packs 8-bit counters: keep <= 255
 enum DType : int { DT_F32 = 0, DT_F64 = 1, DT_I16 = 2, DT_U16 = 3, DT_I32 = 4, DT_U8 = 5 };
 enum Layout : int { LAYOUT_PLANAR = 0, LAYOUT_ECHO_FASTEST = 1 };
 enum Counter : int { CNT_FITTED = 0, CNT_FAILED, CNT_NONFINITE, CNT_OOB, CNT_ITERS, CNT_MAXITER, CNT_COUNT };
-constexpr int kStatSlots = 256;  // power of two
+constexpr int kStatSlots = 1024;  // power of two
 constexpr int kMaxPeers = 8;
 
 template <typename T, int EMAX>
@@ -239,41 +239,36 @@ __device__ __forceinline__ void store_voxel(const KernelArgs<T, EMAX>& a, int64_
   if (a.niter) a.niter[v] = (uint8_t)(iters > 255 ? 255 : iters);
 }
 
-// Statistics: warp ballots/reductions -> shared-memory block totals -> ONE global atomic per block
-// and counter, spread over kStatSlots address slots (same-address atomics serialise in the L2
-// atomic unit; 1.8 M warps hammering six addresses cost more than the fit itself).  The host sums
-// the slots in dfit_get_stats.
-__device__ __forceinline__ void block_stats(unsigned long long* cnt, int st, int iters, unsigned flags) {
-  // four 8-bit counters (fitted, failed, non-finite, out-of-bounds) ride in one word: a 128-thread
-  // CTA cannot overflow a byte, so one warp reduction and one shared atomic cover all four
-  __shared__ unsigned s_pack, s_iters, s_max;
-  if (threadIdx.x == 0) {
-    s_pack = 0;
-    s_iters = 0;
-    s_max = 0;
-  }
-  __syncthreads();
+// Statistics are reduced per warp (dense path) or per CTA (grid-stride paths) and added to one of
+// kStatSlots slots of global counters (same-address atomics serialise in the L2 atomic unit; 1.8 M warps
+// hammering six addresses cost more than the fit itself).  The host sums the slots in dfit_get_stats.
+// Dense path: three warp reductions and two fire-and-forget global reductions
+// per warp (no shared memory, no block barrier), spread over kStatSlots slots; the rare events (failures,
+// non-finite or out-of-bounds voxels) take a separate branch.  Must be reached by all 32 lanes.
+__device__ __forceinline__ void warp_stats(unsigned long long* cnt, int st, int iters, unsigned flags) {
   const unsigned full = 0xffffffffu;
-  const unsigned mine = (unsigned)(st >= ST_CONV_F) | ((unsigned)(st >= ST_MAXITER) << 8) |
-                        ((unsigned)((flags & FLAG_NONFINITE) != 0) << 16) | ((unsigned)((flags & FLAG_OOB) != 0) << 24);
-  const unsigned pack = __reduce_add_sync(full, mine);
-  const unsigned s_it = __reduce_add_sync(full, (unsigned)iters);
-  const unsigned m_it = __reduce_max_sync(full, (unsigned)iters);
+  const unsigned fitted = __popc(__ballot_sync(full, st >= ST_CONV_F));
+  const unsigned its = __reduce_add_sync(full, (unsigned)iters);
+  const unsigned mx = __reduce_max_sync(full, (unsigned)iters);
+  const unsigned rare = __ballot_sync(full, st >= ST_MAXITER || flags != 0u);
   if ((threadIdx.x & 31) == 0) {
-    atomicAdd(&s_pack, pack);
-    atomicAdd(&s_iters, s_it);
-    atomicMax(&s_max, m_it);
+    unsigned long long* dst =
+        cnt + (size_t)((blockIdx.x * (kBlock / 32) + (threadIdx.x >> 5)) & (kStatSlots - 1)) * CNT_COUNT;
+    if (fitted) atomicAdd(dst + CNT_FITTED, (unsigned long long)fitted);
+    if (its) atomicAdd(dst + CNT_ITERS, (unsigned long long)its);
+    if (mx) atomicMax(dst + CNT_MAXITER, (unsigned long long)mx);
   }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    unsigned long long* dst = cnt + (size_t)(blockIdx.x & (kStatSlots - 1)) * CNT_COUNT;
-    const unsigned pk = s_pack;
-    if (pk & 0xffu) atomicAdd(dst + CNT_FITTED, (unsigned long long)(pk & 0xffu));
-    if ((pk >> 8) & 0xffu) atomicAdd(dst + CNT_FAILED, (unsigned long long)((pk >> 8) & 0xffu));
-    if ((pk >> 16) & 0xffu) atomicAdd(dst + CNT_NONFINITE, (unsigned long long)((pk >> 16) & 0xffu));
-    if (pk >> 24) atomicAdd(dst + CNT_OOB, (unsigned long long)(pk >> 24));
-    if (s_iters) atomicAdd(dst + CNT_ITERS, (unsigned long long)s_iters);
-    if (s_max) atomicMax(dst + CNT_MAXITER, (unsigned long long)s_max);
+  if (rare) {
+    const unsigned nfail = __popc(__ballot_sync(full, st >= ST_MAXITER));
+    const unsigned nnf = __popc(__ballot_sync(full, (flags & FLAG_NONFINITE) != 0u));
+    const unsigned noob = __popc(__ballot_sync(full, (flags & FLAG_OOB) != 0u));
+    if ((threadIdx.x & 31) == 0) {
+      unsigned long long* dst =
+          cnt + (size_t)((blockIdx.x * (kBlock / 32) + (threadIdx.x >> 5)) & (kStatSlots - 1)) * CNT_COUNT;
+      if (nfail) atomicAdd(dst + CNT_FAILED, (unsigned long long)nfail);
+      if (nnf) atomicAdd(dst + CNT_NONFINITE, (unsigned long long)nnf);
+      if (noob) atomicAdd(dst + CNT_OOB, (unsigned long long)noob);
+    }
   }
 }
 
@@ -357,12 +352,25 @@ __global__ void __launch_bounds__(kBlock, EMAX <= 8 ? 8 : 1) fit_kernel(const __
     const bool whole_warp = (v | 31) < a.n;  // all 32 voxels of this warp exist: cooperative stores are legal
     if (v < a.n) {
       T p[P], r2 = 0, y[EMAX];
-      load_samples<T, EMAX, EXACT>(a, v, y);
-      load_p0<P, T, EMAX>(a, v, p);
-      st = fit_voxel<M, T, T, EMAX, EXACT>(y, a.xt, a.E, a.vo, p, r2, iters, flags);
-      if (whole_warp) __syncwarp();
+      if (a.layout == LAYOUT_PLANAR && a.y_dtype == DT_F32) {
+        // the common case, kept free of the dtype / layout dispatch: the plane bases are CTA-uniform
+        const float* __restrict__ base = reinterpret_cast<const float*>(a.y) + (int64_t)blockIdx.x * kBlock;
+#pragma unroll
+        for (int e = 0; e < EMAX; ++e) y[e] = (EXACT || e < a.E) ? (T)__ldcs(base + (int64_t)e * a.ld + threadIdx.x) : (T)0;
+      } else {
+        load_samples<T, EMAX, EXACT>(a, v, y);
+      }
+      st = fit_voxel_fast<M, T, EMAX, EXACT>(y, a.xt, a.vo, p, r2, iters);
+      if (st < 0) {  // the general path: LM from the caller's initial guess
+        load_p0<P, T, EMAX>(a, v, p);
+        st = fit_voxel<M, T, T, EMAX, EXACT>(y, a.xt, a.E, a.vo, p, r2, iters, flags);
+      }
+      if (GATHER && whole_warp) __syncwarp();
       store_voxel<P, T, EMAX, GATHER>(a, v, p, r2, true, st, iters, whole_warp);
     }
+    __syncwarp();
+    warp_stats(a.counters, st, iters, flags);
+    return;
   } else {
     // compacted mask path: grid-stride over the index list (its length is only known on the device)
     const unsigned count = *a.index_count;
@@ -374,8 +382,11 @@ __global__ void __launch_bounds__(kBlock, EMAX <= 8 ? 8 : 1) fit_kernel(const __
       int it = 0;
       unsigned fl = 0;
       load_samples<T, EMAX, EXACT>(a, v, y);
-      load_p0<P, T, EMAX>(a, v, p);
-      const int s = fit_voxel<M, T, T, EMAX, EXACT>(y, a.xt, a.E, a.vo, p, r2, it, fl);
+      int s = fit_voxel_fast<M, T, EMAX, EXACT>(y, a.xt, a.vo, p, r2, it);
+      if (s < 0) {
+        load_p0<P, T, EMAX>(a, v, p);
+        s = fit_voxel<M, T, T, EMAX, EXACT>(y, a.xt, a.E, a.vo, p, r2, it, fl);
+      }
       store_voxel<P, T, EMAX, GATHER>(a, v, p, r2, true, s, it);
       it_sum += it;
       iters = it > iters ? it : iters;
@@ -383,9 +394,7 @@ __global__ void __launch_bounds__(kBlock, EMAX <= 8 ? 8 : 1) fit_kernel(const __
               ((unsigned)((fl & FLAG_NONFINITE) != 0) << 16) | ((unsigned)((fl & FLAG_OOB) != 0) << 24);
     }
     block_stats_packed(a.counters, pack, it_sum, iters);
-    return;
   }
-  block_stats(a.counters, st, iters, flags);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -481,8 +490,11 @@ __global__ void __launch_bounds__(kTmaWarps * 32)
       T p[P], r2 = 0;
       st = ST_SKIPPED;
       if (active) {
-        load_p0<P, T, EMAX>(a, v, p);
-        st = fit_voxel<M, T, T, EMAX, true>(y, a.xt, a.E, a.vo, p, r2, iters, flags);
+        st = fit_voxel_fast<M, T, EMAX, true>(y, a.xt, a.vo, p, r2, iters);
+        if (st < 0) {
+          load_p0<P, T, EMAX>(a, v, p);
+          st = fit_voxel<M, T, T, EMAX, true>(y, a.xt, a.E, a.vo, p, r2, iters, flags);
+        }
       }
       store_voxel<P, T, EMAX>(a, v, p, r2, active, st, iters);
     }

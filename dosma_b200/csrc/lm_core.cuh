@@ -728,25 +728,41 @@ inline void fill_xtab(XTab<T, EMAX>& xt, const double* x, int n_echo) {
 // not positive, not converged in kMonoFastPasses, non-finite data): the caller then runs the general path.
 constexpr int kMonoFastPasses = 6;
 
+// On the device the Newton loop is WARP-UNIFORM: every lane that entered together keeps iterating (with
+// its state frozen once it has converged or declined) until all of them are finished, so the warp stays
+// converged and the code after the loop runs once per warp instead of once per exit pass.
+#if defined(__CUDA_ARCH__)
+#define DFIT_LANES() __activemask()
+#define DFIT_ANY(mask, pred) (__any_sync((mask), (pred)) != 0)
+#else
+#define DFIT_LANES() 0u
+#define DFIT_ANY(mask, pred) (pred)
+#endif
+
 template <typename T, int E>
 DFIT_HD int mono_uniform_newton(const T (&y)[E], const XTab<T, E>& xt, const SolverOpts<T>& o, T (&p)[2], T& F_out,
                                 int& iters) {
   static_assert(E >= 3, "needs at least three echoes");
   typedef num<T> nm;
+  const unsigned lanes = DFIT_LANES();
+  (void)lanes;
   // Prony start; sum y^2 falls out of the same recurrence
   pair2<T> nd = p2_mul<T>(p2_bcast<T>(y[0]), p2_make<T>(y[1], y[0]));
 #pragma unroll
   for (int k = 1; k + 1 < E; ++k) nd = p2_fma<T>(p2_bcast<T>(y[k]), p2_make<T>(y[k + 1], y[k]), nd);
   const T ysq = nm::fma_(y[E - 1], y[E - 1], nd.hi);
   T q = nd.lo * nm::rcp_(nd.hi);
-  if (!(q > xt.q_lo && q < xt.q_hi && nm::finite(ysq))) return -1;  // also catches NaN and all-zero voxels
+  // no admissible start (also catches NaN and all-zero voxels): this lane declines, but keeps in step
+  bool active = q > xt.q_lo && q < xt.q_hi && nm::finite(ysq);
+  if (!active) q = (T)0.5;
 
   const T floorF = o.floor_rel * ysq;
   T dprev2 = 0, qf = 0, af = 0;
-  int k = 0;
   bool done = false;
+  int npass = 0;
 #pragma unroll 1
-  for (; k < kMonoFastPasses; ++k) {
+  for (int k = 0; k < kMonoFastPasses; ++k) {
+    if (!DFIT_ANY(lanes, active)) break;
     const T s = q * q;
     const pair2<T> m = p2_make<T>(q, s);
     // Horner with first and (half) second derivative: lo = N(q) chain, hi = D(s) chain
@@ -772,25 +788,31 @@ DFIT_HD int mono_uniform_newton(const T (&y)[E], const XTab<T, E>& xt, const Sol
     const T ap = -u * rD;                  // da'/dq
     const T g = a * (u - N1);              // dphi/dq
     const T h = nm::fma_(a, nm::fma_(a, D2, (T)-4 * N2h), (T)2 * u * ap);  // d2phi/dq2
-    if (!(h > (T)0)) return -1;            // not in the convex basin (or NaN): decline
     T dq = -g * nm::rcp_(h);
     const T pred = (T)-0.5 * g * dq;       // Newton decrement: predicted reduction of phi
     const T Fest = nm::max_(nm::fma_(-N, a, ysq), (T)0);
     const T step2 = dq * dq;
     const T dref2 = k == 0 ? step2 : dprev2;
     const T kap2 = nm::min_(nm::max_(step2, (T)1e-4 * dref2), dref2);  // kappa^2 * dref2
-    done = pred * kap2 <= nm::fma_(o.ftol, Fest, floorF) * dref2;
+    // h > 0: inside the convex basin (false for NaN as well); otherwise the lane declines
+    const bool convex = h > (T)0;
+    const bool conv = convex && pred * kap2 <= nm::fma_(o.ftol, Fest, floorF) * dref2;
     dq = nm::min_(nm::max_(dq, (T)-0.5 * q), q);  // keep q positive whatever happens
-    if (done) {
-      qf = q + dq;
-      af = nm::fma_(ap, dq, a);
-      ++k;
-      break;
+    if (active) {
+      npass = k + 1;
+      if (conv) {
+        qf = q + dq;
+        af = nm::fma_(ap, dq, a);
+        done = true;
+      }
+      active = convex && !conv;
+      if (active) {
+        q += dq;
+        dprev2 = step2;
+      }
     }
-    q += dq;
-    dprev2 = step2;
   }
-  iters = k;
+  iters = npass;
   if (!done || !(qf > xt.q_lo && qf < xt.q_hi) || !nm::finite(af)) return -1;
 
   // cost at the returned point: r_k = y_k - a' q^k, powers two at a time
@@ -854,25 +876,31 @@ struct VoxelOpts {
   int fast;       // 1: try the variable-projection Newton fast path first (mono-exponential only)
 };
 
+// Fast-path attempt for one voxel (mono-exponential model, uniform echo spacing, no y_bounds).  Returns a
+// successful Status with p / r2 / iters filled in, or -1: the caller then loads the initial guess and runs
+// fit_voxel.  The path declines on anything unusual -- zero, non-finite or non-decaying-looking voxels
+// included -- so the skip / failure rules of fitting.py:1065-1073 stay with the general path.
+// Warp-collective on the device: call it with the lanes of a warp converged.
+template <class M, typename T, int EMAX, bool EXACT>
+DFIT_HD int fit_voxel_fast(const T (&y)[EMAX], const XTab<T, EMAX>& xt, const VoxelOpts<T>& vo, T (&p)[M::P], T& r2,
+                           int& iters) {
+  if constexpr (M::MONO && EXACT && EMAX >= 3) {
+    if (vo.fast != 0 && xt.uniform != 0 && vo.has_bounds == 0) {
+      T F;
+      const int st = mono_uniform_newton<T, EMAX>(y, xt, vo.s, p, F, iters);
+      if (st > 0) r2 = (T)1 - F * num<T>::rcp_(ss_total<T, EMAX>(y) + vo.r2_eps);  // fitting.py:1032-1035
+      return st;
+    }
+  }
+  return -1;
+}
+
 // Everything the reference does for one voxel (`_curve_fit`, fitting.py:1026-1073), on samples that
 // are already in registers.  p: in = initial guess, out = fitted parameters (NaN on skip/failure).
 template <class M, typename T, typename TA, int EMAX, bool EXACT>
 DFIT_HD int fit_voxel(const T (&y)[EMAX], const XTab<T, EMAX>& xt, int E, const VoxelOpts<T>& vo, T (&p)[M::P],
                       T& r2, int& iters, unsigned& flags) {
   constexpr int P = M::P;
-  if constexpr (M::MONO && EXACT && EMAX >= 3 && sizeof(T) == sizeof(TA)) {
-    // Fast path first (uniform echo spacing, no y_bounds): it declines (-1) on anything unusual -- zero,
-    // non-finite or non-decaying-looking voxels included -- and those take the general path below.
-    if (vo.fast != 0 && xt.uniform != 0 && vo.has_bounds == 0) {
-      T F;
-      const int st = mono_uniform_newton<T, EMAX>(y, xt, vo.s, p, F, iters);
-      if (st > 0) {
-        flags = 0;
-        r2 = (T)1 - F * num<T>::rcp_(ss_total<T, EMAX>(y) + vo.r2_eps);  // fitting.py:1032-1035
-        return st;
-      }
-    }
-  }
   bool all_zero = true, oob = false, nonfinite = false;
   T ysum = 0;
 #pragma unroll

@@ -259,7 +259,10 @@ extern "C" int dfit_region_metrics_host(dfit_handle* h, int64_t n_vox, const voi
     out[4 * r + 0] = c;
     out[4 * r + 1] = c > 0 ? mean[r] : NAN;
     out[4 * r + 2] = c > 0 ? std::sqrt(var[r][1] / c) : NAN;
-    out[4 * r + 3] = c > 0 ? 0.5 * (key_to_double(s.prefix[qmap[r][0]]) + key_to_double(s.prefix[qmap[r][1]])) : NAN;
+    // the midpoint of the two middle values is taken in the map's own type, like np.nanmedian does
+    const double lo = key_to_double(s.prefix[qmap[r][0]]), hi = key_to_double(s.prefix[qmap[r][1]]);
+    const double med = map_dtype == DFIT_F32 ? (double)(0.5f * ((float)lo + (float)hi)) : 0.5 * (lo + hi);
+    out[4 * r + 3] = c > 0 ? med : NAN;
   }
   return DFIT_OK;
 }

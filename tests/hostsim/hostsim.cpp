@@ -38,7 +38,13 @@ static void run(int E, int64_t N, const double* x, const double* y, const double
     T r2v;
     int it;
     unsigned flags;
-    int st = fit_voxel<M, T, TA, EMAX, EXACT>(yy, xt, E, vo, p, r2v, it, flags);
+    int st = -1;
+    flags = 0;
+    if constexpr (sizeof(T) == sizeof(TA)) st = fit_voxel_fast<M, T, EMAX, EXACT>(yy, xt, vo, p, r2v, it);
+    if (st < 0) {
+      for (int i = 0; i < P; ++i) p[i] = (T)pv[i];
+      st = fit_voxel<M, T, TA, EMAX, EXACT>(yy, xt, E, vo, p, r2v, it, flags);
+    }
     for (int i = 0; i < P; ++i) popt[(size_t)v * P + i] = (double)p[i];
     r2[v] = (double)r2v;
     status[v] = st;

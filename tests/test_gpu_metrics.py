@@ -28,16 +28,15 @@ def test_metrics_match_oracle(dtype):
     # numpy reduces a float32 map in float32 (pairwise), the kernel always accumulates in float64: for float32
     # maps the oracle itself is only good to ~1e-6; fitted maps are float64 (fitting.py:870), the exact case
     rtol = 1e-11 if dtype == np.float64 else 2e-6
-    _check_ = _check
 
-    def _check(got, ref):  # noqa: F811
-        _check_(got, ref, rtol)
+    def check(got, ref):
+        _check(got, ref, rtol)
 
     for kw in (dict(), dict(bounds=(0, 100)), dict(bounds=(0, 100), closed="both"), dict(bounds=(10, 90), closed="neither")):
-        _check(region_metrics(vol, as_frame=False, **kw), M.to_metrics(vol, **kw))
-        _check(region_metrics(vol, mask=lab, as_frame=False, **kw), M.to_metrics(vol, mask=lab, **kw))
+        check(region_metrics(vol, as_frame=False, **kw), M.to_metrics(vol, **kw))
+        check(region_metrics(vol, mask=lab, as_frame=False, **kw), M.to_metrics(vol, mask=lab, **kw))
     sel = {2: "femoral", 4: "tibial", 9: "absent"}
-    _check(region_metrics(vol, mask=lab.astype(np.int32), labels=sel, as_frame=False, bounds=(0, 100)),
+    check(region_metrics(vol, mask=lab.astype(np.int32), labels=sel, as_frame=False, bounds=(0, 100)),
            M.to_metrics(vol, mask=lab, labels=sel, bounds=(0, 100)))
     frame = region_metrics(vol, mask=lab)
     assert list(frame.columns) == ["Category", "Mean", "Std", "Median", "# Voxels"]
