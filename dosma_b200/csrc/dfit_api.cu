@@ -121,7 +121,9 @@ void make_desc(const dfit_opts* o, int n_echo, int64_t n_vox, const double* x, L
   d.init_linear = o->init_linear < 0 ? (o->model == DFIT_MODEL_BIEXP ? 0 : 1) : o->init_linear;
   // The fast path spends at most kMonoFastPasses passes; a budget too small for that means the caller is
   // probing maxfev behaviour (fitting.py:761), which only the LM reproduces.
-  d.fast_path = (o->model == DFIT_MODEL_MONOEXP && o->fast_path != 0 && o->maxfev >= 3 * (kMonoFastPasses + 1)) ? 1 : 0;
+  d.fast_path = (o->model == DFIT_MODEL_MONOEXP && o->fast_path != 0 && o->maxfev >= 3 * (kMonoFastPasses + 1))
+                    ? (o->fast_path == 2 ? 2 : 1)
+                    : 0;
   d.po.enabled = o->post_enabled;
   for (int i = 0; i < 4; ++i) {
     d.po.ufunc[i] = o->ufunc[i];
@@ -136,6 +138,7 @@ void make_desc(const dfit_opts* o, int n_echo, int64_t n_vox, const double* x, L
   d.mask_fill = o->has_nan_fill ? o->nan_fill : std::numeric_limits<double>::quiet_NaN();
   d.use_tma = o->use_tma;
   d.tmap = nullptr;
+  d.tmap2 = nullptr;
   d.sm_count = 148;
   d.index = nullptr;
   d.index_count = nullptr;
@@ -165,14 +168,14 @@ EncodeTiledFn encode_tiled_fn() {
 }
 
 // 2-D tensor map over planar fp32 samples: dim0 = voxels (contiguous), dim1 = echoes (pitch ld).
-// Box = kTmaTile voxels x E echoes; out-of-range voxels of the last tile are zero-filled.
-bool make_sample_tmap(CUtensorMap* map, const void* y, int n_echo, int64_t n_vox, int64_t ld) {
+// Box = box_vox voxels x E echoes; out-of-range voxels of the last tile are zero-filled.
+bool make_sample_tmap(CUtensorMap* map, const void* y, int n_echo, int64_t n_vox, int64_t ld, int box_vox = kTmaTile) {
   EncodeTiledFn fn = encode_tiled_fn();
   if (!fn) return false;
   if ((reinterpret_cast<uintptr_t>(y) & 15) != 0 || (ld * 4) % 16 != 0) return false;
   cuuint64_t dims[2] = {(cuuint64_t)n_vox, (cuuint64_t)n_echo};
   cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
-  cuuint32_t box[2] = {(cuuint32_t)kTmaTile, (cuuint32_t)n_echo};
+  cuuint32_t box[2] = {(cuuint32_t)box_vox, (cuuint32_t)n_echo};
   cuuint32_t estr[2] = {1, 1};
   return fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(y), dims, strides, box, estr,
             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
@@ -183,6 +186,14 @@ bool make_sample_tmap(CUtensorMap* map, const void* y, int n_echo, int64_t n_vox
 bool tma_eligible(const LaunchDesc& d) {
   return d.use_tma == 1 && d.compute_dtype == DFIT_F32 && d.y_dtype == DFIT_F32 && d.layout == DFIT_PLANAR &&
          d.n_echo <= 16 && d.n_vox < (int64_t)1 << 31;
+}
+
+// The two-voxels-per-lane mono-exponential kernel takes its tiles through TMA unless told not to
+// (use_tma = 0); launch_one checks the rest of its conditions.
+bool tma2_eligible(const LaunchDesc& d) {
+  return d.use_tma != 0 && d.model == DFIT_MODEL_MONOEXP && d.fast_path == 1 && d.compute_dtype == DFIT_F32 &&
+         d.y_dtype == DFIT_F32 && d.layout == DFIT_PLANAR && d.mask == nullptr && d.gather_world == 0 &&
+         d.n_echo >= 3 && d.n_echo <= 16 && d.n_vox < (int64_t)1 << 31;
 }
 
 cudaError_t dispatch(const LaunchDesc& d) {
@@ -362,6 +373,8 @@ int dfit_fit_device(dfit_handle* h, const dfit_opts* opts, int n_echo, int64_t n
     d.index_count = reinterpret_cast<unsigned*>(h->index_buf.p);
     d.index = d.index_count + 4;
   }
+  CUtensorMap tmap2;
+  if (n_vox > 0 && tma2_eligible(d) && make_sample_tmap(&tmap2, y, n_echo, n_vox, ld, kM2Tile)) d.tmap2 = &tmap2;
   if (n_vox > 0 && tma_eligible(d)) {
     if (!make_sample_tmap(&tmap, y, n_echo, n_vox, ld))
       return fail(DFIT_ERR_UNSUPPORTED, "use_tma=1 but the samples do not qualify (16-byte aligned base and pitch)");
@@ -452,6 +465,9 @@ int dfit_fit_host(dfit_handle* h, const dfit_opts* opts, int n_echo, int64_t n_v
     d.sm_count = h->sm_count;
     d.tmap = nullptr;
     if (tma_eligible(d) && make_sample_tmap(&tmap, d.y, n_echo, n, chunk)) d.tmap = &tmap;
+    CUtensorMap tmap2;
+    d.tmap2 = nullptr;
+    if (tma2_eligible(d) && make_sample_tmap(&tmap2, d.y, n_echo, n, chunk, kM2Tile)) d.tmap2 = &tmap2;
     CUDA_TRY(dispatch(d));
     h->last_launches += mask && d.tmap == nullptr ? 2 : 1;
     CUDA_TRY(cudaMemcpyAsync((char*)popt + (size_t)v0 * P * osz, sl.popt.p, (size_t)n * P * osz, cudaMemcpyDeviceToHost, st));

@@ -398,6 +398,123 @@ __global__ void __launch_bounds__(kBlock, EMAX <= 8 ? 8 : 1) fit_kernel(const __
 }
 
 // ------------------------------------------------------------------------------------------------
+// Two voxels per lane: the dense mono-exponential fast path (uniform echo spacing, fp32 arithmetic, planar
+// f32 / i16 / u16 samples).  Lane l of a CTA owns voxels 2 (128 b + l) and the next one: one 8-byte (4-byte
+// for 16-bit samples) coalesced load per echo, every packed instruction works on both voxels, and the
+// results leave as one 16-byte [a, b, a, b] store and one 8-byte r2 store.  Voxels the fast path declines
+// run the general LM from the caller's initial guess, one at a time (rare).
+constexpr int kBlock2 = 128;
+
+template <typename S>
+struct Vec2;
+template <> struct Vec2<float> { typedef float2 type; };
+template <> struct Vec2<short> { typedef short2 type; };
+template <> struct Vec2<unsigned short> { typedef ushort2 type; };
+
+template <typename S, int EMAX>
+__device__ __forceinline__ void load_pairs(const void* __restrict__ yv, int64_t ld, int64_t v0, bool both,
+                                           pair2<float> (&Y)[EMAX]) {
+  const S* __restrict__ base = reinterpret_cast<const S*>(yv) + v0;
+  if (both) {
+#pragma unroll
+    for (int e = 0; e < EMAX; ++e) {
+      const typename Vec2<S>::type t = __ldcs(reinterpret_cast<const typename Vec2<S>::type*>(base + (int64_t)e * ld));
+      Y[e] = p2_make<float>((float)t.x, (float)t.y);
+    }
+  } else {  // odd tail: the missing voxel duplicates the last one and is never stored
+#pragma unroll
+    for (int e = 0; e < EMAX; ++e) {
+      const float t = (float)__ldcs(base + (int64_t)e * ld);
+      Y[e] = p2_make<float>(t, t);
+    }
+  }
+}
+
+__device__ __forceinline__ void warp_stats2(unsigned long long* cnt, const int (&st)[2], const int (&iters)[2],
+                                            unsigned flags) {
+  const unsigned full = 0xffffffffu;
+  const unsigned fitted = __popc(__ballot_sync(full, st[0] >= ST_CONV_F)) + __popc(__ballot_sync(full, st[1] >= ST_CONV_F));
+  const unsigned its = __reduce_add_sync(full, (unsigned)(iters[0] + iters[1]));
+  const unsigned mx = __reduce_max_sync(full, (unsigned)(iters[0] > iters[1] ? iters[0] : iters[1]));
+  const unsigned rare = __ballot_sync(full, st[0] >= ST_MAXITER || st[1] >= ST_MAXITER || flags != 0u);
+  const unsigned slot = (blockIdx.x * (kBlock2 / 32) + (threadIdx.x >> 5)) & (kStatSlots - 1);
+  unsigned long long* dst = cnt + (size_t)slot * CNT_COUNT;
+  if ((threadIdx.x & 31) == 0) {
+    if (fitted) atomicAdd(dst + CNT_FITTED, (unsigned long long)fitted);
+    if (its) atomicAdd(dst + CNT_ITERS, (unsigned long long)its);
+    if (mx) atomicMax(dst + CNT_MAXITER, (unsigned long long)mx);
+  }
+  if (rare) {
+    const unsigned nfail = __reduce_add_sync(full, (unsigned)(st[0] >= ST_MAXITER) + (unsigned)(st[1] >= ST_MAXITER));
+    const unsigned nnf = __reduce_add_sync(full, (flags & 0xffu));
+    const unsigned noob = __reduce_add_sync(full, (flags >> 8) & 0xffu);
+    if ((threadIdx.x & 31) == 0) {
+      if (nfail) atomicAdd(dst + CNT_FAILED, (unsigned long long)nfail);
+      if (nnf) atomicAdd(dst + CNT_NONFINITE, (unsigned long long)nnf);
+      if (noob) atomicAdd(dst + CNT_OOB, (unsigned long long)noob);
+    }
+  }
+}
+
+template <class M, int EMAX>
+__global__ void __launch_bounds__(kBlock2, 5) fit_kernel_mono2(const __grid_constant__ KernelArgs<float, EMAX> a) {
+  typedef float T;
+  constexpr int P = 2;
+  const int64_t v0 = ((int64_t)blockIdx.x * kBlock2 + threadIdx.x) * 2;
+  int st[2] = {-1, -1}, iters[2] = {0, 0};
+  unsigned nflags = 0;  // bits 0..7: non-finite voxels of this lane, bits 8..15: out-of-bounds voxels
+  if (v0 < a.n) {
+    const bool both = v0 + 1 < a.n;
+    pair2<T> Y[EMAX], pa, pb, r2;
+    if (a.y_dtype == DT_F32) load_pairs<float, EMAX>(a.y, a.ld, v0, both, Y);
+    else if (a.y_dtype == DT_I16) load_pairs<short, EMAX>(a.y, a.ld, v0, both, Y);
+    else load_pairs<unsigned short, EMAX>(a.y, a.ld, v0, both, Y);
+    fit_voxel_fast2<M, T, EMAX>(Y, a.xt, a.vo, pa, pb, r2, st, iters);
+    if (st[0] < 0 || st[1] < 0) {  // the general path, one voxel at a time
+#pragma unroll 1
+      for (int hsel = 0; hsel < 2; ++hsel) {
+        if ((hsel ? st[1] : st[0]) >= 0) continue;
+        T ys[EMAX], p[P], r = 0;
+        int it = 0;
+        unsigned fl = 0;
+#pragma unroll
+        for (int e = 0; e < EMAX; ++e) ys[e] = hsel ? Y[e].hi : Y[e].lo;
+        load_p0<P, T, EMAX>(a, hsel && both ? v0 + 1 : v0, p);
+        const int s1 = fit_voxel<M, T, T, EMAX, true>(ys, a.xt, a.E, a.vo, p, r, it, fl);
+        if (hsel == 0 || both) nflags += ((fl & FLAG_NONFINITE) ? 1u : 0u) + ((fl & FLAG_OOB) ? 0x100u : 0u);
+        if (hsel) {
+          st[1] = s1; iters[1] = it; pa.hi = p[0]; pb.hi = p[1]; r2.hi = r;
+        } else {
+          st[0] = s1; iters[0] = it; pa.lo = p[0]; pb.lo = p[1]; r2.lo = r;
+        }
+      }
+    }
+    if (!both) {
+      st[1] = -1;
+      iters[1] = 0;
+    }
+    if (!a.po.enabled && a.out_dtype == DT_F32 && both) {
+      __stcs(reinterpret_cast<float4*>(reinterpret_cast<float*>(a.popt) + v0 * P), make_float4(pa.lo, pb.lo, pa.hi, pb.hi));
+      __stcs(reinterpret_cast<float2*>(reinterpret_cast<float*>(a.r2) + v0), make_float2(r2.lo, r2.hi));
+      if (a.status) {
+        a.status[v0] = (uint8_t)st[0];
+        a.status[v0 + 1] = (uint8_t)st[1];
+      }
+      if (a.niter) {
+        a.niter[v0] = (uint8_t)iters[0];
+        a.niter[v0 + 1] = (uint8_t)iters[1];
+      }
+    } else {
+      const T p0_[P] = {pa.lo, pb.lo}, p1_[P] = {pa.hi, pb.hi};
+      store_voxel<P, T, EMAX, false>(a, v0, p0_, r2.lo, true, st[0], iters[0]);
+      if (both) store_voxel<P, T, EMAX, false>(a, v0 + 1, p1_, r2.hi, true, st[1], iters[1]);
+    }
+  }
+  __syncwarp();
+  warp_stats2(a.counters, st, iters, nflags);
+}
+
+// ------------------------------------------------------------------------------------------------
 // TMA-staged variant.  Persistent warps: every warp owns a 2-stage shared-memory ring of
 // [E][32-voxel] sample tiles that the Tensor Memory Accelerator fills (cp.async.bulk.tensor.2d over a
 // 2-D tensor map of the planar (E, ld) array, box = 32 voxels x E echoes) while the warp is busy
@@ -534,6 +651,129 @@ __global__ void __launch_bounds__(kTmaWarps * 32)
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Two voxels per lane + TMA staging: persistent warps, each with its own ring of [E][64-voxel] sample
+// tiles in shared memory.  The Tensor Memory Accelerator fills a stage (one cp.async.bulk.tensor.2d over
+// the 2-D map of the planar samples, box = 64 voxels x E echoes, completion on the stage's mbarrier) while
+// the warp is fitting earlier tiles, so the HBM latency that the plain kernel exposes at the top of every
+// CTA is hidden behind arithmetic.  Lanes read their two voxels of every echo as one conflict-free 8-byte
+// shared load.  No block-level synchronisation inside the loop.
+constexpr int kM2Warps = 4;
+constexpr int kM2Tile = 64;
+constexpr int m2_stages(int E) { return E <= 8 ? 4 : 2; }  // 32 KB of tiles per CTA
+
+template <class M, int EMAX>
+__global__ void __launch_bounds__(kM2Warps * 32, 5)
+    fit_kernel_mono2_tma(const __grid_constant__ KernelArgs<float, EMAX> a, const __grid_constant__ CUtensorMap tmap) {
+  typedef float T;
+  constexpr int P = 2;
+  constexpr int kStages = m2_stages(EMAX);
+  constexpr unsigned kTileBytes = EMAX * kM2Tile * sizeof(float);
+  __shared__ __align__(128) float tiles[kM2Warps][kStages][EMAX][kM2Tile];
+  __shared__ __align__(8) uint64_t full[kM2Warps][kStages];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t n_tiles = (a.n + kM2Tile - 1) / kM2Tile;
+  const int64_t warp_global = (int64_t)blockIdx.x * kM2Warps + warp;
+  const int64_t warp_stride = (int64_t)gridDim.x * kM2Warps;
+
+  if (lane == 0) {
+#pragma unroll
+    for (int s = 0; s < kStages; ++s) mbar_init(&full[warp][s], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+#pragma unroll
+    for (int s = 0; s < kStages; ++s) {  // prologue: fill the ring
+      const int64_t t = warp_global + (int64_t)s * warp_stride;
+      if (t < n_tiles) {
+        mbar_expect_tx(&full[warp][s], kTileBytes);
+        tma_load_2d(&tiles[warp][s][0][0], &tmap, (int)(t * kM2Tile), 0, &full[warp][s]);
+      }
+    }
+  }
+  __syncwarp();
+
+  unsigned n_fit = 0, it_sum = 0, it_max = 0;
+  unsigned long long* const stat_slot = a.counters + (size_t)(warp_global & (kStatSlots - 1)) * CNT_COUNT;
+  int k = 0;
+  for (int64_t t = warp_global; t < n_tiles; t += warp_stride, ++k) {
+    const int s = k % kStages;
+    mbar_wait(&full[warp][s], (unsigned)(k / kStages) & 1u);
+    pair2<T> Y[EMAX], pa, pb, r2;
+#pragma unroll
+    for (int e = 0; e < EMAX; ++e) {
+      const float2 v = *reinterpret_cast<const float2*>(&tiles[warp][s][e][2 * lane]);
+      Y[e] = p2_make<T>(v.x, v.y);
+    }
+    __syncwarp();
+    if (lane == 0) {  // the stage is drained: refill it with the tile kStages trips ahead
+      const int64_t tn = t + (int64_t)kStages * warp_stride;
+      if (tn < n_tiles) {
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        mbar_expect_tx(&full[warp][s], kTileBytes);
+        tma_load_2d(&tiles[warp][s][0][0], &tmap, (int)(tn * kM2Tile), 0, &full[warp][s]);
+      }
+    }
+    const int64_t v0 = t * kM2Tile + 2 * lane;
+    const bool validA = v0 < a.n, validB = v0 + 1 < a.n;
+    int st[2], iters[2];
+    fit_voxel_fast2<M, T, EMAX>(Y, a.xt, a.vo, pa, pb, r2, st, iters);  // voxels past the end are zero-filled: declined
+    if ((st[0] < 0 && validA) || (st[1] < 0 && validB)) {  // the general path, one voxel at a time
+#pragma unroll 1
+      for (int hsel = 0; hsel < 2; ++hsel) {
+        if ((hsel ? st[1] : st[0]) >= 0 || !(hsel ? validB : validA)) continue;
+        T ys[EMAX], p[P], r = 0;
+        int it = 0;
+        unsigned fl = 0;
+#pragma unroll
+        for (int e = 0; e < EMAX; ++e) ys[e] = hsel ? Y[e].hi : Y[e].lo;
+        load_p0<P, T, EMAX>(a, v0 + hsel, p);
+        const int s1 = fit_voxel<M, T, T, EMAX, true>(ys, a.xt, a.E, a.vo, p, r, it, fl);
+        // rare events go straight to the counters (the voxel has just paid for a full LM anyway)
+        if (s1 >= ST_MAXITER) atomicAdd(stat_slot + CNT_FAILED, 1ull);
+        if (fl & FLAG_NONFINITE) atomicAdd(stat_slot + CNT_NONFINITE, 1ull);
+        if (fl & FLAG_OOB) atomicAdd(stat_slot + CNT_OOB, 1ull);
+        if (hsel) {
+          st[1] = s1; iters[1] = it; pa.hi = p[0]; pb.hi = p[1]; r2.hi = r;
+        } else {
+          st[0] = s1; iters[0] = it; pa.lo = p[0]; pb.lo = p[1]; r2.lo = r;
+        }
+      }
+    }
+    if (!validA) { st[0] = -1; iters[0] = 0; }
+    if (!validB) { st[1] = -1; iters[1] = 0; }
+    if (!a.po.enabled && a.out_dtype == DT_F32 && validB) {
+      __stcs(reinterpret_cast<float4*>(reinterpret_cast<float*>(a.popt) + v0 * P), make_float4(pa.lo, pb.lo, pa.hi, pb.hi));
+      __stcs(reinterpret_cast<float2*>(reinterpret_cast<float*>(a.r2) + v0), make_float2(r2.lo, r2.hi));
+      if (a.status) {
+        a.status[v0] = (uint8_t)st[0];
+        a.status[v0 + 1] = (uint8_t)st[1];
+      }
+      if (a.niter) {
+        a.niter[v0] = (uint8_t)iters[0];
+        a.niter[v0 + 1] = (uint8_t)iters[1];
+      }
+    } else {
+      const T p0_[P] = {pa.lo, pb.lo}, p1_[P] = {pa.hi, pb.hi};
+      if (validA) store_voxel<P, T, EMAX, false>(a, v0, p0_, r2.lo, true, st[0], iters[0]);
+      if (validB) store_voxel<P, T, EMAX, false>(a, v0 + 1, p1_, r2.hi, true, st[1], iters[1]);
+    }
+    n_fit += (unsigned)(st[0] >= ST_CONV_F) + (unsigned)(st[1] >= ST_CONV_F);
+    it_sum += (unsigned)(iters[0] + iters[1]);
+    const unsigned im = (unsigned)(iters[0] > iters[1] ? iters[0] : iters[1]);
+    it_max = im > it_max ? im : it_max;
+  }
+  // statistics: per-thread accumulators -> one reduction per warp at the end of the kernel
+  {
+    const unsigned fm = 0xffffffffu;
+    const unsigned v0 = __reduce_add_sync(fm, n_fit);
+    const unsigned v4 = __reduce_add_sync(fm, it_sum), v5 = __reduce_max_sync(fm, it_max);
+    if (lane == 0) {
+      if (v0) atomicAdd(stat_slot + CNT_FITTED, (unsigned long long)v0);
+      if (v4) atomicAdd(stat_slot + CNT_ITERS, (unsigned long long)v4);
+      if (v5) atomicMax(stat_slot + CNT_MAXITER, (unsigned long long)v5);
+    }
+  }
+}
+
 #endif  // __CUDACC__
 
 // Type-erased launch description filled by the C-ABI layer and consumed by the per-model
@@ -568,7 +808,8 @@ struct LaunchDesc {
   float* gather[kMaxPeers];
   int gather_world;
   int64_t gather_row0;
-  const CUtensorMap* tmap;  // host pointer to an encoded 2-D map of the planar fp32 samples, or null
+  const CUtensorMap* tmap;   // host pointer to an encoded 2-D map of the planar fp32 samples (box 32 x E), or null
+  const CUtensorMap* tmap2;  // the same with a 64-voxel box, for the two-voxels-per-lane kernel, or null
   int sm_count;
 };
 
@@ -618,6 +859,30 @@ template <class M, typename T, int EMAX, bool EXACT>
 inline cudaError_t launch_one(const LaunchDesc& d) {
   KernelArgs<T, EMAX> a;
   fill_args<T, EMAX>(d, a);
+  if constexpr (M::MONO && EXACT && sizeof(T) == 4 && EMAX >= 3) {
+    // dense fast path, two voxels per lane (see fit_kernel_mono2 for what it needs)
+    const bool dt_ok = d.y_dtype == DT_F32 || d.y_dtype == DT_I16 || d.y_dtype == DT_U16;
+    const size_t pair_bytes = 2 * dtype_size(d.y_dtype);
+    if (d.fast_path == 1 && a.xt.uniform && !a.vo.has_bounds && d.mask == nullptr && d.gather_world == 0 && dt_ok &&
+        d.layout == LAYOUT_PLANAR && d.popt != nullptr && reinterpret_cast<uintptr_t>(d.y) % pair_bytes == 0 &&
+        d.ld % 2 == 0 && reinterpret_cast<uintptr_t>(d.popt) % 16 == 0 && reinterpret_cast<uintptr_t>(d.r2) % 8 == 0) {
+      if (d.tmap2 != nullptr) {  // persistent, tiles staged through shared memory by TMA
+        int per_sm = 0;
+        cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fit_kernel_mono2_tma<M, EMAX>, kM2Warps * 32, 0);
+        if (e != cudaSuccess) return e;
+        if (per_sm < 1) per_sm = 1;
+        const int64_t n_tiles = (d.n_vox + kM2Tile - 1) / kM2Tile;
+        int64_t g = (int64_t)d.sm_count * per_sm;
+        const int64_t needed = (n_tiles + kM2Warps - 1) / kM2Warps;
+        if (g > needed) g = needed;
+        fit_kernel_mono2_tma<M, EMAX><<<(unsigned)g, kM2Warps * 32, 0, d.stream>>>(a, *d.tmap2);
+        return cudaGetLastError();
+      }
+      const int64_t per_cta = 2 * kBlock2;
+      fit_kernel_mono2<M, EMAX><<<(unsigned)((d.n_vox + per_cta - 1) / per_cta), kBlock2, 0, d.stream>>>(a);
+      return cudaGetLastError();
+    }
+  }
   if constexpr (EXACT && sizeof(T) == 4) {
     if (d.tmap != nullptr) {  // TMA-staged persistent variant (the C-ABI layer checked eligibility)
       int per_sm = 0;

@@ -721,12 +721,22 @@ inline void fill_xtab(XTab<T, EMAX>& xt, const double* x, int n_echo) {
 // few per cent of the minimiser on decaying signals, so two to three passes suffice; the user's p0 only
 // selects the basin MINPACK would start in and is not needed (the general LM below, which honours it,
 // takes over whenever this path declines).  Convergence is judged like the LM's "predicted reduction
-// <= ftol * F" test, applied to the error expected AFTER the step about to be taken: with the observed
-// contraction kappa = |dq_k| / |dq_k-1| (clamped to [1e-2, 1]) that is kappa^2 * pred <= ftol * F.
+// <= ftol * F" test, applied to the error expected AFTER the step about to be taken: with the contraction
+// kappa of newton_contraction() that is kappa^2 * pred <= ftol * F.
 //
 // Returns a Status (ST_CONV_F / ST_EXACT) or -1 when the path declines (no admissible start, curvature
 // not positive, not converged in kMonoFastPasses, non-finite data): the caller then runs the general path.
 constexpr int kMonoFastPasses = 6;
+
+// Expected error after the step about to be taken, relative to that step.  Newton's iteration contracts
+// quadratically, e_k+1 = C e_k^2, and the last two steps estimate C = |dq_k| / dq_k-1^2, so the error left
+// after taking dq_k is about (dq_k / dq_k-1)^2 |dq_k|.  A safety factor of 4 and a floor of 1e-3 (the size
+// of C |dq| for a step that is about to be accepted) guard against a ratio that is small by accident.
+template <typename T>
+DFIT_HD T newton_contraction(T step2, T prev_step2) {
+  return num<T>::min_(num<T>::max_((T)4 * step2 * num<T>::rcp_(prev_step2), (T)1e-3), (T)1);
+}
+
 
 // On the device the Newton loop is WARP-UNIFORM: every lane that entered together keeps iterating (with
 // its state frozen once it has converged or declined) until all of them are finished, so the warp stays
@@ -792,11 +802,10 @@ DFIT_HD int mono_uniform_newton(const T (&y)[E], const XTab<T, E>& xt, const Sol
     const T pred = (T)-0.5 * g * dq;       // Newton decrement: predicted reduction of phi
     const T Fest = nm::max_(nm::fma_(-N, a, ysq), (T)0);
     const T step2 = dq * dq;
-    const T dref2 = k == 0 ? step2 : dprev2;
-    const T kap2 = nm::min_(nm::max_(step2, (T)1e-4 * dref2), dref2);  // kappa^2 * dref2
+    const T kappa = k == 0 ? (T)1 : newton_contraction<T>(step2, dprev2);
     // h > 0: inside the convex basin (false for NaN as well); otherwise the lane declines
     const bool convex = h > (T)0;
-    const bool conv = convex && pred * kap2 <= nm::fma_(o.ftol, Fest, floorF) * dref2;
+    const bool conv = convex && (pred * kappa) * kappa <= nm::fma_(o.ftol, Fest, floorF);
     dq = nm::min_(nm::max_(dq, (T)-0.5 * q), q);  // keep q positive whatever happens
     if (active) {
       npass = k + 1;
@@ -839,6 +848,191 @@ DFIT_HD int mono_uniform_newton(const T (&y)[E], const XTab<T, E>& xt, const Sol
   p[0] = xt.x0 != (T)0 ? af * nm::expbx(-b, xt.x0, xt.x0s) : af;
   F_out = F;
   return F <= floorF ? ST_EXACT : ST_CONV_F;
+}
+
+// ---- two voxels per lane ---------------------------------------------------------------------------
+// The same iteration with the two halves of every packed operation holding two VOXELS (lo = voxel A,
+// hi = voxel B) instead of the N and D chains of one voxel: the Horner work per voxel is unchanged, but the
+// Newton algebra, the convergence test, the residuals, the logarithm and the r2 all run two voxels per
+// instruction.  Only MUFU, min/max, compares and selects remain per voxel.
+
+// ln(v), v positive and normal, both halves: v = m 2^e with m in [sqrt(1/2), sqrt(2)), ln v = e ln 2 +
+// log1p(m - 1); log1p(f) = f - f^2/2 + f^3 P(f), P a degree-7 fit on the interval (relative error 8e-8).
+template <typename T>
+DFIT_HD pair2<T> p2_log_pos(pair2<T> v) {
+  return p2_make<T>(num<T>::log_(v.lo), num<T>::log_(v.hi));
+}
+#if defined(__CUDA_ARCH__)
+template <>
+__device__ __forceinline__ pair2<float> p2_log_pos<float>(pair2<float> v) {
+  const int il = __float_as_int(v.lo), ih = __float_as_int(v.hi);
+  const int el = (il - 0x3f3504f3) >> 23, eh = (ih - 0x3f3504f3) >> 23;
+  const pair2<float> m = p2_make<float>(__int_as_float(il - (el << 23)), __int_as_float(ih - (eh << 23)));
+  const pair2<float> f = p2_add<float>(m, p2_bcast<float>(-1.0f));
+  pair2<float> t = p2_bcast<float>(-0.0790274366736412f);
+  t = p2_fma<float>(t, f, p2_bcast<float>(0.12622319161891937f));
+  t = p2_fma<float>(t, f, p2_bcast<float>(-0.12998183071613312f));
+  t = p2_fma<float>(t, f, p2_bcast<float>(0.14214496314525604f));
+  t = p2_fma<float>(t, f, p2_bcast<float>(-0.166412815451622f));
+  t = p2_fma<float>(t, f, p2_bcast<float>(0.20001044869422913f));
+  t = p2_fma<float>(t, f, p2_bcast<float>(-0.25000306963920593f));
+  t = p2_fma<float>(t, f, p2_bcast<float>(0.3333333134651184f));
+  const pair2<float> f2 = p2_mul<float>(f, f);
+  const pair2<float> r = p2_add<float>(f, p2_fma<float>(p2_mul<float>(t, f), f2, p2_mul<float>(f2, p2_bcast<float>(-0.5f))));
+  return p2_fma<float>(p2_make<float>((float)el, (float)eh), p2_bcast<float>(0.69314718055994531f), r);
+}
+#endif
+
+// Per-voxel (non-packable) part of one Newton pass: convergence test, step clamp, state update.
+template <typename T>
+struct NewtonLane {
+  T q, dprev2, qf, af;
+  bool active, done;
+  int npass;
+};
+
+template <typename T>
+DFIT_HD void newton_lane_step(NewtonLane<T>& L, int k, T h, T pred2, T tol2, T dq, T a, T ap) {
+  typedef num<T> nm;
+  const T step2 = dq * dq;
+  const T kappa = k == 0 ? (T)1 : newton_contraction<T>(step2, L.dprev2);
+  const bool convex = h > (T)0;  // false for NaN as well
+  const bool conv = convex && (pred2 * kappa) * kappa <= tol2;
+  dq = nm::min_(nm::max_(dq, (T)-0.5 * L.q), L.q);                   // keep q positive whatever happens
+  if (L.active) {
+    L.npass = k + 1;
+    if (conv) {
+      L.qf = L.q + dq;
+      L.af = nm::fma_(ap, dq, a);
+      L.done = true;
+    }
+    L.active = convex && !conv;
+    if (L.active) {
+      L.q += dq;
+      L.dprev2 = step2;
+    }
+  }
+}
+
+// Y[e] = (sample e of voxel A, sample e of voxel B).  Outputs per voxel: status (-1 = declined), passes,
+// a, b, cost F at the returned point and sum of squares about the mean.
+template <typename T, int E>
+DFIT_HD void mono_uniform_newton2(const pair2<T> (&Y)[E], const XTab<T, E>& xt, const SolverOpts<T>& o, pair2<T>& pa,
+                                  pair2<T>& pb, pair2<T>& F_out, int (&status)[2], int (&iters)[2]) {
+  static_assert(E >= 3, "needs at least three echoes");
+  typedef num<T> nm;
+  typedef pair2<T> V;
+  const unsigned lanes = DFIT_LANES();
+  (void)lanes;
+  const V one = p2_bcast<T>((T)1);
+  // Prony start q0 = sum y_k y_k+1 / sum y_k^2; sum y^2 falls out of the same recurrence
+  V pn = p2_mul<T>(Y[0], Y[1]), pd = p2_mul<T>(Y[0], Y[0]);
+#pragma unroll
+  for (int k = 1; k + 1 < E; ++k) {
+    pn = p2_fma<T>(Y[k], Y[k + 1], pn);
+    pd = p2_fma<T>(Y[k], Y[k], pd);
+  }
+  const V ysq = p2_fma<T>(Y[E - 1], Y[E - 1], pd);
+  const V q0 = p2_mul<T>(pn, p2_make<T>(nm::rcp_(pd.lo), nm::rcp_(pd.hi)));
+  NewtonLane<T> A, B;
+  A.q = q0.lo;
+  B.q = q0.hi;
+  A.active = A.q > xt.q_lo && A.q < xt.q_hi && nm::finite(ysq.lo);
+  B.active = B.q > xt.q_lo && B.q < xt.q_hi && nm::finite(ysq.hi);
+  if (!A.active) A.q = (T)0.5;
+  if (!B.active) B.q = (T)0.5;
+  A.dprev2 = B.dprev2 = A.qf = B.qf = A.af = B.af = (T)0;
+  A.done = B.done = false;
+  A.npass = B.npass = 0;
+  // tolerance on twice the Newton decrement: 2 (ftol F + floor_rel sum y^2)
+  const V floor2 = p2_mul<T>(ysq, p2_bcast<T>((T)2 * o.floor_rel));
+  const V ftol2 = p2_bcast<T>((T)2 * o.ftol);
+#pragma unroll 1
+  for (int k = 0; k < kMonoFastPasses; ++k) {
+    if (!DFIT_ANY(lanes, A.active || B.active)) break;
+    const V q = p2_make<T>(A.q, B.q);
+    const V s = p2_mul<T>(q, q);
+    // Horner with first and (half) second derivative: N(q) over the samples, D(s) over ones
+    V N0 = Y[E - 1], N1 = N0, N2, D0 = one, D1 = one, D2;
+    N0 = p2_fma<T>(N0, q, Y[E - 2]);
+    D0 = p2_add<T>(s, one);
+    N2 = N1;
+    D2 = D1;
+    N1 = p2_fma<T>(N1, q, N0);
+    D1 = p2_add<T>(s, D0);
+    N0 = p2_fma<T>(N0, q, Y[E - 3]);
+    D0 = p2_fma<T>(D0, s, one);
+#pragma unroll
+    for (int j = E - 4; j >= 0; --j) {
+      N2 = p2_fma<T>(N2, q, N1);
+      D2 = p2_fma<T>(D2, s, D1);
+      N1 = p2_fma<T>(N1, q, N0);
+      D1 = p2_fma<T>(D1, s, D0);
+      N0 = p2_fma<T>(N0, q, Y[j]);
+      D0 = p2_fma<T>(D0, s, one);
+    }
+    // N0 = N, N1 = dN/dq, N2 = (d2N/dq2)/2;  D0 = D(s), D1 = dD/ds, D2 = (d2D/ds2)/2
+    const V nDq = p2_mul<T>(p2_mul<T>(q, p2_bcast<T>((T)-2)), D1);                     // -dD/dq
+    const V Dqq = p2_fma<T>(p2_mul<T>(s, p2_bcast<T>((T)8)), D2, p2_add<T>(D1, D1));  // d2D/dq2
+    const V rD = p2_make<T>(nm::rcp_(D0.lo), nm::rcp_(D0.hi));
+    const V a = p2_mul<T>(N0, rD);           // projected amplitude a'(q)
+    const V w = p2_fma<T>(a, nDq, N1);       // = D da'/dq
+    const V ap = p2_mul<T>(w, rD);           // da'/dq
+    const V mg = p2_mul<T>(a, p2_add<T>(w, N1));  // -dphi/dq
+    const V t2 = p2_fma<T>(N2, p2_bcast<T>((T)-4), p2_mul<T>(a, Dqq));
+    const V h = p2_fma<T>(a, t2, p2_mul<T>(p2_mul<T>(w, ap), p2_bcast<T>((T)-2)));  // d2phi/dq2
+    const V dq = p2_mul<T>(mg, p2_make<T>(nm::rcp_(h.lo), nm::rcp_(h.hi)));
+    const V pred2 = p2_mul<T>(mg, dq);       // twice the Newton decrement
+    // projected cost estimate sum y^2 - N a (clamped at 0 per voxel below) -> tolerance
+    const V Fe = p2_fma<T>(p2_mul<T>(N0, p2_bcast<T>((T)-1)), a, ysq);
+    const V tol2 = p2_fma<T>(ftol2, p2_make<T>(nm::max_(Fe.lo, (T)0), nm::max_(Fe.hi, (T)0)), floor2);
+    newton_lane_step<T>(A, k, h.lo, pred2.lo, tol2.lo, dq.lo, a.lo, ap.lo);
+    newton_lane_step<T>(B, k, h.hi, pred2.hi, tol2.hi, dq.hi, a.hi, ap.hi);
+  }
+  iters[0] = A.npass;
+  iters[1] = B.npass;
+  const bool okA = A.done && A.qf > xt.q_lo && A.qf < xt.q_hi && nm::finite(A.af);
+  const bool okB = B.done && B.qf > xt.q_lo && B.qf < xt.q_hi && nm::finite(B.af);
+  // a declined voxel rides along on harmless values
+  const V qf = p2_make<T>(okA ? A.qf : (T)0.5, okB ? B.qf : (T)0.5);
+  const V af = p2_make<T>(okA ? A.af : (T)0, okB ? B.af : (T)0);
+  // cost at the returned point: r_k = y_k - a' q^k
+  V ee = qf, F = p2_bcast<T>((T)0);
+  const V naf = p2_mul<T>(af, p2_bcast<T>((T)-1));
+  {
+    const V r0 = p2_add<T>(Y[0], naf);
+    F = p2_mul<T>(r0, r0);
+  }
+#pragma unroll
+  for (int e = 1; e < E; ++e) {
+    const V r = p2_fma<T>(naf, ee, Y[e]);
+    F = p2_fma<T>(r, r, F);
+    if (e + 1 < E) ee = p2_mul<T>(ee, qf);
+  }
+  // back to the reference's parameters: b = ln(q) / dx, a = a' exp(-b x0)
+  const V b = p2_mul<T>(p2_log_pos<T>(qf), p2_bcast<T>(xt.inv_dx));
+  pb = b;
+  pa = af;
+  if (xt.x0 != (T)0) pa = p2_mul<T>(af, p2_make<T>(nm::expbx(-b.lo, xt.x0, xt.x0s), nm::expbx(-b.hi, xt.x0, xt.x0s)));
+  F_out = F;
+  status[0] = okA ? (F.lo <= o.floor_rel * ysq.lo ? ST_EXACT : ST_CONV_F) : -1;
+  status[1] = okB ? (F.hi <= o.floor_rel * ysq.hi ? ST_EXACT : ST_CONV_F) : -1;
+}
+
+// sum (y - mean)^2 of two voxels at once
+template <typename T, int E>
+DFIT_HD pair2<T> ss_total2(const pair2<T> (&Y)[E]) {
+  pair2<T> s = Y[0];
+#pragma unroll
+  for (int e = 1; e < E; ++e) s = p2_add<T>(s, Y[e]);
+  const pair2<T> nmean = p2_mul<T>(s, p2_bcast<T>((T)(-1.0 / E)));
+  pair2<T> t = p2_bcast<T>((T)0);
+#pragma unroll
+  for (int e = 0; e < E; ++e) {
+    const pair2<T> d = p2_add<T>(Y[e], nmean);
+    t = p2_fma<T>(d, d, t);
+  }
+  return t;
 }
 
 // sum (y - mean)^2 for the r2 of fitting.py:1032-1035, two samples per instruction
@@ -893,6 +1087,18 @@ DFIT_HD int fit_voxel_fast(const T (&y)[EMAX], const XTab<T, EMAX>& xt, const Vo
     }
   }
   return -1;
+}
+
+// Fast-path attempt for two voxels: status[i] = -1 where voxel i has to take the general path.
+template <class M, typename T, int EMAX>
+DFIT_HD void fit_voxel_fast2(const pair2<T> (&Y)[EMAX], const XTab<T, EMAX>& xt, const VoxelOpts<T>& vo, pair2<T>& pa,
+                             pair2<T>& pb, pair2<T>& r2, int (&status)[2], int (&iters)[2]) {
+  static_assert(M::MONO && EMAX >= 3, "mono-exponential model only");
+  pair2<T> F;
+  mono_uniform_newton2<T, EMAX>(Y, xt, vo.s, pa, pb, F, status, iters);
+  const pair2<T> den = p2_add<T>(ss_total2<T, EMAX>(Y), p2_bcast<T>(vo.r2_eps));
+  const pair2<T> nr = p2_make<T>(-num<T>::rcp_(den.lo), -num<T>::rcp_(den.hi));
+  r2 = p2_fma<T>(F, nr, p2_bcast<T>((T)1));  // fitting.py:1032-1035
 }
 
 // Everything the reference does for one voxel (`_curve_fit`, fitting.py:1026-1073), on samples that

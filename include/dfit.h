@@ -118,7 +118,8 @@ typedef struct dfit_opts {
   int32_t decimals[DFIT_MAX_PARAMS]; /* np.around per parameter, < 0 = none (fitting.py:736-737) */
   int32_t fast_path;     /* mono-exponential model on uniformly spaced echoes: variable-projection Newton on
                             q = exp(b dx) from a data-driven (Prony) start, falling back per voxel to the LM
-                            from p0 whenever it declines.  -1 auto (on), 0 off (always LM from p0), 1 on */
+                            from p0 whenever it declines.  -1 auto (on), 0 off (always LM from p0), 1 on, 2 on but never
+                            with the two-voxels-per-lane kernel (diagnostic) */
   int32_t use_tma;         /* -1 auto, 0 plain coalesced loads, 1 TMA-staged tiles */
 } dfit_opts;
 

@@ -25,8 +25,9 @@ out = {"voxels": n}
 ref = None
 popt = torch.empty((n, 2), device="cuda")
 r2 = torch.empty((n,), device="cuda")
-for name, kw in (("lm_ldg", dict(fast_path=0, use_tma=0)), ("fast_ldg", dict(fast_path=1, use_tma=0)),
-                 ("fast_tma", dict(fast_path=1, use_tma=1)), ("lm_tma", dict(fast_path=0, use_tma=1))):
+for name, kw in (("lm_ldg", dict(fast_path=0, use_tma=0)), ("fast1_ldg", dict(fast_path=2, use_tma=0)),
+                 ("fast2_ldg", dict(fast_path=1, use_tma=0)), ("fast2_tma", dict(fast_path=1, use_tma=1)),
+                 ("default", dict())):
     o, P = A.make_opts(D.monoexponential, p0=(1.0, -1 / 30), **kw)
     A.fit_device(o, P, x, y, popt=popt, r2=r2)
     torch.cuda.synchronize()

@@ -29,6 +29,39 @@ static void run(int E, int64_t N, const double* x, const double* y, const double
   vo.init_mode = init_mode;
   vo.has_bounds = (y_lo > -1.7e308 || y_hi < 1.7e308) ? 1 : 0;
   vo.fast = fast;
+  // fast == 2: the two-voxels-per-lane variant of the fast path on consecutive voxel pairs (what
+  // fit_kernel_mono2 runs), general path for the voxels it declines
+  if constexpr (M::MONO && EXACT && EMAX >= 3 && sizeof(T) == sizeof(TA)) {
+    if (fast == 2 && xt.uniform && !vo.has_bounds) {
+      for (int64_t v = 0; v < N; v += 2) {
+        const bool both = v + 1 < N;
+        pair2<T> Y[EMAX], pa, pb, r2p;
+        for (int e = 0; e < EMAX; ++e)
+          Y[e] = p2_make<T>((T)y[(size_t)e * N + v], (T)y[(size_t)e * N + (both ? v + 1 : v)]);
+        int st2[2], it2[2];
+        fit_voxel_fast2<M, T, EMAX>(Y, xt, vo, pa, pb, r2p, st2, it2);
+        for (int hsel = 0; hsel < (both ? 2 : 1); ++hsel) {
+          T p[P], r2v = hsel ? r2p.hi : r2p.lo;
+          int st = st2[hsel], it = it2[hsel];
+          p[0] = hsel ? pa.hi : pa.lo;
+          p[P - 1] = hsel ? pb.hi : pb.lo;
+          if (st < 0) {
+            T yy[EMAX];
+            unsigned flags;
+            for (int e = 0; e < EMAX; ++e) yy[e] = hsel ? Y[e].hi : Y[e].lo;
+            const double* pv = p0 + (n_p0 > 1 ? (size_t)(v + hsel) * P : 0);
+            for (int i = 0; i < P; ++i) p[i] = (T)pv[i];
+            st = fit_voxel<M, T, TA, EMAX, EXACT>(yy, xt, E, vo, p, r2v, it, flags);
+          }
+          for (int i = 0; i < P; ++i) popt[(size_t)(v + hsel) * P + i] = (double)p[i];
+          r2[v + hsel] = (double)r2v;
+          status[v + hsel] = st;
+          iters[v + hsel] = it;
+        }
+      }
+      return;
+    }
+  }
   for (int64_t v = 0; v < N; ++v) {
     T yy[EMAX];
     for (int e = 0; e < EMAX; ++e) yy[e] = e < E ? (T)y[(size_t)e * N + v] : (T)0;

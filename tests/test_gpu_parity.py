@@ -265,6 +265,79 @@ def test_tma_staged_variant_is_bitwise_identical(D):
         A.fit_device(o1, P, x, y.t().contiguous(), layout="echo_fastest")
 
 
+def test_two_voxel_fast_kernels_agree_with_lm(D):
+    """The dense mono-exponential fast path (variable-projection Newton, two voxels per lane; plain loads
+    and the TMA-staged persistent variant) against the LM from p0 (fast_path=0): same minimiser, ragged
+    and odd sizes, int16 samples, status / pass-count outputs, fused epilogue, degenerate voxels."""
+    import torch
+
+    from dosma_b200 import _cabi, device_api as A
+
+    g = torch.Generator(device="cuda").manual_seed(11)
+    x = np.arange(1, 9) * 10.0
+    xt = torch.tensor(x, device="cuda", dtype=torch.float32)[:, None]
+    for n in (1, 2, 63, 64, 65, 100_003, 1_000_000):
+        y = (500 + 1000 * torch.rand(n, device="cuda", generator=g)) * torch.exp(
+            -xt / (10 + 70 * torch.rand(n, device="cuda", generator=g))) + 10 * torch.randn(8, n, device="cuda", generator=g)
+        if n > 100:
+            y[:, 5] = 0.0          # all-zero voxel: skipped (fitting.py:1065-1067)
+            y[:, 8] = -y[:, 8]     # negative amplitude
+            y[:, 11] = 7.0         # constant signal
+            y[:, 14] = 10 * torch.randn(8, device="cuda", generator=g)  # pure noise
+        o_lm, P = A.make_opts(D.monoexponential, p0=(1.0, -1 / 30), fast_path=0, use_tma=0)
+        p_lm, r_lm = A.fit_device(o_lm, P, x, y)
+        ref = None
+        for kw in (dict(fast_path=2, use_tma=0), dict(fast_path=1, use_tma=0), dict(fast_path=1, use_tma=1), dict()):
+            if kw.get("use_tma") == 1 and n % 4:
+                continue  # an explicit use_tma=1 refuses rows whose pitch is not a multiple of 16 bytes
+            o, _ = A.make_opts(D.monoexponential, p0=(1.0, -1 / 30), **kw)
+            st = torch.zeros(n, dtype=torch.uint8, device="cuda")
+            it = torch.zeros(n, dtype=torch.uint8, device="cuda")
+            p, r = A.fit_device(o, P, x, y, status=st, niter=it)
+            torch.cuda.synchronize()
+            stats = _cabi.get_handle(0).stats()
+            ok = ~torch.isnan(p_lm[:, 0]) & ~torch.isnan(p[:, 0])
+            assert torch.equal(torch.isnan(p_lm[:, 0]), torch.isnan(p[:, 0])) or ok.float().mean() > 0.999
+            rel = ((p[ok] - p_lm[ok]).abs() / p_lm[ok].abs())
+            assert rel.max() < 2e-3 and (rel > 1e-4).float().mean() < 1e-3, (n, kw, float(rel.max()))
+            assert (r[ok] - r_lm[ok]).abs().max() < 1e-5
+            assert int(((st >= 1) & (st <= 4)).sum()) == stats["n_fitted"] and stats["n_voxels"] == n
+            assert int(it.sum()) == stats["sum_iters"]
+            if n > 100:
+                assert int(st[5]) == 0 and torch.isnan(p[5]).all() and float(r[5]) == 0.0
+            if ref is None:
+                ref = (p, r)
+            else:  # all fast variants run the same arithmetic per voxel up to packing order
+                okr = ~torch.isnan(ref[0][:, 0]) & ~torch.isnan(p[:, 0])
+                assert ((p[okr] - ref[0][okr]).abs() / ref[0][okr].abs()).max() < 1e-5
+    # int16 samples and the fused MonoExponentialFit epilogue (ufunc, bounds, r2 threshold, fill, rounding)
+    n = 200_001
+    yi = ((500 + 1000 * torch.rand(n, device="cuda", generator=g)) * torch.exp(
+        -xt / (10 + 70 * torch.rand(n, device="cuda", generator=g))) + 10 * torch.randn(8, n, device="cuda", generator=g)
+          ).round().to(torch.int16)
+    post = dict(ufunc=[0, 1], lb=[-np.inf, 0.0], ub=[np.inf, 100.0], decimals=[-1, 3], r2_threshold=0.9, nan_to_num=0.0)
+    outs = []
+    for kw in (dict(fast_path=0, use_tma=0), dict(fast_path=1, use_tma=0), dict()):
+        o, P = A.make_opts(D.monoexponential, p0=(1.0, -1 / 30), post=post, **kw)
+        p, r = A.fit_device(o, P, x, yi, out_dtype=torch.float64)
+        torch.cuda.synchronize()
+        outs.append((p, r))
+    for p, r in outs[1:]:
+        same = (p[:, 1] - outs[0][0][:, 1]).abs() <= 1.001e-3  # one rounding step
+        assert same.float().mean() > 0.999
+        assert (r - outs[0][1]).abs().max() < 1e-5
+    # non-uniform echo spacing and y_bounds keep using the LM (and say so through identical results)
+    xn = np.array([10.0, 20.0, 40.0, 80.0])
+    yn = (1000 * torch.exp(-torch.tensor(xn, device="cuda", dtype=torch.float32)[:, None] / (
+        10 + 70 * torch.rand(5000, device="cuda", generator=g)))).contiguous()
+    o0, P = A.make_opts(D.monoexponential, p0=(1.0, -1 / 30), fast_path=0)
+    o1, _ = A.make_opts(D.monoexponential, p0=(1.0, -1 / 30))
+    pa_, ra_ = A.fit_device(o0, P, xn, yn)
+    pb_, rb_ = A.fit_device(o1, P, xn, yn)
+    torch.cuda.synchronize()
+    assert torch.equal(pa_, pb_) and torch.equal(ra_, rb_)
+
+
 def test_scaling_and_permutation_properties(D):
     """Size-independent properties at a BASELINE-sized workload (384 x 384 x 16 slab, 8 echoes):
     scaling y by 2 scales a by 2 and leaves b (to rounding); permuting voxels permutes results exactly."""
