@@ -81,9 +81,12 @@ def cpu_baseline(target_seconds=12.0):
     from oracle import dosma_oracle as O
 
     cores = O.host_cores()
-    rate, _ = cpu_port_rate(256 * cores, cores)  # calibration
+    rate, _ = cpu_port_rate(256 * cores, cores)  # calibration (dominated by pool start-up: a lower bound)
     n = int(min(max(rate * target_seconds, 1024), 2_000_000))
     rate, dt = cpu_port_rate(n, cores)
+    if dt < 0.6 * target_seconds:  # the calibration under-estimated the rate: one more run at the right size
+        n = int(min(max(rate * target_seconds, 1024), 2_000_000))
+        rate, dt = cpu_port_rate(n, cores)
     return {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
             "sample": f"{n} voxels of the same workload (seed 1234), scipy.optimize.curve_fit per voxel via "
                       f"oracle/dosma_oracle.py with a {cores}-process pool, {dt:.1f} s"}
@@ -348,9 +351,11 @@ def run_gpu(args):
             "gpu_launches": args.steps * stats["n_launches"],
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": tpv * n if tpv else None, "peak_source": peak_src,
-                         "kernel": "dfit::fit_kernel<MonoExp,float,8,true>", "kernel_ms": kernel_ms,
-                         "algorithmic_bytes_per_voxel": BYTES_PER_VOXEL,
-                         "note": "compute-bound path (LM iterations x exp), HBM fraction is the contract figure"},
+                         "kernel": ("dfit::fit_kernel_mono2_tma<MonoExp,8>" if world == 1 else
+                                    "dfit::fit_kernel<MonoExp,float,8,true,GATHER>"),
+                         "kernel_ms": kernel_ms, "algorithmic_bytes_per_voxel": BYTES_PER_VOXEL,
+                         "note": "variable-projection Newton on q = exp(b dx), two voxels per lane, tiles staged by "
+                                 "TMA; FP32-pipe / issue bound, HBM fraction is the contract figure"},
             "lm": {"mean_iters": stats["sum_iters"] / max(stats["n_fitted"], 1), "max_iters": stats["max_iters"],
                    "failed_voxels": stats["n_failed"], "fitted_voxels": stats["n_fitted"]},
         }

@@ -297,7 +297,13 @@ def test_two_voxel_fast_kernels_agree_with_lm(D):
             torch.cuda.synchronize()
             stats = _cabi.get_handle(0).stats()
             ok = ~torch.isnan(p_lm[:, 0]) & ~torch.isnan(p[:, 0])
-            assert torch.equal(torch.isnan(p_lm[:, 0]), torch.isnan(p[:, 0])) or ok.float().mean() > 0.999
+            if n > 100:
+                # the constant voxel has b = 0 (no relative error) and pure noise has several local minima
+                # (the LM finds the one in p0's basin): checked on their own terms below
+                ok[11] = ok[14] = False
+                assert abs(float(p[11, 1])) < 1e-6 and abs(float(p[11, 0]) - 7.0) < 1e-4 and int(st[11]) in (1, 2, 3, 4)
+                assert int(st[14]) in (1, 2, 3, 4, 5) and int(st[8]) in (1, 2, 3, 4) and float(p[8, 0]) < 0
+            assert ok.float().mean() > 0.999
             rel = ((p[ok] - p_lm[ok]).abs() / p_lm[ok].abs())
             assert rel.max() < 2e-3 and (rel > 1e-4).float().mean() < 1e-3, (n, kw, float(rel.max()))
             assert (r[ok] - r_lm[ok]).abs().max() < 1e-5
@@ -309,7 +315,7 @@ def test_two_voxel_fast_kernels_agree_with_lm(D):
                 ref = (p, r)
             else:  # all fast variants run the same arithmetic per voxel up to packing order
                 okr = ~torch.isnan(ref[0][:, 0]) & ~torch.isnan(p[:, 0])
-                assert ((p[okr] - ref[0][okr]).abs() / ref[0][okr].abs()).max() < 1e-5
+                assert ((p[okr] - ref[0][okr]).abs() / ref[0][okr].abs().clamp_min(1e-30)).max() < 1e-5
     # int16 samples and the fused MonoExponentialFit epilogue (ufunc, bounds, r2 threshold, fill, rounding)
     n = 200_001
     yi = ((500 + 1000 * torch.rand(n, device="cuda", generator=g)) * torch.exp(
