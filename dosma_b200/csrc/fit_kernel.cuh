@@ -17,7 +17,7 @@
 
 namespace dfit {
 
-constexpr int kBlock = 128;  // block_stats packs 8-bit counters: keep <= 255
+constexpr int kBlock = 128;
 
 enum DType : int { DT_F32 = 0, DT_F64 = 1, DT_I16 = 2, DT_U16 = 3, DT_I32 = 4, DT_U8 = 5 };
 enum Layout : int { LAYOUT_PLANAR = 0, LAYOUT_ECHO_FASTEST = 1 };
@@ -276,7 +276,8 @@ __device__ __forceinline__ void warp_stats(unsigned long long* cnt, int st, int 
 // index list -- each warp claims a contiguous run with one atomic, so neighbours stay neighbours -- and
 // (b) writes the fill value for every voxel outside the mask (fitting.py:205-215).  Step 2 is the fit
 // kernel over the list: all 32 lanes of a warp fit, however thin the tissue mask is.
-__device__ __forceinline__ void block_stats_packed(unsigned long long* cnt, unsigned pack, int it_sum, int it_max) {
+__device__ __forceinline__ void block_stats_counts(unsigned long long* cnt, unsigned n_fit, unsigned n_fail, unsigned n_nf,
+                                                   unsigned n_oob, int it_sum, int it_max) {
   __shared__ unsigned s_c[4], s_iters, s_max;
   if (threadIdx.x < 4) s_c[threadIdx.x] = 0;
   if (threadIdx.x == 0) {
@@ -285,9 +286,8 @@ __device__ __forceinline__ void block_stats_packed(unsigned long long* cnt, unsi
   }
   __syncthreads();
   const unsigned full = 0xffffffffu;
-  unsigned c[4];
-#pragma unroll
-  for (int k = 0; k < 4; ++k) c[k] = __reduce_add_sync(full, (pack >> (8 * k)) & 0xffu);
+  const unsigned c[4] = {__reduce_add_sync(full, n_fit), __reduce_add_sync(full, n_fail), __reduce_add_sync(full, n_nf),
+                         __reduce_add_sync(full, n_oob)};
   const unsigned s_it = __reduce_add_sync(full, (unsigned)it_sum);
   const unsigned m_it = __reduce_max_sync(full, (unsigned)it_max);
   if ((threadIdx.x & 31) == 0) {
@@ -375,7 +375,7 @@ __global__ void __launch_bounds__(kBlock, EMAX <= 8 ? 8 : 1) fit_kernel(const __
     // compacted mask path: grid-stride over the index list (its length is only known on the device)
     const unsigned count = *a.index_count;
     int it_sum = 0;
-    unsigned pack = 0;
+    unsigned n_fit = 0, n_fail = 0, n_nf = 0, n_oob = 0;
     for (unsigned i = blockIdx.x * kBlock + threadIdx.x; i < count; i += gridDim.x * kBlock) {
       const int64_t v = (int64_t)a.index[i];
       T p[P], r2 = 0, y[EMAX];
@@ -390,10 +390,12 @@ __global__ void __launch_bounds__(kBlock, EMAX <= 8 ? 8 : 1) fit_kernel(const __
       store_voxel<P, T, EMAX, GATHER>(a, v, p, r2, true, s, it);
       it_sum += it;
       iters = it > iters ? it : iters;
-      pack += (unsigned)(s >= ST_CONV_F) | ((unsigned)(s >= ST_MAXITER) << 8) |
-              ((unsigned)((fl & FLAG_NONFINITE) != 0) << 16) | ((unsigned)((fl & FLAG_OOB) != 0) << 24);
+      n_fit += (unsigned)(s >= ST_CONV_F);
+      n_fail += (unsigned)(s >= ST_MAXITER);
+      n_nf += (unsigned)((fl & FLAG_NONFINITE) != 0);
+      n_oob += (unsigned)((fl & FLAG_OOB) != 0);
     }
-    block_stats_packed(a.counters, pack, it_sum, iters);
+    block_stats_counts(a.counters, n_fit, n_fail, n_nf, n_oob, it_sum, iters);
   }
 }
 
@@ -512,6 +514,61 @@ __global__ void __launch_bounds__(kBlock2, 5) fit_kernel_mono2(const __grid_cons
   }
   __syncwarp();
   warp_stats2(a.counters, st, iters, nflags);
+}
+
+// Two voxels per lane over the compacted voxel list of the mask path (any echo spacing, any sample type):
+// lane i takes list entries 2i and 2i+1, gathers their samples and runs the same packed fast path; voxels
+// it declines run the LM.  Grid-stride, because the list length is only known on the device.
+template <class M, int EMAX>
+__global__ void __launch_bounds__(kBlock, 5) fit_kernel_mono2_list(const __grid_constant__ KernelArgs<float, EMAX> a) {
+  typedef float T;
+  constexpr int P = 2;
+  const unsigned count = *a.index_count;
+  const unsigned npairs = (count + 1u) >> 1;
+  int it_sum = 0, it_max = 0;
+  unsigned n_fit = 0, n_fail = 0, n_nf = 0, n_oob = 0;
+  for (unsigned i = blockIdx.x * kBlock + threadIdx.x; i < npairs; i += gridDim.x * kBlock) {
+    const bool both = 2u * i + 1u < count;
+    const int64_t vA = (int64_t)a.index[2u * i], vB = both ? (int64_t)a.index[2u * i + 1u] : vA;
+    T yA[EMAX], yB[EMAX];
+    load_samples<T, EMAX, true>(a, vA, yA);
+    load_samples<T, EMAX, true>(a, vB, yB);
+    pair2<T> Y[EMAX], pa, pb, r2;
+#pragma unroll
+    for (int e = 0; e < EMAX; ++e) Y[e] = p2_make<T>(yA[e], yB[e]);
+    int st[2], iters[2];
+    fit_voxel_fast2<M, T, EMAX>(Y, a.xt, a.vo, pa, pb, r2, st, iters);
+    if (st[0] < 0 || (st[1] < 0 && both)) {
+#pragma unroll 1
+      for (int hsel = 0; hsel < 2; ++hsel) {
+        if ((hsel ? st[1] : st[0]) >= 0 || (hsel && !both)) continue;
+        T ys[EMAX], p[P], r = 0;
+        int it = 0;
+        unsigned fl = 0;
+#pragma unroll
+        for (int e = 0; e < EMAX; ++e) ys[e] = hsel ? Y[e].hi : Y[e].lo;
+        load_p0<P, T, EMAX>(a, hsel ? vB : vA, p);
+        const int s1 = fit_voxel<M, T, T, EMAX, true>(ys, a.xt, a.E, a.vo, p, r, it, fl);
+        n_nf += (unsigned)((fl & FLAG_NONFINITE) != 0);
+        n_oob += (unsigned)((fl & FLAG_OOB) != 0);
+        if (hsel) {
+          st[1] = s1; iters[1] = it; pa.hi = p[0]; pb.hi = p[1]; r2.hi = r;
+        } else {
+          st[0] = s1; iters[0] = it; pa.lo = p[0]; pb.lo = p[1]; r2.lo = r;
+        }
+      }
+    }
+    const T p0_[P] = {pa.lo, pb.lo}, p1_[P] = {pa.hi, pb.hi};
+    store_voxel<P, T, EMAX, false>(a, vA, p0_, r2.lo, true, st[0], iters[0]);
+    if (both) store_voxel<P, T, EMAX, false>(a, vB, p1_, r2.hi, true, st[1], iters[1]);
+    else { st[1] = -1; iters[1] = 0; }
+    it_sum += iters[0] + iters[1];
+    it_max = iters[0] > it_max ? iters[0] : it_max;
+    it_max = iters[1] > it_max ? iters[1] : it_max;
+    n_fit += (unsigned)(st[0] >= ST_CONV_F) + (unsigned)(st[1] >= ST_CONV_F);
+    n_fail += (unsigned)(st[0] >= ST_MAXITER) + (unsigned)(st[1] >= ST_MAXITER);
+  }
+  block_stats_counts(a.counters, n_fit, n_fail, n_nf, n_oob, it_sum, it_max);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -663,7 +720,7 @@ constexpr int kM2Tile = 64;
 constexpr int m2_stages(int E) { return E <= 8 ? 4 : 2; }  // 32 KB of tiles per CTA
 
 template <class M, int EMAX>
-__global__ void __launch_bounds__(kM2Warps * 32, 5)
+__global__ void __launch_bounds__(kM2Warps * 32, 5)  // 5 CTAs/SM: 6 spills, 4 is slower (measured: 0.743 / 0.689 / 0.696 ms)
     fit_kernel_mono2_tma(const __grid_constant__ KernelArgs<float, EMAX> a, const __grid_constant__ CUtensorMap tmap) {
   typedef float T;
   constexpr int P = 2;
@@ -672,9 +729,11 @@ __global__ void __launch_bounds__(kM2Warps * 32, 5)
   __shared__ __align__(128) float tiles[kM2Warps][kStages][EMAX][kM2Tile];
   __shared__ __align__(8) uint64_t full[kM2Warps][kStages];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int64_t n_tiles = (a.n + kM2Tile - 1) / kM2Tile;
-  const int64_t warp_global = (int64_t)blockIdx.x * kM2Warps + warp;
-  const int64_t warp_stride = (int64_t)gridDim.x * kM2Warps;
+  // 32-bit indexing: the launcher admits fewer than 2^31 voxels
+  const int n_vox = (int)a.n;
+  const int n_tiles = (n_vox + kM2Tile - 1) / kM2Tile;
+  const int warp_global = (int)blockIdx.x * kM2Warps + warp;
+  const int warp_stride = (int)gridDim.x * kM2Warps;
 
   if (lane == 0) {
 #pragma unroll
@@ -682,10 +741,10 @@ __global__ void __launch_bounds__(kM2Warps * 32, 5)
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 #pragma unroll
     for (int s = 0; s < kStages; ++s) {  // prologue: fill the ring
-      const int64_t t = warp_global + (int64_t)s * warp_stride;
+      const int t = warp_global + s * warp_stride;
       if (t < n_tiles) {
         mbar_expect_tx(&full[warp][s], kTileBytes);
-        tma_load_2d(&tiles[warp][s][0][0], &tmap, (int)(t * kM2Tile), 0, &full[warp][s]);
+        tma_load_2d(&tiles[warp][s][0][0], &tmap, t * kM2Tile, 0, &full[warp][s]);
       }
     }
   }
@@ -694,7 +753,7 @@ __global__ void __launch_bounds__(kM2Warps * 32, 5)
   unsigned n_fit = 0, it_sum = 0, it_max = 0;
   unsigned long long* const stat_slot = a.counters + (size_t)(warp_global & (kStatSlots - 1)) * CNT_COUNT;
   int k = 0;
-  for (int64_t t = warp_global; t < n_tiles; t += warp_stride, ++k) {
+  for (int t = warp_global; t < n_tiles; t += warp_stride, ++k) {
     const int s = k % kStages;
     mbar_wait(&full[warp][s], (unsigned)(k / kStages) & 1u);
     pair2<T> Y[EMAX], pa, pb, r2;
@@ -705,15 +764,15 @@ __global__ void __launch_bounds__(kM2Warps * 32, 5)
     }
     __syncwarp();
     if (lane == 0) {  // the stage is drained: refill it with the tile kStages trips ahead
-      const int64_t tn = t + (int64_t)kStages * warp_stride;
+      const int tn = t + kStages * warp_stride;
       if (tn < n_tiles) {
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         mbar_expect_tx(&full[warp][s], kTileBytes);
-        tma_load_2d(&tiles[warp][s][0][0], &tmap, (int)(tn * kM2Tile), 0, &full[warp][s]);
+        tma_load_2d(&tiles[warp][s][0][0], &tmap, tn * kM2Tile, 0, &full[warp][s]);
       }
     }
-    const int64_t v0 = t * kM2Tile + 2 * lane;
-    const bool validA = v0 < a.n, validB = v0 + 1 < a.n;
+    const int v0 = t * kM2Tile + 2 * lane;
+    const bool validA = v0 < n_vox, validB = v0 + 1 < n_vox;
     int st[2], iters[2];
     fit_voxel_fast2<M, T, EMAX>(Y, a.xt, a.vo, pa, pb, r2, st, iters);  // voxels past the end are zero-filled: declined
     if ((st[0] < 0 && validA) || (st[1] < 0 && validB)) {  // the general path, one voxel at a time
@@ -741,7 +800,7 @@ __global__ void __launch_bounds__(kM2Warps * 32, 5)
     if (!validA) { st[0] = -1; iters[0] = 0; }
     if (!validB) { st[1] = -1; iters[1] = 0; }
     if (!a.po.enabled && a.out_dtype == DT_F32 && validB) {
-      __stcs(reinterpret_cast<float4*>(reinterpret_cast<float*>(a.popt) + v0 * P), make_float4(pa.lo, pb.lo, pa.hi, pb.hi));
+      __stcs(reinterpret_cast<float4*>(reinterpret_cast<float*>(a.popt) + (int64_t)v0 * P), make_float4(pa.lo, pb.lo, pa.hi, pb.hi));
       __stcs(reinterpret_cast<float2*>(reinterpret_cast<float*>(a.r2) + v0), make_float2(r2.lo, r2.hi));
       if (a.status) {
         a.status[v0] = (uint8_t)st[0];
@@ -863,19 +922,20 @@ inline cudaError_t launch_one(const LaunchDesc& d) {
     // dense fast path, two voxels per lane (see fit_kernel_mono2 for what it needs)
     const bool dt_ok = d.y_dtype == DT_F32 || d.y_dtype == DT_I16 || d.y_dtype == DT_U16;
     const size_t pair_bytes = 2 * dtype_size(d.y_dtype);
-    if (d.fast_path == 1 && a.xt.uniform && !a.vo.has_bounds && d.mask == nullptr && d.gather_world == 0 && dt_ok &&
+    if (d.fast_path == 1 && !a.vo.has_bounds && d.mask == nullptr && d.gather_world == 0 && dt_ok &&
         d.layout == LAYOUT_PLANAR && d.popt != nullptr && reinterpret_cast<uintptr_t>(d.y) % pair_bytes == 0 &&
         d.ld % 2 == 0 && reinterpret_cast<uintptr_t>(d.popt) % 16 == 0 && reinterpret_cast<uintptr_t>(d.r2) % 8 == 0) {
       if (d.tmap2 != nullptr) {  // persistent, tiles staged through shared memory by TMA
+        auto kfn = fit_kernel_mono2_tma<M, EMAX>;
         int per_sm = 0;
-        cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fit_kernel_mono2_tma<M, EMAX>, kM2Warps * 32, 0);
+        cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kfn, kM2Warps * 32, 0);
         if (e != cudaSuccess) return e;
         if (per_sm < 1) per_sm = 1;
         const int64_t n_tiles = (d.n_vox + kM2Tile - 1) / kM2Tile;
         int64_t g = (int64_t)d.sm_count * per_sm;
         const int64_t needed = (n_tiles + kM2Warps - 1) / kM2Warps;
         if (g > needed) g = needed;
-        fit_kernel_mono2_tma<M, EMAX><<<(unsigned)g, kM2Warps * 32, 0, d.stream>>>(a, *d.tmap2);
+        kfn<<<(unsigned)g, kM2Warps * 32, 0, d.stream>>>(a, *d.tmap2);
         return cudaGetLastError();
       }
       const int64_t per_cta = 2 * kBlock2;
@@ -909,6 +969,12 @@ inline cudaError_t launch_one(const LaunchDesc& d) {
     a.index_count = d.index_count;
     int64_t g = (int64_t)d.sm_count * 16;
     if (g > blocks) g = blocks;
+    if constexpr (M::MONO && EXACT && sizeof(T) == 4 && EMAX >= 3) {
+      if (d.fast_path == 1 && !a.vo.has_bounds && d.gather_world == 0) {  // two voxels per lane over the list
+        fit_kernel_mono2_list<M, EMAX><<<(unsigned)g, kBlock, 0, d.stream>>>(a);
+        return cudaGetLastError();
+      }
+    }
     if (d.gather_world > 0) {
       if constexpr (sizeof(T) == 4) fit_kernel<M, T, EMAX, EXACT, true><<<(unsigned)g, kBlock, 0, d.stream>>>(a);
       else return cudaErrorNotSupported;

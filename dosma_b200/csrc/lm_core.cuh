@@ -672,6 +672,8 @@ struct XTab {
   T x0, x0s;     // first echo time and x0 * log2(e)
   T inv_dx;      // 1 / dx
   T q_lo, q_hi;  // admissible range of q: q^(2E-2) must stay finite
+  T xx[EMAX];    // x^2, for the second derivatives of the general (non-uniform) fast path
+  T inv_xmax;    // 1 / max |x|: the largest step in b the general fast path takes at once
 };
 
 // Host-side fill of the echo table (shared by the C-ABI layer and the test-only host build).
@@ -704,6 +706,8 @@ inline void fill_xtab(XTab<T, EMAX>& xt, const double* x, int n_echo) {
   const double decades = sizeof(T) == 4 ? 30.0 : 280.0;
   xt.q_hi = (T)pow(10.0, decades / (2.0 * (n_echo > 1 ? n_echo : 2) - 2.0));
   xt.q_lo = (T)(sizeof(T) == 4 ? 1e-30 : 1e-280);
+  for (int e = 0; e < EMAX; ++e) xt.xx[e] = (T)(e < n_echo ? x[e] * x[e] : 0.0);
+  xt.inv_xmax = (T)(xmax > 0 ? 1.0 / xmax : 0.0);
 }
 
 // ------------------------------------------------------------------------------------ fast path
@@ -892,13 +896,13 @@ struct NewtonLane {
 };
 
 template <typename T>
-DFIT_HD void newton_lane_step(NewtonLane<T>& L, int k, T h, T pred2, T tol2, T dq, T a, T ap) {
+DFIT_HD void newton_lane_step(NewtonLane<T>& L, int k, T h, T pred2, T tol2, T dq, T a, T ap, T step_lo, T step_hi) {
   typedef num<T> nm;
   const T step2 = dq * dq;
   const T kappa = k == 0 ? (T)1 : newton_contraction<T>(step2, L.dprev2);
   const bool convex = h > (T)0;  // false for NaN as well
   const bool conv = convex && (pred2 * kappa) * kappa <= tol2;
-  dq = nm::min_(nm::max_(dq, (T)-0.5 * L.q), L.q);                   // keep q positive whatever happens
+  dq = nm::min_(nm::max_(dq, step_lo), step_hi);  // trust clamp (keeps q positive / b x bounded)
   if (L.active) {
     L.npass = k + 1;
     if (conv) {
@@ -986,8 +990,8 @@ DFIT_HD void mono_uniform_newton2(const pair2<T> (&Y)[E], const XTab<T, E>& xt, 
     // projected cost estimate sum y^2 - N a (clamped at 0 per voxel below) -> tolerance
     const V Fe = p2_fma<T>(p2_mul<T>(N0, p2_bcast<T>((T)-1)), a, ysq);
     const V tol2 = p2_fma<T>(ftol2, p2_make<T>(nm::max_(Fe.lo, (T)0), nm::max_(Fe.hi, (T)0)), floor2);
-    newton_lane_step<T>(A, k, h.lo, pred2.lo, tol2.lo, dq.lo, a.lo, ap.lo);
-    newton_lane_step<T>(B, k, h.hi, pred2.hi, tol2.hi, dq.hi, a.hi, ap.hi);
+    newton_lane_step<T>(A, k, h.lo, pred2.lo, tol2.lo, dq.lo, a.lo, ap.lo, (T)-0.5 * A.q, A.q);
+    newton_lane_step<T>(B, k, h.hi, pred2.hi, tol2.hi, dq.hi, a.hi, ap.hi, (T)-0.5 * B.q, B.q);
   }
   iters[0] = A.npass;
   iters[1] = B.npass;
@@ -1014,6 +1018,127 @@ DFIT_HD void mono_uniform_newton2(const pair2<T> (&Y)[E], const XTab<T, E>& xt, 
   pb = b;
   pa = af;
   if (xt.x0 != (T)0) pa = p2_mul<T>(af, p2_make<T>(nm::expbx(-b.lo, xt.x0, xt.x0s), nm::expbx(-b.hi, xt.x0, xt.x0s)));
+  F_out = F;
+  status[0] = okA ? (F.lo <= o.floor_rel * ysq.lo ? ST_EXACT : ST_CONV_F) : -1;
+  status[1] = okB ? (F.hi <= o.floor_rel * ysq.hi ? ST_EXACT : ST_CONV_F) : -1;
+}
+
+// ---- general echo times ------------------------------------------------------------------------------
+// The same variable-projection Newton iteration for ARBITRARY echo times (T1rho spin-lock times, 10/20/40/80
+// ms protocols ...), in the reference's own parameter b: e_k = exp(b x_k), N = sum y_k e_k, D = sum e_k^2 and
+// their b-derivatives carry one and two factors of x_k.  One ex2 per sample and pass instead of none, so a
+// pass costs about 1.5x the uniform one.  The start is a weighted log-linear fit (weights max(y^2 - c sum
+// y^2, 0): samples near the noise floor drop out, no sign tests), two voxels per lane like above.
+template <typename T, int E>
+DFIT_HD void mono_general_newton2(const pair2<T> (&Y)[E], const XTab<T, E>& xt, const SolverOpts<T>& o, pair2<T>& pa,
+                                  pair2<T>& pb, pair2<T>& F_out, int (&status)[2], int (&iters)[2]) {
+  static_assert(E >= 3, "needs at least three echoes");
+  typedef num<T> nm;
+  typedef pair2<T> V;
+  const unsigned lanes = DFIT_LANES();
+  (void)lanes;
+  V ysq = p2_mul<T>(Y[0], Y[0]);
+#pragma unroll
+  for (int e = 1; e < E; ++e) ysq = p2_fma<T>(Y[e], Y[e], ysq);
+  // weighted log-linear start: minimise sum w (log2 y^2 - alpha - beta x)^2, b0 = beta ln2 / 2
+  V S0 = p2_bcast<T>((T)0), S1 = S0, S2 = S0, T0 = S0, T1 = S0;
+  {
+    const V cut = p2_mul<T>(ysq, p2_bcast<T>((T)-0.004));
+    const V tiny = p2_bcast<T>(nm::tiny());
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+      const V y2 = p2_mul<T>(Y[e], Y[e]);
+      const V y2t = p2_add<T>(y2, tiny);
+#if defined(__CUDA_ARCH__)
+      V l;
+      if constexpr (sizeof(T) == 4) {
+        asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l.lo) : "f"(y2t.lo));
+        asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l.hi) : "f"(y2t.hi));
+      } else {
+        l = p2_make<T>(log2(y2t.lo), log2(y2t.hi));
+      }
+#else
+      const V l = p2_make<T>((T)log2((double)y2t.lo), (T)log2((double)y2t.hi));
+#endif
+      V w = p2_add<T>(y2, cut);
+      w = p2_make<T>(nm::max_(w.lo, (T)0), nm::max_(w.hi, (T)0));
+      const V xe = p2_bcast<T>(xt.x[e]), xxe = p2_bcast<T>(xt.xx[e]);
+      const V wl = p2_mul<T>(w, l);
+      S0 = p2_add<T>(S0, w);
+      S1 = p2_fma<T>(xe, w, S1);
+      S2 = p2_fma<T>(xxe, w, S2);
+      T0 = p2_add<T>(T0, wl);
+      T1 = p2_fma<T>(xe, wl, T1);
+    }
+  }
+  const V num_ = p2_fma<T>(S0, T1, p2_mul<T>(p2_mul<T>(S1, T0), p2_bcast<T>((T)-1)));
+  const V den_ = p2_fma<T>(S0, S2, p2_mul<T>(p2_mul<T>(S1, S1), p2_bcast<T>((T)-1)));
+  const V b0 = p2_mul<T>(p2_mul<T>(num_, p2_make<T>(nm::rcp_(den_.lo), nm::rcp_(den_.hi))), p2_bcast<T>((T)0.34657359027997264));
+  NewtonLane<T> A, B;
+  A.q = b0.lo;
+  B.q = b0.hi;
+  // |b x| <= 40 keeps every e_k^2 finite in fp32; den > 0 rules out a single surviving sample
+  const T blim = (T)(sizeof(T) == 4 ? 40.0 : 300.0) * xt.inv_xmax;
+  A.active = den_.lo > (T)0 && nm::abs_(A.q) < blim && nm::finite(ysq.lo) && ysq.lo > (T)0;
+  B.active = den_.hi > (T)0 && nm::abs_(B.q) < blim && nm::finite(ysq.hi) && ysq.hi > (T)0;
+  if (!A.active) A.q = (T)0;
+  if (!B.active) B.q = (T)0;
+  A.dprev2 = B.dprev2 = A.qf = B.qf = A.af = B.af = (T)0;
+  A.done = B.done = false;
+  A.npass = B.npass = 0;
+  const V floor2 = p2_mul<T>(ysq, p2_bcast<T>((T)2 * o.floor_rel));
+  const V ftol2 = p2_bcast<T>((T)2 * o.ftol);
+  const T smax = xt.inv_xmax;  // largest step in b: exp(b x) changes by at most a factor e per pass
+#pragma unroll 1
+  for (int k = 0; k < kMonoFastPasses; ++k) {
+    if (!DFIT_ANY(lanes, A.active || B.active)) break;
+    const V b = p2_make<T>(A.q, B.q);
+    V N0 = p2_bcast<T>((T)0), N1 = N0, N2 = N0, D0 = N0, D1 = N0, D2 = N0;
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+      const V ex = p2_make<T>(nm::expbx(b.lo, xt.x[e], xt.xs[e]), nm::expbx(b.hi, xt.x[e], xt.xs[e]));
+      const V ye = p2_mul<T>(Y[e], ex), ee = p2_mul<T>(ex, ex);
+      const V xe = p2_bcast<T>(xt.x[e]), xxe = p2_bcast<T>(xt.xx[e]);
+      N0 = p2_add<T>(N0, ye);
+      N1 = p2_fma<T>(xe, ye, N1);
+      N2 = p2_fma<T>(xxe, ye, N2);
+      D0 = p2_add<T>(D0, ee);
+      D1 = p2_fma<T>(xe, ee, D1);
+      D2 = p2_fma<T>(xxe, ee, D2);
+    }
+    // N1 = dN/db, N2 = d2N/db2;  dD/db = 2 D1, d2D/db2 = 4 D2
+    const V nDb = p2_mul<T>(D1, p2_bcast<T>((T)-2));
+    const V rD = p2_make<T>(nm::rcp_(D0.lo), nm::rcp_(D0.hi));
+    const V a = p2_mul<T>(N0, rD);
+    const V w = p2_fma<T>(a, nDb, N1);
+    const V ap = p2_mul<T>(w, rD);
+    const V mg = p2_mul<T>(a, p2_add<T>(w, N1));
+    const V t2 = p2_fma<T>(N2, p2_bcast<T>((T)-2), p2_mul<T>(a, p2_mul<T>(D2, p2_bcast<T>((T)4))));
+    const V h = p2_fma<T>(a, t2, p2_mul<T>(p2_mul<T>(w, ap), p2_bcast<T>((T)-2)));
+    const V db = p2_mul<T>(mg, p2_make<T>(nm::rcp_(h.lo), nm::rcp_(h.hi)));
+    const V pred2 = p2_mul<T>(mg, db);
+    const V Fe = p2_fma<T>(p2_mul<T>(N0, p2_bcast<T>((T)-1)), a, ysq);
+    const V tol2 = p2_fma<T>(ftol2, p2_make<T>(nm::max_(Fe.lo, (T)0), nm::max_(Fe.hi, (T)0)), floor2);
+    newton_lane_step<T>(A, k, h.lo, pred2.lo, tol2.lo, db.lo, a.lo, ap.lo, -smax, smax);
+    newton_lane_step<T>(B, k, h.hi, pred2.hi, tol2.hi, db.hi, a.hi, ap.hi, -smax, smax);
+  }
+  iters[0] = A.npass;
+  iters[1] = B.npass;
+  const bool okA = A.done && nm::abs_(A.qf) < blim && nm::finite(A.af);
+  const bool okB = B.done && nm::abs_(B.qf) < blim && nm::finite(B.af);
+  const V bf = p2_make<T>(okA ? A.qf : (T)0, okB ? B.qf : (T)0);
+  const V af = p2_make<T>(okA ? A.af : (T)0, okB ? B.af : (T)0);
+  // cost at the returned point
+  const V naf = p2_mul<T>(af, p2_bcast<T>((T)-1));
+  V F = p2_bcast<T>((T)0);
+#pragma unroll
+  for (int e = 0; e < E; ++e) {
+    const V ex = p2_make<T>(nm::expbx(bf.lo, xt.x[e], xt.xs[e]), nm::expbx(bf.hi, xt.x[e], xt.xs[e]));
+    const V r = p2_fma<T>(naf, ex, Y[e]);
+    F = p2_fma<T>(r, r, F);
+  }
+  pa = af;
+  pb = bf;
   F_out = F;
   status[0] = okA ? (F.lo <= o.floor_rel * ysq.lo ? ST_EXACT : ST_CONV_F) : -1;
   status[1] = okB ? (F.hi <= o.floor_rel * ysq.hi ? ST_EXACT : ST_CONV_F) : -1;
@@ -1079,9 +1204,23 @@ template <class M, typename T, int EMAX, bool EXACT>
 DFIT_HD int fit_voxel_fast(const T (&y)[EMAX], const XTab<T, EMAX>& xt, const VoxelOpts<T>& vo, T (&p)[M::P], T& r2,
                            int& iters) {
   if constexpr (M::MONO && EXACT && EMAX >= 3) {
-    if (vo.fast != 0 && xt.uniform != 0 && vo.has_bounds == 0) {
+    if (vo.fast != 0 && vo.has_bounds == 0) {
       T F;
-      const int st = mono_uniform_newton<T, EMAX>(y, xt, vo.s, p, F, iters);
+      int st;
+      if (xt.uniform != 0) {
+        st = mono_uniform_newton<T, EMAX>(y, xt, vo.s, p, F, iters);
+      } else {  // the general solver is written for two voxels per lane: run it on the voxel twice
+        pair2<T> Y[EMAX], pa, pb, F2;
+#pragma unroll
+        for (int e = 0; e < EMAX; ++e) Y[e] = p2_bcast<T>(y[e]);
+        int st2[2], it2[2];
+        mono_general_newton2<T, EMAX>(Y, xt, vo.s, pa, pb, F2, st2, it2);
+        st = st2[0];
+        iters = it2[0];
+        p[0] = pa.lo;
+        p[1] = pb.lo;
+        F = F2.lo;
+      }
       if (st > 0) r2 = (T)1 - F * num<T>::rcp_(ss_total<T, EMAX>(y) + vo.r2_eps);  // fitting.py:1032-1035
       return st;
     }
@@ -1095,7 +1234,8 @@ DFIT_HD void fit_voxel_fast2(const pair2<T> (&Y)[EMAX], const XTab<T, EMAX>& xt,
                              pair2<T>& pb, pair2<T>& r2, int (&status)[2], int (&iters)[2]) {
   static_assert(M::MONO && EMAX >= 3, "mono-exponential model only");
   pair2<T> F;
-  mono_uniform_newton2<T, EMAX>(Y, xt, vo.s, pa, pb, F, status, iters);
+  if (xt.uniform != 0) mono_uniform_newton2<T, EMAX>(Y, xt, vo.s, pa, pb, F, status, iters);
+  else mono_general_newton2<T, EMAX>(Y, xt, vo.s, pa, pb, F, status, iters);
   const pair2<T> den = p2_add<T>(ss_total2<T, EMAX>(Y), p2_bcast<T>(vo.r2_eps));
   const pair2<T> nr = p2_make<T>(-num<T>::rcp_(den.lo), -num<T>::rcp_(den.hi));
   r2 = p2_fma<T>(F, nr, p2_bcast<T>((T)1));  // fitting.py:1032-1035

@@ -32,7 +32,7 @@ static void run(int E, int64_t N, const double* x, const double* y, const double
   // fast == 2: the two-voxels-per-lane variant of the fast path on consecutive voxel pairs (what
   // fit_kernel_mono2 runs), general path for the voxels it declines
   if constexpr (M::MONO && EXACT && EMAX >= 3 && sizeof(T) == sizeof(TA)) {
-    if (fast == 2 && xt.uniform && !vo.has_bounds) {
+    if (fast == 2 && !vo.has_bounds) {
       for (int64_t v = 0; v < N; v += 2) {
         const bool both = v + 1 < N;
         pair2<T> Y[EMAX], pa, pb, r2p;

@@ -332,16 +332,35 @@ def test_two_voxel_fast_kernels_agree_with_lm(D):
         same = (p[:, 1] - outs[0][0][:, 1]).abs() <= 1.001e-3  # one rounding step
         assert same.float().mean() > 0.999
         assert (r - outs[0][1]).abs().max() < 1e-5
-    # non-uniform echo spacing and y_bounds keep using the LM (and say so through identical results)
-    xn = np.array([10.0, 20.0, 40.0, 80.0])
-    yn = (1000 * torch.exp(-torch.tensor(xn, device="cuda", dtype=torch.float32)[:, None] / (
-        10 + 70 * torch.rand(5000, device="cuda", generator=g)))).contiguous()
-    o0, P = A.make_opts(D.monoexponential, p0=(1.0, -1 / 30), fast_path=0)
-    o1, _ = A.make_opts(D.monoexponential, p0=(1.0, -1 / 30))
-    pa_, ra_ = A.fit_device(o0, P, xn, yn)
-    pb_, rb_ = A.fit_device(o1, P, xn, yn)
+    # non-uniform echo times: the general (exp-based) fast path, dense and through a mask, against the LM
+    for xn in (np.array([10.0, 20.0, 40.0, 80.0]), np.array([0.0, 10.0, 12.847, 25.695, 40.0, 51.39, 80.0])):
+        n = 300_001
+        xg = torch.tensor(xn, device="cuda", dtype=torch.float32)[:, None]
+        yn = ((500 + 1000 * torch.rand(n, device="cuda", generator=g)) * torch.exp(
+            -xg / (10 + 70 * torch.rand(n, device="cuda", generator=g))) + 10 * torch.randn(len(xn), n, device="cuda", generator=g))
+        mask = torch.rand(n, device="cuda", generator=g) > 0.7
+        o0, P = A.make_opts(D.monoexponential, p0=(1.0, -1 / 30), fast_path=0)
+        o1, _ = A.make_opts(D.monoexponential, p0=(1.0, -1 / 30))
+        pa_, ra_ = A.fit_device(o0, P, xn, yn)
+        pb_, rb_ = A.fit_device(o1, P, xn, yn)
+        pm_, rm_ = A.fit_device(o1, P, xn, yn, mask=mask)
+        torch.cuda.synchronize()
+        assert _cabi.get_handle(0).stats()["n_fitted"] == int(mask.sum())
+        ok = ~torch.isnan(pa_[:, 0]) & ~torch.isnan(pb_[:, 0])
+        assert ok.float().mean() > 0.999
+        rel = (pb_[ok] - pa_[ok]).abs() / pa_[ok].abs()
+        assert rel.max() < 2e-3 and (rel > 1e-4).float().mean() < 1e-3 and (rb_[ok] - ra_[ok]).abs().max() < 1e-5
+        # the mask path runs the same per-voxel arithmetic: identical inside, NaN outside
+        assert torch.equal(pm_[mask].nan_to_num(-1), pb_[mask].nan_to_num(-1)) and torch.equal(rm_[mask], rb_[mask])
+        assert torch.isnan(pm_[~mask]).all()
+    # y_bounds keep the voxel-skipping rules with the LM: identical results with and without the fast path
+    xn = np.arange(1, 9) * 10.0
+    o0, P = A.make_opts(D.monoexponential, p0=(1.0, -1 / 30), fast_path=0, y_bounds=(0, 1400))
+    o1, _ = A.make_opts(D.monoexponential, p0=(1.0, -1 / 30), y_bounds=(0, 1400))
+    pa_, ra_ = A.fit_device(o0, P, xn, y)
+    pb_, rb_ = A.fit_device(o1, P, xn, y)
     torch.cuda.synchronize()
-    assert torch.equal(pa_, pb_) and torch.equal(ra_, rb_)
+    assert torch.equal(pa_.nan_to_num(-1), pb_.nan_to_num(-1)) and torch.equal(ra_, rb_)
 
 
 def test_scaling_and_permutation_properties(D):
