@@ -343,7 +343,7 @@ __global__ void __launch_bounds__(256) mask_compact_kernel(const __grid_constant
 }
 
 template <class M, typename T, int EMAX, bool EXACT, bool GATHER>
-__global__ void __launch_bounds__(kBlock, EMAX <= 8 ? 8 : 1) fit_kernel(const __grid_constant__ KernelArgs<T, EMAX> a) {
+__global__ void __launch_bounds__(kBlock, sizeof(T) == 4 ? (EMAX <= 8 ? 8 : 3) : (EMAX <= 8 ? 4 : 1)) fit_kernel(const __grid_constant__ KernelArgs<T, EMAX> a) {
   constexpr int P = M::P;
   int st = -1, iters = 0;
   unsigned flags = 0;

@@ -1195,7 +1195,20 @@ struct VoxelOpts {
   int fast;       // 1: try the variable-projection Newton fast path first (mono-exponential only)
 };
 
-// Fast-path attempt for one voxel (mono-exponential model, uniform echo spacing, no y_bounds).  Returns a
+// Fast-path attempt for two voxels: status[i] = -1 where voxel i has to take the general path.
+template <class M, typename T, int EMAX>
+DFIT_HD void fit_voxel_fast2(const pair2<T> (&Y)[EMAX], const XTab<T, EMAX>& xt, const VoxelOpts<T>& vo, pair2<T>& pa,
+                             pair2<T>& pb, pair2<T>& r2, int (&status)[2], int (&iters)[2]) {
+  static_assert(M::MONO && EMAX >= 3, "mono-exponential model only");
+  pair2<T> F;
+  if (xt.uniform != 0) mono_uniform_newton2<T, EMAX>(Y, xt, vo.s, pa, pb, F, status, iters);
+  else mono_general_newton2<T, EMAX>(Y, xt, vo.s, pa, pb, F, status, iters);
+  const pair2<T> den = p2_add<T>(ss_total2<T, EMAX>(Y), p2_bcast<T>(vo.r2_eps));
+  const pair2<T> nr = p2_make<T>(-num<T>::rcp_(den.lo), -num<T>::rcp_(den.hi));
+  r2 = p2_fma<T>(F, nr, p2_bcast<T>((T)1));  // fitting.py:1032-1035
+}
+
+// Fast-path attempt for one voxel (mono-exponential model, no y_bounds).  Returns a
 // successful Status with p / r2 / iters filled in, or -1: the caller then loads the initial guess and runs
 // fit_voxel.  The path declines on anything unusual -- zero, non-finite or non-decaying-looking voxels
 // included -- so the skip / failure rules of fitting.py:1065-1073 stay with the general path.
@@ -1210,35 +1223,22 @@ DFIT_HD int fit_voxel_fast(const T (&y)[EMAX], const XTab<T, EMAX>& xt, const Vo
       if (xt.uniform != 0) {
         st = mono_uniform_newton<T, EMAX>(y, xt, vo.s, p, F, iters);
       } else {  // the general solver is written for two voxels per lane: run it on the voxel twice
-        pair2<T> Y[EMAX], pa, pb, F2;
+        pair2<T> Y[EMAX], pa, pb, r2p;
 #pragma unroll
         for (int e = 0; e < EMAX; ++e) Y[e] = p2_bcast<T>(y[e]);
         int st2[2], it2[2];
-        mono_general_newton2<T, EMAX>(Y, xt, vo.s, pa, pb, F2, st2, it2);
-        st = st2[0];
+        fit_voxel_fast2<M, T, EMAX>(Y, xt, vo, pa, pb, r2p, st2, it2);
         iters = it2[0];
         p[0] = pa.lo;
         p[1] = pb.lo;
-        F = F2.lo;
+        r2 = r2p.lo;
+        return st2[0];
       }
       if (st > 0) r2 = (T)1 - F * num<T>::rcp_(ss_total<T, EMAX>(y) + vo.r2_eps);  // fitting.py:1032-1035
       return st;
     }
   }
   return -1;
-}
-
-// Fast-path attempt for two voxels: status[i] = -1 where voxel i has to take the general path.
-template <class M, typename T, int EMAX>
-DFIT_HD void fit_voxel_fast2(const pair2<T> (&Y)[EMAX], const XTab<T, EMAX>& xt, const VoxelOpts<T>& vo, pair2<T>& pa,
-                             pair2<T>& pb, pair2<T>& r2, int (&status)[2], int (&iters)[2]) {
-  static_assert(M::MONO && EMAX >= 3, "mono-exponential model only");
-  pair2<T> F;
-  if (xt.uniform != 0) mono_uniform_newton2<T, EMAX>(Y, xt, vo.s, pa, pb, F, status, iters);
-  else mono_general_newton2<T, EMAX>(Y, xt, vo.s, pa, pb, F, status, iters);
-  const pair2<T> den = p2_add<T>(ss_total2<T, EMAX>(Y), p2_bcast<T>(vo.r2_eps));
-  const pair2<T> nr = p2_make<T>(-num<T>::rcp_(den.lo), -num<T>::rcp_(den.hi));
-  r2 = p2_fma<T>(F, nr, p2_bcast<T>((T)1));  // fitting.py:1032-1035
 }
 
 // Everything the reference does for one voxel (`_curve_fit`, fitting.py:1026-1073), on samples that

@@ -252,13 +252,24 @@ def test_tma_staged_variant_is_bitwise_identical(D):
             -xt / (10 + 70 * torch.rand(n, device="cuda", generator=g))) + 10 * torch.randn(8, n, device="cuda", generator=g)
         mask = torch.rand(n, device="cuda", generator=g) > 0.3
         for init in ("given", "loglinear"):
-            o0, P = A.make_opts(D.monoexponential, p0=(1.0, -1 / 30), init=init, use_tma=0)
-            o1, _ = A.make_opts(D.monoexponential, p0=(1.0, -1 / 30), init=init, use_tma=1)
+            # the LM (fast_path=0) is the same code in both kernels: bit-identical
+            o0, P = A.make_opts(D.monoexponential, p0=(1.0, -1 / 30), init=init, use_tma=0, fast_path=0)
+            o1, _ = A.make_opts(D.monoexponential, p0=(1.0, -1 / 30), init=init, use_tma=1, fast_path=0)
             p0_, r0_ = A.fit_device(o0, P, x, y, mask=mask)
             p1_, r1_ = A.fit_device(o1, P, x, y, mask=mask)
             torch.cuda.synchronize()
             assert torch.equal(p0_.nan_to_num(-1), p1_.nan_to_num(-1))
             assert torch.equal(r0_.nan_to_num(-1), r1_.nan_to_num(-1))
+            # with the fast path the masked voxels go through the two-voxel list kernel (use_tma=0) or the
+            # one-voxel TMA kernel (use_tma=1): same iteration, different packing -> equal to rounding
+            o0, P = A.make_opts(D.monoexponential, p0=(1.0, -1 / 30), init=init, use_tma=0)
+            o1, _ = A.make_opts(D.monoexponential, p0=(1.0, -1 / 30), init=init, use_tma=1)
+            p0_, r0_ = A.fit_device(o0, P, x, y, mask=mask)
+            p1_, r1_ = A.fit_device(o1, P, x, y, mask=mask)
+            torch.cuda.synchronize()
+            assert torch.equal(torch.isnan(p0_), torch.isnan(p1_))
+            assert ((p0_ - p1_).abs() / p1_.abs()).nan_to_num(0).max() < 1e-5
+            assert (r0_ - r1_).abs().nan_to_num(0).max() < 1e-6
     # ineligible inputs must be refused loudly, not silently rerouted
     o1, P = A.make_opts(D.monoexponential, p0=(1.0, -1 / 30), use_tma=1)
     with pytest.raises(Exception):
@@ -334,25 +345,25 @@ def test_two_voxel_fast_kernels_agree_with_lm(D):
         assert (r - outs[0][1]).abs().max() < 1e-5
     # non-uniform echo times: the general (exp-based) fast path, dense and through a mask, against the LM
     for xn in (np.array([10.0, 20.0, 40.0, 80.0]), np.array([0.0, 10.0, 12.847, 25.695, 40.0, 51.39, 80.0])):
-        n = 300_001
-        xg = torch.tensor(xn, device="cuda", dtype=torch.float32)[:, None]
-        yn = ((500 + 1000 * torch.rand(n, device="cuda", generator=g)) * torch.exp(
-            -xg / (10 + 70 * torch.rand(n, device="cuda", generator=g))) + 10 * torch.randn(len(xn), n, device="cuda", generator=g))
-        mask = torch.rand(n, device="cuda", generator=g) > 0.7
-        o0, P = A.make_opts(D.monoexponential, p0=(1.0, -1 / 30), fast_path=0)
-        o1, _ = A.make_opts(D.monoexponential, p0=(1.0, -1 / 30))
-        pa_, ra_ = A.fit_device(o0, P, xn, yn)
-        pb_, rb_ = A.fit_device(o1, P, xn, yn)
-        pm_, rm_ = A.fit_device(o1, P, xn, yn, mask=mask)
-        torch.cuda.synchronize()
-        assert _cabi.get_handle(0).stats()["n_fitted"] == int(mask.sum())
-        ok = ~torch.isnan(pa_[:, 0]) & ~torch.isnan(pb_[:, 0])
-        assert ok.float().mean() > 0.999
-        rel = (pb_[ok] - pa_[ok]).abs() / pa_[ok].abs()
-        assert rel.max() < 2e-3 and (rel > 1e-4).float().mean() < 1e-3 and (rb_[ok] - ra_[ok]).abs().max() < 1e-5
-        # the mask path runs the same per-voxel arithmetic: identical inside, NaN outside
-        assert torch.equal(pm_[mask].nan_to_num(-1), pb_[mask].nan_to_num(-1)) and torch.equal(rm_[mask], rb_[mask])
-        assert torch.isnan(pm_[~mask]).all()
+        for n in (300_001, 300_032):  # odd: one-voxel kernel (no pair loads); multiple of 4: TMA two-voxel kernel
+            xg = torch.tensor(xn, device="cuda", dtype=torch.float32)[:, None]
+            yn = ((500 + 1000 * torch.rand(n, device="cuda", generator=g)) * torch.exp(
+                -xg / (10 + 70 * torch.rand(n, device="cuda", generator=g))) + 10 * torch.randn(len(xn), n, device="cuda", generator=g))
+            mask = torch.rand(n, device="cuda", generator=g) > 0.7
+            o0, P = A.make_opts(D.monoexponential, p0=(1.0, -1 / 30), fast_path=0)
+            o1, _ = A.make_opts(D.monoexponential, p0=(1.0, -1 / 30))
+            pa_, ra_ = A.fit_device(o0, P, xn, yn)
+            pb_, rb_ = A.fit_device(o1, P, xn, yn)
+            pm_, rm_ = A.fit_device(o1, P, xn, yn, mask=mask)
+            torch.cuda.synchronize()
+            assert _cabi.get_handle(0).stats()["n_fitted"] == int(mask.sum())
+            ok = ~torch.isnan(pa_[:, 0]) & ~torch.isnan(pb_[:, 0])
+            assert ok.float().mean() > 0.999
+            rel = (pb_[ok] - pa_[ok]).abs() / pa_[ok].abs()
+            assert rel.max() < 2e-3 and (rel > 1e-4).float().mean() < 1e-3 and (rb_[ok] - ra_[ok]).abs().max() < 1e-5
+            # the mask path runs the same per-voxel arithmetic: identical inside, NaN outside
+            assert torch.equal(pm_[mask].nan_to_num(-1), pb_[mask].nan_to_num(-1)) and torch.equal(rm_[mask], rb_[mask])
+            assert torch.isnan(pm_[~mask]).all()
     # y_bounds keep the voxel-skipping rules with the LM: identical results with and without the fast path
     xn = np.arange(1, 9) * 10.0
     o0, P = A.make_opts(D.monoexponential, p0=(1.0, -1 / 30), fast_path=0, y_bounds=(0, 1400))
