@@ -131,6 +131,7 @@ void make_desc(const dfit_opts* o, int n_echo, int64_t n_vox, const double* x, L
     d.po.ub[i] = o->ub[i];
     d.po.decimals[i] = o->decimals[i];
   }
+  set_post_scales(d.po);
   d.po.has_r2_thresh = o->has_r2_threshold;
   d.po.r2_thresh = o->r2_threshold;
   d.po.has_fill = o->has_nan_fill;

@@ -175,10 +175,7 @@ __device__ __forceinline__ void store_voxel(const KernelArgs<T, EMAX>& a, int64_
 #pragma unroll
     for (int i = 0; i < P; ++i) {
       q[i] = a.mask_fill;
-      if (a.po.enabled && a.po.decimals[i] >= 0) {
-        const double s = pow10i(a.po.decimals[i]);
-        q[i] = rint(q[i] * s) / s;
-      }
+      if (a.po.enabled && a.po.decimals[i] >= 0) q[i] = div_pow10(rint(q[i] * a.po.scale[i]), a.po.scale[i], a.po.inv_scale[i]);
     }
   }
   if (a.popt != nullptr) {

@@ -123,6 +123,7 @@ extern "C" double hostsim_post_param(int enabled, const int* ufunc, const double
     po.ub[k] = ub[k];
     po.decimals[k] = decimals[k];
   }
+  set_post_scales(po);
   po.has_r2_thresh = has_thr;
   po.r2_thresh = thr;
   po.has_fill = has_fill;
