@@ -731,6 +731,7 @@ inline void fill_xtab(XTab<T, EMAX>& xt, const double* x, int n_echo) {
 // Returns a Status (ST_CONV_F / ST_EXACT) or -1 when the path declines (no admissible start, curvature
 // not positive, not converged in kMonoFastPasses, non-finite data): the caller then runs the general path.
 constexpr int kMonoFastPasses = 6;
+constexpr float kFirstStepCap = 0.2f;  // largest relative first Newton step in q the fast path accepts
 
 // Expected error after the step about to be taken, relative to that step.  Newton's iteration contracts
 // quadratically, e_k+1 = C e_k^2, and the last two steps estimate C = |dq_k| / dq_k-1^2, so the error left
@@ -765,7 +766,8 @@ DFIT_HD int mono_uniform_newton(const T (&y)[E], const XTab<T, E>& xt, const Sol
 #pragma unroll
   for (int k = 1; k + 1 < E; ++k) nd = p2_fma<T>(p2_bcast<T>(y[k]), p2_make<T>(y[k + 1], y[k]), nd);
   const T ysq = nm::fma_(y[E - 1], y[E - 1], nd.hi);
-  T q = nd.lo * nm::rcp_(nd.hi);
+  const T pdb = nm::fma_(-y[0], y[0], ysq);  // growing sequences are predicted backwards (see mono_uniform_newton2)
+  T q = pdb > nd.hi ? pdb * nm::rcp_(nd.lo) : nd.lo * nm::rcp_(nd.hi);
   // no admissible start (also catches NaN and all-zero voxels): this lane declines, but keeps in step
   bool active = q > xt.q_lo && q < xt.q_hi && nm::finite(ysq);
   if (!active) q = (T)0.5;
@@ -808,7 +810,7 @@ DFIT_HD int mono_uniform_newton(const T (&y)[E], const XTab<T, E>& xt, const Sol
     const T step2 = dq * dq;
     const T kappa = k == 0 ? (T)1 : newton_contraction<T>(step2, dprev2);
     // h > 0: inside the convex basin (false for NaN as well); otherwise the lane declines
-    const bool convex = h > (T)0;
+    const bool convex = h > (T)0 && (k != 0 || step2 <= (T)(kFirstStepCap * kFirstStepCap) * q * q);  // see newton_lane_step
     const bool conv = convex && (pred * kappa) * kappa <= nm::fma_(o.ftol, Fest, floorF);
     dq = nm::min_(nm::max_(dq, (T)-0.5 * q), q);  // keep q positive whatever happens
     if (active) {
@@ -896,11 +898,15 @@ struct NewtonLane {
 };
 
 template <typename T>
-DFIT_HD void newton_lane_step(NewtonLane<T>& L, int k, T h, T pred2, T tol2, T dq, T a, T ap, T step_lo, T step_hi) {
+DFIT_HD void newton_lane_step(NewtonLane<T>& L, int k, T h, T pred2, T tol2, T dq, T a, T ap, T step_lo, T step_hi,
+                              T first_cap) {
   typedef num<T> nm;
   const T step2 = dq * dq;
   const T kappa = k == 0 ? (T)1 : newton_contraction<T>(step2, L.dprev2);
-  const bool convex = h > (T)0;  // false for NaN as well
+  // h > 0: inside the convex basin (false for NaN as well).  A first step beyond first_cap says the
+  // data-driven start is not near a minimum (low-SNR voxels with several local minima): decline, so that
+  // the LM decides from the caller's p0 like the reference does.
+  const bool convex = h > (T)0 && (k != 0 || step2 <= first_cap * first_cap);
   const bool conv = convex && (pred2 * kappa) * kappa <= tol2;
   dq = nm::min_(nm::max_(dq, step_lo), step_hi);  // trust clamp (keeps q positive / b x bounded)
   if (L.active) {
@@ -937,10 +943,12 @@ DFIT_HD void mono_uniform_newton2(const pair2<T> (&Y)[E], const XTab<T, E>& xt, 
     pd = p2_fma<T>(Y[k], Y[k], pd);
   }
   const V ysq = p2_fma<T>(Y[E - 1], Y[E - 1], pd);
-  const V q0 = p2_mul<T>(pn, p2_make<T>(nm::rcp_(pd.lo), nm::rcp_(pd.hi)));
+  // a sequence that grows with the echo index (descending echo times, b > 0) is predicted backwards,
+  // q0 = sum y_k+1^2 / sum y_k y_k+1, so that the large samples carry the estimate either way
+  const V pdb = p2_fma<T>(p2_mul<T>(Y[0], p2_bcast<T>((T)-1)), Y[0], ysq);
   NewtonLane<T> A, B;
-  A.q = q0.lo;
-  B.q = q0.hi;
+  A.q = pdb.lo > pd.lo ? pdb.lo * nm::rcp_(pn.lo) : pn.lo * nm::rcp_(pd.lo);
+  B.q = pdb.hi > pd.hi ? pdb.hi * nm::rcp_(pn.hi) : pn.hi * nm::rcp_(pd.hi);
   A.active = A.q > xt.q_lo && A.q < xt.q_hi && nm::finite(ysq.lo);
   B.active = B.q > xt.q_lo && B.q < xt.q_hi && nm::finite(ysq.hi);
   if (!A.active) A.q = (T)0.5;
@@ -990,8 +998,8 @@ DFIT_HD void mono_uniform_newton2(const pair2<T> (&Y)[E], const XTab<T, E>& xt, 
     // projected cost estimate sum y^2 - N a (clamped at 0 per voxel below) -> tolerance
     const V Fe = p2_fma<T>(p2_mul<T>(N0, p2_bcast<T>((T)-1)), a, ysq);
     const V tol2 = p2_fma<T>(ftol2, p2_make<T>(nm::max_(Fe.lo, (T)0), nm::max_(Fe.hi, (T)0)), floor2);
-    newton_lane_step<T>(A, k, h.lo, pred2.lo, tol2.lo, dq.lo, a.lo, ap.lo, (T)-0.5 * A.q, A.q);
-    newton_lane_step<T>(B, k, h.hi, pred2.hi, tol2.hi, dq.hi, a.hi, ap.hi, (T)-0.5 * B.q, B.q);
+    newton_lane_step<T>(A, k, h.lo, pred2.lo, tol2.lo, dq.lo, a.lo, ap.lo, (T)-0.5 * A.q, A.q, kFirstStepCap * A.q);
+    newton_lane_step<T>(B, k, h.hi, pred2.hi, tol2.hi, dq.hi, a.hi, ap.hi, (T)-0.5 * B.q, B.q, kFirstStepCap * B.q);
   }
   iters[0] = A.npass;
   iters[1] = B.npass;
@@ -1089,6 +1097,7 @@ DFIT_HD void mono_general_newton2(const pair2<T> (&Y)[E], const XTab<T, E>& xt, 
   const V floor2 = p2_mul<T>(ysq, p2_bcast<T>((T)2 * o.floor_rel));
   const V ftol2 = p2_bcast<T>((T)2 * o.ftol);
   const T smax = xt.inv_xmax;  // largest step in b: exp(b x) changes by at most a factor e per pass
+  const T bcap = (T)kFirstStepCap * (T)(E - 1) * xt.inv_xmax;  // the same first-step gate per mean echo spacing
 #pragma unroll 1
   for (int k = 0; k < kMonoFastPasses; ++k) {
     if (!DFIT_ANY(lanes, A.active || B.active)) break;
@@ -1119,8 +1128,8 @@ DFIT_HD void mono_general_newton2(const pair2<T> (&Y)[E], const XTab<T, E>& xt, 
     const V pred2 = p2_mul<T>(mg, db);
     const V Fe = p2_fma<T>(p2_mul<T>(N0, p2_bcast<T>((T)-1)), a, ysq);
     const V tol2 = p2_fma<T>(ftol2, p2_make<T>(nm::max_(Fe.lo, (T)0), nm::max_(Fe.hi, (T)0)), floor2);
-    newton_lane_step<T>(A, k, h.lo, pred2.lo, tol2.lo, db.lo, a.lo, ap.lo, -smax, smax);
-    newton_lane_step<T>(B, k, h.hi, pred2.hi, tol2.hi, db.hi, a.hi, ap.hi, -smax, smax);
+    newton_lane_step<T>(A, k, h.lo, pred2.lo, tol2.lo, db.lo, a.lo, ap.lo, -smax, smax, bcap);
+    newton_lane_step<T>(B, k, h.hi, pred2.hi, tol2.hi, db.hi, a.hi, ap.hi, -smax, smax, bcap);
   }
   iters[0] = A.npass;
   iters[1] = B.npass;

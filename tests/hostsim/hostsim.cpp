@@ -93,7 +93,9 @@ extern "C" int hostsim_fit(int model, int dtype, int acc64, int E, int64_t N, co
 #define ARGS E, N, x, y, p0, n_p0, init_mode, init_linear, fast, ftol, xtol, lambda0, floor_rel, max_iter, r2_eps, y_lo, y_hi, popt, r2, status, iters
 #define RUN_E(M, T, TA)                                                                     \
   switch (E) {                                                                                \
-    case 4: if (4 >= M::P) { run<M, T, TA, 4, true>(ARGS); break; }                           \
+    case 3: if (E == 3 && 3 >= M::P) { run<M, T, TA, 3, true>(ARGS); break; }                 \
+    case 4: if (E == 4 && 4 >= M::P) { run<M, T, TA, 4, true>(ARGS); break; }                 \
+    case 5: if (E == 5 && 5 >= M::P) { run<M, T, TA, 5, true>(ARGS); break; }                 \
     case 7: if (E == 7 && 7 >= M::P) { run<M, T, TA, 7, true>(ARGS); break; }                 \
     case 8: if (E == 8) { run<M, T, TA, 8, true>(ARGS); break; }                              \
     case 16: if (E == 16) { run<M, T, TA, 16, true>(ARGS); break; }                           \
