@@ -468,7 +468,7 @@ __global__ void __launch_bounds__(kBlock2, 5) fit_kernel_mono2(const __grid_cons
     if (a.y_dtype == DT_F32) load_pairs<float, EMAX>(a.y, a.ld, v0, both, Y);
     else if (a.y_dtype == DT_I16) load_pairs<short, EMAX>(a.y, a.ld, v0, both, Y);
     else load_pairs<unsigned short, EMAX>(a.y, a.ld, v0, both, Y);
-    fit_voxel_fast2<M, T, EMAX>(Y, a.xt, a.vo, pa, pb, r2, st, iters);
+    fit_voxel_fast2<M, T, EMAX, pair2<T>[EMAX]>(Y, a.xt, a.vo, pa, pb, r2, st, iters);
     if (st[0] < 0 || st[1] < 0) {  // the general path, one voxel at a time
 #pragma unroll 1
       for (int hsel = 0; hsel < 2; ++hsel) {
@@ -534,7 +534,7 @@ __global__ void __launch_bounds__(kBlock, 5) fit_kernel_mono2_list(const __grid_
 #pragma unroll
     for (int e = 0; e < EMAX; ++e) Y[e] = p2_make<T>(yA[e], yB[e]);
     int st[2], iters[2];
-    fit_voxel_fast2<M, T, EMAX>(Y, a.xt, a.vo, pa, pb, r2, st, iters);
+    fit_voxel_fast2<M, T, EMAX, pair2<T>[EMAX]>(Y, a.xt, a.vo, pa, pb, r2, st, iters);
     if (st[0] < 0 || (st[1] < 0 && both)) {
 #pragma unroll 1
       for (int hsel = 0; hsel < 2; ++hsel) {
@@ -717,7 +717,9 @@ constexpr int kM2Tile = 64;
 constexpr int m2_stages(int E) { return E <= 8 ? 4 : 2; }  // 32 KB of tiles per CTA
 
 template <class M, int EMAX>
-__global__ void __launch_bounds__(kM2Warps * 32, 5)  // 5 CTAs/SM: 6 spills, 4 is slower (measured: 0.743 / 0.689 / 0.696 ms)
+__global__ void __launch_bounds__(kM2Warps * 32, 5)  // 5 CTAs/SM: 6 spills, 4 is slower (measured: 0.743 / 0.689 / 0.696 ms);
+                                                     // reading the samples from the tile on every use to free 16 registers
+                                                     // (6-7 CTAs/SM) was measured too: 3 % slower
     fit_kernel_mono2_tma(const __grid_constant__ KernelArgs<float, EMAX> a, const __grid_constant__ CUtensorMap tmap) {
   typedef float T;
   constexpr int P = 2;
@@ -771,7 +773,7 @@ __global__ void __launch_bounds__(kM2Warps * 32, 5)  // 5 CTAs/SM: 6 spills, 4 i
     const int v0 = t * kM2Tile + 2 * lane;
     const bool validA = v0 < n_vox, validB = v0 + 1 < n_vox;
     int st[2], iters[2];
-    fit_voxel_fast2<M, T, EMAX>(Y, a.xt, a.vo, pa, pb, r2, st, iters);  // voxels past the end are zero-filled: declined
+    fit_voxel_fast2<M, T, EMAX, pair2<T>[EMAX]>(Y, a.xt, a.vo, pa, pb, r2, st, iters);  // voxels past the end are zero-filled: declined
     if ((st[0] < 0 && validA) || (st[1] < 0 && validB)) {  // the general path, one voxel at a time
 #pragma unroll 1
       for (int hsel = 0; hsel < 2; ++hsel) {

@@ -767,7 +767,7 @@ DFIT_HD int mono_uniform_newton(const T (&y)[E], const XTab<T, E>& xt, const Sol
   for (int k = 1; k + 1 < E; ++k) nd = p2_fma<T>(p2_bcast<T>(y[k]), p2_make<T>(y[k + 1], y[k]), nd);
   const T ysq = nm::fma_(y[E - 1], y[E - 1], nd.hi);
   const T pdb = nm::fma_(-y[0], y[0], ysq);  // growing sequences are predicted backwards (see mono_uniform_newton2)
-  T q = pdb > nd.hi ? pdb * nm::rcp_(nd.lo) : nd.lo * nm::rcp_(nd.hi);
+  T q = (pdb > nd.hi ? pdb : nd.lo) * nm::rcp_(pdb > nd.hi ? nd.lo : nd.hi);
   // no admissible start (also catches NaN and all-zero voxels): this lane declines, but keeps in step
   bool active = q > xt.q_lo && q < xt.q_hi && nm::finite(ysq);
   if (!active) q = (T)0.5;
@@ -889,6 +889,11 @@ __device__ __forceinline__ pair2<float> p2_log_pos<float>(pair2<float> v) {
 }
 #endif
 
+template <bool B>
+struct FirstPass {
+  static constexpr bool value = B;
+};
+
 // Per-voxel (non-packable) part of one Newton pass: convergence test, step clamp, state update.
 template <typename T>
 struct NewtonLane {
@@ -897,16 +902,21 @@ struct NewtonLane {
   int npass;
 };
 
-template <typename T>
+template <bool FIRST, typename T>
 DFIT_HD void newton_lane_step(NewtonLane<T>& L, int k, T h, T pred2, T tol2, T dq, T a, T ap, T step_lo, T step_hi,
                               T first_cap) {
   typedef num<T> nm;
   const T step2 = dq * dq;
-  const T kappa = k == 0 ? (T)1 : newton_contraction<T>(step2, L.dprev2);
-  // h > 0: inside the convex basin (false for NaN as well).  A first step beyond first_cap says the
-  // data-driven start is not near a minimum (low-SNR voxels with several local minima): decline, so that
-  // the LM decides from the caller's p0 like the reference does.
-  const bool convex = h > (T)0 && (k != 0 || step2 <= first_cap * first_cap);
+  T kappa = (T)1;
+  // h > 0: inside the convex basin (false for NaN as well).
+  bool convex = h > (T)0;
+  if constexpr (FIRST) {
+    // A first step beyond first_cap says the data-driven start is not near a minimum (low-SNR voxels with
+    // several local minima): decline, so that the LM decides from the caller's p0 like the reference does.
+    convex = convex && step2 <= first_cap * first_cap;
+  } else {
+    kappa = newton_contraction<T>(step2, L.dprev2);
+  }
   const bool conv = convex && (pred2 * kappa) * kappa <= tol2;
   dq = nm::min_(nm::max_(dq, step_lo), step_hi);  // trust clamp (keeps q positive / b x bounded)
   if (L.active) {
@@ -924,10 +934,12 @@ DFIT_HD void newton_lane_step(NewtonLane<T>& L, int k, T h, T pred2, T tol2, T d
   }
 }
 
-// Y[e] = (sample e of voxel A, sample e of voxel B).  Outputs per voxel: status (-1 = declined), passes,
+// Y[e] = (sample e of voxel A, sample e of voxel B); Y is an array of pair2<T> or any object whose operator[]
+// returns one (the TMA kernel reads the samples from its shared-memory tile on every use instead of holding
+// them in 2 E registers).  Outputs per voxel: status (-1 = declined), passes,
 // a, b, cost F at the returned point and sum of squares about the mean.
-template <typename T, int E>
-DFIT_HD void mono_uniform_newton2(const pair2<T> (&Y)[E], const XTab<T, E>& xt, const SolverOpts<T>& o, pair2<T>& pa,
+template <typename T, int E, class YS>
+DFIT_HD void mono_uniform_newton2(const YS& Y, const XTab<T, E>& xt, const SolverOpts<T>& o, pair2<T>& pa,
                                   pair2<T>& pb, pair2<T>& F_out, int (&status)[2], int (&iters)[2]) {
   static_assert(E >= 3, "needs at least three echoes");
   typedef num<T> nm;
@@ -947,8 +959,11 @@ DFIT_HD void mono_uniform_newton2(const pair2<T> (&Y)[E], const XTab<T, E>& xt, 
   // q0 = sum y_k+1^2 / sum y_k y_k+1, so that the large samples carry the estimate either way
   const V pdb = p2_fma<T>(p2_mul<T>(Y[0], p2_bcast<T>((T)-1)), Y[0], ysq);
   NewtonLane<T> A, B;
-  A.q = pdb.lo > pd.lo ? pdb.lo * nm::rcp_(pn.lo) : pn.lo * nm::rcp_(pd.lo);
-  B.q = pdb.hi > pd.hi ? pdb.hi * nm::rcp_(pn.hi) : pn.hi * nm::rcp_(pd.hi);
+  {
+    const bool ga = pdb.lo > pd.lo, gb = pdb.hi > pd.hi;
+    A.q = (ga ? pdb.lo : pn.lo) * nm::rcp_(ga ? pn.lo : pd.lo);
+    B.q = (gb ? pdb.hi : pn.hi) * nm::rcp_(gb ? pn.hi : pd.hi);
+  }
   A.active = A.q > xt.q_lo && A.q < xt.q_hi && nm::finite(ysq.lo);
   B.active = B.q > xt.q_lo && B.q < xt.q_hi && nm::finite(ysq.hi);
   if (!A.active) A.q = (T)0.5;
@@ -959,9 +974,9 @@ DFIT_HD void mono_uniform_newton2(const pair2<T> (&Y)[E], const XTab<T, E>& xt, 
   // tolerance on twice the Newton decrement: 2 (ftol F + floor_rel sum y^2)
   const V floor2 = p2_mul<T>(ysq, p2_bcast<T>((T)2 * o.floor_rel));
   const V ftol2 = p2_bcast<T>((T)2 * o.ftol);
-#pragma unroll 1
-  for (int k = 0; k < kMonoFastPasses; ++k) {
-    if (!DFIT_ANY(lanes, A.active || B.active)) break;
+  // one pass; the first one is a separate instance (first-step gate, no contraction estimate yet)
+  auto pass = [&](auto first_tag, int k) {
+    constexpr bool FIRST = decltype(first_tag)::value;
     const V q = p2_make<T>(A.q, B.q);
     const V s = p2_mul<T>(q, q);
     // Horner with first and (half) second derivative: N(q) over the samples, D(s) over ones
@@ -998,8 +1013,14 @@ DFIT_HD void mono_uniform_newton2(const pair2<T> (&Y)[E], const XTab<T, E>& xt, 
     // projected cost estimate sum y^2 - N a (clamped at 0 per voxel below) -> tolerance
     const V Fe = p2_fma<T>(p2_mul<T>(N0, p2_bcast<T>((T)-1)), a, ysq);
     const V tol2 = p2_fma<T>(ftol2, p2_make<T>(nm::max_(Fe.lo, (T)0), nm::max_(Fe.hi, (T)0)), floor2);
-    newton_lane_step<T>(A, k, h.lo, pred2.lo, tol2.lo, dq.lo, a.lo, ap.lo, (T)-0.5 * A.q, A.q, kFirstStepCap * A.q);
-    newton_lane_step<T>(B, k, h.hi, pred2.hi, tol2.hi, dq.hi, a.hi, ap.hi, (T)-0.5 * B.q, B.q, kFirstStepCap * B.q);
+    newton_lane_step<FIRST, T>(A, k, h.lo, pred2.lo, tol2.lo, dq.lo, a.lo, ap.lo, (T)-0.5 * A.q, A.q, kFirstStepCap * A.q);
+    newton_lane_step<FIRST, T>(B, k, h.hi, pred2.hi, tol2.hi, dq.hi, a.hi, ap.hi, (T)-0.5 * B.q, B.q, kFirstStepCap * B.q);
+  };
+  if (DFIT_ANY(lanes, A.active || B.active)) pass(FirstPass<true>(), 0);
+#pragma unroll 1
+  for (int k = 1; k < kMonoFastPasses; ++k) {
+    if (!DFIT_ANY(lanes, A.active || B.active)) break;
+    pass(FirstPass<false>(), k);
   }
   iters[0] = A.npass;
   iters[1] = B.npass;
@@ -1037,8 +1058,8 @@ DFIT_HD void mono_uniform_newton2(const pair2<T> (&Y)[E], const XTab<T, E>& xt, 
 // their b-derivatives carry one and two factors of x_k.  One ex2 per sample and pass instead of none, so a
 // pass costs about 1.5x the uniform one.  The start is a weighted log-linear fit (weights max(y^2 - c sum
 // y^2, 0): samples near the noise floor drop out, no sign tests), two voxels per lane like above.
-template <typename T, int E>
-DFIT_HD void mono_general_newton2(const pair2<T> (&Y)[E], const XTab<T, E>& xt, const SolverOpts<T>& o, pair2<T>& pa,
+template <typename T, int E, class YS>
+DFIT_HD void mono_general_newton2(const YS& Y, const XTab<T, E>& xt, const SolverOpts<T>& o, pair2<T>& pa,
                                   pair2<T>& pb, pair2<T>& F_out, int (&status)[2], int (&iters)[2]) {
   static_assert(E >= 3, "needs at least three echoes");
   typedef num<T> nm;
@@ -1098,9 +1119,8 @@ DFIT_HD void mono_general_newton2(const pair2<T> (&Y)[E], const XTab<T, E>& xt, 
   const V ftol2 = p2_bcast<T>((T)2 * o.ftol);
   const T smax = xt.inv_xmax;  // largest step in b: exp(b x) changes by at most a factor e per pass
   const T bcap = (T)kFirstStepCap * (T)(E - 1) * xt.inv_xmax;  // the same first-step gate per mean echo spacing
-#pragma unroll 1
-  for (int k = 0; k < kMonoFastPasses; ++k) {
-    if (!DFIT_ANY(lanes, A.active || B.active)) break;
+  auto pass = [&](auto first_tag, int k) {
+    constexpr bool FIRST = decltype(first_tag)::value;
     const V b = p2_make<T>(A.q, B.q);
     V N0 = p2_bcast<T>((T)0), N1 = N0, N2 = N0, D0 = N0, D1 = N0, D2 = N0;
 #pragma unroll
@@ -1128,8 +1148,14 @@ DFIT_HD void mono_general_newton2(const pair2<T> (&Y)[E], const XTab<T, E>& xt, 
     const V pred2 = p2_mul<T>(mg, db);
     const V Fe = p2_fma<T>(p2_mul<T>(N0, p2_bcast<T>((T)-1)), a, ysq);
     const V tol2 = p2_fma<T>(ftol2, p2_make<T>(nm::max_(Fe.lo, (T)0), nm::max_(Fe.hi, (T)0)), floor2);
-    newton_lane_step<T>(A, k, h.lo, pred2.lo, tol2.lo, db.lo, a.lo, ap.lo, -smax, smax, bcap);
-    newton_lane_step<T>(B, k, h.hi, pred2.hi, tol2.hi, db.hi, a.hi, ap.hi, -smax, smax, bcap);
+    newton_lane_step<FIRST, T>(A, k, h.lo, pred2.lo, tol2.lo, db.lo, a.lo, ap.lo, -smax, smax, bcap);
+    newton_lane_step<FIRST, T>(B, k, h.hi, pred2.hi, tol2.hi, db.hi, a.hi, ap.hi, -smax, smax, bcap);
+  };
+  if (DFIT_ANY(lanes, A.active || B.active)) pass(FirstPass<true>(), 0);
+#pragma unroll 1
+  for (int k = 1; k < kMonoFastPasses; ++k) {
+    if (!DFIT_ANY(lanes, A.active || B.active)) break;
+    pass(FirstPass<false>(), k);
   }
   iters[0] = A.npass;
   iters[1] = B.npass;
@@ -1154,8 +1180,8 @@ DFIT_HD void mono_general_newton2(const pair2<T> (&Y)[E], const XTab<T, E>& xt, 
 }
 
 // sum (y - mean)^2 of two voxels at once
-template <typename T, int E>
-DFIT_HD pair2<T> ss_total2(const pair2<T> (&Y)[E]) {
+template <typename T, int E, class YS>
+DFIT_HD pair2<T> ss_total2(const YS& Y) {
   pair2<T> s = Y[0];
 #pragma unroll
   for (int e = 1; e < E; ++e) s = p2_add<T>(s, Y[e]);
@@ -1205,14 +1231,14 @@ struct VoxelOpts {
 };
 
 // Fast-path attempt for two voxels: status[i] = -1 where voxel i has to take the general path.
-template <class M, typename T, int EMAX>
-DFIT_HD void fit_voxel_fast2(const pair2<T> (&Y)[EMAX], const XTab<T, EMAX>& xt, const VoxelOpts<T>& vo, pair2<T>& pa,
+template <class M, typename T, int EMAX, class YS>
+DFIT_HD void fit_voxel_fast2(const YS& Y, const XTab<T, EMAX>& xt, const VoxelOpts<T>& vo, pair2<T>& pa,
                              pair2<T>& pb, pair2<T>& r2, int (&status)[2], int (&iters)[2]) {
   static_assert(M::MONO && EMAX >= 3, "mono-exponential model only");
   pair2<T> F;
-  if (xt.uniform != 0) mono_uniform_newton2<T, EMAX>(Y, xt, vo.s, pa, pb, F, status, iters);
-  else mono_general_newton2<T, EMAX>(Y, xt, vo.s, pa, pb, F, status, iters);
-  const pair2<T> den = p2_add<T>(ss_total2<T, EMAX>(Y), p2_bcast<T>(vo.r2_eps));
+  if (xt.uniform != 0) mono_uniform_newton2<T, EMAX, YS>(Y, xt, vo.s, pa, pb, F, status, iters);
+  else mono_general_newton2<T, EMAX, YS>(Y, xt, vo.s, pa, pb, F, status, iters);
+  const pair2<T> den = p2_add<T>(ss_total2<T, EMAX, YS>(Y), p2_bcast<T>(vo.r2_eps));
   const pair2<T> nr = p2_make<T>(-num<T>::rcp_(den.lo), -num<T>::rcp_(den.hi));
   r2 = p2_fma<T>(F, nr, p2_bcast<T>((T)1));  // fitting.py:1032-1035
 }
@@ -1236,7 +1262,7 @@ DFIT_HD int fit_voxel_fast(const T (&y)[EMAX], const XTab<T, EMAX>& xt, const Vo
 #pragma unroll
         for (int e = 0; e < EMAX; ++e) Y[e] = p2_bcast<T>(y[e]);
         int st2[2], it2[2];
-        fit_voxel_fast2<M, T, EMAX>(Y, xt, vo, pa, pb, r2p, st2, it2);
+        fit_voxel_fast2<M, T, EMAX, pair2<T>[EMAX]>(Y, xt, vo, pa, pb, r2p, st2, it2);
         iters = it2[0];
         p[0] = pa.lo;
         p[1] = pb.lo;

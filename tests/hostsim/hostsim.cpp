@@ -39,7 +39,7 @@ static void run(int E, int64_t N, const double* x, const double* y, const double
         for (int e = 0; e < EMAX; ++e)
           Y[e] = p2_make<T>((T)y[(size_t)e * N + v], (T)y[(size_t)e * N + (both ? v + 1 : v)]);
         int st2[2], it2[2];
-        fit_voxel_fast2<M, T, EMAX>(Y, xt, vo, pa, pb, r2p, st2, it2);
+        fit_voxel_fast2<M, T, EMAX, pair2<T>[EMAX]>(Y, xt, vo, pa, pb, r2p, st2, it2);
         for (int hsel = 0; hsel < (both ? 2 : 1); ++hsel) {
           T p[P], r2v = hsel ? r2p.hi : r2p.lo;
           int st = st2[hsel], it = it2[hsel];
