@@ -193,7 +193,7 @@ bool tma_eligible(const LaunchDesc& d) {
 // (use_tma = 0); launch_one checks the rest of its conditions.
 bool tma2_eligible(const LaunchDesc& d) {
   return d.use_tma != 0 && d.model == DFIT_MODEL_MONOEXP && d.fast_path == 1 && d.compute_dtype == DFIT_F32 &&
-         d.y_dtype == DFIT_F32 && d.layout == DFIT_PLANAR && d.mask == nullptr && d.gather_world == 0 &&
+         d.y_dtype == DFIT_F32 && d.layout == DFIT_PLANAR && d.mask == nullptr &&
          d.n_echo >= 3 && d.n_echo <= 16 && d.n_vox < (int64_t)1 << 31;
 }
 

@@ -716,7 +716,7 @@ constexpr int kM2Warps = 4;
 constexpr int kM2Tile = 64;
 constexpr int m2_stages(int E) { return E <= 8 ? 4 : 2; }  // 32 KB of tiles per CTA
 
-template <class M, int EMAX>
+template <class M, int EMAX, bool GATHER>
 __global__ void __launch_bounds__(kM2Warps * 32, 5)  // 5 CTAs/SM: 6 spills, 4 is slower (measured: 0.743 / 0.689 / 0.696 ms);
                                                      // reading the samples from the tile on every use to free 16 registers
                                                      // (6-7 CTAs/SM) was measured too: 3 % slower
@@ -798,7 +798,49 @@ __global__ void __launch_bounds__(kM2Warps * 32, 5)  // 5 CTAs/SM: 6 spills, 4 i
     }
     if (!validA) { st[0] = -1; iters[0] = 0; }
     if (!validB) { st[1] = -1; iters[1] = 0; }
-    if (!a.po.enabled && a.out_dtype == DT_F32 && validB) {
+    if constexpr (GATHER) {
+      // Fused all-gather: the tile's 64 rows [a, b, r2] are one contiguous 768-byte block in every rank's map.
+      // Stage them in shared memory (double-buffered) and let the TMA push the block to every rank with one
+      // bulk store each (cp.async.bulk global <- shared): the SM's load/store path never waits on NVLink.  The
+      // launcher admits this kernel only without the epilogue and with 16-byte-aligned rank blocks.
+      __shared__ __align__(128) float rows[kM2Warps][2][kM2Tile * 3];
+      float* sg = rows[warp][k & 1];
+      if (t * kM2Tile + kM2Tile <= n_vox) {
+        // the staging buffer used two tiles ago must have been read by its bulk copies
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+        __syncwarp();
+        *reinterpret_cast<float2*>(sg + 6 * lane) = make_float2(pa.lo, pb.lo);
+        *reinterpret_cast<float2*>(sg + 6 * lane + 2) = make_float2(r2.lo, pa.hi);
+        *reinterpret_cast<float2*>(sg + 6 * lane + 4) = make_float2(pb.hi, r2.hi);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) {
+          // one TMA bulk store of the 768-byte block per rank: local HBM for the own rank, NVLink otherwise
+          const int64_t base = (a.gather_row0 + (int64_t)t * kM2Tile) * 3;
+#pragma unroll
+          for (int r = 0; r < kMaxPeers; ++r) {
+            if (r < a.gather_world) {
+              asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(a.gather[r] + base),
+                           "r"(smem_u32(sg)), "n"(kM2Tile * 3 * 4)
+                           : "memory");
+            }
+          }
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+      } else {  // ragged last tile: row by row
+#pragma unroll
+        for (int r = 0; r < kMaxPeers; ++r) {
+          if (r < a.gather_world) {
+            float* dst = a.gather[r] + (a.gather_row0 + v0) * 3;
+            if (validA) { dst[0] = pa.lo; dst[1] = pb.lo; dst[2] = r2.lo; }
+            if (validB) { dst[3] = pa.hi; dst[4] = pb.hi; dst[5] = r2.hi; }
+          }
+        }
+      }
+    }
+    if (GATHER && a.popt == nullptr) {
+      // the maps are the only output
+    } else if (!a.po.enabled && a.out_dtype == DT_F32 && validB) {
       __stcs(reinterpret_cast<float4*>(reinterpret_cast<float*>(a.popt) + (int64_t)v0 * P), make_float4(pa.lo, pb.lo, pa.hi, pb.hi));
       __stcs(reinterpret_cast<float2*>(reinterpret_cast<float*>(a.r2) + v0), make_float2(r2.lo, r2.hi));
       if (a.status) {
@@ -818,6 +860,9 @@ __global__ void __launch_bounds__(kM2Warps * 32, 5)  // 5 CTAs/SM: 6 spills, 4 i
     it_sum += (unsigned)(iters[0] + iters[1]);
     const unsigned im = (unsigned)(iters[0] > iters[1] ? iters[0] : iters[1]);
     it_max = im > it_max ? im : it_max;
+  }
+  if constexpr (GATHER) {
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // all bulk stores of this warp are done
   }
   // statistics: per-thread accumulators -> one reduction per warp at the end of the kernel
   {
@@ -921,11 +966,13 @@ inline cudaError_t launch_one(const LaunchDesc& d) {
     // dense fast path, two voxels per lane (see fit_kernel_mono2 for what it needs)
     const bool dt_ok = d.y_dtype == DT_F32 || d.y_dtype == DT_I16 || d.y_dtype == DT_U16;
     const size_t pair_bytes = 2 * dtype_size(d.y_dtype);
-    if (d.fast_path == 1 && !a.vo.has_bounds && d.mask == nullptr && d.gather_world == 0 && dt_ok &&
-        d.layout == LAYOUT_PLANAR && d.popt != nullptr && reinterpret_cast<uintptr_t>(d.y) % pair_bytes == 0 &&
-        d.ld % 2 == 0 && reinterpret_cast<uintptr_t>(d.popt) % 16 == 0 && reinterpret_cast<uintptr_t>(d.r2) % 8 == 0) {
+    // with the fused all-gather only the TMA kernel qualifies (raw parameters, 16-byte-aligned rank blocks)
+    const bool gather_ok = d.gather_world == 0 || (d.tmap2 != nullptr && !d.po.enabled && d.gather_row0 % 4 == 0);
+    if (d.fast_path == 1 && !a.vo.has_bounds && d.mask == nullptr && gather_ok && dt_ok && d.layout == LAYOUT_PLANAR &&
+        (d.popt != nullptr || d.gather_world > 0) && reinterpret_cast<uintptr_t>(d.y) % pair_bytes == 0 && d.ld % 2 == 0 &&
+        reinterpret_cast<uintptr_t>(d.popt) % 16 == 0 && reinterpret_cast<uintptr_t>(d.r2) % 8 == 0) {
       if (d.tmap2 != nullptr) {  // persistent, tiles staged through shared memory by TMA
-        auto kfn = fit_kernel_mono2_tma<M, EMAX>;
+        auto kfn = d.gather_world > 0 ? fit_kernel_mono2_tma<M, EMAX, true> : fit_kernel_mono2_tma<M, EMAX, false>;
         int per_sm = 0;
         cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kfn, kM2Warps * 32, 0);
         if (e != cudaSuccess) return e;

@@ -19,11 +19,21 @@ from dosma_b200 import device_api as A, sharding  # noqa: E402
 
 
 def main():
-    n = int(sys.argv[1]) if len(sys.argv) > 1 else 100_000
+    sizes = [int(v) for v in sys.argv[1:]] or [100_000]
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     dist.init_process_group("nccl", device_id=dev)
+    ok = True
+    for n in sizes:  # odd sizes take the one-voxel kernel, multiples of 4 the two-voxel TMA kernel (ragged or not)
+        ok = check(n, rank, world, dev) and ok
+    dist.barrier()
+    dist.destroy_process_group()
+    if not ok:
+        sys.exit(1)
+
+
+def check(n, rank, world, dev):
     g = torch.Generator(device=dev).manual_seed(100 + rank)
     x = np.arange(1, 9) * 10.0
     xt = torch.tensor(x, device=dev, dtype=torch.float32)[:, None]
@@ -47,12 +57,10 @@ def main():
     A.fit_device(opts, P, x, y, popt=popt, r2=r2)
     peer.synchronize()
     same = torch.equal(peer.local.nan_to_num(-1.0), ref.nan_to_num(-1.0))
-    print(f"[rank {rank}] fused gather == nccl all_gather: {same}", flush=True)
+    print(f"[rank {rank}] n={n} fused gather == nccl all_gather: {same}", flush=True)
     peer.close()
     dist.barrier()
-    dist.destroy_process_group()
-    if not same:
-        sys.exit(1)
+    return same
 
 
 if __name__ == "__main__":

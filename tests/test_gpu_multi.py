@@ -18,7 +18,7 @@ def test_fused_gather_matches_nccl():
     world = 2
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
            "--master-addr", "127.0.0.1", "--master-port", "29533",
-           os.path.join(ROOT, "tests", "gpu_scripts", "check_fused_gather.py"), "200003"]
+           os.path.join(ROOT, "tests", "gpu_scripts", "check_fused_gather.py"), "200003", "200192", "200068"]
     res = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
-    assert res.stdout.count("fused gather == nccl all_gather: True") == world
+    assert res.stdout.count("fused gather == nccl all_gather: True") == 3 * world
