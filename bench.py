@@ -87,9 +87,13 @@ def cpu_baseline(target_seconds=12.0):
     if dt < 0.6 * target_seconds:  # the calibration under-estimated the rate: one more run at the right size
         n = int(min(max(rate * target_seconds, 1024), 2_000_000))
         rate, dt = cpu_port_rate(n, cores)
+    # BASELINE.json's configs[0] names the reference's num_workers=1 case: time that too (a few seconds)
+    n1 = int(min(max(rate / max(cores, 1) * 3.0, 512), 65536))
+    rate1, dt1 = cpu_port_rate(n1, 1, seed=4321)
     return {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
             "sample": f"{n} voxels of the same workload (seed 1234), scipy.optimize.curve_fit per voxel via "
-                      f"oracle/dosma_oracle.py with a {cores}-process pool, {dt:.1f} s"}
+                      f"oracle/dosma_oracle.py with a {cores}-process pool, {dt:.1f} s",
+            "single_core_value": rate1, "single_core_sample": f"{n1} voxels, num_workers=1, {dt1:.1f} s"}
 
 
 def run_reference(args):
