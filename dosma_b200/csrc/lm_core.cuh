@@ -669,6 +669,7 @@ struct XTab {
   // Uniform spacing x_k = x0 + k dx (multi-echo spin echo, cones, ...): exp(b x_k) = e0 q^k with
   // q = exp(b dx), so the mono-exponential model is a POLYNOMIAL in q (mono_uniform_newton).
   int uniform;   // 1: spacing is uniform to within the arithmetic's resolution (host decides)
+  int backward;  // 1: dx < 0 (descending echo times): the Prony start is taken backwards
   T x0, x0s;     // first echo time and x0 * log2(e)
   T inv_dx;      // 1 / dx
   T q_lo, q_hi;  // admissible range of q: q^(2E-2) must stay finite
@@ -700,6 +701,7 @@ inline void fill_xtab(XTab<T, EMAX>& xt, const double* x, int n_echo) {
   const double tol = (double)num<T>::eps() * xmax;
   for (int e = 0; e < n_echo && uni; ++e) uni = fabs(x[e] - (x[0] + e * dx)) <= tol;
   xt.uniform = uni ? 1 : 0;
+  xt.backward = dx < 0 ? 1 : 0;
   xt.x0 = (T)(n_echo ? x[0] : 0.0);
   xt.x0s = (T)(n_echo ? x[0] * 1.4426950408889634074 : 0.0);
   xt.inv_dx = (T)(uni ? 1.0 / dx : 0.0);
@@ -766,8 +768,8 @@ DFIT_HD int mono_uniform_newton(const T (&y)[E], const XTab<T, E>& xt, const Sol
 #pragma unroll
   for (int k = 1; k + 1 < E; ++k) nd = p2_fma<T>(p2_bcast<T>(y[k]), p2_make<T>(y[k + 1], y[k]), nd);
   const T ysq = nm::fma_(y[E - 1], y[E - 1], nd.hi);
-  const T pdb = nm::fma_(-y[0], y[0], ysq);  // growing sequences are predicted backwards (see mono_uniform_newton2)
-  T q = (pdb > nd.hi ? pdb : nd.lo) * nm::rcp_(pdb > nd.hi ? nd.lo : nd.hi);
+  const T pdb = nm::fma_(-y[0], y[0], ysq);  // descending echo times: predicted backwards (see mono_uniform_newton2)
+  T q = xt.backward != 0 ? pdb * nm::rcp_(nd.lo) : nd.lo * nm::rcp_(nd.hi);
   // no admissible start (also catches NaN and all-zero voxels): this lane declines, but keeps in step
   bool active = q > xt.q_lo && q < xt.q_hi && nm::finite(ysq);
   if (!active) q = (T)0.5;
@@ -955,14 +957,16 @@ DFIT_HD void mono_uniform_newton2(const YS& Y, const XTab<T, E>& xt, const Solve
     pd = p2_fma<T>(Y[k], Y[k], pd);
   }
   const V ysq = p2_fma<T>(Y[E - 1], Y[E - 1], pd);
-  // a sequence that grows with the echo index (descending echo times, b > 0) is predicted backwards,
-  // q0 = sum y_k+1^2 / sum y_k y_k+1, so that the large samples carry the estimate either way
+  // with descending echo times a decaying signal grows with the echo index: predict backwards,
+  // q0 = sum y_k+1^2 / sum y_k y_k+1, so that the large samples carry the estimate (a per-launch choice)
   const V pdb = p2_fma<T>(p2_mul<T>(Y[0], p2_bcast<T>((T)-1)), Y[0], ysq);
   NewtonLane<T> A, B;
-  {
-    const bool ga = pdb.lo > pd.lo, gb = pdb.hi > pd.hi;
-    A.q = (ga ? pdb.lo : pn.lo) * nm::rcp_(ga ? pn.lo : pd.lo);
-    B.q = (gb ? pdb.hi : pn.hi) * nm::rcp_(gb ? pn.hi : pd.hi);
+  if (xt.backward != 0) {
+    A.q = pdb.lo * nm::rcp_(pn.lo);
+    B.q = pdb.hi * nm::rcp_(pn.hi);
+  } else {
+    A.q = pn.lo * nm::rcp_(pd.lo);
+    B.q = pn.hi * nm::rcp_(pd.hi);
   }
   A.active = A.q > xt.q_lo && A.q < xt.q_hi && nm::finite(ysq.lo);
   B.active = B.q > xt.q_lo && B.q < xt.q_hi && nm::finite(ysq.hi);
