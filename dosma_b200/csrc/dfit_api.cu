@@ -170,15 +170,18 @@ EncodeTiledFn encode_tiled_fn() {
 
 // 2-D tensor map over planar fp32 samples: dim0 = voxels (contiguous), dim1 = echoes (pitch ld).
 // Box = box_vox voxels x E echoes; out-of-range voxels of the last tile are zero-filled.
-bool make_sample_tmap(CUtensorMap* map, const void* y, int n_echo, int64_t n_vox, int64_t ld, int box_vox = kTmaTile) {
+bool make_sample_tmap(CUtensorMap* map, const void* y, int n_echo, int64_t n_vox, int64_t ld, int box_vox = kTmaTile,
+                      int y_dtype = DFIT_F32) {
   EncodeTiledFn fn = encode_tiled_fn();
   if (!fn) return false;
-  if ((reinterpret_cast<uintptr_t>(y) & 15) != 0 || (ld * 4) % 16 != 0) return false;
+  const size_t esz = dtype_size(y_dtype);
+  if ((reinterpret_cast<uintptr_t>(y) & 15) != 0 || (ld * esz) % 16 != 0) return false;
   cuuint64_t dims[2] = {(cuuint64_t)n_vox, (cuuint64_t)n_echo};
-  cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * esz};
   cuuint32_t box[2] = {(cuuint32_t)box_vox, (cuuint32_t)n_echo};
   cuuint32_t estr[2] = {1, 1};
-  return fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(y), dims, strides, box, estr,
+  const CUtensorMapDataType dt = y_dtype == DFIT_F32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_UINT16;
+  return fn(map, dt, 2, const_cast<void*>(y), dims, strides, box, estr,
             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
@@ -193,7 +196,8 @@ bool tma_eligible(const LaunchDesc& d) {
 // (use_tma = 0); launch_one checks the rest of its conditions.
 bool tma2_eligible(const LaunchDesc& d) {
   return d.use_tma != 0 && d.model == DFIT_MODEL_MONOEXP && d.fast_path == 1 && d.compute_dtype == DFIT_F32 &&
-         d.y_dtype == DFIT_F32 && d.layout == DFIT_PLANAR && d.mask == nullptr &&
+         (d.y_dtype == DFIT_F32 || d.y_dtype == DFIT_I16 || d.y_dtype == DFIT_U16) && d.layout == DFIT_PLANAR &&
+         d.mask == nullptr &&
          d.n_echo >= 3 && d.n_echo <= 16 && d.n_vox < (int64_t)1 << 31;
 }
 
@@ -375,13 +379,15 @@ int dfit_fit_device(dfit_handle* h, const dfit_opts* opts, int n_echo, int64_t n
     d.index = d.index_count + 4;
   }
   CUtensorMap tmap2;
-  if (n_vox > 0 && tma2_eligible(d) && make_sample_tmap(&tmap2, y, n_echo, n_vox, ld, kM2Tile)) d.tmap2 = &tmap2;
+  if (n_vox > 0 && tma2_eligible(d) && make_sample_tmap(&tmap2, y, n_echo, n_vox, ld, kM2Tile, y_dtype)) d.tmap2 = &tmap2;
   if (n_vox > 0 && tma_eligible(d)) {
     if (!make_sample_tmap(&tmap, y, n_echo, n_vox, ld))
       return fail(DFIT_ERR_UNSUPPORTED, "use_tma=1 but the samples do not qualify (16-byte aligned base and pitch)");
     d.tmap = &tmap;
-  } else if (opts->use_tma == 1) {
-    return fail(DFIT_ERR_UNSUPPORTED, "use_tma=1 needs fp32 planar samples, fp32 arithmetic and <= 16 echoes");
+  } else if (opts->use_tma == 1 && d.tmap2 == nullptr) {
+    return fail(DFIT_ERR_UNSUPPORTED,
+                "use_tma=1 needs planar fp32 (mono-exponential fast path: also 16-bit) samples with a 16-byte aligned "
+                "base and pitch, fp32 arithmetic and <= 16 echoes");
   }
   if (n_vox > 0) {
     CUDA_TRY(dispatch(d));
@@ -468,7 +474,7 @@ int dfit_fit_host(dfit_handle* h, const dfit_opts* opts, int n_echo, int64_t n_v
     if (tma_eligible(d) && make_sample_tmap(&tmap, d.y, n_echo, n, chunk)) d.tmap = &tmap;
     CUtensorMap tmap2;
     d.tmap2 = nullptr;
-    if (tma2_eligible(d) && make_sample_tmap(&tmap2, d.y, n_echo, n, chunk, kM2Tile)) d.tmap2 = &tmap2;
+    if (tma2_eligible(d) && make_sample_tmap(&tmap2, d.y, n_echo, n, chunk, kM2Tile, y_dtype)) d.tmap2 = &tmap2;
     CUDA_TRY(dispatch(d));
     h->last_launches += mask && d.tmap == nullptr ? 2 : 1;
     CUDA_TRY(cudaMemcpyAsync((char*)popt + (size_t)v0 * P * osz, sl.popt.p, (size_t)n * P * osz, cudaMemcpyDeviceToHost, st));

@@ -706,8 +706,8 @@ __global__ void __launch_bounds__(kTmaWarps * 32)
 }
 
 // ------------------------------------------------------------------------------------------------
-// Two voxels per lane + TMA staging: persistent warps, each with its own ring of [E][64-voxel] sample
-// tiles in shared memory.  The Tensor Memory Accelerator fills a stage (one cp.async.bulk.tensor.2d over
+// Two voxels per lane + TMA staging (fp32 or raw 16-bit samples, converted on the way to registers):
+// persistent warps, each with its own ring of [E][64-voxel] sample tiles in shared memory.  The Tensor Memory Accelerator fills a stage (one cp.async.bulk.tensor.2d over
 // the 2-D map of the planar samples, box = 64 voxels x E echoes, completion on the stage's mbarrier) while
 // the warp is fitting earlier tiles, so the HBM latency that the plain kernel exposes at the top of every
 // CTA is hidden behind arithmetic.  Lanes read their two voxels of every echo as one conflict-free 8-byte
@@ -716,7 +716,7 @@ constexpr int kM2Warps = 4;
 constexpr int kM2Tile = 64;
 constexpr int m2_stages(int E) { return E <= 8 ? 4 : 2; }  // 32 KB of tiles per CTA
 
-template <class M, int EMAX, bool GATHER>
+template <class M, int EMAX, bool GATHER, typename S>
 __global__ void __launch_bounds__(kM2Warps * 32, 5)  // 5 CTAs/SM: 6 spills, 4 is slower (measured: 0.743 / 0.689 / 0.696 ms);
                                                      // reading the samples from the tile on every use to free 16 registers
                                                      // (6-7 CTAs/SM) was measured too: 3 % slower
@@ -724,8 +724,8 @@ __global__ void __launch_bounds__(kM2Warps * 32, 5)  // 5 CTAs/SM: 6 spills, 4 i
   typedef float T;
   constexpr int P = 2;
   constexpr int kStages = m2_stages(EMAX);
-  constexpr unsigned kTileBytes = EMAX * kM2Tile * sizeof(float);
-  __shared__ __align__(128) float tiles[kM2Warps][kStages][EMAX][kM2Tile];
+  constexpr unsigned kTileBytes = EMAX * kM2Tile * sizeof(S);  // S = float, or the raw 16-bit DICOM sample type
+  __shared__ __align__(128) S tiles[kM2Warps][kStages][EMAX][kM2Tile];
   __shared__ __align__(8) uint64_t full[kM2Warps][kStages];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // 32-bit indexing: the launcher admits fewer than 2^31 voxels
@@ -758,8 +758,8 @@ __global__ void __launch_bounds__(kM2Warps * 32, 5)  // 5 CTAs/SM: 6 spills, 4 i
     pair2<T> Y[EMAX], pa, pb, r2;
 #pragma unroll
     for (int e = 0; e < EMAX; ++e) {
-      const float2 v = *reinterpret_cast<const float2*>(&tiles[warp][s][e][2 * lane]);
-      Y[e] = p2_make<T>(v.x, v.y);
+      const typename Vec2<S>::type v = *reinterpret_cast<const typename Vec2<S>::type*>(&tiles[warp][s][e][2 * lane]);
+      Y[e] = p2_make<T>((T)v.x, (T)v.y);
     }
     __syncwarp();
     if (lane == 0) {  // the stage is drained: refill it with the tile kStages trips ahead
@@ -967,12 +967,16 @@ inline cudaError_t launch_one(const LaunchDesc& d) {
     const bool dt_ok = d.y_dtype == DT_F32 || d.y_dtype == DT_I16 || d.y_dtype == DT_U16;
     const size_t pair_bytes = 2 * dtype_size(d.y_dtype);
     // with the fused all-gather only the TMA kernel qualifies (raw parameters, 16-byte-aligned rank blocks)
-    const bool gather_ok = d.gather_world == 0 || (d.tmap2 != nullptr && !d.po.enabled && d.gather_row0 % 4 == 0);
+    const bool gather_ok =
+        d.gather_world == 0 || (d.tmap2 != nullptr && d.y_dtype == DT_F32 && !d.po.enabled && d.gather_row0 % 4 == 0);
     if (d.fast_path == 1 && !a.vo.has_bounds && d.mask == nullptr && gather_ok && dt_ok && d.layout == LAYOUT_PLANAR &&
         (d.popt != nullptr || d.gather_world > 0) && reinterpret_cast<uintptr_t>(d.y) % pair_bytes == 0 && d.ld % 2 == 0 &&
         reinterpret_cast<uintptr_t>(d.popt) % 16 == 0 && reinterpret_cast<uintptr_t>(d.r2) % 8 == 0) {
       if (d.tmap2 != nullptr) {  // persistent, tiles staged through shared memory by TMA
-        auto kfn = d.gather_world > 0 ? fit_kernel_mono2_tma<M, EMAX, true> : fit_kernel_mono2_tma<M, EMAX, false>;
+        auto kfn = d.gather_world > 0    ? fit_kernel_mono2_tma<M, EMAX, true, float>
+                   : d.y_dtype == DT_I16 ? fit_kernel_mono2_tma<M, EMAX, false, short>
+                   : d.y_dtype == DT_U16 ? fit_kernel_mono2_tma<M, EMAX, false, unsigned short>
+                                         : fit_kernel_mono2_tma<M, EMAX, false, float>;
         int per_sm = 0;
         cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kfn, kM2Warps * 32, 0);
         if (e != cudaSuccess) return e;

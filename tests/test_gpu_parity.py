@@ -328,21 +328,21 @@ def test_two_voxel_fast_kernels_agree_with_lm(D):
                 okr = ~torch.isnan(ref[0][:, 0]) & ~torch.isnan(p[:, 0])
                 assert ((p[okr] - ref[0][okr]).abs() / ref[0][okr].abs().clamp_min(1e-30)).max() < 1e-5
     # int16 samples and the fused MonoExponentialFit epilogue (ufunc, bounds, r2 threshold, fill, rounding)
-    n = 200_001
-    yi = ((500 + 1000 * torch.rand(n, device="cuda", generator=g)) * torch.exp(
-        -xt / (10 + 70 * torch.rand(n, device="cuda", generator=g))) + 10 * torch.randn(8, n, device="cuda", generator=g)
-          ).round().to(torch.int16)
-    post = dict(ufunc=[0, 1], lb=[-np.inf, 0.0], ub=[np.inf, 100.0], decimals=[-1, 3], r2_threshold=0.9, nan_to_num=0.0)
-    outs = []
-    for kw in (dict(fast_path=0, use_tma=0), dict(fast_path=1, use_tma=0), dict()):
-        o, P = A.make_opts(D.monoexponential, p0=(1.0, -1 / 30), post=post, **kw)
-        p, r = A.fit_device(o, P, x, yi, out_dtype=torch.float64)
-        torch.cuda.synchronize()
-        outs.append((p, r))
-    for p, r in outs[1:]:
-        same = (p[:, 1] - outs[0][0][:, 1]).abs() <= 1.001e-3  # one rounding step
-        assert same.float().mean() > 0.999
-        assert (r - outs[0][1]).abs().max() < 1e-5
+    for n in (200_001, 200_064):  # odd: plain 4-byte pair loads; multiple of 8: 16-bit tiles through TMA
+        yi = ((500 + 1000 * torch.rand(n, device="cuda", generator=g)) * torch.exp(
+            -xt / (10 + 70 * torch.rand(n, device="cuda", generator=g))) + 10 * torch.randn(8, n, device="cuda", generator=g)
+              ).round().to(torch.int16)
+        post = dict(ufunc=[0, 1], lb=[-np.inf, 0.0], ub=[np.inf, 100.0], decimals=[-1, 3], r2_threshold=0.9, nan_to_num=0.0)
+        outs = []
+        for kw in (dict(fast_path=0, use_tma=0), dict(fast_path=1, use_tma=0), dict()):
+            o, P = A.make_opts(D.monoexponential, p0=(1.0, -1 / 30), post=post, **kw)
+            p, r = A.fit_device(o, P, x, yi, out_dtype=torch.float64)
+            torch.cuda.synchronize()
+            outs.append((p, r))
+        for p, r in outs[1:]:
+            same = (p[:, 1] - outs[0][0][:, 1]).abs() <= 1.001e-3  # one rounding step
+            assert same.float().mean() > 0.999
+            assert (r - outs[0][1]).abs().max() < 1e-5
     # non-uniform echo times: the general (exp-based) fast path, dense and through a mask, against the LM
     for xn in (np.array([10.0, 20.0, 40.0, 80.0]), np.array([0.0, 10.0, 12.847, 25.695, 40.0, 51.39, 80.0])):
         for n in (300_001, 300_032):  # odd: one-voxel kernel (no pair loads); multiple of 4: TMA two-voxel kernel
