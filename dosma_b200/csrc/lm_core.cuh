@@ -1373,13 +1373,12 @@ DFIT_HD double fast_recip(double v) {
 }
 
 DFIT_HD double apply_ufunc(int id, double v) {
-  switch (id) {
-    case UF_INV_ABS: return fast_recip(fabs(v));
-    case UF_NEG_INV: return -fast_recip(v);
-    case UF_ABS: return fabs(v);
-    case UF_INV: return fast_recip(v);
-    default: return v;
-  }
+  // (an if-chain on purpose: a switch becomes an indirect branch through a jump table on the device, and the
+  // three reciprocal kinds share one reciprocal)
+  if (id == UF_NONE) return v;
+  if (id == UF_ABS) return fabs(v);
+  const double r = fast_recip(id == UF_INV_ABS ? fabs(v) : v);
+  return id == UF_NEG_INV ? -r : r;
 }
 
 DFIT_HD double pow10i(int d) {
