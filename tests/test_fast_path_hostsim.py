@@ -105,3 +105,50 @@ def test_declines_to_lm_where_it_must():
     b = H.fit("monoexponential", x, y, p0=(1.0, -1 / 30), fast=2, y_bounds=(0, 1400))
     for u, v in zip(a, b):
         assert np.array_equal(u, v, equal_nan=True)
+
+
+@pytest.mark.parametrize("name", ["uniform8", "t1rho7"])
+def test_invariances(name):
+    """Properties of the least-squares minimiser that do not depend on the data: scaling the samples scales a
+    and leaves b; stretching the echo times by c divides b by c; the result of a voxel does not depend on its
+    neighbour in the lane pair (two-voxel packing) nor on its position."""
+    x = SPACINGS[name]
+    y = _synth(x, 6001, 10.0, (10, 80), 23)
+    p, r, s, it = H.fit("monoexponential", x, y, p0=(1.0, -1 / 30), fast=2)
+    assert ((s >= 1) & (s <= 4)).all()
+    for c in (0.125, 8.0, 1000.0):
+        pc, rc, sc, _ = H.fit("monoexponential", x, y * np.float32(c), p0=(1.0, -1 / 30), fast=2)
+        tol = 2e-5  # the solver's own tolerance: the start and the rounding differ with the scale
+        assert (np.abs(pc[:, 0] / c - p[:, 0]) / np.abs(p[:, 0])).max() < tol
+        assert (np.abs(pc[:, 1] - p[:, 1]) / np.abs(p[:, 1])).max() < tol
+        assert np.abs(rc - r).max() < 1e-5
+    for c in (0.5, 4.0):
+        pc, rc, sc, _ = H.fit("monoexponential", x * c, y, p0=(1.0, -1 / (30 * c)), fast=2)
+        assert (np.abs(pc[:, 1] * c - p[:, 1]) / np.abs(p[:, 1])).max() < 1e-5
+        assert (np.abs(pc[:, 0] - p[:, 0]) / np.abs(p[:, 0])).max() < 1e-5
+    perm = np.random.default_rng(1).permutation(y.shape[1])
+    pp, rp, sp, ip = H.fit("monoexponential", x, y[:, perm], p0=(1.0, -1 / 30), fast=2)
+    assert np.array_equal(pp, p[perm]) and np.array_equal(rp, r[perm]) and np.array_equal(ip, it[perm])
+
+
+def test_recovers_truth_over_decades_of_decay():
+    """Noise-free signals from T = 0.3 dx to 3000 dx (q from 0.04 to 0.9997) and growing ones: the fast path
+    (or the LM it hands over to) must return the generating parameters."""
+    x = SPACINGS["uniform8"]
+    rng = np.random.default_rng(9)
+    n = 4000
+    T = 10.0 ** rng.uniform(np.log10(3.0), np.log10(3e4), n)
+    sign = np.where(rng.random(n) < 0.15, -1.0, 1.0)  # 15 % growing exponentials (b > 0), capped below
+    b = -sign / np.maximum(T, np.where(sign < 0, 40.0, 0.0))
+    a = rng.uniform(1, 3000, n)
+    y = a * np.exp(b * x[:, None])
+    for dtype, tol in (("f64", 1e-9), ("f32", 2e-4)):
+        p, r, s, it = H.fit("monoexponential", x, y, p0=(1.0, -1 / 30), dtype=dtype, fast=2)
+        ok = (s >= 1) & (s <= 4)
+        assert ok.mean() > 0.995  # the rest: T << dx, nothing but the first echo left in fp32
+        relb = np.abs(p[ok, 1] - b[ok]) / np.abs(b[ok])
+        # fp32 resolves b dx to ~1e-7 absolute: slow decays lose relative precision in b accordingly
+        lim = tol + (2e-7 / np.abs(b[ok] * 10.0) if dtype == "f32" else 0)
+        assert (relb < lim).all(), (dtype, float((relb / lim).max()))
+        assert (np.abs(p[ok, 0] - a[ok]) / a[ok] < 50 * lim).all()
+        assert (r[ok] > 1 - 1e-4).all()
