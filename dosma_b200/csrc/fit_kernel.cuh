@@ -967,8 +967,11 @@ inline cudaError_t launch_one(const LaunchDesc& d) {
     const bool dt_ok = d.y_dtype == DT_F32 || d.y_dtype == DT_I16 || d.y_dtype == DT_U16;
     const size_t pair_bytes = 2 * dtype_size(d.y_dtype);
     // with the fused all-gather only the TMA kernel qualifies (raw parameters, 16-byte-aligned rank blocks)
-    const bool gather_ok =
-        d.gather_world == 0 || (d.tmap2 != nullptr && d.y_dtype == DT_F32 && !d.po.enabled && d.gather_row0 % 4 == 0);
+    // Measured (weak scaling, 384^3 x 8 echoes per GPU): the one-voxel kernel's warp-transposed peer stores reach
+    // 696 / 680 GB/s of NVLink egress at 4 / 8 GPUs, the TMA bulk stores of this kernel 652 / 657 GB/s (equal at 2),
+    // and the step is NVLink-bound there -- so the bulk-store gather is opt-in (use_tma = 1).
+    const bool gather_ok = d.gather_world == 0 || (d.use_tma == 1 && d.tmap2 != nullptr && d.y_dtype == DT_F32 &&
+                                                   !d.po.enabled && d.gather_row0 % 4 == 0);
     if (d.fast_path == 1 && !a.vo.has_bounds && d.mask == nullptr && gather_ok && dt_ok && d.layout == LAYOUT_PLANAR &&
         (d.popt != nullptr || d.gather_world > 0) && reinterpret_cast<uintptr_t>(d.y) % pair_bytes == 0 && d.ld % 2 == 0 &&
         reinterpret_cast<uintptr_t>(d.popt) % 16 == 0 && reinterpret_cast<uintptr_t>(d.r2) % 8 == 0) {

@@ -40,9 +40,21 @@ def check(n, rank, world, dev):
     a = 500 + 1000 * torch.rand(n, device=dev, generator=g)
     t2 = 10 + 70 * torch.rand(n, device=dev, generator=g)
     y = a * torch.exp(-xt / t2) + 10 * torch.randn(8, n, device=dev, generator=g)
-    opts, P = A.make_opts(D.monoexponential, p0=(1.0, -1 / 30))
+    ok = True
+    # default: the one-voxel kernel's warp-transposed peer stores; use_tma=1 (16-byte-aligned pitch only): the
+    # two-voxel TMA kernel with bulk stores of 768-byte row blocks
+    for kw in [dict()] + ([dict(use_tma=1)] if n % 4 == 0 else []):
+        ok = check_one(n, rank, world, dev, x, y, kw) and ok
+    return ok
 
-    popt, r2 = A.fit_device(opts, P, x, y)
+
+def check_one(n, rank, world, dev, x, y, kw):
+    opts, P = A.make_opts(D.monoexponential, p0=(1.0, -1 / 30), **kw)
+    # the NCCL reference must come from the same kernel arithmetic as the fused run: without use_tma=1 the
+    # gather runs in the one-voxel kernel, which a plain fit only uses with fast_path=2 (or an odd pitch)
+    ref_opts, _ = A.make_opts(D.monoexponential, p0=(1.0, -1 / 30), **(kw or dict(fast_path=2)))
+
+    popt, r2 = A.fit_device(ref_opts, P, x, y)
     torch.cuda.synchronize()
     ref = sharding.gather_maps(torch.cat([popt, r2[:, None]], dim=1), [n] * world)
 
@@ -57,7 +69,7 @@ def check(n, rank, world, dev):
     A.fit_device(opts, P, x, y, popt=popt, r2=r2)
     peer.synchronize()
     same = torch.equal(peer.local.nan_to_num(-1.0), ref.nan_to_num(-1.0))
-    print(f"[rank {rank}] n={n} fused gather == nccl all_gather: {same}", flush=True)
+    print(f"[rank {rank}] n={n} {kw} fused gather == nccl all_gather: {same}", flush=True)
     peer.close()
     dist.barrier()
     return same
