@@ -216,14 +216,17 @@ def run_gpu(args):
     world = env_int("WORLD_SIZE", 1)
     rank = env_int("RANK", 0)
     local_rank = env_int("LOCAL_RANK", 0)
+    # stdout carries exactly one JSON line: anything libraries print on the way (NCCL's version banner ...) goes
+    # to stderr -- file descriptor 1 is pointed at stderr until the line is printed
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
     if world != args.gpus:
         raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}; launch with torch.distributed.run")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-            os.environ["NCCL_DEBUG"] = "WARN"  # keep NCCL's version banner out of stdout: one JSON line only
         dist.init_process_group("nccl", device_id=dev)
 
     n = int(np.prod(SHAPE))
@@ -367,7 +370,10 @@ def run_gpu(args):
         }
         if not args.no_cpu and world == 1:
             line["cpu_baseline"] = cpu_baseline()
+        sys.stdout.flush()
+        os.dup2(saved_stdout, 1)
         print(json.dumps(line), flush=True)
+        os.dup2(2, 1)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

@@ -525,6 +525,9 @@ int dfit_ipc_alloc(dfit_handle* h, size_t bytes, void** dev_ptr, unsigned char* 
   void* p = nullptr;
   CUDA_TRY(cudaMalloc(&p, bytes));
   CUDA_TRY(cudaMemset(p, 0, bytes));
+  // cudaMemset of device memory may return before the fill has run: it must not land on top of a peer's
+  // stores once the handle has been published
+  CUDA_TRY(cudaDeviceSynchronize());
   cudaIpcMemHandle_t hd;
   cudaError_t e = cudaIpcGetMemHandle(&hd, p);
   if (e != cudaSuccess) {
