@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define DFIT_VERSION 100 /* major*10000 + minor*100 + patch */
+#define DFIT_VERSION 200 /* major*10000 + minor*100 + patch */
 #define DFIT_MAX_PARAMS 4
 #define DFIT_MAX_ECHOES 32
 
