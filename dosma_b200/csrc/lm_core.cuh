@@ -897,17 +897,30 @@ struct FirstPass {
 };
 
 // Per-voxel (non-packable) part of one Newton pass: convergence test, step clamp, state update.
+// The lane's life cycle is encoded in `dprev2` (no boolean registers to juggle): >= 0 while it iterates
+// (the squared previous step), kLaneDone once it has converged, kLaneDeclined once it has given up.  `q`
+// always holds the latest iterate: the step that ends the iteration is taken like any other.
+constexpr float kLaneDone = -1.0f, kLaneDeclined = -2.0f;
+
 template <typename T>
 struct NewtonLane {
-  T q, dprev2, qf, af;
-  bool active, done;
+  T q, dprev2, af;
   int npass;
+  DFIT_HD bool active() const { return dprev2 >= (T)0; }
+  DFIT_HD bool done() const { return dprev2 == (T)kLaneDone; }
+  DFIT_HD void start(T q0, bool ok, T fallback) {
+    q = ok ? q0 : fallback;
+    dprev2 = ok ? (T)0 : (T)kLaneDeclined;
+    af = (T)0;
+    npass = 0;
+  }
 };
 
 template <bool FIRST, typename T>
 DFIT_HD void newton_lane_step(NewtonLane<T>& L, int k, T h, T pred2, T tol2, T dq, T a, T ap, T step_lo, T step_hi,
                               T first_cap) {
   typedef num<T> nm;
+  const bool act = L.active();
   const T step2 = dq * dq;
   T kappa = (T)1;
   // h > 0: inside the convex basin (false for NaN as well).
@@ -921,19 +934,10 @@ DFIT_HD void newton_lane_step(NewtonLane<T>& L, int k, T h, T pred2, T tol2, T d
   }
   const bool conv = convex && (pred2 * kappa) * kappa <= tol2;
   dq = nm::min_(nm::max_(dq, step_lo), step_hi);  // trust clamp (keeps q positive / b x bounded)
-  if (L.active) {
-    L.npass = k + 1;
-    if (conv) {
-      L.qf = L.q + dq;
-      L.af = nm::fma_(ap, dq, a);
-      L.done = true;
-    }
-    L.active = convex && !conv;
-    if (L.active) {
-      L.q += dq;
-      L.dprev2 = step2;
-    }
-  }
+  L.q = (act && convex) ? L.q + dq : L.q;
+  L.af = (act && conv) ? nm::fma_(ap, dq, a) : L.af;
+  L.npass = act ? k + 1 : L.npass;
+  L.dprev2 = act ? (conv ? (T)kLaneDone : (convex ? step2 : (T)kLaneDeclined)) : L.dprev2;
 }
 
 // Y[e] = (sample e of voxel A, sample e of voxel B); Y is an array of pair2<T> or any object whose operator[]
@@ -961,20 +965,19 @@ DFIT_HD void mono_uniform_newton2(const YS& Y, const XTab<T, E>& xt, const Solve
   // q0 = sum y_k+1^2 / sum y_k y_k+1, so that the large samples carry the estimate (a per-launch choice)
   const V pdb = p2_fma<T>(p2_mul<T>(Y[0], p2_bcast<T>((T)-1)), Y[0], ysq);
   NewtonLane<T> A, B;
-  if (xt.backward != 0) {
-    A.q = pdb.lo * nm::rcp_(pn.lo);
-    B.q = pdb.hi * nm::rcp_(pn.hi);
-  } else {
-    A.q = pn.lo * nm::rcp_(pd.lo);
-    B.q = pn.hi * nm::rcp_(pd.hi);
+  {
+    T qa, qb;
+    if (xt.backward != 0) {
+      qa = pdb.lo * nm::rcp_(pn.lo);
+      qb = pdb.hi * nm::rcp_(pn.hi);
+    } else {
+      qa = pn.lo * nm::rcp_(pd.lo);
+      qb = pn.hi * nm::rcp_(pd.hi);
+    }
+    // no admissible start (also catches NaN and all-zero voxels): the lane declines but keeps in step
+    A.start(qa, qa > xt.q_lo && qa < xt.q_hi && nm::finite(ysq.lo), (T)0.5);
+    B.start(qb, qb > xt.q_lo && qb < xt.q_hi && nm::finite(ysq.hi), (T)0.5);
   }
-  A.active = A.q > xt.q_lo && A.q < xt.q_hi && nm::finite(ysq.lo);
-  B.active = B.q > xt.q_lo && B.q < xt.q_hi && nm::finite(ysq.hi);
-  if (!A.active) A.q = (T)0.5;
-  if (!B.active) B.q = (T)0.5;
-  A.dprev2 = B.dprev2 = A.qf = B.qf = A.af = B.af = (T)0;
-  A.done = B.done = false;
-  A.npass = B.npass = 0;
   // tolerance on twice the Newton decrement: 2 (ftol F + floor_rel sum y^2)
   const V floor2 = p2_mul<T>(ysq, p2_bcast<T>((T)2 * o.floor_rel));
   const V ftol2 = p2_bcast<T>((T)2 * o.ftol);
@@ -1020,18 +1023,18 @@ DFIT_HD void mono_uniform_newton2(const YS& Y, const XTab<T, E>& xt, const Solve
     newton_lane_step<FIRST, T>(A, k, h.lo, pred2.lo, tol2.lo, dq.lo, a.lo, ap.lo, (T)-0.5 * A.q, A.q, kFirstStepCap * A.q);
     newton_lane_step<FIRST, T>(B, k, h.hi, pred2.hi, tol2.hi, dq.hi, a.hi, ap.hi, (T)-0.5 * B.q, B.q, kFirstStepCap * B.q);
   };
-  if (DFIT_ANY(lanes, A.active || B.active)) pass(FirstPass<true>(), 0);
+  if (DFIT_ANY(lanes, A.active() || B.active())) pass(FirstPass<true>(), 0);
 #pragma unroll 1
   for (int k = 1; k < kMonoFastPasses; ++k) {
-    if (!DFIT_ANY(lanes, A.active || B.active)) break;
+    if (!DFIT_ANY(lanes, A.active() || B.active())) break;
     pass(FirstPass<false>(), k);
   }
   iters[0] = A.npass;
   iters[1] = B.npass;
-  const bool okA = A.done && A.qf > xt.q_lo && A.qf < xt.q_hi && nm::finite(A.af);
-  const bool okB = B.done && B.qf > xt.q_lo && B.qf < xt.q_hi && nm::finite(B.af);
+  const bool okA = A.done() && A.q > xt.q_lo && A.q < xt.q_hi && nm::finite(A.af);
+  const bool okB = B.done() && B.q > xt.q_lo && B.q < xt.q_hi && nm::finite(B.af);
   // a declined voxel rides along on harmless values
-  const V qf = p2_make<T>(okA ? A.qf : (T)0.5, okB ? B.qf : (T)0.5);
+  const V qf = p2_make<T>(okA ? A.q : (T)0.5, okB ? B.q : (T)0.5);
   const V af = p2_make<T>(okA ? A.af : (T)0, okB ? B.af : (T)0);
   // cost at the returned point: r_k = y_k - a' q^k
   V ee = qf, F = p2_bcast<T>((T)0);
@@ -1108,17 +1111,10 @@ DFIT_HD void mono_general_newton2(const YS& Y, const XTab<T, E>& xt, const Solve
   const V den_ = p2_fma<T>(S0, S2, p2_mul<T>(p2_mul<T>(S1, S1), p2_bcast<T>((T)-1)));
   const V b0 = p2_mul<T>(p2_mul<T>(num_, p2_make<T>(nm::rcp_(den_.lo), nm::rcp_(den_.hi))), p2_bcast<T>((T)0.34657359027997264));
   NewtonLane<T> A, B;
-  A.q = b0.lo;
-  B.q = b0.hi;
   // |b x| <= 40 keeps every e_k^2 finite in fp32; den > 0 rules out a single surviving sample
   const T blim = (T)(sizeof(T) == 4 ? 40.0 : 300.0) * xt.inv_xmax;
-  A.active = den_.lo > (T)0 && nm::abs_(A.q) < blim && nm::finite(ysq.lo) && ysq.lo > (T)0;
-  B.active = den_.hi > (T)0 && nm::abs_(B.q) < blim && nm::finite(ysq.hi) && ysq.hi > (T)0;
-  if (!A.active) A.q = (T)0;
-  if (!B.active) B.q = (T)0;
-  A.dprev2 = B.dprev2 = A.qf = B.qf = A.af = B.af = (T)0;
-  A.done = B.done = false;
-  A.npass = B.npass = 0;
+  A.start(b0.lo, den_.lo > (T)0 && nm::abs_(b0.lo) < blim && nm::finite(ysq.lo) && ysq.lo > (T)0, (T)0);
+  B.start(b0.hi, den_.hi > (T)0 && nm::abs_(b0.hi) < blim && nm::finite(ysq.hi) && ysq.hi > (T)0, (T)0);
   const V floor2 = p2_mul<T>(ysq, p2_bcast<T>((T)2 * o.floor_rel));
   const V ftol2 = p2_bcast<T>((T)2 * o.ftol);
   const T smax = xt.inv_xmax;  // largest step in b: exp(b x) changes by at most a factor e per pass
@@ -1155,17 +1151,17 @@ DFIT_HD void mono_general_newton2(const YS& Y, const XTab<T, E>& xt, const Solve
     newton_lane_step<FIRST, T>(A, k, h.lo, pred2.lo, tol2.lo, db.lo, a.lo, ap.lo, -smax, smax, bcap);
     newton_lane_step<FIRST, T>(B, k, h.hi, pred2.hi, tol2.hi, db.hi, a.hi, ap.hi, -smax, smax, bcap);
   };
-  if (DFIT_ANY(lanes, A.active || B.active)) pass(FirstPass<true>(), 0);
+  if (DFIT_ANY(lanes, A.active() || B.active())) pass(FirstPass<true>(), 0);
 #pragma unroll 1
   for (int k = 1; k < kMonoFastPasses; ++k) {
-    if (!DFIT_ANY(lanes, A.active || B.active)) break;
+    if (!DFIT_ANY(lanes, A.active() || B.active())) break;
     pass(FirstPass<false>(), k);
   }
   iters[0] = A.npass;
   iters[1] = B.npass;
-  const bool okA = A.done && nm::abs_(A.qf) < blim && nm::finite(A.af);
-  const bool okB = B.done && nm::abs_(B.qf) < blim && nm::finite(B.af);
-  const V bf = p2_make<T>(okA ? A.qf : (T)0, okB ? B.qf : (T)0);
+  const bool okA = A.done() && nm::abs_(A.q) < blim && nm::finite(A.af);
+  const bool okB = B.done() && nm::abs_(B.q) < blim && nm::finite(B.af);
+  const V bf = p2_make<T>(okA ? A.q : (T)0, okB ? B.q : (T)0);
   const V af = p2_make<T>(okA ? A.af : (T)0, okB ? B.af : (T)0);
   // cost at the returned point
   const V naf = p2_mul<T>(af, p2_bcast<T>((T)-1));
