@@ -149,14 +149,18 @@ template <int P, typename T, int EMAX, bool GATHER = true>
 __device__ __forceinline__ void store_voxel(const KernelArgs<T, EMAX>& a, int64_t v, const T (&p)[P], T r2, bool fitted,
                                             int st, int iters, bool warp_rows = false) {
   if constexpr (sizeof(T) == 4) {
-    // Raw fp32 parameters into fp32 maps (curve_fit without an epilogue): no trip through double.
-    if (fitted && !a.po.enabled && a.out_dtype == DT_F32 && a.popt != nullptr && !(GATHER && a.gather_world > 0)) {
+    // fp32 parameters into fp32 maps: raw (curve_fit without an epilogue) or through the fp32-where-exact
+    // epilogue -- no trip through double for r2 and the comparisons-only parameters.
+    if (fitted && a.out_dtype == DT_F32 && a.popt != nullptr && !(GATHER && a.gather_world > 0)) {
+      float q[P];
+#pragma unroll
+      for (int i = 0; i < P; ++i) q[i] = post_param_f32(a.po, i, p[i], r2);
       float* dst = reinterpret_cast<float*>(a.popt) + v * P;
-      if constexpr (P == 2) __stcs(reinterpret_cast<float2*>(dst), make_float2(p[0], p[1]));
-      else if constexpr (P == 4) __stcs(reinterpret_cast<float4*>(dst), make_float4(p[0], p[1], p[2], p[3]));
+      if constexpr (P == 2) __stcs(reinterpret_cast<float2*>(dst), make_float2(q[0], q[1]));
+      else if constexpr (P == 4) __stcs(reinterpret_cast<float4*>(dst), make_float4(q[0], q[1], q[2], q[3]));
       else {
 #pragma unroll
-        for (int i = 0; i < P; ++i) __stcs(dst + i, p[i]);
+        for (int i = 0; i < P; ++i) __stcs(dst + i, q[i]);
       }
       __stcs(reinterpret_cast<float*>(a.r2) + v, r2);
       if (a.status) a.status[v] = (uint8_t)st;

@@ -1347,6 +1347,11 @@ struct PostOpts {
   double fill;
   int decimals[4];    // np.around per parameter, < 0: none (fitting.py:736-737)
   double scale[4], inv_scale[4];  // 10^decimals and its reciprocal, filled by set_post_scales()
+  // fp32 twins for parameters whose post-processing is comparisons only (no ufunc, no rounding): a float v
+  // satisfies (double)v < lb exactly when v < lbf with lbf the smallest float >= lb, and so on, so the
+  // epilogue of such a parameter is exact in fp32.  Filled by set_post_scales().
+  int simple[4];
+  float lbf[4], ubf[4], r2_thresh_f, fill_f;
 };
 
 // 1 / v in double.  On the device: MUFU.RCP of the fp32 image of v, refined by two Newton steps in fp64
@@ -1383,10 +1388,27 @@ DFIT_HD double pow10i(int d) {
   return s;
 }
 
+inline float float_at_least(double v) {  // smallest float >= v (v itself when it is +-inf / NaN)
+  float f = (float)v;
+  if ((double)f < v) f = nextafterf(f, INFINITY);
+  return f;
+}
+inline float float_at_most(double v) {  // largest float <= v
+  float f = (float)v;
+  if ((double)f > v) f = nextafterf(f, -INFINITY);
+  return f;
+}
+
 inline void set_post_scales(PostOpts& po) {
+  po.fill_f = (float)po.fill;
+  const bool fill_ok = !po.has_fill || (double)po.fill_f == po.fill;
+  po.r2_thresh_f = float_at_least(po.r2_thresh);
   for (int i = 0; i < 4; ++i) {
     po.scale[i] = po.decimals[i] >= 0 ? pow10i(po.decimals[i]) : 1.0;
     po.inv_scale[i] = 1.0 / po.scale[i];
+    po.simple[i] = (po.ufunc[i] == UF_NONE && po.decimals[i] < 0 && fill_ok) ? 1 : 0;
+    po.lbf[i] = float_at_least(po.lb[i]);
+    po.ubf[i] = float_at_most(po.ub[i]);
   }
 }
 
@@ -1419,6 +1441,20 @@ DFIT_HD double post_param(const PostOpts& po, int i, double v, double r2) {
     v = div_pow10(rint(v * s), s, po.inv_scale[i]);  // numpy.around: round-half-even of the scaled value, divided back
   }
   return v;
+}
+
+
+// Epilogue of one fp32 parameter into an fp32 map: comparisons-only parameters stay in fp32 (exactly the
+// decisions the float64 evaluation takes, see PostOpts::simple); everything else goes through post_param.
+DFIT_HD float post_param_f32(const PostOpts& po, int i, float v, float r2) {
+  if (!po.enabled) return v;
+  if (po.simple[i] && !(fabsf(v) > 3.4028234e38f)) {  // finite or NaN (+-inf takes the nan_to_num branch in double)
+    const bool bad = v < po.lbf[i] || v > po.ubf[i] || (po.has_r2_thresh && r2 < po.r2_thresh_f);
+    if (bad) v = NAN;
+    if (po.has_fill && v != v) v = po.fill_f;
+    return v;
+  }
+  return (float)post_param(po, i, (double)v, (double)r2);
 }
 
 }  // namespace dfit

@@ -132,3 +132,26 @@ extern "C" double hostsim_post_param(int enabled, const int* ufunc, const double
   po.fill = fill;
   return post_param(po, i, v, r2);
 }
+
+// fp32 epilogue (post_param_f32) next to the float64 one (post_param) on the same inputs: returns both
+extern "C" void hostsim_post_param_f32(int enabled, const int* ufunc, const double* lb, const double* ub, int has_thr,
+                                       double thr, int has_fill, double fill, const int* decimals, int i, int64_t n,
+                                       const float* v, const float* r2, float* out_f32, float* out_f64path) {
+  PostOpts po;
+  po.enabled = enabled;
+  for (int k = 0; k < 4; ++k) {
+    po.ufunc[k] = ufunc[k];
+    po.lb[k] = lb[k];
+    po.ub[k] = ub[k];
+    po.decimals[k] = decimals[k];
+  }
+  po.has_r2_thresh = has_thr;
+  po.r2_thresh = thr;
+  po.has_fill = has_fill;
+  po.fill = fill;
+  set_post_scales(po);
+  for (int64_t k = 0; k < n; ++k) {
+    out_f32[k] = post_param_f32(po, i, v[k], r2[k]);
+    out_f64path[k] = (float)post_param(po, i, (double)v[k], (double)r2[k]);
+  }
+}

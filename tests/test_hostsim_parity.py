@@ -92,3 +92,36 @@ def test_post_param_matches_process_params():
         got = np.array([lib.hostsim_post_param(1, uf, lb, ub, 1, ctypes.c_double(0.9), 1, ctypes.c_double(0.0), dec, i,
                                                ctypes.c_double(a), ctypes.c_double(b)) for a, b in zip(v, r2)])
         assert np.array_equal(got, ref[:, i])
+
+
+def test_fp32_epilogue_takes_the_float64_decisions():
+    """post_param_f32 (fp32 where the epilogue is comparisons only) must return exactly what the float64
+    epilogue returns after conversion to float32, including at bounds / thresholds that are not representable
+    in float32 and on NaN / inf inputs."""
+    lib = H._load()
+    rng = np.random.default_rng(0)
+    n = 200000
+    v = rng.uniform(-5, 130, n).astype(np.float32)
+    r2 = rng.uniform(0.5, 1.0, n).astype(np.float32)
+    # values sitting exactly on / next to the float32 neighbours of the bounds and of the threshold
+    lb, ub, thr = 0.1, 100.00000123, 0.9
+    for k, x0 in enumerate((lb, ub)):
+        f = np.float32(x0)
+        v[k * 3: k * 3 + 3] = [np.nextafter(f, np.float32(-np.inf)), f, np.nextafter(f, np.float32(np.inf))]
+    t = np.float32(thr)
+    r2[10:13] = [np.nextafter(t, np.float32(0)), t, np.nextafter(t, np.float32(2))]
+    v[20:24] = [np.nan, np.inf, -np.inf, 0.0]
+    ip = ctypes.POINTER(ctypes.c_int)
+    dp = ctypes.POINTER(ctypes.c_double)
+    fp = ctypes.POINTER(ctypes.c_float)
+    for ufunc, decimals, fill in ((0, -1, 0.0), (0, -1, None), (0, -1, 0.1), (1, 3, 0.0), (0, 2, 0.0)):
+        uf = (ctypes.c_int * 4)(ufunc, ufunc, 0, 0)
+        dec = (ctypes.c_int * 4)(decimals, decimals, -1, -1)
+        lbs = (ctypes.c_double * 4)(lb, lb, -np.inf, -np.inf)
+        ubs = (ctypes.c_double * 4)(ub, ub, np.inf, np.inf)
+        a = np.empty(n, np.float32)
+        b = np.empty(n, np.float32)
+        lib.hostsim_post_param_f32(1, uf, lbs, ubs, 1, ctypes.c_double(thr), int(fill is not None),
+                                   ctypes.c_double(fill or 0.0), dec, 0, ctypes.c_int64(n), v.ctypes.data_as(fp),
+                                   r2.ctypes.data_as(fp), a.ctypes.data_as(fp), b.ctypes.data_as(fp))
+        assert np.array_equal(a, b, equal_nan=True), (ufunc, decimals, fill)
