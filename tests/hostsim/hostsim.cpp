@@ -155,3 +155,16 @@ extern "C" void hostsim_post_param_f32(int enabled, const int* ufunc, const doub
     out_f64path[k] = (float)post_param(po, i, (double)v[k], (double)r2[k]);
   }
 }
+
+// echo-table classification the launcher relies on: bit 0 uniform spacing, bit 1 descending (backward Prony)
+extern "C" int hostsim_xtab_flags(int dtype, int E, const double* x) {
+  if (E < 1 || E > 16) return -1;
+  if (dtype == 0) {
+    XTab<float, 16> xt;
+    fill_xtab<float, 16>(xt, x, E);
+    return xt.uniform | (xt.backward << 1);
+  }
+  XTab<double, 16> xt;
+  fill_xtab<double, 16>(xt, x, E);
+  return xt.uniform | (xt.backward << 1);
+}

@@ -152,3 +152,26 @@ def test_recovers_truth_over_decades_of_decay():
         assert (relb < lim).all(), (dtype, float((relb / lim).max()))
         assert (np.abs(p[ok, 0] - a[ok]) / a[ok] < 50 * lim).all()
         assert (r[ok] > 1 - 1e-4).all()
+
+
+def test_echo_table_classification():
+    """Which solver a launch gets: uniform spacing is recognised to within the arithmetic's resolution of the
+    largest echo time (so that treating the spacing as uniform cannot change the model), descending order selects
+    the backward start."""
+    import ctypes
+
+    lib = H._load()
+
+    def flags(x, dtype="f32"):
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        return lib.hostsim_xtab_flags(0 if dtype == "f32" else 1, len(x), x.ctypes.data_as(ctypes.POINTER(ctypes.c_double)))
+
+    assert flags(np.arange(1, 9) * 10.0) == 1
+    assert flags(np.linspace(4.6, 32.6, 8)) == 1 and flags(np.linspace(4.6, 32.6, 8), "f64") == 1
+    assert flags(np.arange(8, 0, -1) * 10.0) == 3
+    assert flags([10.0, 20.0, 40.0, 80.0]) == 0
+    assert flags([0.0, 10.0, 12.847, 25.695, 40.0, 51.39, 80.0]) == 0
+    assert flags([10.0, 20.0, 30.0, 40.0 + 1e-3]) == 0               # 2.5e-5 off the grid: not uniform in fp32
+    assert flags([10.0, 20.0, 30.0, 40.0 + 1e-6]) == 1               # below fp32's resolution of 40
+    assert flags([10.0, 20.0, 30.0, 40.0 + 1e-6], "f64") == 0        # but visible in fp64
+    assert flags([10.0, 20.0]) == 0 and flags([5.0, 5.0, 5.0]) == 0  # too few echoes / zero spacing
