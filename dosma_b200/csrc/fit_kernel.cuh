@@ -14,6 +14,7 @@
 #include <stdint.h>
 
 #include "lm_core.cuh"
+#include "mono_fast.cuh"
 
 namespace dfit {
 

@@ -14,7 +14,8 @@ MODELS = {"monoexponential": (0, 2), "biexponential": (1, 4), "linear": (2, 1)}
 def _load():
     global _lib
     if _lib is None:
-        srcs = [os.path.join(_HERE, "hostsim.cpp"), os.path.join(_HERE, "..", "..", "dosma_b200", "csrc", "lm_core.cuh")]
+        csrc = os.path.join(_HERE, "..", "..", "dosma_b200", "csrc")
+        srcs = [os.path.join(_HERE, "hostsim.cpp"), os.path.join(csrc, "lm_core.cuh"), os.path.join(csrc, "mono_fast.cuh")]
         if not os.path.exists(_SO) or os.path.getmtime(_SO) < max(os.path.getmtime(s) for s in srcs):
             subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=fast", "-march=native",
                                    "-o", _SO, srcs[0]])

@@ -1,4 +1,4 @@
-// TEST-ONLY harness: compiles the device solver header (dosma_b200/csrc/lm_core.cuh) with g++ so the
+// TEST-ONLY harness: compiles the device solver headers (dosma_b200/csrc/lm_core.cuh, mono_fast.cuh) with g++ so the
 // CPU test-suite (-m "not gpu") can exercise the exact per-voxel arithmetic the CUDA kernels run.
 // It is NOT part of the product: dosma_b200/ never loads it and the shipped library (libdfit.so)
 // contains no host implementation of the fit (no CPU fallback).
@@ -6,6 +6,7 @@
 #include <cstring>
 
 #include "../../dosma_b200/csrc/lm_core.cuh"
+#include "../../dosma_b200/csrc/mono_fast.cuh"
 
 using namespace dfit;
 
