@@ -1,0 +1,417 @@
+// Shared by every fit kernel: kernel arguments, sample loads, the per-voxel store / fused epilogue and the
+// all-gather epilogue, statistics, the TMA / mbarrier primitives, and the launch description the C-ABI
+// layer fills.  See fit_kernel.cuh for the map of the kernels.
+#pragma once
+
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "lm_core.cuh"
+#include "mono_fast.cuh"
+
+namespace dfit {
+
+
+constexpr int kBlock = 128;
+
+enum DType : int { DT_F32 = 0, DT_F64 = 1, DT_I16 = 2, DT_U16 = 3, DT_I32 = 4, DT_U8 = 5 };
+enum Layout : int { LAYOUT_PLANAR = 0, LAYOUT_ECHO_FASTEST = 1 };
+enum Counter : int { CNT_FITTED = 0, CNT_FAILED, CNT_NONFINITE, CNT_OOB, CNT_ITERS, CNT_MAXITER, CNT_COUNT };
+constexpr int kStatSlots = 1024;  // power of two
+constexpr int kMaxPeers = 8;
+
+template <typename T, int EMAX>
+struct KernelArgs {
+  XTab<T, EMAX> xt;
+  VoxelOpts<T> vo;
+  PostOpts po;
+  const void* y;
+  int64_t ld;
+  int64_t n;
+  int y_dtype, layout, E;
+  const uint8_t* mask;
+  const unsigned* index;        // compacted list of voxels to fit (mask path), or null: fit voxel v = thread id
+  const unsigned* index_count;  // device counter: number of entries in `index`
+  const void* p0v;  // [N, P] per-voxel initial guess or null
+  int p0_dtype;
+  unsigned p0_voxel_bits;  // bit i set: parameter i comes from p0v
+  T p0s[4];
+  void* popt;
+  void* r2;
+  int out_dtype;
+  uint8_t* status;
+  uint8_t* niter;
+  double mask_fill;  // value written outside the mask: NaN or nan_to_num (fitting.py:207-212)
+  unsigned long long* counters;
+  // Fused all-gather epilogue: when gather_world > 0 every voxel's packed row [popt..., r2] (fp32) is
+  // also stored straight into the reassembled map of EVERY rank (peer-mapped over NVLink) at row
+  // gather_row0 + v -- the collective overlaps the fit instead of following it.
+  float* gather[kMaxPeers];
+  int gather_world;
+  int64_t gather_row0;
+};
+
+static inline size_t dtype_size(int dt) {
+  switch (dt) {
+    case DT_F32: case DT_I32: return 4;
+    case DT_F64: return 8;
+    case DT_I16: case DT_U16: return 2;
+    default: return 1;
+  }
+}
+
+#if defined(__CUDACC__)
+
+template <typename T>
+__device__ __forceinline__ T load_as(const void* __restrict__ base, int dtype, int64_t idx) {
+  switch (dtype) {
+    case DT_F32: return (T)__ldcs(reinterpret_cast<const float*>(base) + idx);
+    case DT_F64: return (T)__ldcs(reinterpret_cast<const double*>(base) + idx);
+    case DT_I16: return (T)__ldcs(reinterpret_cast<const short*>(base) + idx);
+    case DT_U16: return (T)__ldcs(reinterpret_cast<const unsigned short*>(base) + idx);
+    case DT_I32: return (T)__ldcs(reinterpret_cast<const int*>(base) + idx);
+    default: return (T)__ldcs(reinterpret_cast<const unsigned char*>(base) + idx);
+  }
+}
+
+template <typename T, typename S, int EMAX, bool EXACT>
+__device__ __forceinline__ void load_strided(const S* __restrict__ src, int64_t stride, int E, T (&y)[EMAX]) {
+#pragma unroll
+  for (int e = 0; e < EMAX; ++e) y[e] = (EXACT || e < E) ? (T)__ldcs(src + (int64_t)e * stride) : (T)0;
+}
+
+template <typename T, int EMAX, bool EXACT>
+__device__ __forceinline__ void load_samples(const KernelArgs<T, EMAX>& a, int64_t v, T (&y)[EMAX]) {
+  if (a.layout == LAYOUT_ECHO_FASTEST && a.y_dtype == DT_F32 && (EMAX % 4 == 0) && (a.ld % 4 == 0) &&
+      (EXACT || a.E == EMAX) && ((reinterpret_cast<uintptr_t>(a.y) & 15) == 0)) {
+    const float4* src = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(a.y) + v * a.ld);
+#pragma unroll
+    for (int q = 0; q < EMAX / 4; ++q) {
+      const float4 t = __ldcs(src + q);
+      y[4 * q + 0] = (T)t.x;
+      y[4 * q + 1] = (T)t.y;
+      y[4 * q + 2] = (T)t.z;
+      y[4 * q + 3] = (T)t.w;
+    }
+    return;
+  }
+  // Planar: lane l of a warp reads voxel v0 + l of every echo plane -- one fully coalesced line per
+  // echo.  The element type is switched once, outside the echo loop.
+  const bool planar = a.layout == LAYOUT_PLANAR;
+  const int64_t first = planar ? v : v * a.ld, stride = planar ? a.ld : 1;
+  switch (a.y_dtype) {
+    case DT_F32: load_strided<T, float, EMAX, EXACT>(reinterpret_cast<const float*>(a.y) + first, stride, a.E, y); break;
+    case DT_F64: load_strided<T, double, EMAX, EXACT>(reinterpret_cast<const double*>(a.y) + first, stride, a.E, y); break;
+    case DT_I16: load_strided<T, short, EMAX, EXACT>(reinterpret_cast<const short*>(a.y) + first, stride, a.E, y); break;
+    case DT_U16:
+      load_strided<T, unsigned short, EMAX, EXACT>(reinterpret_cast<const unsigned short*>(a.y) + first, stride, a.E, y);
+      break;
+    case DT_I32: load_strided<T, int, EMAX, EXACT>(reinterpret_cast<const int*>(a.y) + first, stride, a.E, y); break;
+    default:
+      load_strided<T, unsigned char, EMAX, EXACT>(reinterpret_cast<const unsigned char*>(a.y) + first, stride, a.E, y);
+      break;
+  }
+}
+
+template <int P, typename T, int EMAX>
+__device__ __forceinline__ void load_p0(const KernelArgs<T, EMAX>& a, int64_t v, T (&p)[P]) {
+#pragma unroll
+  for (int i = 0; i < P; ++i) {
+    p[i] = a.p0s[i];
+    if ((a.p0_voxel_bits >> i) & 1u) p[i] = load_as<T>(a.p0v, a.p0_dtype, v * P + i);
+  }
+}
+
+template <int P, typename TO>
+__device__ __forceinline__ void store_vec(TO* __restrict__ dst, const double (&q)[P]) {
+  if constexpr (sizeof(TO) == 4 && P == 2) {
+    __stcs(reinterpret_cast<float2*>(dst), make_float2((float)q[0], (float)q[1]));
+  } else if constexpr (sizeof(TO) == 4 && P == 4) {
+    __stcs(reinterpret_cast<float4*>(dst), make_float4((float)q[0], (float)q[1], (float)q[2], (float)q[3]));
+  } else if constexpr (sizeof(TO) == 8 && P == 2) {
+    __stcs(reinterpret_cast<double2*>(dst), make_double2(q[0], q[1]));
+  } else if constexpr (sizeof(TO) == 8 && P == 4) {
+    __stcs(reinterpret_cast<double2*>(dst), make_double2(q[0], q[1]));
+    __stcs(reinterpret_cast<double2*>(dst) + 1, make_double2(q[2], q[3]));
+  } else {
+#pragma unroll
+    for (int i = 0; i < P; ++i) dst[i] = (TO)q[i];
+  }
+}
+
+// Epilogue + stores for one voxel.  `fitted` false: voxel outside the mask.
+template <int P, typename T, int EMAX, bool GATHER = true>
+__device__ __forceinline__ void store_voxel(const KernelArgs<T, EMAX>& a, int64_t v, const T (&p)[P], T r2, bool fitted,
+                                            int st, int iters, bool warp_rows = false) {
+  if constexpr (sizeof(T) == 4) {
+    // fp32 parameters into fp32 maps: raw (curve_fit without an epilogue) or through the fp32-where-exact
+    // epilogue -- no trip through double for r2 and the comparisons-only parameters.
+    if (fitted && a.out_dtype == DT_F32 && a.popt != nullptr && !(GATHER && a.gather_world > 0)) {
+      float q[P];
+#pragma unroll
+      for (int i = 0; i < P; ++i) q[i] = post_param_f32(a.po, i, p[i], r2);
+      float* dst = reinterpret_cast<float*>(a.popt) + v * P;
+      if constexpr (P == 2) __stcs(reinterpret_cast<float2*>(dst), make_float2(q[0], q[1]));
+      else if constexpr (P == 4) __stcs(reinterpret_cast<float4*>(dst), make_float4(q[0], q[1], q[2], q[3]));
+      else {
+#pragma unroll
+        for (int i = 0; i < P; ++i) __stcs(dst + i, q[i]);
+      }
+      __stcs(reinterpret_cast<float*>(a.r2) + v, r2);
+      if (a.status) a.status[v] = (uint8_t)st;
+      if (a.niter) a.niter[v] = (uint8_t)(iters > 255 ? 255 : iters);
+      return;
+    }
+  }
+  double q[P];
+  double r2o;
+  if (fitted) {
+    r2o = (double)r2;
+#pragma unroll
+    for (int i = 0; i < P; ++i) q[i] = post_param(a.po, i, (double)p[i], r2o);
+  } else {
+    r2o = a.mask_fill;
+#pragma unroll
+    for (int i = 0; i < P; ++i) {
+      q[i] = a.mask_fill;
+      if (a.po.enabled && a.po.decimals[i] >= 0) q[i] = div_pow10(rint(q[i] * a.po.scale[i]), a.po.scale[i], a.po.inv_scale[i]);
+    }
+  }
+  if (a.popt != nullptr) {
+    if (a.out_dtype == DT_F32) {
+      store_vec<P, float>(reinterpret_cast<float*>(a.popt) + v * P, q);
+      __stcs(reinterpret_cast<float*>(a.r2) + v, (float)r2o);
+    } else {
+      store_vec<P, double>(reinterpret_cast<double*>(a.popt) + v * P, q);
+      __stcs(reinterpret_cast<double*>(a.r2) + v, r2o);
+    }
+  }
+  if (GATHER && a.gather_world > 0) {
+    constexpr int C = P + 1;
+    float row[C];
+#pragma unroll
+    for (int i = 0; i < P; ++i) row[i] = (float)q[i];
+    row[P] = (float)r2o;
+    if (warp_rows) {
+      // The warp's 32 rows are one contiguous block of 32*C floats in every map.  Transpose it through
+      // shuffles so that each of the C store instructions writes 128 contiguous bytes per warp: NVLink
+      // carries full write packets instead of 4-byte fragments at a 4*C-byte stride.
+      const int lane = threadIdx.x & 31;
+      float word[C];
+#pragma unroll
+      for (int k = 0; k < C; ++k) {
+        const int w = k * 32 + lane;  // word of the block this lane stores in round k
+        const int src = w / C, col = w - src * C;
+        float val = 0.f;
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+          const float t = __shfl_sync(0xffffffffu, row[c], src);
+          if (c == col) val = t;
+        }
+        word[k] = val;
+      }
+      const int64_t block0 = (a.gather_row0 + (v - lane)) * C;
+#pragma unroll
+      for (int r = 0; r < kMaxPeers; ++r) {
+        if (r < a.gather_world) {
+          float* dst = a.gather[r] + block0 + lane;  // local HBM for r == own rank, a peer's over NVLink otherwise
+#pragma unroll
+          for (int k = 0; k < C; ++k) dst[k * 32] = word[k];
+        }
+      }
+    } else {
+      const int64_t off = (a.gather_row0 + v) * C;
+#pragma unroll
+      for (int r = 0; r < kMaxPeers; ++r) {
+        if (r < a.gather_world) {
+          float* dst = a.gather[r] + off;
+#pragma unroll
+          for (int i = 0; i < C; ++i) dst[i] = row[i];
+        }
+      }
+    }
+  }
+  if (a.status) a.status[v] = (uint8_t)st;
+  if (a.niter) a.niter[v] = (uint8_t)(iters > 255 ? 255 : iters);
+}
+
+// Statistics are reduced per warp (dense path) or per CTA (grid-stride paths) and added to one of
+// kStatSlots slots of global counters (same-address atomics serialise in the L2 atomic unit; 1.8 M warps
+// hammering six addresses cost more than the fit itself).  The host sums the slots in dfit_get_stats.
+// Dense path: three warp reductions and two fire-and-forget global reductions
+// per warp (no shared memory, no block barrier), spread over kStatSlots slots; the rare events (failures,
+// non-finite or out-of-bounds voxels) take a separate branch.  Must be reached by all 32 lanes.
+__device__ __forceinline__ void warp_stats(unsigned long long* cnt, int st, int iters, unsigned flags) {
+  const unsigned full = 0xffffffffu;
+  const unsigned fitted = __popc(__ballot_sync(full, st >= ST_CONV_F));
+  const unsigned its = __reduce_add_sync(full, (unsigned)iters);
+  const unsigned mx = __reduce_max_sync(full, (unsigned)iters);
+  const unsigned rare = __ballot_sync(full, st >= ST_MAXITER || flags != 0u);
+  if ((threadIdx.x & 31) == 0) {
+    unsigned long long* dst =
+        cnt + (size_t)((blockIdx.x * (kBlock / 32) + (threadIdx.x >> 5)) & (kStatSlots - 1)) * CNT_COUNT;
+    if (fitted) atomicAdd(dst + CNT_FITTED, (unsigned long long)fitted);
+    if (its) atomicAdd(dst + CNT_ITERS, (unsigned long long)its);
+    if (mx) atomicMax(dst + CNT_MAXITER, (unsigned long long)mx);
+  }
+  if (rare) {
+    const unsigned nfail = __popc(__ballot_sync(full, st >= ST_MAXITER));
+    const unsigned nnf = __popc(__ballot_sync(full, (flags & FLAG_NONFINITE) != 0u));
+    const unsigned noob = __popc(__ballot_sync(full, (flags & FLAG_OOB) != 0u));
+    if ((threadIdx.x & 31) == 0) {
+      unsigned long long* dst =
+          cnt + (size_t)((blockIdx.x * (kBlock / 32) + (threadIdx.x >> 5)) & (kStatSlots - 1)) * CNT_COUNT;
+      if (nfail) atomicAdd(dst + CNT_FAILED, (unsigned long long)nfail);
+      if (nnf) atomicAdd(dst + CNT_NONFINITE, (unsigned long long)nnf);
+      if (noob) atomicAdd(dst + CNT_OOB, (unsigned long long)noob);
+    }
+  }
+}
+
+// Mask path, step 1: one streaming pass over the mask that (a) appends the voxels to fit to a compact
+// index list -- each warp claims a contiguous run with one atomic, so neighbours stay neighbours -- and
+// (b) writes the fill value for every voxel outside the mask (fitting.py:205-215).  Step 2 is the fit
+// kernel over the list: all 32 lanes of a warp fit, however thin the tissue mask is.
+__device__ __forceinline__ void block_stats_counts(unsigned long long* cnt, unsigned n_fit, unsigned n_fail, unsigned n_nf,
+                                                   unsigned n_oob, int it_sum, int it_max) {
+  __shared__ unsigned s_c[4], s_iters, s_max;
+  if (threadIdx.x < 4) s_c[threadIdx.x] = 0;
+  if (threadIdx.x == 0) {
+    s_iters = 0;
+    s_max = 0;
+  }
+  __syncthreads();
+  const unsigned full = 0xffffffffu;
+  const unsigned c[4] = {__reduce_add_sync(full, n_fit), __reduce_add_sync(full, n_fail), __reduce_add_sync(full, n_nf),
+                         __reduce_add_sync(full, n_oob)};
+  const unsigned s_it = __reduce_add_sync(full, (unsigned)it_sum);
+  const unsigned m_it = __reduce_max_sync(full, (unsigned)it_max);
+  if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      if (c[k]) atomicAdd(&s_c[k], c[k]);
+    atomicAdd(&s_iters, s_it);
+    atomicMax(&s_max, m_it);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned long long* dst = cnt + (size_t)(blockIdx.x & (kStatSlots - 1)) * CNT_COUNT;
+    if (s_c[0]) atomicAdd(dst + CNT_FITTED, (unsigned long long)s_c[0]);
+    if (s_c[1]) atomicAdd(dst + CNT_FAILED, (unsigned long long)s_c[1]);
+    if (s_c[2]) atomicAdd(dst + CNT_NONFINITE, (unsigned long long)s_c[2]);
+    if (s_c[3]) atomicAdd(dst + CNT_OOB, (unsigned long long)s_c[3]);
+    if (s_iters) atomicAdd(dst + CNT_ITERS, (unsigned long long)s_iters);
+    if (s_max) atomicMax(dst + CNT_MAXITER, (unsigned long long)s_max);
+  }
+}
+
+// ---- TMA / mbarrier primitives --------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t}" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+          smem_u32(dst)),
+      "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+      : "memory");
+}
+
+#endif  // __CUDACC__
+
+// Type-erased launch description filled by the C-ABI layer and consumed by the per-model
+// translation units (inst_*.cu).
+struct LaunchDesc {
+  int model, compute_dtype, n_echo;
+  int64_t n_vox;
+  const double* x;  // host
+  const void* y;
+  int y_dtype, layout;
+  int64_t ld;
+  const uint8_t* mask;
+  unsigned* index;        // device scratch for the compacted mask path (n_vox entries) or null
+  unsigned* index_count;  // device counter
+  const void* p0v;
+  int p0_dtype;
+  unsigned p0_voxel_bits;
+  double p0s[4];
+  void* popt;
+  void* r2;
+  int out_dtype;
+  uint8_t* status;
+  uint8_t* niter;
+  unsigned long long* counters;
+  // solver
+  double ftol, xtol, lambda0, floor_rel, r2_eps, y_lo, y_hi;
+  int maxfev, init_mode, init_linear, fast_path;
+  PostOpts po;
+  double mask_fill;
+  int use_tma;
+  cudaStream_t stream;
+  float* gather[kMaxPeers];
+  int gather_world;
+  int64_t gather_row0;
+  const CUtensorMap* tmap;   // host pointer to an encoded 2-D map of the planar fp32 samples (box 32 x E), or null
+  const CUtensorMap* tmap2;  // the same with a 64-voxel box, for the two-voxels-per-lane kernel, or null
+  int sm_count;
+};
+
+template <typename T, int EMAX>
+inline void fill_args(const LaunchDesc& d, KernelArgs<T, EMAX>& a) {
+  fill_xtab<T, EMAX>(a.xt, d.x, d.n_echo);
+  a.vo.s.ftol = (T)d.ftol;
+  a.vo.s.xtol = (T)d.xtol;
+  a.vo.s.lambda0 = (T)d.lambda0;
+  a.vo.s.floor_rel = (T)d.floor_rel;
+  a.vo.s.maxfev = d.maxfev;
+  a.vo.s.init_linear = d.init_linear;
+  a.vo.y_lo = (T)d.y_lo;
+  a.vo.y_hi = (T)d.y_hi;
+  a.vo.r2_eps = (T)d.r2_eps;
+  a.vo.init_mode = d.init_mode;
+  a.vo.has_bounds = (d.y_lo > -1.7e308 || d.y_hi < 1.7e308) ? 1 : 0;
+  a.vo.fast = d.fast_path;
+  a.po = d.po;
+  a.y = d.y;
+  a.ld = d.ld;
+  a.n = d.n_vox;
+  a.y_dtype = d.y_dtype;
+  a.layout = d.layout;
+  a.E = d.n_echo;
+  a.mask = d.mask;
+  a.index = nullptr;
+  a.index_count = nullptr;
+  a.p0v = d.p0v;
+  a.p0_dtype = d.p0_dtype;
+  a.p0_voxel_bits = d.p0_voxel_bits;
+  for (int i = 0; i < 4; ++i) a.p0s[i] = (T)d.p0s[i];
+  a.popt = d.popt;
+  a.r2 = d.r2;
+  a.out_dtype = d.out_dtype;
+  a.status = d.status;
+  a.niter = d.niter;
+  a.mask_fill = d.mask_fill;
+  a.counters = d.counters;
+  for (int r = 0; r < kMaxPeers; ++r) a.gather[r] = d.gather[r];
+  a.gather_world = d.gather_world;
+  a.gather_row0 = d.gather_row0;
+}
+
+}  // namespace dfit

@@ -1,0 +1,358 @@
+// Two voxels per lane: the mono-exponential fast-path kernels -- plain loads (fit_kernel_mono2), the compacted
+// voxel list of the mask path (fit_kernel_mono2_list) and the persistent TMA-staged kernel that the headline
+// number runs (fit_kernel_mono2_tma, optionally with the fused all-gather by TMA bulk stores).
+#pragma once
+
+#include "kernel_common.cuh"
+
+namespace dfit {
+
+#if defined(__CUDACC__)
+
+// ------------------------------------------------------------------------------------------------
+// Two voxels per lane: the dense mono-exponential fast path (uniform echo spacing, fp32 arithmetic, planar
+// f32 / i16 / u16 samples).  Lane l of a CTA owns voxels 2 (128 b + l) and the next one: one 8-byte (4-byte
+// for 16-bit samples) coalesced load per echo, every packed instruction works on both voxels, and the
+// results leave as one 16-byte [a, b, a, b] store and one 8-byte r2 store.  Voxels the fast path declines
+// run the general LM from the caller's initial guess, one at a time (rare).
+constexpr int kBlock2 = 128;
+
+template <typename S>
+struct Vec2;
+template <> struct Vec2<float> { typedef float2 type; };
+template <> struct Vec2<short> { typedef short2 type; };
+template <> struct Vec2<unsigned short> { typedef ushort2 type; };
+
+template <typename S, int EMAX>
+__device__ __forceinline__ void load_pairs(const void* __restrict__ yv, int64_t ld, int64_t v0, bool both,
+                                           pair2<float> (&Y)[EMAX]) {
+  const S* __restrict__ base = reinterpret_cast<const S*>(yv) + v0;
+  if (both) {
+#pragma unroll
+    for (int e = 0; e < EMAX; ++e) {
+      const typename Vec2<S>::type t = __ldcs(reinterpret_cast<const typename Vec2<S>::type*>(base + (int64_t)e * ld));
+      Y[e] = p2_make<float>((float)t.x, (float)t.y);
+    }
+  } else {  // odd tail: the missing voxel duplicates the last one and is never stored
+#pragma unroll
+    for (int e = 0; e < EMAX; ++e) {
+      const float t = (float)__ldcs(base + (int64_t)e * ld);
+      Y[e] = p2_make<float>(t, t);
+    }
+  }
+}
+
+__device__ __forceinline__ void warp_stats2(unsigned long long* cnt, const int (&st)[2], const int (&iters)[2],
+                                            unsigned flags) {
+  const unsigned full = 0xffffffffu;
+  const unsigned fitted = __popc(__ballot_sync(full, st[0] >= ST_CONV_F)) + __popc(__ballot_sync(full, st[1] >= ST_CONV_F));
+  const unsigned its = __reduce_add_sync(full, (unsigned)(iters[0] + iters[1]));
+  const unsigned mx = __reduce_max_sync(full, (unsigned)(iters[0] > iters[1] ? iters[0] : iters[1]));
+  const unsigned rare = __ballot_sync(full, st[0] >= ST_MAXITER || st[1] >= ST_MAXITER || flags != 0u);
+  const unsigned slot = (blockIdx.x * (kBlock2 / 32) + (threadIdx.x >> 5)) & (kStatSlots - 1);
+  unsigned long long* dst = cnt + (size_t)slot * CNT_COUNT;
+  if ((threadIdx.x & 31) == 0) {
+    if (fitted) atomicAdd(dst + CNT_FITTED, (unsigned long long)fitted);
+    if (its) atomicAdd(dst + CNT_ITERS, (unsigned long long)its);
+    if (mx) atomicMax(dst + CNT_MAXITER, (unsigned long long)mx);
+  }
+  if (rare) {
+    const unsigned nfail = __reduce_add_sync(full, (unsigned)(st[0] >= ST_MAXITER) + (unsigned)(st[1] >= ST_MAXITER));
+    const unsigned nnf = __reduce_add_sync(full, (flags & 0xffu));
+    const unsigned noob = __reduce_add_sync(full, (flags >> 8) & 0xffu);
+    if ((threadIdx.x & 31) == 0) {
+      if (nfail) atomicAdd(dst + CNT_FAILED, (unsigned long long)nfail);
+      if (nnf) atomicAdd(dst + CNT_NONFINITE, (unsigned long long)nnf);
+      if (noob) atomicAdd(dst + CNT_OOB, (unsigned long long)noob);
+    }
+  }
+}
+
+template <class M, int EMAX>
+__global__ void __launch_bounds__(kBlock2, 5) fit_kernel_mono2(const __grid_constant__ KernelArgs<float, EMAX> a) {
+  typedef float T;
+  constexpr int P = 2;
+  const int64_t v0 = ((int64_t)blockIdx.x * kBlock2 + threadIdx.x) * 2;
+  int st[2] = {-1, -1}, iters[2] = {0, 0};
+  unsigned nflags = 0;  // bits 0..7: non-finite voxels of this lane, bits 8..15: out-of-bounds voxels
+  if (v0 < a.n) {
+    const bool both = v0 + 1 < a.n;
+    pair2<T> Y[EMAX], pa, pb, r2;
+    if (a.y_dtype == DT_F32) load_pairs<float, EMAX>(a.y, a.ld, v0, both, Y);
+    else if (a.y_dtype == DT_I16) load_pairs<short, EMAX>(a.y, a.ld, v0, both, Y);
+    else load_pairs<unsigned short, EMAX>(a.y, a.ld, v0, both, Y);
+    fit_voxel_fast2<M, T, EMAX, pair2<T>[EMAX]>(Y, a.xt, a.vo, pa, pb, r2, st, iters);
+    if (st[0] < 0 || st[1] < 0) {  // the general path, one voxel at a time
+#pragma unroll 1
+      for (int hsel = 0; hsel < 2; ++hsel) {
+        if ((hsel ? st[1] : st[0]) >= 0) continue;
+        T ys[EMAX], p[P], r = 0;
+        int it = 0;
+        unsigned fl = 0;
+#pragma unroll
+        for (int e = 0; e < EMAX; ++e) ys[e] = hsel ? Y[e].hi : Y[e].lo;
+        load_p0<P, T, EMAX>(a, hsel && both ? v0 + 1 : v0, p);
+        const int s1 = fit_voxel<M, T, T, EMAX, true>(ys, a.xt, a.E, a.vo, p, r, it, fl);
+        if (hsel == 0 || both) nflags += ((fl & FLAG_NONFINITE) ? 1u : 0u) + ((fl & FLAG_OOB) ? 0x100u : 0u);
+        if (hsel) {
+          st[1] = s1; iters[1] = it; pa.hi = p[0]; pb.hi = p[1]; r2.hi = r;
+        } else {
+          st[0] = s1; iters[0] = it; pa.lo = p[0]; pb.lo = p[1]; r2.lo = r;
+        }
+      }
+    }
+    if (!both) {
+      st[1] = -1;
+      iters[1] = 0;
+    }
+    if (!a.po.enabled && a.out_dtype == DT_F32 && both) {
+      __stcs(reinterpret_cast<float4*>(reinterpret_cast<float*>(a.popt) + v0 * P), make_float4(pa.lo, pb.lo, pa.hi, pb.hi));
+      __stcs(reinterpret_cast<float2*>(reinterpret_cast<float*>(a.r2) + v0), make_float2(r2.lo, r2.hi));
+      if (a.status) {
+        a.status[v0] = (uint8_t)st[0];
+        a.status[v0 + 1] = (uint8_t)st[1];
+      }
+      if (a.niter) {
+        a.niter[v0] = (uint8_t)iters[0];
+        a.niter[v0 + 1] = (uint8_t)iters[1];
+      }
+    } else {
+      const T p0_[P] = {pa.lo, pb.lo}, p1_[P] = {pa.hi, pb.hi};
+      store_voxel<P, T, EMAX, false>(a, v0, p0_, r2.lo, true, st[0], iters[0]);
+      if (both) store_voxel<P, T, EMAX, false>(a, v0 + 1, p1_, r2.hi, true, st[1], iters[1]);
+    }
+  }
+  __syncwarp();
+  warp_stats2(a.counters, st, iters, nflags);
+}
+
+// Two voxels per lane over the compacted voxel list of the mask path (any echo spacing, any sample type):
+// lane i takes list entries 2i and 2i+1, gathers their samples and runs the same packed fast path; voxels
+// it declines run the LM.  Grid-stride, because the list length is only known on the device.
+template <class M, int EMAX>
+__global__ void __launch_bounds__(kBlock, 5) fit_kernel_mono2_list(const __grid_constant__ KernelArgs<float, EMAX> a) {
+  typedef float T;
+  constexpr int P = 2;
+  const unsigned count = *a.index_count;
+  const unsigned npairs = (count + 1u) >> 1;
+  int it_sum = 0, it_max = 0;
+  unsigned n_fit = 0, n_fail = 0, n_nf = 0, n_oob = 0;
+  for (unsigned i = blockIdx.x * kBlock + threadIdx.x; i < npairs; i += gridDim.x * kBlock) {
+    const bool both = 2u * i + 1u < count;
+    const int64_t vA = (int64_t)a.index[2u * i], vB = both ? (int64_t)a.index[2u * i + 1u] : vA;
+    T yA[EMAX], yB[EMAX];
+    load_samples<T, EMAX, true>(a, vA, yA);
+    load_samples<T, EMAX, true>(a, vB, yB);
+    pair2<T> Y[EMAX], pa, pb, r2;
+#pragma unroll
+    for (int e = 0; e < EMAX; ++e) Y[e] = p2_make<T>(yA[e], yB[e]);
+    int st[2], iters[2];
+    fit_voxel_fast2<M, T, EMAX, pair2<T>[EMAX]>(Y, a.xt, a.vo, pa, pb, r2, st, iters);
+    if (st[0] < 0 || (st[1] < 0 && both)) {
+#pragma unroll 1
+      for (int hsel = 0; hsel < 2; ++hsel) {
+        if ((hsel ? st[1] : st[0]) >= 0 || (hsel && !both)) continue;
+        T ys[EMAX], p[P], r = 0;
+        int it = 0;
+        unsigned fl = 0;
+#pragma unroll
+        for (int e = 0; e < EMAX; ++e) ys[e] = hsel ? Y[e].hi : Y[e].lo;
+        load_p0<P, T, EMAX>(a, hsel ? vB : vA, p);
+        const int s1 = fit_voxel<M, T, T, EMAX, true>(ys, a.xt, a.E, a.vo, p, r, it, fl);
+        n_nf += (unsigned)((fl & FLAG_NONFINITE) != 0);
+        n_oob += (unsigned)((fl & FLAG_OOB) != 0);
+        if (hsel) {
+          st[1] = s1; iters[1] = it; pa.hi = p[0]; pb.hi = p[1]; r2.hi = r;
+        } else {
+          st[0] = s1; iters[0] = it; pa.lo = p[0]; pb.lo = p[1]; r2.lo = r;
+        }
+      }
+    }
+    const T p0_[P] = {pa.lo, pb.lo}, p1_[P] = {pa.hi, pb.hi};
+    store_voxel<P, T, EMAX, false>(a, vA, p0_, r2.lo, true, st[0], iters[0]);
+    if (both) store_voxel<P, T, EMAX, false>(a, vB, p1_, r2.hi, true, st[1], iters[1]);
+    else { st[1] = -1; iters[1] = 0; }
+    it_sum += iters[0] + iters[1];
+    it_max = iters[0] > it_max ? iters[0] : it_max;
+    it_max = iters[1] > it_max ? iters[1] : it_max;
+    n_fit += (unsigned)(st[0] >= ST_CONV_F) + (unsigned)(st[1] >= ST_CONV_F);
+    n_fail += (unsigned)(st[0] >= ST_MAXITER) + (unsigned)(st[1] >= ST_MAXITER);
+  }
+  block_stats_counts(a.counters, n_fit, n_fail, n_nf, n_oob, it_sum, it_max);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Two voxels per lane + TMA staging (fp32 or raw 16-bit samples, converted on the way to registers):
+// persistent warps, each with its own ring of [E][64-voxel] sample tiles in shared memory.  The Tensor Memory Accelerator fills a stage (one cp.async.bulk.tensor.2d over
+// the 2-D map of the planar samples, box = 64 voxels x E echoes, completion on the stage's mbarrier) while
+// the warp is fitting earlier tiles, so the HBM latency that the plain kernel exposes at the top of every
+// CTA is hidden behind arithmetic.  Lanes read their two voxels of every echo as one conflict-free 8-byte
+// shared load.  No block-level synchronisation inside the loop.
+constexpr int kM2Warps = 4;
+constexpr int kM2Tile = 64;
+constexpr int m2_stages(int E) { return E <= 8 ? 4 : 2; }  // 32 KB of tiles per CTA
+
+template <class M, int EMAX, bool GATHER, typename S>
+__global__ void __launch_bounds__(kM2Warps * 32, 5)  // 5 CTAs/SM: 6 spills, 4 is slower (measured: 0.743 / 0.689 / 0.696 ms);
+                                                     // reading the samples from the tile on every use to free 16 registers
+                                                     // (6-7 CTAs/SM) was measured too: 3 % slower
+    fit_kernel_mono2_tma(const __grid_constant__ KernelArgs<float, EMAX> a, const __grid_constant__ CUtensorMap tmap) {
+  typedef float T;
+  constexpr int P = 2;
+  constexpr int kStages = m2_stages(EMAX);
+  constexpr unsigned kTileBytes = EMAX * kM2Tile * sizeof(S);  // S = float, or the raw 16-bit DICOM sample type
+  __shared__ __align__(128) S tiles[kM2Warps][kStages][EMAX][kM2Tile];
+  __shared__ __align__(8) uint64_t full[kM2Warps][kStages];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // 32-bit indexing: the launcher admits fewer than 2^31 voxels
+  const int n_vox = (int)a.n;
+  const int n_tiles = (n_vox + kM2Tile - 1) / kM2Tile;
+  const int warp_global = (int)blockIdx.x * kM2Warps + warp;
+  const int warp_stride = (int)gridDim.x * kM2Warps;
+
+  if (lane == 0) {
+#pragma unroll
+    for (int s = 0; s < kStages; ++s) mbar_init(&full[warp][s], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+#pragma unroll
+    for (int s = 0; s < kStages; ++s) {  // prologue: fill the ring
+      const int t = warp_global + s * warp_stride;
+      if (t < n_tiles) {
+        mbar_expect_tx(&full[warp][s], kTileBytes);
+        tma_load_2d(&tiles[warp][s][0][0], &tmap, t * kM2Tile, 0, &full[warp][s]);
+      }
+    }
+  }
+  __syncwarp();
+
+  unsigned n_fit = 0, it_sum = 0, it_max = 0;
+  unsigned long long* const stat_slot = a.counters + (size_t)(warp_global & (kStatSlots - 1)) * CNT_COUNT;
+  int k = 0;
+  for (int t = warp_global; t < n_tiles; t += warp_stride, ++k) {
+    const int s = k % kStages;
+    mbar_wait(&full[warp][s], (unsigned)(k / kStages) & 1u);
+    pair2<T> Y[EMAX], pa, pb, r2;
+#pragma unroll
+    for (int e = 0; e < EMAX; ++e) {
+      const typename Vec2<S>::type v = *reinterpret_cast<const typename Vec2<S>::type*>(&tiles[warp][s][e][2 * lane]);
+      Y[e] = p2_make<T>((T)v.x, (T)v.y);
+    }
+    __syncwarp();
+    if (lane == 0) {  // the stage is drained: refill it with the tile kStages trips ahead
+      const int tn = t + kStages * warp_stride;
+      if (tn < n_tiles) {
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        mbar_expect_tx(&full[warp][s], kTileBytes);
+        tma_load_2d(&tiles[warp][s][0][0], &tmap, tn * kM2Tile, 0, &full[warp][s]);
+      }
+    }
+    const int v0 = t * kM2Tile + 2 * lane;
+    const bool validA = v0 < n_vox, validB = v0 + 1 < n_vox;
+    int st[2], iters[2];
+    fit_voxel_fast2<M, T, EMAX, pair2<T>[EMAX]>(Y, a.xt, a.vo, pa, pb, r2, st, iters);  // voxels past the end are zero-filled: declined
+    if ((st[0] < 0 && validA) || (st[1] < 0 && validB)) {  // the general path, one voxel at a time
+#pragma unroll 1
+      for (int hsel = 0; hsel < 2; ++hsel) {
+        if ((hsel ? st[1] : st[0]) >= 0 || !(hsel ? validB : validA)) continue;
+        T ys[EMAX], p[P], r = 0;
+        int it = 0;
+        unsigned fl = 0;
+#pragma unroll
+        for (int e = 0; e < EMAX; ++e) ys[e] = hsel ? Y[e].hi : Y[e].lo;
+        load_p0<P, T, EMAX>(a, v0 + hsel, p);
+        const int s1 = fit_voxel<M, T, T, EMAX, true>(ys, a.xt, a.E, a.vo, p, r, it, fl);
+        // rare events go straight to the counters (the voxel has just paid for a full LM anyway)
+        if (s1 >= ST_MAXITER) atomicAdd(stat_slot + CNT_FAILED, 1ull);
+        if (fl & FLAG_NONFINITE) atomicAdd(stat_slot + CNT_NONFINITE, 1ull);
+        if (fl & FLAG_OOB) atomicAdd(stat_slot + CNT_OOB, 1ull);
+        if (hsel) {
+          st[1] = s1; iters[1] = it; pa.hi = p[0]; pb.hi = p[1]; r2.hi = r;
+        } else {
+          st[0] = s1; iters[0] = it; pa.lo = p[0]; pb.lo = p[1]; r2.lo = r;
+        }
+      }
+    }
+    if (!validA) { st[0] = -1; iters[0] = 0; }
+    if (!validB) { st[1] = -1; iters[1] = 0; }
+    if constexpr (GATHER) {
+      // Fused all-gather: the tile's 64 rows [a, b, r2] are one contiguous 768-byte block in every rank's map.
+      // Stage them in shared memory (double-buffered) and let the TMA push the block to every rank with one
+      // bulk store each (cp.async.bulk global <- shared): the SM's load/store path never waits on NVLink.  The
+      // launcher admits this kernel only without the epilogue and with 16-byte-aligned rank blocks.
+      __shared__ __align__(128) float rows[kM2Warps][2][kM2Tile * 3];
+      float* sg = rows[warp][k & 1];
+      if (t * kM2Tile + kM2Tile <= n_vox) {
+        // the staging buffer used two tiles ago must have been read by its bulk copies
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+        __syncwarp();
+        *reinterpret_cast<float2*>(sg + 6 * lane) = make_float2(pa.lo, pb.lo);
+        *reinterpret_cast<float2*>(sg + 6 * lane + 2) = make_float2(r2.lo, pa.hi);
+        *reinterpret_cast<float2*>(sg + 6 * lane + 4) = make_float2(pb.hi, r2.hi);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) {
+          // one TMA bulk store of the 768-byte block per rank: local HBM for the own rank, NVLink otherwise
+          const int64_t base = (a.gather_row0 + (int64_t)t * kM2Tile) * 3;
+#pragma unroll
+          for (int r = 0; r < kMaxPeers; ++r) {
+            if (r < a.gather_world) {
+              asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(a.gather[r] + base),
+                           "r"(smem_u32(sg)), "n"(kM2Tile * 3 * 4)
+                           : "memory");
+            }
+          }
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+      } else {  // ragged last tile: row by row
+#pragma unroll
+        for (int r = 0; r < kMaxPeers; ++r) {
+          if (r < a.gather_world) {
+            float* dst = a.gather[r] + (a.gather_row0 + v0) * 3;
+            if (validA) { dst[0] = pa.lo; dst[1] = pb.lo; dst[2] = r2.lo; }
+            if (validB) { dst[3] = pa.hi; dst[4] = pb.hi; dst[5] = r2.hi; }
+          }
+        }
+      }
+    }
+    if (GATHER && a.popt == nullptr) {
+      // the maps are the only output
+    } else if (!a.po.enabled && a.out_dtype == DT_F32 && validB) {
+      __stcs(reinterpret_cast<float4*>(reinterpret_cast<float*>(a.popt) + (int64_t)v0 * P), make_float4(pa.lo, pb.lo, pa.hi, pb.hi));
+      __stcs(reinterpret_cast<float2*>(reinterpret_cast<float*>(a.r2) + v0), make_float2(r2.lo, r2.hi));
+      if (a.status) {
+        a.status[v0] = (uint8_t)st[0];
+        a.status[v0 + 1] = (uint8_t)st[1];
+      }
+      if (a.niter) {
+        a.niter[v0] = (uint8_t)iters[0];
+        a.niter[v0 + 1] = (uint8_t)iters[1];
+      }
+    } else {
+      const T p0_[P] = {pa.lo, pb.lo}, p1_[P] = {pa.hi, pb.hi};
+      if (validA) store_voxel<P, T, EMAX, false>(a, v0, p0_, r2.lo, true, st[0], iters[0]);
+      if (validB) store_voxel<P, T, EMAX, false>(a, v0 + 1, p1_, r2.hi, true, st[1], iters[1]);
+    }
+    n_fit += (unsigned)(st[0] >= ST_CONV_F) + (unsigned)(st[1] >= ST_CONV_F);
+    it_sum += (unsigned)(iters[0] + iters[1]);
+    const unsigned im = (unsigned)(iters[0] > iters[1] ? iters[0] : iters[1]);
+    it_max = im > it_max ? im : it_max;
+  }
+  if constexpr (GATHER) {
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // all bulk stores of this warp are done
+  }
+  // statistics: per-thread accumulators -> one reduction per warp at the end of the kernel
+  {
+    const unsigned fm = 0xffffffffu;
+    const unsigned v0 = __reduce_add_sync(fm, n_fit);
+    const unsigned v4 = __reduce_add_sync(fm, it_sum), v5 = __reduce_max_sync(fm, it_max);
+    if (lane == 0) {
+      if (v0) atomicAdd(stat_slot + CNT_FITTED, (unsigned long long)v0);
+      if (v4) atomicAdd(stat_slot + CNT_ITERS, (unsigned long long)v4);
+      if (v5) atomicMax(stat_slot + CNT_MAXITER, (unsigned long long)v5);
+    }
+  }
+}
+
+#endif  // __CUDACC__
+
+}  // namespace dfit

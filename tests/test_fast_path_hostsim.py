@@ -1,4 +1,4 @@
-"""CPU tests of the mono-exponential fast path (variable-projection Newton, dosma_b200/csrc/lm_core.cuh
+"""CPU tests of the mono-exponential fast path (variable-projection Newton, dosma_b200/csrc/mono_fast.cuh
 compiled by g++ through tests/hostsim): the two-voxels-per-lane solvers that the CUDA kernels run, against
 the LM from p0 (fast=0) and against the C oracle (MINPACK restatement), over echo spacings, echo counts,
 SNR and decay ranges.  High SNR: same minimiser to rounding.  Low SNR: the cost function has several

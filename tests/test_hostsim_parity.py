@@ -1,4 +1,4 @@
-"""CPU tests of the *device* arithmetic: dosma_b200/csrc/lm_core.cuh compiled by g++ (tests/hostsim)
+"""CPU tests of the *device* arithmetic: dosma_b200/csrc/lm_core.cuh and mono_fast.cuh compiled by g++ (tests/hostsim)
 against the golden fixtures and the oracle.  The GPU tests repeat these through the real kernels;
 this file is what keeps the solver honest in the CPU-only build container."""
 import ctypes
