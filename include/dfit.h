@@ -130,8 +130,8 @@ typedef struct dfit_stats {
   int64_t n_failed;     /* solver ran but did not converge (status >= 5) */
   int64_t n_nonfinite;  /* voxels with NaN/Inf input -- the reference raises ValueError for these */
   int64_t n_oob;        /* voxels skipped by y_bounds */
-  int64_t sum_iters;    /* total LM trial steps */
-  int32_t max_iters;    /* largest per-voxel trial-step count */
+  int64_t sum_iters;    /* total passes over the echoes (Newton passes of the fast path, LM trial steps otherwise) */
+  int32_t max_iters;    /* largest per-voxel pass count */
   int32_t n_launches;   /* kernels launched by the call */
   float kernel_ms;      /* device time of the fit kernel(s), CUDA events on the engine's stream */
   float total_ms;       /* device time of the whole call incl. copies (host entry point only) */
