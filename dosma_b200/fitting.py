@@ -225,9 +225,12 @@ def curve_fit(func, x, y, y_bounds=None, p0=None, maxfev=100, ftol=1e-5, eps=1e-
         maxfev, ftol, eps: as in the reference (defaults 100, 1e-5, 1e-8).
         show_pbar, num_workers, chunksize: accepted for compatibility; the GPU fits all N sequences
             in one launch, so they have no effect.
-        kwargs: engine options (``compute_dtype``, ``device``, ``xtol``, ``lambda0`` ...).  SciPy
-            options that change the algorithm (``bounds``, ``method``, ``sigma``, ``jac``) are not
-            supported and raise NotImplementedError.
+        kwargs: engine options (``compute_dtype``, ``device``, ``xtol``, ``lambda0``, ``fast_path`` ...).
+            ``fast_path=0`` forces the Levenberg-Marquardt iteration from ``p0`` for every sequence; by
+            default mono-exponential sequences are fitted by a variable-projection Newton iteration from
+            a data-driven start (same minimiser; ``p0`` then only serves the sequences that path
+            declines, e.g. low-SNR ones).  SciPy options that change the algorithm (``bounds``,
+            ``method``, ``sigma``, ``jac``) are not supported and raise NotImplementedError.
 
     Returns:
         popts (N, P) float64 and r2 (N,) float64, NaN / 0 where the fit failed (fitting.py:870).
