@@ -443,7 +443,8 @@ int dfit_fit_host(dfit_handle* h, const dfit_opts* opts, int n_echo, int64_t n_v
     plane_pitch = (const char*)y_planes[1] - (const char*)y_planes[0];
     for (int e = 2; e < n_echo && plane_pitch > 0; ++e)
       if ((const char*)y_planes[e] - (const char*)y_planes[e - 1] != plane_pitch) plane_pitch = 0;
-    if (plane_pitch < (ptrdiff_t)((size_t)n_vox * ysz)) plane_pitch = 0;
+    // (cudaMemcpy2D pitches are limited to cudaDeviceProp::memPitch = 2^31 - 1 bytes)
+    if (plane_pitch < (ptrdiff_t)((size_t)n_vox * ysz) || plane_pitch > (ptrdiff_t)0x7fffffff) plane_pitch = 0;
   }
   int64_t idx = 0;
   for (int64_t v0 = 0; v0 < n_vox; v0 += chunk, ++idx) {
