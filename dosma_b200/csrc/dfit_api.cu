@@ -198,7 +198,7 @@ bool tma2_eligible(const LaunchDesc& d) {
   return d.use_tma != 0 && d.model == DFIT_MODEL_MONOEXP && d.fast_path == 1 && d.compute_dtype == DFIT_F32 &&
          (d.y_dtype == DFIT_F32 || d.y_dtype == DFIT_I16 || d.y_dtype == DFIT_U16) && d.layout == DFIT_PLANAR &&
          d.mask == nullptr &&
-         d.n_echo >= 3 && d.n_echo <= 16 && d.n_vox < (int64_t)1 << 31;
+         d.n_echo >= 3 && d.n_echo <= 16 && d.n_vox < ((int64_t)1 << 31) - 2 * kM2Tile;  // 32-bit tile arithmetic
 }
 
 cudaError_t dispatch(const LaunchDesc& d) {
