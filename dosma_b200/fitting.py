@@ -28,7 +28,7 @@ __all__ = ["CurveFitter", "MonoExponentialFit", "curve_fit", "monoexponential", 
 _R2_THRESHOLD_TEMPLATE = 0.9  # dosma/resources/templates/.preferences.yml:3-4 (fitting/r2.threshold)
 _AFFINE_DECIMAL_PRECISION = 4  # dosma/defaults.py AFFINE_DECIMAL_PRECISION, used at fitting.py:104
 _ENGINE_KWARGS = ("compute_dtype", "device", "xtol", "lambda0", "ftol_scale", "init_linear", "use_tma",
-                  "fast_path", "return_stats")
+                  "fast_path", "out_dtype", "return_stats")
 
 _default_compute_dtype = "auto"
 
@@ -151,15 +151,20 @@ def _engine_fit(model_id, nparams, x, planes, mask, p0_cols, *, init_mode=_cabi.
         if mask_u8.shape[0] != N:
             raise ValueError("mask size mismatch")
 
-    popt = np.empty((N, nparams), dtype=np.float64)
-    r2 = np.empty(N, dtype=np.float64)
+    # float64 like the reference's results (fitting.py:870) unless the caller opts into float32 maps
+    # (out_dtype="f32": half the device-to-host bytes; fp32 arithmetic carries no more information anyway)
+    out_dt = {"f64": np.float64, "f32": np.float32}.get(engine.get("out_dtype") or "f64")
+    if out_dt is None:
+        raise ValueError("out_dtype must be 'f64' or 'f32'")
+    popt = np.empty((N, nparams), dtype=out_dt)
+    r2 = np.empty(N, dtype=out_dt)
     plane_ptrs = (ctypes.c_void_p * E)(*[p.ctypes.data for p in planes])
     h = _cabi.get_handle(engine.get("device", _default_device()))
     _cabi.check(lib.dfit_fit_host(
         h.ptr, ctypes.byref(o), E, N, x.ctypes.data, ctypes.cast(plane_ptrs, ctypes.c_void_p),
         _cabi.NP_TO_DTYPE[planes[0].dtype], mask_u8.ctypes.data if mask_u8 is not None else None,
         p0v.ctypes.data if p0v is not None else None, _cabi.F64 if cd == "f64" else _cabi.F32,
-        popt.ctypes.data, r2.ctypes.data, _cabi.F64, None, None))
+        popt.ctypes.data, r2.ctypes.data, _cabi.F64 if out_dt == np.float64 else _cabi.F32, None, None))
     stats = h.stats()
     if stats["n_nonfinite"]:
         # SciPy's asarray_chkfinite aborts the whole reference fit the same way
@@ -225,7 +230,8 @@ def curve_fit(func, x, y, y_bounds=None, p0=None, maxfev=100, ftol=1e-5, eps=1e-
         maxfev, ftol, eps: as in the reference (defaults 100, 1e-5, 1e-8).
         show_pbar, num_workers, chunksize: accepted for compatibility; the GPU fits all N sequences
             in one launch, so they have no effect.
-        kwargs: engine options (``compute_dtype``, ``device``, ``xtol``, ``lambda0``, ``fast_path`` ...).
+        kwargs: engine options (``compute_dtype``, ``device``, ``xtol``, ``lambda0``, ``fast_path``,
+            ``out_dtype`` ...).
             ``fast_path=0`` forces the Levenberg-Marquardt iteration from ``p0`` for every sequence; by
             default mono-exponential sequences are fitted by a variable-projection Newton iteration from
             a data-driven start (same minimiser; ``p0`` then only serves the sequences that path

@@ -542,3 +542,14 @@ def test_api_errors_and_forms(D):
     # bounds (TestCurveFitter.test_bounds)
     popt, _ = D.CurveFitter(D.monoexponential, out_bounds=[(-np.inf, np.inf), (0, 0.6)]).fit(x, y)
     assert np.isnan(popt.volume[..., 1][b > 0.6001]).all() and np.allclose(popt.volume[..., 1][b < 0.5999], b[b < 0.5999])
+
+
+def test_float32_result_maps_option(D):
+    """out_dtype="f32": the same fit, results as float32 maps (what the kernel computes in), half the D2H bytes."""
+    c = G.load("curvefit_mono8_snr100_f32")
+    p64, r64 = D.curve_fit(D.monoexponential, c["x"], c["y"], p0=(1.0, -1 / 30))
+    p32, r32 = D.curve_fit(D.monoexponential, c["x"], c["y"], p0=(1.0, -1 / 30), out_dtype="f32")
+    assert p32.dtype == np.float32 and r32.dtype == np.float32 and p64.dtype == np.float64
+    assert np.array_equal(p32, p64.astype(np.float32), equal_nan=True) and np.array_equal(r32, r64.astype(np.float32))
+    with pytest.raises(ValueError):
+        D.curve_fit(D.monoexponential, c["x"], c["y"], out_dtype="f16")
