@@ -9,6 +9,8 @@
 #include <cstring>
 #include <limits>
 #include <new>
+#include <thread>
+#include <vector>
 
 #include "dfit_internal.h"
 
@@ -39,9 +41,57 @@ int ensure(DevBuf& b, size_t bytes) {
   return DFIT_OK;
 }
 
+int ensure_host(HostBuf& b, size_t bytes) {
+  if (bytes <= b.cap) return DFIT_OK;
+  if (b.p) cudaFreeHost(b.p);
+  b.p = nullptr;
+  b.cap = 0;
+  const size_t want = bytes + (bytes >> 3) + 256;
+  CUDA_TRY(cudaHostAlloc(&b.p, want, cudaHostAllocDefault));
+  b.cap = want;
+  return DFIT_OK;
+}
+
 }  // namespace dfit
 
 namespace {
+
+// Copy `count` segments {dst, src, bytes} with a few host threads (1 MiB blocks, static partition).  A single
+// core moves ~10 GB/s; the pageable side of the host entry point needs several to keep up with PCIe.
+struct CopySeg {
+  void* dst;
+  const void* src;
+  size_t bytes;
+};
+
+void par_copy(const CopySeg* segs, int count) {
+  constexpr size_t kBlk = (size_t)1 << 20;
+  size_t total_blocks = 0;
+  for (int i = 0; i < count; ++i) total_blocks += (segs[i].bytes + kBlk - 1) / kBlk;
+  unsigned hw = std::thread::hardware_concurrency();
+  int nt = (int)(hw == 0 ? 4 : (hw > 16 ? 16 : hw));
+  if ((size_t)nt > total_blocks) nt = (int)total_blocks;
+  auto work = [&](int t) {
+    size_t b = 0;  // global block counter; thread t takes blocks with b % nt == t
+    for (int i = 0; i < count; ++i) {
+      const size_t nb = (segs[i].bytes + kBlk - 1) / kBlk;
+      for (size_t k = 0; k < nb; ++k, ++b) {
+        if ((int)(b % (size_t)nt) != t) continue;
+        const size_t off = k * kBlk, len = segs[i].bytes - off < kBlk ? segs[i].bytes - off : kBlk;
+        std::memcpy((char*)segs[i].dst + off, (const char*)segs[i].src + off, len);
+      }
+    }
+  };
+  if (nt <= 1) {
+    if (total_blocks) work(0);
+    return;
+  }
+  std::vector<std::thread> th;
+  th.reserve(nt - 1);
+  for (int t = 1; t < nt; ++t) th.emplace_back(work, t);
+  work(0);
+  for (auto& x : th) x.join();
+}
 
 int model_nparams(int model) {
   switch (model) {
@@ -298,7 +348,11 @@ int dfit_create(int device, dfit_handle** out) {
   }
   h->sm_count = prop.multiProcessorCount;
   CUDA_TRY(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
-  for (int s = 0; s < kSlots; ++s) CUDA_TRY(cudaStreamCreateWithFlags(&h->slots[s].stream, cudaStreamNonBlocking));
+  for (int s = 0; s < kSlots; ++s) {
+    CUDA_TRY(cudaStreamCreateWithFlags(&h->slots[s].stream, cudaStreamNonBlocking));
+    CUDA_TRY(cudaEventCreateWithFlags(&h->slots[s].ev_in, cudaEventDisableTiming));
+    CUDA_TRY(cudaEventCreateWithFlags(&h->slots[s].ev_out, cudaEventDisableTiming));
+  }
   CUDA_TRY(cudaMalloc(&h->counters, kStatSlots * CNT_COUNT * sizeof(unsigned long long)));
   CUDA_TRY(cudaMemset(h->counters, 0, kStatSlots * CNT_COUNT * sizeof(unsigned long long)));
   CUDA_TRY(cudaEventCreate(&h->ev_start));
@@ -316,6 +370,11 @@ int dfit_destroy(dfit_handle* h) {
     DevBuf* bufs[] = {&sl.y, &sl.mask, &sl.p0, &sl.popt, &sl.r2, &sl.status, &sl.niter, &sl.index};
     for (DevBuf* b : bufs)
       if (b->p) cudaFree(b->p);
+    HostBuf* hbufs[] = {&sl.hin, &sl.hpopt, &sl.hr2};
+    for (HostBuf* b : hbufs)
+      if (b->p) cudaFreeHost(b->p);
+    if (sl.ev_in) cudaEventDestroy(sl.ev_in);
+    if (sl.ev_out) cudaEventDestroy(sl.ev_out);
     if (sl.stream) cudaStreamDestroy(sl.stream);
   }
   if (h->stream) cudaStreamDestroy(h->stream);
@@ -446,6 +505,24 @@ int dfit_fit_host(dfit_handle* h, const dfit_opts* opts, int n_echo, int64_t n_v
     // (cudaMemcpy2D pitches are limited to cudaDeviceProp::memPitch = 2^31 - 1 bytes)
     if (plane_pitch < (ptrdiff_t)((size_t)n_vox * ysz) || plane_pitch > (ptrdiff_t)0x7fffffff) plane_pitch = 0;
   }
+  // Pageable caller buffers (numpy arrays ...) go through page-locked staging, copied by host threads:
+  // in:  planes -> slot.hin  (host threads)  -> device (one DMA per chunk)
+  // out: device -> slot.hpopt / hr2 (DMA)    -> caller's arrays (host threads), one chunk behind the GPU
+  bool in_pageable = false;
+  for (int e = 0; e < n_echo && n_vox > 0; ++e) in_pageable = in_pageable || !is_pinned_or_device(y_planes[e]);
+  const bool out_pageable = n_vox > 0 && (!is_pinned_or_device(popt) || !is_pinned_or_device(r2));
+  struct Pending {
+    int64_t v0, n;
+  } pending[kSlots];
+  auto drain = [&](int64_t j) -> int {  // chunk j's results: staging -> caller's arrays
+    Slot& sj = h->slots[j % kSlots];
+    CUDA_TRY(cudaEventSynchronize(sj.ev_out));
+    const Pending& pj = pending[j % kSlots];
+    const CopySeg segs[2] = {{(char*)popt + (size_t)pj.v0 * P * osz, sj.hpopt.p, (size_t)pj.n * P * osz},
+                             {(char*)r2 + (size_t)pj.v0 * osz, sj.hr2.p, (size_t)pj.n * osz}};
+    par_copy(segs, 2);
+    return DFIT_OK;
+  };
   int64_t idx = 0;
   for (int64_t v0 = 0; v0 < n_vox; v0 += chunk, ++idx) {
     const int64_t n = n_vox - v0 < chunk ? n_vox - v0 : chunk;
@@ -459,7 +536,21 @@ int dfit_fit_host(dfit_handle* h, const dfit_opts* opts, int n_echo, int64_t n_v
     if (status && (rc = ensure(sl.status, (size_t)chunk)) != DFIT_OK) return rc;
     if (niter && (rc = ensure(sl.niter, (size_t)chunk)) != DFIT_OK) return rc;
     cudaStream_t st = sl.stream;
-    if (plane_pitch > 0) {  // equidistant planes (one (E, N) array): one strided copy per chunk instead of E
+    if (in_pageable) {
+      if ((rc = ensure_host(sl.hin, (size_t)n_echo * chunk * ysz)) != DFIT_OK) return rc;
+      if (idx >= kSlots) CUDA_TRY(cudaEventSynchronize(sl.ev_in));  // the DMA that last read this staging block is done
+      CopySeg segs[DFIT_MAX_ECHOES];
+      for (int e = 0; e < n_echo; ++e)
+        segs[e] = CopySeg{(char*)sl.hin.p + (size_t)e * chunk * ysz, (const char*)y_planes[e] + (size_t)v0 * ysz, (size_t)n * ysz};
+      par_copy(segs, n_echo);
+      if (n == chunk) {
+        CUDA_TRY(cudaMemcpyAsync(sl.y.p, sl.hin.p, (size_t)n_echo * chunk * ysz, cudaMemcpyHostToDevice, st));
+      } else {
+        CUDA_TRY(cudaMemcpy2DAsync(sl.y.p, (size_t)chunk * ysz, sl.hin.p, (size_t)chunk * ysz, (size_t)n * ysz, (size_t)n_echo,
+                                   cudaMemcpyHostToDevice, st));
+      }
+      CUDA_TRY(cudaEventRecord(sl.ev_in, st));
+    } else if (plane_pitch > 0) {  // equidistant planes (one (E, N) array): one strided copy per chunk instead of E
       CUDA_TRY(cudaMemcpy2DAsync(sl.y.p, (size_t)chunk * ysz, (const char*)y_planes[0] + (size_t)v0 * ysz, (size_t)plane_pitch,
                                  (size_t)n * ysz, (size_t)n_echo, cudaMemcpyHostToDevice, st));
     } else {
@@ -491,17 +582,30 @@ int dfit_fit_host(dfit_handle* h, const dfit_opts* opts, int n_echo, int64_t n_v
     if (tma2_eligible(d) && make_sample_tmap(&tmap2, d.y, n_echo, n, chunk, kM2Tile, y_dtype)) d.tmap2 = &tmap2;
     CUDA_TRY(dispatch(d));
     h->last_launches += mask && d.tmap == nullptr ? 2 : 1;
-    CUDA_TRY(cudaMemcpyAsync((char*)popt + (size_t)v0 * P * osz, sl.popt.p, (size_t)n * P * osz, cudaMemcpyDeviceToHost, st));
-    CUDA_TRY(cudaMemcpyAsync((char*)r2 + (size_t)v0 * osz, sl.r2.p, (size_t)n * osz, cudaMemcpyDeviceToHost, st));
+    if (out_pageable) {
+      if ((rc = ensure_host(sl.hpopt, (size_t)chunk * P * osz)) != DFIT_OK) return rc;
+      if ((rc = ensure_host(sl.hr2, (size_t)chunk * osz)) != DFIT_OK) return rc;
+      CUDA_TRY(cudaMemcpyAsync(sl.hpopt.p, sl.popt.p, (size_t)n * P * osz, cudaMemcpyDeviceToHost, st));
+      CUDA_TRY(cudaMemcpyAsync(sl.hr2.p, sl.r2.p, (size_t)n * osz, cudaMemcpyDeviceToHost, st));
+      CUDA_TRY(cudaEventRecord(sl.ev_out, st));
+      pending[idx % kSlots] = Pending{v0, n};
+      // the staging blocks of a slot are emptied before the slot is used again: drain the oldest chunk in flight
+      if (idx >= kSlots - 1 && (rc = drain(idx - (kSlots - 1))) != DFIT_OK) return rc;
+    } else {
+      CUDA_TRY(cudaMemcpyAsync((char*)popt + (size_t)v0 * P * osz, sl.popt.p, (size_t)n * P * osz, cudaMemcpyDeviceToHost, st));
+      CUDA_TRY(cudaMemcpyAsync((char*)r2 + (size_t)v0 * osz, sl.r2.p, (size_t)n * osz, cudaMemcpyDeviceToHost, st));
+    }
     if (status) CUDA_TRY(cudaMemcpyAsync(status + v0, sl.status.p, (size_t)n, cudaMemcpyDeviceToHost, st));
     if (niter) CUDA_TRY(cudaMemcpyAsync(niter + v0, sl.niter.p, (size_t)n, cudaMemcpyDeviceToHost, st));
   }
+  if (out_pageable)  // the chunks still in flight
+    for (int64_t j = idx >= kSlots - 1 ? idx - (kSlots - 1) : 0; j < idx; ++j)
+      if ((rc = drain(j)) != DFIT_OK) return rc;
   for (int s = 0; s < kSlots; ++s) CUDA_TRY(cudaStreamSynchronize(h->slots[s].stream));
   const auto t1 = std::chrono::steady_clock::now();
   h->last_total_ms = std::chrono::duration<float, std::milli>(t1 - t0).count();
   h->ev_valid = false;
   h->last_n = n_vox;
-  (void)is_pinned_or_device;
   return DFIT_OK;
 }
 

@@ -32,9 +32,20 @@ struct DevBuf {
 
 int ensure(DevBuf& b, size_t bytes);
 
+// Page-locked host staging (cudaHostAlloc): pageable caller buffers are copied through these by a few host
+// threads so that the GPU side of dfit_fit_host always DMAs at the full PCIe rate.
+struct HostBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+};
+
+int ensure_host(HostBuf& b, size_t bytes);
+
 struct Slot {
   cudaStream_t stream = nullptr;
   DevBuf y, mask, p0, popt, r2, status, niter, index;
+  HostBuf hin, hpopt, hr2;
+  cudaEvent_t ev_in = nullptr, ev_out = nullptr;  // staging consumed by the H2D copy / filled by the D2H copies
 };
 
 }  // namespace dfit
