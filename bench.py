@@ -336,6 +336,19 @@ def run_gpu(args):
     e2e_s = time.perf_counter() - t0
     e2e_launches = handle.stats()["n_launches"]
 
+    # the same step through the Python drop-in API on pageable numpy data (what a DOSMA user calls), N = 1 only
+    py_api = None
+    if world == 1:
+        y_np = yh.numpy().copy()  # pageable
+        D.curve_fit(D.monoexponential, xs, y_np[:, :1 << 20], p0=P0)
+        t0 = time.perf_counter()
+        for _ in range(2):
+            p_np, r_np = D.curve_fit(D.monoexponential, xs, y_np, p0=P0)
+        py_s = (time.perf_counter() - t0) / 2
+        py_api = {"value": n / py_s, "unit": UNIT, "api": "dosma_b200.curve_fit on pageable numpy arrays, float64 results",
+                  "seconds_per_step": py_s}
+        del y_np, p_np, r_np
+
     times = torch.tensor([total_ms, e2e_s * 1e3, kernel_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
@@ -368,6 +381,8 @@ def run_gpu(args):
             "lm": {"mean_iters": stats["sum_iters"] / max(stats["n_fitted"], 1), "max_iters": stats["max_iters"],
                    "failed_voxels": stats["n_failed"], "fitted_voxels": stats["n_fitted"]},
         }
+        if py_api is not None:
+            line["e2e_python_api"] = py_api
         if not args.no_cpu and world == 1:
             line["cpu_baseline"] = cpu_baseline()
         sys.stdout.flush()
