@@ -678,6 +678,7 @@ struct XTab {
   T q_lo, q_hi;  // admissible range of q: q^(2E-2) must stay finite
   T xx[EMAX];    // x^2, for the second derivatives of the general (non-uniform) fast path
   T inv_xmax;    // 1 / max |x|: the largest step in b the general fast path takes at once
+  T span2;       // (max x - min x)^2
 };
 
 // Host-side fill of the echo table (shared by the C-ABI layer and the test-only host build).
@@ -713,6 +714,12 @@ inline void fill_xtab(XTab<T, EMAX>& xt, const double* x, int n_echo) {
   xt.q_lo = (T)(sizeof(T) == 4 ? 1e-30 : 1e-280);
   for (int e = 0; e < EMAX; ++e) xt.xx[e] = (T)(e < n_echo ? x[e] * x[e] : 0.0);
   xt.inv_xmax = (T)(xmax > 0 ? 1.0 / xmax : 0.0);
+  double xlo = n_echo ? x[0] : 0.0, xhi = xlo;
+  for (int e = 1; e < n_echo; ++e) {
+    xlo = fmin(xlo, x[e]);
+    xhi = fmax(xhi, x[e]);
+  }
+  xt.span2 = (T)((xhi - xlo) * (xhi - xlo));
 }
 
 // ------------------------------------------------------------------------------------ one voxel

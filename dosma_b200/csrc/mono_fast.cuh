@@ -397,7 +397,8 @@ DFIT_HD void mono_general_newton2(const YS& Y, const XTab<T, E>& xt, const Solve
 #endif
       V w = p2_add<T>(y2, cut);
       w = p2_make<T>(nm::max_(w.lo, (T)0), nm::max_(w.hi, (T)0));
-      const V xe = p2_bcast<T>(xt.x[e]), xxe = p2_bcast<T>(xt.xx[e]);
+      // moments about the mean echo time: the determinant below must not drown in cancellation
+      const V xe = p2_bcast<T>(xt.xc[e]), xxe = p2_bcast<T>(xt.xc[e] * xt.xc[e]);
       const V wl = p2_mul<T>(w, l);
       S0 = p2_add<T>(S0, w);
       S1 = p2_fma<T>(xe, w, S1);
@@ -410,10 +411,14 @@ DFIT_HD void mono_general_newton2(const YS& Y, const XTab<T, E>& xt, const Solve
   const V den_ = p2_fma<T>(S0, S2, p2_mul<T>(p2_mul<T>(S1, S1), p2_bcast<T>((T)-1)));
   const V b0 = p2_mul<T>(p2_mul<T>(num_, p2_make<T>(nm::rcp_(den_.lo), nm::rcp_(den_.hi))), p2_bcast<T>((T)0.34657359027997264));
   NewtonLane<T> A, B;
-  // |b x| <= 40 keeps every e_k^2 finite in fp32; den > 0 rules out a single surviving sample
+  // |b x| <= 40 keeps every e_k^2 finite in fp32
   const T blim = (T)(sizeof(T) == 4 ? 40.0 : 300.0) * xt.inv_xmax;
-  A.start(b0.lo, den_.lo > (T)0 && nm::abs_(b0.lo) < blim && nm::finite(ysq.lo) && ysq.lo > (T)0, (T)0);
-  B.start(b0.hi, den_.hi > (T)0 && nm::abs_(b0.hi) < blim && nm::finite(ysq.hi) && ysq.hi > (T)0, (T)0);
+  // den / S0^2 is the weighted variance of the echo times that carry the start: when (nearly) one sample
+  // survives the cut it is zero up to rounding and the slope is noise -- such voxels decline.  1e-4 span^2
+  // still admits two neighbouring samples of a 16-echo protocol.
+  const V dmin = p2_mul<T>(p2_mul<T>(S0, S0), p2_bcast<T>((T)1e-4 * xt.span2));
+  A.start(b0.lo, den_.lo > dmin.lo && nm::abs_(b0.lo) < blim && nm::finite(ysq.lo) && ysq.lo > (T)0, (T)0);
+  B.start(b0.hi, den_.hi > dmin.hi && nm::abs_(b0.hi) < blim && nm::finite(ysq.hi) && ysq.hi > (T)0, (T)0);
   const V floor2 = p2_mul<T>(ysq, p2_bcast<T>((T)2 * o.floor_rel));
   const V ftol2 = p2_bcast<T>((T)2 * o.ftol);
   const T smax = xt.inv_xmax;  // largest step in b: exp(b x) changes by at most a factor e per pass

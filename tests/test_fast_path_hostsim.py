@@ -175,3 +175,27 @@ def test_echo_table_classification():
     assert flags([10.0, 20.0, 30.0, 40.0 + 1e-6]) == 1               # below fp32's resolution of 40
     assert flags([10.0, 20.0, 30.0, 40.0 + 1e-6], "f64") == 0        # but visible in fp64
     assert flags([10.0, 20.0]) == 0 and flags([5.0, 5.0, 5.0]) == 0  # too few echoes / zero spacing
+
+
+def test_random_echo_times_fuzz():
+    """Seeded fuzz over echo counts, random (non-uniform, unsorted-free) echo times and decay ranges: the general
+    fast path must land on the LM's minimiser (high SNR) for every spacing, or hand the voxel over."""
+    rng = np.random.default_rng(2024)
+    worst = 0.0
+    for trial in range(24):
+        E = int(rng.choice([3, 4, 5, 7, 8, 16]))
+        span = 10.0 ** rng.uniform(0.5, 2.5)                       # 3 .. 300 time units
+        x = np.sort(rng.uniform(0.0, span, E))
+        x += np.arange(E) * span * 0.02                             # no (near-)coincident echo times
+        t_lo, t_hi = 0.15 * span, 1.5 * span
+        y = _synth(x, 1500, 5.0, (t_lo, t_hi), 100 + trial)
+        p0 = (1.0, -1.0 / (0.5 * span))
+        pl, rl, sl, il = H.fit("monoexponential", x, y, p0=p0, fast=0)
+        pf, rf, sf, itf = H.fit("monoexponential", x, y, p0=p0, fast=2)
+        ok = (sl >= 1) & (sl <= 4)
+        assert ok.mean() > 0.99 and ((sf >= 1) & (sf <= 4))[ok].all(), (trial, E, x)
+        rel = _relb(pf[ok], pl[ok])
+        worst = max(worst, float(rel.max()))
+        assert rel.max() < 3e-4 and np.abs(rf[ok] - rl[ok]).max() < 2e-4, (trial, E, x, float(rel.max()))
+        assert itf[ok].mean() < il[ok].mean()                       # and it is the cheaper path
+    assert worst < 3e-4
