@@ -378,7 +378,9 @@ DFIT_HD void mono_general_newton2(const YS& Y, const XTab<T, E>& xt, const Solve
   // weighted log-linear start: minimise sum w (log2 y^2 - alpha - beta x)^2, b0 = beta ln2 / 2
   V S0 = p2_bcast<T>((T)0), S1 = S0, S2 = S0, T0 = S0, T1 = S0;
   {
-    const V cut = p2_mul<T>(ysq, p2_bcast<T>((T)-0.004));
+    // weights relative to sum y^2 (scale-free: the moments cannot overflow whatever the signal scale)
+    const V rysq = p2_make<T>(nm::rcp_(ysq.lo), nm::rcp_(ysq.hi));
+    const V cut = p2_bcast<T>((T)-0.004);
     const V tiny = p2_bcast<T>(nm::tiny());
 #pragma unroll
     for (int e = 0; e < E; ++e) {
@@ -395,7 +397,7 @@ DFIT_HD void mono_general_newton2(const YS& Y, const XTab<T, E>& xt, const Solve
 #else
       const V l = p2_make<T>((T)log2((double)y2t.lo), (T)log2((double)y2t.hi));
 #endif
-      V w = p2_add<T>(y2, cut);
+      V w = p2_fma<T>(y2, rysq, cut);
       w = p2_make<T>(nm::max_(w.lo, (T)0), nm::max_(w.hi, (T)0));
       // moments about the mean echo time: the determinant below must not drown in cancellation
       const V xe = p2_bcast<T>(xt.xc[e]), xxe = p2_bcast<T>(xt.xc[e] * xt.xc[e]);

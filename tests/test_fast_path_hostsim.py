@@ -116,8 +116,9 @@ def test_invariances(name):
     y = _synth(x, 6001, 10.0, (10, 80), 23)
     p, r, s, it = H.fit("monoexponential", x, y, p0=(1.0, -1 / 30), fast=2)
     assert ((s >= 1) & (s <= 4)).all()
-    for c in (0.125, 8.0, 1000.0):
-        pc, rc, sc, _ = H.fit("monoexponential", x, y * np.float32(c), p0=(1.0, -1 / 30), fast=2)
+    for c in (1e-6, 0.125, 8.0, 1000.0, 1e6):
+        pc, rc, sc, ic = H.fit("monoexponential", x, y * np.float32(c), p0=(1.0, -1 / 30), fast=2)
+        assert ic.mean() < 2.5  # still the fast path (its moments are scale-free), not the LM
         tol = 2e-5  # the solver's own tolerance: the start and the rounding differ with the scale
         assert (np.abs(pc[:, 0] / c - p[:, 0]) / np.abs(p[:, 0])).max() < tol
         assert (np.abs(pc[:, 1] - p[:, 1]) / np.abs(p[:, 1])).max() < tol
