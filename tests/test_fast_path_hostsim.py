@@ -122,7 +122,8 @@ def test_invariances(name):
         tol = 2e-5  # the solver's own tolerance: the start and the rounding differ with the scale
         assert (np.abs(pc[:, 0] / c - p[:, 0]) / np.abs(p[:, 0])).max() < tol
         assert (np.abs(pc[:, 1] - p[:, 1]) / np.abs(p[:, 1])).max() < tol
-        assert np.abs(rc - r).max() < 1e-5
+        if c >= 0.1:  # (r2 carries the reference's absolute eps = 1e-8 in its denominator: not scale-free for tiny signals)
+            assert np.abs(rc - r).max() < 1e-5
     for c in (0.5, 4.0):
         pc, rc, sc, _ = H.fit("monoexponential", x * c, y, p0=(1.0, -1 / (30 * c)), fast=2)
         assert (np.abs(pc[:, 1] * c - p[:, 1]) / np.abs(p[:, 1])).max() < 1e-5
