@@ -201,3 +201,48 @@ def test_random_echo_times_fuzz():
         assert rel.max() < 3e-4 and np.abs(rf[ok] - rl[ok]).max() < 2e-4, (trial, E, x, float(rel.max()))
         assert itf[ok].mean() < il[ok].mean()                       # and it is the cheaper path
     assert worst < 3e-4
+
+
+def test_broad_protocol_fuzz():
+    """Seeded fuzz over whole protocols: 3-16 echoes, uniform / random / descending echo times with and without an
+    offset, signal scales 1e-4 .. 1e5, both signs of a and b, time constants from 0.2 to 10 spans, SNR 30 .. inf and
+    an optional baseline.  Wherever the fast path, the LM and a tight fp64 LM all converge, the fast path's cost must
+    not exceed the tight solution's by more than 0.1 % (nor may it return anything non-finite)."""
+    rng = np.random.default_rng(99)
+    total = worse = 0
+    for trial in range(300):
+        E = int(rng.choice([3, 4, 5, 7, 8, 16]))
+        span = 10.0 ** rng.uniform(0.0, 3.0)
+        x0 = span * rng.uniform(0, 2) if rng.random() < 0.5 else 0.0
+        if rng.random() < 0.4:
+            x = x0 + np.arange(E) * span / E
+        else:
+            x = x0 + np.sort(rng.uniform(0.0, span, E)) + np.arange(E) * span * 0.02
+        if rng.random() < 0.2:
+            x = x[::-1].copy()
+        n = 300
+        scale = 10.0 ** rng.uniform(-4, 5)
+        a = rng.uniform(0.3, 3, n) * scale * np.where(rng.random(n) < 0.2, -1, 1)
+        T = 10.0 ** rng.uniform(np.log10(0.2 * span), np.log10(10 * span), n)
+        sgn = np.where(rng.random(n) < 0.1, 1.0, -1.0)
+        T = np.where(sgn > 0, np.maximum(T, span), T)
+        snr = float(rng.choice([np.inf, 300, 100, 30]))
+        clean = a * np.exp(sgn * (x[:, None] - x.min()) / T)
+        sigma = 0.0 if np.isinf(snr) else scale / snr
+        y = (clean + rng.normal(0, 1, clean.shape) * sigma + (rng.random() < 0.2) * 0.05 * scale).astype(np.float32)
+        p0 = (1.0, -1.0 / (0.5 * span))
+        pl, rl, sl, il = H.fit("monoexponential", x, y, p0=p0, fast=0)
+        pf, rf, sf, itf = H.fit("monoexponential", x, y, p0=p0, fast=2)
+        pd, rd, sd, itd = H.fit("monoexponential", x, y, p0=p0, fast=0, dtype="f64", ftol=1e-13)
+        okf = (sf >= 1) & (sf <= 4)
+        assert np.isfinite(pf[okf]).all() and np.isfinite(rf[okf]).all(), trial
+        ok = okf & (sl >= 1) & (sl <= 4) & (sd >= 1) & (sd <= 4)
+
+        def sse(p):
+            with np.errstate(all="ignore"):
+                return ((p[:, 0].astype(np.float64) * np.exp(p[:, 1].astype(np.float64) * x[:, None]) - y.astype(np.float64)) ** 2).sum(0)
+
+        ys = (y.astype(np.float64) ** 2).sum(0)
+        total += int(ok.sum())
+        worse += int((ok & (sse(pf) > sse(pd) * (1 + 1e-3) + 1e-6 * ys)).sum())
+    assert total > 70000 and worse == 0, (total, worse)
