@@ -30,10 +30,11 @@ def _p0(c, P):
                                   "curvefit_mono4_unit_f64_p0ones", "curvefit_mono4_unit_f64_p0dict",
                                   "curvefit_linear4_f64"])
 @pytest.mark.parametrize("dtype", ["f32", "f64"])
-def test_noise_free_rtol(name, dtype):
+@pytest.mark.parametrize("fast", [0, 1, 2])  # LM from p0 / one-voxel fast path / two-voxel fast path (what the GPU runs)
+def test_noise_free_rtol(name, dtype, fast):
     c = G.load(name)
     model = {"_linear": "linear"}.get(c["meta"]["func"], c["meta"]["func"])
-    popt, r2, st, it = H.fit(model, c["x"], c["y"], p0=_p0(c, 2), dtype=dtype)
+    popt, r2, st, it = H.fit(model, c["x"], c["y"], p0=_p0(c, 2), dtype=dtype, fast=fast)
     assert ((st >= 1) & (st <= 4)).all()
     assert _rel(popt, c["popt"], atol=2e-6 if dtype == "f32" else 1e-12).max() < (1e-4 if dtype == "f32" else 1e-8)
     assert np.abs(r2 - c["r2"]).max() < (1e-5 if dtype == "f32" else 1e-9)
@@ -41,9 +42,10 @@ def test_noise_free_rtol(name, dtype):
 
 @pytest.mark.parametrize("name,frac", [("curvefit_mono8_snr100_f32", 2e-3), ("curvefit_mono7_t1rho_snr100_f32", 5e-3),
                                        ("curvefit_mono8_snr30_f32", 5e-2)])
-def test_noisy_percentiles(name, frac):
+@pytest.mark.parametrize("fast", [0, 1, 2])
+def test_noisy_percentiles(name, frac, fast):
     c = G.load(name)
-    popt, r2, st, it = H.fit("monoexponential", c["x"], c["y"], p0=(1.0, -1 / 30), dtype="f32")
+    popt, r2, st, it = H.fit("monoexponential", c["x"], c["y"], p0=(1.0, -1 / 30), dtype="f32", fast=fast)
     ok = ~np.isnan(c["popt"][:, 0]) & (st >= 1) & (st <= 4)
     assert ok.mean() > 0.999
     rel = _rel(popt[ok], c["popt"][ok]).max(axis=1)
