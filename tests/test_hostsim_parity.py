@@ -127,3 +127,40 @@ def test_fp32_epilogue_takes_the_float64_decisions():
                                    ctypes.c_double(fill or 0.0), dec, 0, ctypes.c_int64(n), v.ctypes.data_as(fp),
                                    r2.ctypes.data_as(fp), a.ctypes.data_as(fp), b.ctypes.data_as(fp))
         assert np.array_equal(a, b, equal_nan=True), (ufunc, decimals, fill)
+
+
+@pytest.mark.parametrize("name", G.names("monoexpfit_"))
+@pytest.mark.parametrize("fast", [0, 2])
+def test_monoexpfit_chain_on_the_host_build(name, fast):
+    """The whole device chain of `MonoExponentialFit.fit` -- fit (LM or two-voxel fast path), r2, fused epilogue
+    (1/|b|, bounds, r2 threshold, fill 0, rounding), mask fill -- compiled by g++, against the golden maps
+    generated by the real reference (same acceptance as the GPU test `test_monoexpfit_golden`)."""
+    c = G.load(name)
+    m = c["meta"]
+    y = c["y"].astype(np.float32) if c["y"].dtype != np.float64 else c["y"]
+    init_mode = 1 if m["tc0"] == "polyfit" else 0
+    p0 = (1.0, -1.0 / float(m["tc0"])) if init_mode == 0 else (1.0, 1.0)
+    popt, r2, st, it = H.fit("monoexponential", c["x"], y, p0=p0, dtype="f32", init_mode=init_mode, fast=fast)
+    lib = H._load()
+    ip = lambda a: (ctypes.c_int * 4)(*a)  # noqa: E731
+    dp = lambda a: (ctypes.c_double * 4)(*a)  # noqa: E731
+    lb, ub = float(m["bounds"][0]), float(m["bounds"][1])
+    tc = np.array([lib.hostsim_post_param(1, ip([0, 1, 0, 0]), dp([-np.inf, lb, -np.inf, -np.inf]),
+                                          dp([np.inf, ub, np.inf, np.inf]), 1, ctypes.c_double(m["r2_threshold"]), 1,
+                                          ctypes.c_double(0.0), ip([-1, m["decimal_precision"], -1, -1]), 1,
+                                          ctypes.c_double(float(np.float32(b))), ctypes.c_double(float(np.float32(r))))
+                   for b, r in zip(popt[:, 1], r2)])
+    r2 = r2.copy()
+    ref_tc, ref_r2 = c["tc"].reshape(-1), c["r2"].reshape(-1)
+    if m["use_mask"]:
+        mask = c["mask"].reshape(-1)
+        tc[~mask] = 0.0
+        r2[~mask] = 0.0
+    step = 10.0 ** (-m["decimal_precision"])
+    zeroed = (tc == 0) != (ref_tc == 0)
+    assert zeroed.mean() < (0.03 if "snr30" in name else 0.01), zeroed.mean()
+    close = np.abs(tc - ref_tc)[~zeroed] <= 1.001 * step
+    need = 0.95 if "snr30" in name else (0.99 if "zeros_negatives" in name else 0.995)
+    assert close.mean() > need, close.mean()
+    kept = (tc != 0) & (ref_tc != 0)
+    assert np.quantile(np.abs(r2 - ref_r2)[kept], 0.99) < 1e-4
