@@ -11,7 +11,7 @@
 
 namespace dfit {
 
-// ------------------------------------------------------------------------------------ fast path
+// ------------------------------------------------------------------------------------ one voxel per lane
 // Mono-exponential fit on UNIFORMLY spaced echoes x_k = x0 + k dx, by variable projection.
 //
 // With q = exp(b dx) and a' = a exp(b x0) the model is a' q^k: a polynomial in q.  For a given q the
@@ -24,7 +24,7 @@ namespace dfit {
 //
 // The start is the linear-prediction (Prony) estimate q0 = sum y_k y_k+1 / sum y_k^2, which is within a
 // few per cent of the minimiser on decaying signals, so two to three passes suffice; the user's p0 only
-// selects the basin MINPACK would start in and is not needed (the general LM below, which honours it,
+// selects the basin MINPACK would start in and is not needed (the general LM of lm_core.cuh, which honours it,
 // takes over whenever this path declines).  Convergence is judged like the LM's "predicted reduction
 // <= ftol * F" test, applied to the error expected AFTER the step about to be taken: with the contraction
 // kappa of newton_contraction() that is kappa^2 * pred <= ftol * F.
