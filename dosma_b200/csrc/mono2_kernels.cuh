@@ -81,8 +81,14 @@ __global__ void __launch_bounds__(kBlock2, 5) fit_kernel_mono2(const __grid_cons
     if (a.y_dtype == DT_F32) load_pairs<float, EMAX>(a.y, a.ld, v0, both, Y);
     else if (a.y_dtype == DT_I16) load_pairs<short, EMAX>(a.y, a.ld, v0, both, Y);
     else load_pairs<unsigned short, EMAX>(a.y, a.ld, v0, both, Y);
-    fit_voxel_fast2<M, T, EMAX, pair2<T>[EMAX]>(Y, a.xt, a.vo, pa, pb, r2, st, iters);
-    if (st[0] < 0 || st[1] < 0) {  // the general path, one voxel at a time
+    {
+      bool ok[2];
+      fit_voxel_fast2s<M, T, EMAX, pair2<T>[EMAX]>(Y, a.xt, a.vo, pa, pb, r2, ok);
+      st[0] = ok[0] ? (int)ST_CONV_F : -1;
+      st[1] = ok[1] ? (int)ST_CONV_F : -1;
+      iters[0] = iters[1] = kFast2Passes;
+    }
+    if (st[0] < 0 || st[1] < 0) {  // turned down: the one-voxel path (generic Newton loop, then the LM), one at a time
 #pragma unroll 1
       for (int hsel = 0; hsel < 2; ++hsel) {
         if ((hsel ? st[1] : st[0]) >= 0) continue;
@@ -91,8 +97,11 @@ __global__ void __launch_bounds__(kBlock2, 5) fit_kernel_mono2(const __grid_cons
         unsigned fl = 0;
 #pragma unroll
         for (int e = 0; e < EMAX; ++e) ys[e] = hsel ? Y[e].hi : Y[e].lo;
-        load_p0<P, T, EMAX>(a, hsel && both ? v0 + 1 : v0, p);
-        const int s1 = fit_voxel<M, T, T, EMAX, true>(ys, a.xt, a.E, a.vo, p, r, it, fl);
+        int s1 = fit_voxel_fast<M, T, EMAX, true>(ys, a.xt, a.vo, p, r, it);
+        if (s1 < 0) {
+          load_p0<P, T, EMAX>(a, hsel && both ? v0 + 1 : v0, p);
+          s1 = fit_voxel<M, T, T, EMAX, true>(ys, a.xt, a.E, a.vo, p, r, it, fl);
+        }
         if (hsel == 0 || both) nflags += ((fl & FLAG_NONFINITE) ? 1u : 0u) + ((fl & FLAG_OOB) ? 0x100u : 0u);
         if (hsel) {
           st[1] = s1; iters[1] = it; pa.hi = p[0]; pb.hi = p[1]; r2.hi = r;
@@ -147,7 +156,13 @@ __global__ void __launch_bounds__(kBlock, 5) fit_kernel_mono2_list(const __grid_
 #pragma unroll
     for (int e = 0; e < EMAX; ++e) Y[e] = p2_make<T>(yA[e], yB[e]);
     int st[2], iters[2];
-    fit_voxel_fast2<M, T, EMAX, pair2<T>[EMAX]>(Y, a.xt, a.vo, pa, pb, r2, st, iters);
+    {
+      bool ok[2];
+      fit_voxel_fast2s<M, T, EMAX, pair2<T>[EMAX]>(Y, a.xt, a.vo, pa, pb, r2, ok);
+      st[0] = ok[0] ? (int)ST_CONV_F : -1;
+      st[1] = ok[1] ? (int)ST_CONV_F : -1;
+      iters[0] = iters[1] = kFast2Passes;
+    }
     if (st[0] < 0 || (st[1] < 0 && both)) {
 #pragma unroll 1
       for (int hsel = 0; hsel < 2; ++hsel) {
@@ -157,8 +172,11 @@ __global__ void __launch_bounds__(kBlock, 5) fit_kernel_mono2_list(const __grid_
         unsigned fl = 0;
 #pragma unroll
         for (int e = 0; e < EMAX; ++e) ys[e] = hsel ? Y[e].hi : Y[e].lo;
-        load_p0<P, T, EMAX>(a, hsel ? vB : vA, p);
-        const int s1 = fit_voxel<M, T, T, EMAX, true>(ys, a.xt, a.E, a.vo, p, r, it, fl);
+        int s1 = fit_voxel_fast<M, T, EMAX, true>(ys, a.xt, a.vo, p, r, it);
+        if (s1 < 0) {
+          load_p0<P, T, EMAX>(a, hsel ? vB : vA, p);
+          s1 = fit_voxel<M, T, T, EMAX, true>(ys, a.xt, a.E, a.vo, p, r, it, fl);
+        }
         n_nf += (unsigned)((fl & FLAG_NONFINITE) != 0);
         n_oob += (unsigned)((fl & FLAG_OOB) != 0);
         if (hsel) {
@@ -190,12 +208,42 @@ __global__ void __launch_bounds__(kBlock, 5) fit_kernel_mono2_list(const __grid_
 // shared load.  No block-level synchronisation inside the loop.
 constexpr int kM2Warps = 4;
 constexpr int kM2Tile = 64;
+constexpr int kDeferCap = 96;  // per-warp queue of deferred voxels: at most 31 left over + 64 from one tile
 constexpr int m2_stages(int E) { return E <= 8 ? 4 : 2; }  // 32 KB of tiles per CTA
 
+// One voxel per lane over a warp's queue of deferred voxels (indices into the launch's voxel range): the
+// generic Newton loop of the fast path first, the LM from the caller's initial guess where that declines.
+// `lane < cnt` lanes work; the samples are re-read from global memory (the tile they came from is usually
+// still in L2; deferred voxels are rare on tissue and LM-bound on noise).
+template <class M, int EMAX, bool GATHER>
+__device__ __forceinline__ void fit_deferred(const KernelArgs<float, EMAX>& a, const unsigned* __restrict__ queue, int cnt,
+                                             int lane, unsigned& n_fit, unsigned& n_fail, unsigned& n_nf, unsigned& n_oob,
+                                             unsigned& it_sum, unsigned& it_max) {
+  typedef float T;
+  constexpr int P = 2;
+  if (lane < cnt) {
+    const int64_t v = (int64_t)queue[lane];
+    T y[EMAX], p[P], r2 = 0;
+    int it = 0;
+    unsigned fl = 0;
+    load_samples<T, EMAX, true>(a, v, y);
+    int st = fit_voxel_fast<M, T, EMAX, true>(y, a.xt, a.vo, p, r2, it);
+    if (st < 0) {
+      load_p0<P, T, EMAX>(a, v, p);
+      st = fit_voxel<M, T, T, EMAX, true>(y, a.xt, a.E, a.vo, p, r2, it, fl);
+    }
+    store_voxel<P, T, EMAX, GATHER>(a, v, p, r2, true, st, it);
+    n_fit += (unsigned)(st >= ST_CONV_F);
+    n_fail += (unsigned)(st >= ST_MAXITER);
+    n_nf += (unsigned)((fl & FLAG_NONFINITE) != 0);
+    n_oob += (unsigned)((fl & FLAG_OOB) != 0);
+    it_sum += (unsigned)it;
+    it_max = (unsigned)it > it_max ? (unsigned)it : it_max;
+  }
+}
+
 template <class M, int EMAX, bool GATHER, typename S>
-__global__ void __launch_bounds__(kM2Warps * 32, 5)  // 5 CTAs/SM: 6 spills, 4 is slower (measured: 0.743 / 0.689 / 0.696 ms);
-                                                     // reading the samples from the tile on every use to free 16 registers
-                                                     // (6-7 CTAs/SM) was measured too: 3 % slower
+__global__ void __launch_bounds__(kM2Warps * 32, 5)  // 5 CTAs/SM: 6 spills, 4 is slower (measured: 0.743 / 0.689 / 0.696 ms)
     fit_kernel_mono2_tma(const __grid_constant__ KernelArgs<float, EMAX> a, const __grid_constant__ CUtensorMap tmap) {
   typedef float T;
   constexpr int P = 2;
@@ -203,6 +251,7 @@ __global__ void __launch_bounds__(kM2Warps * 32, 5)  // 5 CTAs/SM: 6 spills, 4 i
   constexpr unsigned kTileBytes = EMAX * kM2Tile * sizeof(S);  // S = float, or the raw 16-bit DICOM sample type
   __shared__ __align__(128) S tiles[kM2Warps][kStages][EMAX][kM2Tile];
   __shared__ __align__(8) uint64_t full[kM2Warps][kStages];
+  __shared__ unsigned defer_q[kM2Warps][kDeferCap];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // 32-bit indexing: the launcher admits fewer than 2^31 voxels
   const int n_vox = (int)a.n;
@@ -225,8 +274,12 @@ __global__ void __launch_bounds__(kM2Warps * 32, 5)  // 5 CTAs/SM: 6 spills, 4 i
   }
   __syncwarp();
 
-  unsigned n_fit = 0, it_sum = 0, it_max = 0;
-  unsigned long long* const stat_slot = a.counters + (size_t)(warp_global & (kStatSlots - 1)) * CNT_COUNT;
+  unsigned n_fast = 0, n_fit = 0, n_fail = 0, n_nf = 0, n_oob = 0, it_sum = 0, it_max = 0;
+  int n_def = 0;  // entries in this warp's queue (warp-uniform)
+  // raw fp32 parameters into fp32 maps and nothing else to write: two vector stores per lane
+  const bool plain = !a.po.enabled && a.out_dtype == DT_F32 && a.popt != nullptr && a.status == nullptr && a.niter == nullptr;
+  char* const popt_lane = reinterpret_cast<char*>(a.popt) + lane * (2 * P * sizeof(float));
+  char* const r2_lane = reinterpret_cast<char*>(a.r2) + lane * (2 * sizeof(float));
   int k = 0;
   for (int t = warp_global; t < n_tiles; t += warp_stride, ++k) {
     const int s = k % kStages;
@@ -247,38 +300,22 @@ __global__ void __launch_bounds__(kM2Warps * 32, 5)  // 5 CTAs/SM: 6 spills, 4 i
       }
     }
     const int v0 = t * kM2Tile + 2 * lane;
-    const bool validA = v0 < n_vox, validB = v0 + 1 < n_vox;
-    int st[2], iters[2];
-    fit_voxel_fast2<M, T, EMAX, pair2<T>[EMAX]>(Y, a.xt, a.vo, pa, pb, r2, st, iters);  // voxels past the end are zero-filled: declined
-    if ((st[0] < 0 && validA) || (st[1] < 0 && validB)) {  // the general path, one voxel at a time
-#pragma unroll 1
-      for (int hsel = 0; hsel < 2; ++hsel) {
-        if ((hsel ? st[1] : st[0]) >= 0 || !(hsel ? validB : validA)) continue;
-        T ys[EMAX], p[P], r = 0;
-        int it = 0;
-        unsigned fl = 0;
-#pragma unroll
-        for (int e = 0; e < EMAX; ++e) ys[e] = hsel ? Y[e].hi : Y[e].lo;
-        load_p0<P, T, EMAX>(a, v0 + hsel, p);
-        const int s1 = fit_voxel<M, T, T, EMAX, true>(ys, a.xt, a.E, a.vo, p, r, it, fl);
-        // rare events go straight to the counters (the voxel has just paid for a full LM anyway)
-        if (s1 >= ST_MAXITER) atomicAdd(stat_slot + CNT_FAILED, 1ull);
-        if (fl & FLAG_NONFINITE) atomicAdd(stat_slot + CNT_NONFINITE, 1ull);
-        if (fl & FLAG_OOB) atomicAdd(stat_slot + CNT_OOB, 1ull);
-        if (hsel) {
-          st[1] = s1; iters[1] = it; pa.hi = p[0]; pb.hi = p[1]; r2.hi = r;
-        } else {
-          st[0] = s1; iters[0] = it; pa.lo = p[0]; pb.lo = p[1]; r2.lo = r;
-        }
-      }
+    bool ok[2];
+    fit_voxel_fast2s<M, T, EMAX, pair2<T>[EMAX]>(Y, a.xt, a.vo, pa, pb, r2, ok);
+    bool defA = !ok[0], defB = !ok[1];
+    if (t == n_tiles - 1) {  // the last tile may be ragged: voxels past the end are zero-filled and must go nowhere
+      const bool validA = v0 < n_vox, validB = v0 + 1 < n_vox;
+      ok[0] = ok[0] && validA;
+      ok[1] = ok[1] && validB;
+      defA = defA && validA;
+      defB = defB && validB;
     }
-    if (!validA) { st[0] = -1; iters[0] = 0; }
-    if (!validB) { st[1] = -1; iters[1] = 0; }
     if constexpr (GATHER) {
       // Fused all-gather: the tile's 64 rows [a, b, r2] are one contiguous 768-byte block in every rank's map.
       // Stage them in shared memory (double-buffered) and let the TMA push the block to every rank with one
       // bulk store each (cp.async.bulk global <- shared): the SM's load/store path never waits on NVLink.  The
-      // launcher admits this kernel only without the epilogue and with 16-byte-aligned rank blocks.
+      // launcher admits this kernel only without the epilogue and with 16-byte-aligned rank blocks.  Rows of
+      // deferred voxels are overwritten when their queue is run (after the bulk stores have completed).
       __shared__ __align__(128) float rows[kM2Warps][2][kM2Tile * 3];
       float* sg = rows[warp][k & 1];
       if (t * kM2Tile + kM2Tile <= n_vox) {
@@ -308,47 +345,73 @@ __global__ void __launch_bounds__(kM2Warps * 32, 5)  // 5 CTAs/SM: 6 spills, 4 i
         for (int r = 0; r < kMaxPeers; ++r) {
           if (r < a.gather_world) {
             float* dst = a.gather[r] + (a.gather_row0 + v0) * 3;
-            if (validA) { dst[0] = pa.lo; dst[1] = pb.lo; dst[2] = r2.lo; }
-            if (validB) { dst[3] = pa.hi; dst[4] = pb.hi; dst[5] = r2.hi; }
+            if (ok[0]) { dst[0] = pa.lo; dst[1] = pb.lo; dst[2] = r2.lo; }
+            if (ok[1]) { dst[3] = pa.hi; dst[4] = pb.hi; dst[5] = r2.hi; }
           }
         }
       }
     }
-    if (GATHER && a.popt == nullptr) {
-      // the maps are the only output
-    } else if (!a.po.enabled && a.out_dtype == DT_F32 && validB) {
-      __stcs(reinterpret_cast<float4*>(reinterpret_cast<float*>(a.popt) + (int64_t)v0 * P), make_float4(pa.lo, pb.lo, pa.hi, pb.hi));
-      __stcs(reinterpret_cast<float2*>(reinterpret_cast<float*>(a.r2) + v0), make_float2(r2.lo, r2.hi));
-      if (a.status) {
-        a.status[v0] = (uint8_t)st[0];
-        a.status[v0 + 1] = (uint8_t)st[1];
+    if (plain) {
+      if (ok[0] && ok[1]) {
+        __stcs(reinterpret_cast<float4*>(popt_lane + (int64_t)t * (kM2Tile * P * sizeof(float))), make_float4(pa.lo, pb.lo, pa.hi, pb.hi));
+        __stcs(reinterpret_cast<float2*>(r2_lane + (int64_t)t * (kM2Tile * sizeof(float))), make_float2(r2.lo, r2.hi));
+      } else {
+        float2* pp = reinterpret_cast<float2*>(popt_lane + (int64_t)t * (kM2Tile * P * sizeof(float)));
+        float* pr = reinterpret_cast<float*>(r2_lane + (int64_t)t * (kM2Tile * sizeof(float)));
+        if (ok[0]) { __stcs(pp, make_float2(pa.lo, pb.lo)); __stcs(pr, r2.lo); }
+        if (ok[1]) { __stcs(pp + 1, make_float2(pa.hi, pb.hi)); __stcs(pr + 1, r2.hi); }
       }
-      if (a.niter) {
-        a.niter[v0] = (uint8_t)iters[0];
-        a.niter[v0 + 1] = (uint8_t)iters[1];
-      }
-    } else {
+    } else if (!(GATHER && a.popt == nullptr)) {  // (with the fused gather the maps may be the only output)
       const T p0_[P] = {pa.lo, pb.lo}, p1_[P] = {pa.hi, pb.hi};
-      if (validA) store_voxel<P, T, EMAX, false>(a, v0, p0_, r2.lo, true, st[0], iters[0]);
-      if (validB) store_voxel<P, T, EMAX, false>(a, v0 + 1, p1_, r2.hi, true, st[1], iters[1]);
+      if (ok[0]) store_voxel<P, T, EMAX, false>(a, v0, p0_, r2.lo, true, ST_CONV_F, kFast2Passes);
+      if (ok[1]) store_voxel<P, T, EMAX, false>(a, v0 + 1, p1_, r2.hi, true, ST_CONV_F, kFast2Passes);
     }
-    n_fit += (unsigned)(st[0] >= ST_CONV_F) + (unsigned)(st[1] >= ST_CONV_F);
-    it_sum += (unsigned)(iters[0] + iters[1]);
-    const unsigned im = (unsigned)(iters[0] > iters[1] ? iters[0] : iters[1]);
-    it_max = im > it_max ? im : it_max;
+    n_fast += (unsigned)ok[0] + (unsigned)ok[1];
+    // voxels the straight-line attempt turned down join the warp's queue; full warps of them are fitted at once
+    const unsigned mA = __ballot_sync(0xffffffffu, defA), mB = __ballot_sync(0xffffffffu, defB);
+    if ((mA | mB) != 0u) {
+      const unsigned below = (1u << lane) - 1u;
+      const int nA = __popc(mA);
+      if (defA) defer_q[warp][n_def + __popc(mA & below)] = (unsigned)v0;
+      if (defB) defer_q[warp][n_def + nA + __popc(mB & below)] = (unsigned)(v0 + 1);
+      n_def += nA + __popc(mB);
+      __syncwarp();
+      if (n_def >= 32) {
+        if constexpr (GATHER) {  // their rows must land after the tile blocks that contain them
+          if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+          __syncwarp();
+        }
+        do {
+          n_def -= 32;
+          fit_deferred<M, EMAX, GATHER>(a, &defer_q[warp][n_def], 32, lane, n_fit, n_fail, n_nf, n_oob, it_sum, it_max);
+        } while (n_def >= 32);
+        __syncwarp();
+      }
+    }
   }
   if constexpr (GATHER) {
     if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // all bulk stores of this warp are done
+    __syncwarp();
   }
+  if (n_def > 0) fit_deferred<M, EMAX, GATHER>(a, &defer_q[warp][0], n_def, lane, n_fit, n_fail, n_nf, n_oob, it_sum, it_max);
   // statistics: per-thread accumulators -> one reduction per warp at the end of the kernel
   {
     const unsigned fm = 0xffffffffu;
-    const unsigned v0 = __reduce_add_sync(fm, n_fit);
-    const unsigned v4 = __reduce_add_sync(fm, it_sum), v5 = __reduce_max_sync(fm, it_max);
+    unsigned long long* const stat_slot = a.counters + (size_t)(warp_global & (kStatSlots - 1)) * CNT_COUNT;
+    const unsigned c_fast = __reduce_add_sync(fm, n_fast);  // straight-line voxels: kFast2Passes passes each
+    const unsigned c_fit = __reduce_add_sync(fm, n_fit) + c_fast, c_fail = __reduce_add_sync(fm, n_fail);
+    const unsigned c_nf = __reduce_add_sync(fm, n_nf), c_oob = __reduce_add_sync(fm, n_oob);
+    const unsigned c_it = __reduce_add_sync(fm, it_sum);
+    unsigned c_max = __reduce_max_sync(fm, it_max);
+    if (c_fast != 0u && c_max < (unsigned)kFast2Passes) c_max = (unsigned)kFast2Passes;
     if (lane == 0) {
-      if (v0) atomicAdd(stat_slot + CNT_FITTED, (unsigned long long)v0);
-      if (v4) atomicAdd(stat_slot + CNT_ITERS, (unsigned long long)v4);
-      if (v5) atomicMax(stat_slot + CNT_MAXITER, (unsigned long long)v5);
+      const unsigned long long its = (unsigned long long)c_it + (unsigned long long)kFast2Passes * c_fast;
+      if (c_fit) atomicAdd(stat_slot + CNT_FITTED, (unsigned long long)c_fit);
+      if (c_fail) atomicAdd(stat_slot + CNT_FAILED, (unsigned long long)c_fail);
+      if (c_nf) atomicAdd(stat_slot + CNT_NONFINITE, (unsigned long long)c_nf);
+      if (c_oob) atomicAdd(stat_slot + CNT_OOB, (unsigned long long)c_oob);
+      if (its) atomicAdd(stat_slot + CNT_ITERS, its);
+      if (c_max) atomicMax(stat_slot + CNT_MAXITER, (unsigned long long)c_max);
     }
   }
 }

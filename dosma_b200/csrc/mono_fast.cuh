@@ -485,6 +485,274 @@ DFIT_HD void mono_general_newton2(const YS& Y, const XTab<T, E>& xt, const Solve
   status[1] = okB ? (F.hi <= o.floor_rel * ysq.hi ? ST_EXACT : ST_CONV_F) : -1;
 }
 
+// ---- straight-line two-pass variants (what the dense kernels run first) ---------------------------------
+// Measured on the benchmark volume: 99.65 % of the voxels converge in exactly two Newton passes from the
+// data-driven start.  The variants below therefore run exactly two passes for BOTH voxels of a lane with no
+// per-lane state machine, no warp votes and no loop -- one basic block the scheduler can interleave freely --
+// and simply report `ok = false` for a voxel that would have needed anything else (no admissible start, first
+// step beyond the gate, curvature not positive, not converged after the second pass, non-finite result).
+// Such voxels are fitted by the one-voxel path (generic Newton loop, then the LM from the caller's p0), which
+// the kernels run on whole warps of deferred voxels.  Differences from the loop versions above, all within the
+// parity budget (the CPU test-suite runs this very code through the test-only host build, tests/hostsim):
+//   * sum (y - mean)^2 comes from the moments, sum y^2 - (sum y)^2 / E (error ~2 eps sum y^2, i.e. an r2 error of
+//     (1 - r2) 2 eps sum y^2 / ss_tot), unless that is ill-conditioned (nearly constant signal: below 4 % of
+//     sum y^2), where the two-pass form is used.  (The cost F itself cannot be had from the projected cost
+//     sum y^2 - N a the same way: its ~2 eps sum y^2 error is divided by ss_tot without the (1 - r2) factor.)
+constexpr float kSsTotCond = 0.04f;
+
+template <typename T, int E, class YS>
+DFIT_HD pair2<T> ss_total2_fast(const YS& Y, pair2<T> ysq, pair2<T> S) {
+  pair2<T> t = p2_fma<T>(p2_mul<T>(S, p2_bcast<T>((T)(-1.0 / E))), S, ysq);
+  if (t.lo < (T)kSsTotCond * ysq.lo || t.hi < (T)kSsTotCond * ysq.hi) {  // rare: nearly constant signals
+    const pair2<T> nmean = p2_mul<T>(S, p2_bcast<T>((T)(-1.0 / E)));
+    t = p2_bcast<T>((T)0);
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+      const pair2<T> d = p2_add<T>(Y[e], nmean);
+      t = p2_fma<T>(d, d, t);
+    }
+  }
+  return t;
+}
+
+// The convergence rule of newton_lane_step for the second pass, on packed quantities: kappa^2 pred2 <= tol2
+// with kappa = clamp(4 step2 / prev_step2, 1e-3, 1).
+template <typename T>
+DFIT_HD void second_pass_converged(pair2<T> pred2, pair2<T> tol2, pair2<T> step2, pair2<T> prev2, pair2<T> h,
+                                   bool (&conv)[2]) {
+  typedef num<T> nm;
+  const pair2<T> rr = p2_mul<T>(p2_mul<T>(step2, p2_bcast<T>((T)4)), p2_make<T>(nm::rcp_(prev2.lo), nm::rcp_(prev2.hi)));
+  const pair2<T> kap = p2_make<T>(nm::min_(nm::max_(rr.lo, (T)1e-3), (T)1), nm::min_(nm::max_(rr.hi, (T)1e-3), (T)1));
+  const pair2<T> lhs = p2_mul<T>(p2_mul<T>(pred2, kap), kap);
+  conv[0] = h.lo > (T)0 && lhs.lo <= tol2.lo;
+  conv[1] = h.hi > (T)0 && lhs.hi <= tol2.hi;
+}
+
+template <typename T, int E, class YS>
+DFIT_HD void mono_uniform_fast2(const YS& Y, const XTab<T, E>& xt, const SolverOpts<T>& o, T r2_eps, pair2<T>& pa,
+                                pair2<T>& pb, pair2<T>& r2, bool (&ok)[2]) {
+  static_assert(E >= 3, "needs at least three echoes");
+  typedef num<T> nm;
+  typedef pair2<T> V;
+  const V one = p2_bcast<T>((T)1);
+  // Prony start q0 = sum y_k y_k+1 / sum y_k^2; sum y^2 and sum y fall out of the same recurrence
+  V pn = p2_mul<T>(Y[0], Y[1]), pd = p2_mul<T>(Y[0], Y[0]), S = p2_add<T>(Y[0], Y[1]);
+#pragma unroll
+  for (int k = 1; k + 1 < E; ++k) {
+    pn = p2_fma<T>(Y[k], Y[k + 1], pn);
+    pd = p2_fma<T>(Y[k], Y[k], pd);
+    S = p2_add<T>(S, Y[k + 1]);
+  }
+  const V ysq = p2_fma<T>(Y[E - 1], Y[E - 1], pd);
+  V q;
+  if (xt.backward != 0) {  // descending echo times: predicted backwards (see mono_uniform_newton2)
+    const V pdb = p2_fma<T>(p2_mul<T>(Y[0], p2_bcast<T>((T)-1)), Y[0], ysq);
+    q = p2_mul<T>(pdb, p2_make<T>(nm::rcp_(pn.lo), nm::rcp_(pn.hi)));
+  } else {
+    q = p2_mul<T>(pn, p2_make<T>(nm::rcp_(pd.lo), nm::rcp_(pd.hi)));
+  }
+  // One evaluation of the projected problem at q: amplitude a, da/dq, Newton step, curvature, twice the
+  // Newton decrement and the projected cost.
+  V a, ap, dq, h, pred2, Fe;
+  auto evaluate = [&]() {
+    const V s = p2_mul<T>(q, q);
+    // Horner with first and (half) second derivative: N(q) over the samples, D(s) over ones
+    V N0 = Y[E - 1], N1 = N0, N2, D0 = one, D1 = one, D2;
+    N0 = p2_fma<T>(N0, q, Y[E - 2]);
+    D0 = p2_add<T>(s, one);
+    N2 = N1;
+    D2 = D1;
+    N1 = p2_fma<T>(N1, q, N0);
+    D1 = p2_add<T>(s, D0);
+    N0 = p2_fma<T>(N0, q, Y[E - 3]);
+    D0 = p2_fma<T>(D0, s, one);
+#pragma unroll
+    for (int j = E - 4; j >= 0; --j) {
+      N2 = p2_fma<T>(N2, q, N1);
+      D2 = p2_fma<T>(D2, s, D1);
+      N1 = p2_fma<T>(N1, q, N0);
+      D1 = p2_fma<T>(D1, s, D0);
+      N0 = p2_fma<T>(N0, q, Y[j]);
+      D0 = p2_fma<T>(D0, s, one);
+    }
+    const V nDq = p2_mul<T>(p2_mul<T>(q, p2_bcast<T>((T)-2)), D1);                     // -dD/dq
+    const V Dqq = p2_fma<T>(p2_mul<T>(s, p2_bcast<T>((T)8)), D2, p2_add<T>(D1, D1));  // d2D/dq2
+    const V rD = p2_make<T>(nm::rcp_(D0.lo), nm::rcp_(D0.hi));
+    a = p2_mul<T>(N0, rD);
+    const V w = p2_fma<T>(a, nDq, N1);       // = D da/dq
+    ap = p2_mul<T>(w, rD);
+    const V mg = p2_mul<T>(a, p2_add<T>(w, N1));  // -dphi/dq
+    const V t2 = p2_fma<T>(N2, p2_bcast<T>((T)-4), p2_mul<T>(a, Dqq));
+    h = p2_fma<T>(a, t2, p2_mul<T>(p2_mul<T>(w, ap), p2_bcast<T>((T)-2)));  // d2phi/dq2
+    dq = p2_mul<T>(mg, p2_make<T>(nm::rcp_(h.lo), nm::rcp_(h.hi)));
+    pred2 = p2_mul<T>(mg, dq);
+    Fe = p2_fma<T>(p2_mul<T>(N0, p2_bcast<T>((T)-1)), a, ysq);
+  };
+  // pass 1: first-step gate (see newton_lane_step): inside the convex basin and no further than kFirstStepCap q
+  evaluate();
+  const V step2a = p2_mul<T>(dq, dq);
+  {
+    const V lim = p2_mul<T>(p2_mul<T>(q, q), p2_bcast<T>((T)(kFirstStepCap * kFirstStepCap)));
+    ok[0] = h.lo > (T)0 && step2a.lo <= lim.lo;
+    ok[1] = h.hi > (T)0 && step2a.hi <= lim.hi;
+  }
+  q = p2_add<T>(q, dq);
+  // pass 2: convergence judged like the loop version's second pass
+  evaluate();
+  {
+    const V tol2 = p2_fma<T>(p2_bcast<T>((T)2 * o.ftol), p2_make<T>(nm::max_(Fe.lo, (T)0), nm::max_(Fe.hi, (T)0)),
+                             p2_mul<T>(ysq, p2_bcast<T>((T)2 * o.floor_rel)));
+    bool conv[2];
+    second_pass_converged<T>(pred2, tol2, p2_mul<T>(dq, dq), step2a, h, conv);
+    ok[0] = ok[0] && conv[0];
+    ok[1] = ok[1] && conv[1];
+  }
+  const V qf = p2_add<T>(q, dq);
+  const V af = p2_fma<T>(ap, dq, a);
+  ok[0] = ok[0] && qf.lo > xt.q_lo && qf.lo < xt.q_hi && nm::finite(af.lo);
+  ok[1] = ok[1] && qf.hi > xt.q_lo && qf.hi < xt.q_hi && nm::finite(af.hi);
+  // cost at the returned point, r_k = y_k - a' q^k (the projected cost sum y^2 - N a cancels to ~2 eps sum y^2,
+  // which a nearly constant signal's r2 does not forgive); r2 of fitting.py:1032-1035
+  V m = af, F;
+  {
+    const V r0 = p2_add<T>(Y[0], p2_mul<T>(m, p2_bcast<T>((T)-1)));
+    F = p2_mul<T>(r0, r0);
+  }
+  const V nqf = p2_mul<T>(qf, p2_bcast<T>((T)-1));
+  m = p2_mul<T>(m, nqf);  // m = -a' q^k from here on
+#pragma unroll
+  for (int e = 1; e < E; ++e) {
+    const V r = p2_add<T>(Y[e], m);
+    F = p2_fma<T>(r, r, F);
+    if (e + 1 < E) m = p2_mul<T>(m, qf);
+  }
+  const V den = p2_add<T>(ss_total2_fast<T, E, YS>(Y, ysq, S), p2_bcast<T>(r2_eps));
+  r2 = p2_fma<T>(F, p2_make<T>(-nm::rcp_(den.lo), -nm::rcp_(den.hi)), one);
+  // back to the reference's parameters: b = ln(q) / dx, a = a' exp(-b x0)
+  const V b = p2_mul<T>(p2_log_pos<T>(qf), p2_bcast<T>(xt.inv_dx));
+  pb = b;
+  pa = af;
+  if (xt.x0 != (T)0) pa = p2_mul<T>(af, p2_make<T>(nm::expbx(-b.lo, xt.x0, xt.x0s), nm::expbx(-b.hi, xt.x0, xt.x0s)));
+}
+
+// The same for ARBITRARY echo times (see mono_general_newton2 for the start and the iteration).
+template <typename T, int E, class YS>
+DFIT_HD void mono_general_fast2(const YS& Y, const XTab<T, E>& xt, const SolverOpts<T>& o, T r2_eps, pair2<T>& pa,
+                                pair2<T>& pb, pair2<T>& r2, bool (&ok)[2]) {
+  static_assert(E >= 3, "needs at least three echoes");
+  typedef num<T> nm;
+  typedef pair2<T> V;
+  V ysq = p2_mul<T>(Y[0], Y[0]), S = Y[0];
+#pragma unroll
+  for (int e = 1; e < E; ++e) {
+    ysq = p2_fma<T>(Y[e], Y[e], ysq);
+    S = p2_add<T>(S, Y[e]);
+  }
+  // weighted log-linear start: minimise sum w (log2 y^2 - alpha - beta x)^2, b0 = beta ln2 / 2
+  V S0 = p2_bcast<T>((T)0), S1 = S0, S2 = S0, T0 = S0, T1 = S0;
+  {
+    const V rysq = p2_make<T>(nm::rcp_(ysq.lo), nm::rcp_(ysq.hi));
+    const V cut = p2_bcast<T>((T)-0.004);
+    const V tiny = p2_bcast<T>(nm::tiny());
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+      const V y2 = p2_mul<T>(Y[e], Y[e]);
+      const V y2t = p2_add<T>(y2, tiny);
+#if defined(__CUDA_ARCH__)
+      V l;
+      if constexpr (sizeof(T) == 4) {
+        asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l.lo) : "f"(y2t.lo));
+        asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l.hi) : "f"(y2t.hi));
+      } else {
+        l = p2_make<T>(log2(y2t.lo), log2(y2t.hi));
+      }
+#else
+      const V l = p2_make<T>((T)log2((double)y2t.lo), (T)log2((double)y2t.hi));
+#endif
+      V w = p2_fma<T>(y2, rysq, cut);
+      w = p2_make<T>(nm::max_(w.lo, (T)0), nm::max_(w.hi, (T)0));
+      const V xe = p2_bcast<T>(xt.xc[e]), xxe = p2_bcast<T>(xt.xc[e] * xt.xc[e]);
+      const V wl = p2_mul<T>(w, l);
+      S0 = p2_add<T>(S0, w);
+      S1 = p2_fma<T>(xe, w, S1);
+      S2 = p2_fma<T>(xxe, w, S2);
+      T0 = p2_add<T>(T0, wl);
+      T1 = p2_fma<T>(xe, wl, T1);
+    }
+  }
+  const V num_ = p2_fma<T>(S0, T1, p2_mul<T>(p2_mul<T>(S1, T0), p2_bcast<T>((T)-1)));
+  const V den_ = p2_fma<T>(S0, S2, p2_mul<T>(p2_mul<T>(S1, S1), p2_bcast<T>((T)-1)));
+  V b = p2_mul<T>(p2_mul<T>(num_, p2_make<T>(nm::rcp_(den_.lo), nm::rcp_(den_.hi))), p2_bcast<T>((T)0.34657359027997264));
+  const T blim = (T)(sizeof(T) == 4 ? 40.0 : 300.0) * xt.inv_xmax;  // |b x| <= 40 keeps every e_k^2 finite in fp32
+  {
+    const V dmin = p2_mul<T>(p2_mul<T>(S0, S0), p2_bcast<T>((T)1e-4 * xt.span2));  // see mono_general_newton2
+    ok[0] = den_.lo > dmin.lo && nm::abs_(b.lo) < blim && nm::finite(ysq.lo) && ysq.lo > (T)0;
+    ok[1] = den_.hi > dmin.hi && nm::abs_(b.hi) < blim && nm::finite(ysq.hi) && ysq.hi > (T)0;
+  }
+  V a, ap, db, h, pred2, Fe;
+  auto evaluate = [&]() {
+    V N0 = p2_bcast<T>((T)0), N1 = N0, N2 = N0, D0 = N0, D1 = N0, D2 = N0;
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+      const V ex = p2_make<T>(nm::expbx(b.lo, xt.x[e], xt.xs[e]), nm::expbx(b.hi, xt.x[e], xt.xs[e]));
+      const V ye = p2_mul<T>(Y[e], ex), ee = p2_mul<T>(ex, ex);
+      const V xe = p2_bcast<T>(xt.x[e]), xxe = p2_bcast<T>(xt.xx[e]);
+      N0 = p2_add<T>(N0, ye);
+      N1 = p2_fma<T>(xe, ye, N1);
+      N2 = p2_fma<T>(xxe, ye, N2);
+      D0 = p2_add<T>(D0, ee);
+      D1 = p2_fma<T>(xe, ee, D1);
+      D2 = p2_fma<T>(xxe, ee, D2);
+    }
+    const V nDb = p2_mul<T>(D1, p2_bcast<T>((T)-2));
+    const V rD = p2_make<T>(nm::rcp_(D0.lo), nm::rcp_(D0.hi));
+    a = p2_mul<T>(N0, rD);
+    const V w = p2_fma<T>(a, nDb, N1);
+    ap = p2_mul<T>(w, rD);
+    const V mg = p2_mul<T>(a, p2_add<T>(w, N1));
+    const V t2 = p2_fma<T>(N2, p2_bcast<T>((T)-2), p2_mul<T>(a, p2_mul<T>(D2, p2_bcast<T>((T)4))));
+    h = p2_fma<T>(a, t2, p2_mul<T>(p2_mul<T>(w, ap), p2_bcast<T>((T)-2)));
+    db = p2_mul<T>(mg, p2_make<T>(nm::rcp_(h.lo), nm::rcp_(h.hi)));
+    pred2 = p2_mul<T>(mg, db);
+    Fe = p2_fma<T>(p2_mul<T>(N0, p2_bcast<T>((T)-1)), a, ysq);
+  };
+  evaluate();
+  const V step2a = p2_mul<T>(db, db);
+  {
+    // first-step gate per mean echo spacing, and never further than exp(b x) changing by a factor e
+    const T cap = nm::min_((T)kFirstStepCap * (T)(E - 1), (T)1) * xt.inv_xmax;
+    ok[0] = ok[0] && h.lo > (T)0 && step2a.lo <= cap * cap;
+    ok[1] = ok[1] && h.hi > (T)0 && step2a.hi <= cap * cap;
+  }
+  b = p2_add<T>(b, db);
+  evaluate();
+  {
+    const V tol2 = p2_fma<T>(p2_bcast<T>((T)2 * o.ftol), p2_make<T>(nm::max_(Fe.lo, (T)0), nm::max_(Fe.hi, (T)0)),
+                             p2_mul<T>(ysq, p2_bcast<T>((T)2 * o.floor_rel)));
+    bool conv[2];
+    second_pass_converged<T>(pred2, tol2, p2_mul<T>(db, db), step2a, h, conv);
+    ok[0] = ok[0] && conv[0];
+    ok[1] = ok[1] && conv[1];
+  }
+  const V bf = p2_add<T>(b, db);
+  const V af = p2_fma<T>(ap, db, a);
+  ok[0] = ok[0] && nm::abs_(bf.lo) < blim && nm::finite(af.lo);
+  ok[1] = ok[1] && nm::abs_(bf.hi) < blim && nm::finite(af.hi);
+  // cost at the returned point (explicit residuals, see mono_uniform_fast2)
+  const V naf = p2_mul<T>(af, p2_bcast<T>((T)-1));
+  V F = p2_bcast<T>((T)0);
+#pragma unroll
+  for (int e = 0; e < E; ++e) {
+    const V ex = p2_make<T>(nm::expbx(bf.lo, xt.x[e], xt.xs[e]), nm::expbx(bf.hi, xt.x[e], xt.xs[e]));
+    const V r = p2_fma<T>(naf, ex, Y[e]);
+    F = p2_fma<T>(r, r, F);
+  }
+  const V den = p2_add<T>(ss_total2_fast<T, E, YS>(Y, ysq, S), p2_bcast<T>(r2_eps));
+  r2 = p2_fma<T>(F, p2_make<T>(-nm::rcp_(den.lo), -nm::rcp_(den.hi)), p2_bcast<T>((T)1));
+  pa = af;
+  pb = bf;
+}
+
 // sum (y - mean)^2 of two voxels at once
 template <typename T, int E, class YS>
 DFIT_HD pair2<T> ss_total2(const YS& Y) {
@@ -534,6 +802,17 @@ DFIT_HD void fit_voxel_fast2(const YS& Y, const XTab<T, EMAX>& xt, const VoxelOp
   const pair2<T> den = p2_add<T>(ss_total2<T, EMAX, YS>(Y), p2_bcast<T>(vo.r2_eps));
   const pair2<T> nr = p2_make<T>(-num<T>::rcp_(den.lo), -num<T>::rcp_(den.hi));
   r2 = p2_fma<T>(F, nr, p2_bcast<T>((T)1));  // fitting.py:1032-1035
+}
+
+// Straight-line fast-path attempt for two voxels (what the dense kernels run): ok[i] = false where voxel i has
+// to take the one-voxel path (fit_voxel_fast, then fit_voxel).  Passes spent by a voxel that is ok:
+constexpr int kFast2Passes = 2;
+template <class M, typename T, int EMAX, class YS>
+DFIT_HD void fit_voxel_fast2s(const YS& Y, const XTab<T, EMAX>& xt, const VoxelOpts<T>& vo, pair2<T>& pa, pair2<T>& pb,
+                              pair2<T>& r2, bool (&ok)[2]) {
+  static_assert(M::MONO && EMAX >= 3, "mono-exponential model only");
+  if (xt.uniform != 0) mono_uniform_fast2<T, EMAX, YS>(Y, xt, vo.s, vo.r2_eps, pa, pb, r2, ok);
+  else mono_general_fast2<T, EMAX, YS>(Y, xt, vo.s, vo.r2_eps, pa, pb, r2, ok);
 }
 
 // Fast-path attempt for one voxel (mono-exponential model, no y_bounds).  Returns a

@@ -39,20 +39,25 @@ static void run(int E, int64_t N, const double* x, const double* y, const double
         pair2<T> Y[EMAX], pa, pb, r2p;
         for (int e = 0; e < EMAX; ++e)
           Y[e] = p2_make<T>((T)y[(size_t)e * N + v], (T)y[(size_t)e * N + (both ? v + 1 : v)]);
-        int st2[2], it2[2];
-        fit_voxel_fast2<M, T, EMAX, pair2<T>[EMAX]>(Y, xt, vo, pa, pb, r2p, st2, it2);
+        // what the dense GPU kernels do: the straight-line two-pass attempt for the pair; a voxel it turns
+        // down goes through the one-voxel path (generic Newton loop, then the LM from p0)
+        bool ok2[2];
+        fit_voxel_fast2s<M, T, EMAX, pair2<T>[EMAX]>(Y, xt, vo, pa, pb, r2p, ok2);
         for (int hsel = 0; hsel < (both ? 2 : 1); ++hsel) {
           T p[P], r2v = hsel ? r2p.hi : r2p.lo;
-          int st = st2[hsel], it = it2[hsel];
+          int st = ok2[hsel] ? (int)ST_CONV_F : -1, it = kFast2Passes;
           p[0] = hsel ? pa.hi : pa.lo;
           p[P - 1] = hsel ? pb.hi : pb.lo;
           if (st < 0) {
             T yy[EMAX];
             unsigned flags;
             for (int e = 0; e < EMAX; ++e) yy[e] = hsel ? Y[e].hi : Y[e].lo;
-            const double* pv = p0 + (n_p0 > 1 ? (size_t)(v + hsel) * P : 0);
-            for (int i = 0; i < P; ++i) p[i] = (T)pv[i];
-            st = fit_voxel<M, T, TA, EMAX, EXACT>(yy, xt, E, vo, p, r2v, it, flags);
+            st = fit_voxel_fast<M, T, EMAX, EXACT>(yy, xt, vo, p, r2v, it);
+            if (st < 0) {
+              const double* pv = p0 + (n_p0 > 1 ? (size_t)(v + hsel) * P : 0);
+              for (int i = 0; i < P; ++i) p[i] = (T)pv[i];
+              st = fit_voxel<M, T, TA, EMAX, EXACT>(yy, xt, E, vo, p, r2v, it, flags);
+            }
           }
           for (int i = 0; i < P; ++i) popt[(size_t)(v + hsel) * P + i] = (double)p[i];
           r2[v + hsel] = (double)r2v;

@@ -59,7 +59,12 @@ def test_two_voxel_and_one_voxel_solvers_agree():
     y = _synth(x, 20001, 10.0, (10, 80), 11)
     p1, r1, s1, i1 = H.fit("monoexponential", x, y, p0=(1.0, -1 / 30), fast=1)
     p2, r2, s2, i2 = H.fit("monoexponential", x, y, p0=(1.0, -1 / 30), fast=2)
-    assert (i1 == i2).all() and (s1 == s2).all()
+    # the two-voxel attempt is straight-line (exactly two passes); what it turns down (here: the ~0.4 % of the voxels
+    # that want a third pass) goes through the one-voxel solver, so those voxels are bit-identical
+    assert ((s1 >= 1) & (s1 <= 4)).all() and ((s2 >= 1) & (s2 <= 4)).all()
+    two = i2 == 2
+    assert two.mean() > 0.99 and (i1[two] <= 2).all()
+    assert np.array_equal(p1[~two], p2[~two]) and np.array_equal(r1[~two], r2[~two]) and (i1[~two] == i2[~two]).all()
     assert (np.abs(p1 - p2) / np.abs(p2)).max() < 5e-6 and np.abs(r1 - r2).max() < 1e-6
 
 
