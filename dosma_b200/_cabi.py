@@ -10,7 +10,8 @@ import threading
 import numpy as np
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG, "libdfit.so")
+# DOSMA_B200_LIB: developer hook for kernel A/B runs (a variant built by `python -m dosma_b200.build --variant=...`)
+LIB_PATH = os.environ.get("DOSMA_B200_LIB") or os.path.join(_PKG, "libdfit.so")
 
 MAX_PARAMS = 4
 MAX_ECHOES = 32

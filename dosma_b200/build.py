@@ -51,20 +51,24 @@ def _stale(target, deps):
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force=False, verbose=False):
-    os.makedirs(OBJ, exist_ok=True)
+def build(force=False, verbose=False, variant=None, extra_flags=()):
+    """Build libdfit.so, or -- for kernel experiments -- a variant `libdfit_<variant>.so` compiled with
+    `extra_flags` (e.g. ("-DDFIT_M2_MIN_CTAS=6",)); a variant is loaded by setting DOSMA_B200_LIB to its path."""
+    obj_dir = OBJ if variant is None else OBJ + "_" + variant
+    lib_path = LIB if variant is None else os.path.join(PKG, f"libdfit_{variant}.so")
+    os.makedirs(obj_dir, exist_ok=True)
     hdrs = _headers()
     jobs = []
     objs = []
     for src in sources():
-        obj = os.path.join(OBJ, os.path.basename(src)[:-3] + ".o")
+        obj = os.path.join(obj_dir, os.path.basename(src)[:-3] + ".o")
         objs.append(obj)
         if force or _stale(obj, [src] + hdrs):
             jobs.append((src, obj))
 
     def compile_one(job):
         src, obj = job
-        cmd = [_nvcc()] + NVCC_FLAGS + ["-I", INCLUDE, "-c", src, "-o", obj]
+        cmd = [_nvcc()] + NVCC_FLAGS + list(extra_flags) + ["-I", INCLUDE, "-c", src, "-o", obj]
         res = subprocess.run(cmd, capture_output=True, text=True)
         log = obj[:-2] + ".ptxas.log"
         with open(log, "w") as f:
@@ -78,14 +82,20 @@ def build(force=False, verbose=False):
     if jobs:
         with ThreadPoolExecutor(max_workers=min(len(jobs), os.cpu_count() or 4)) as ex:
             list(ex.map(compile_one, jobs))
-    if jobs or force or _stale(LIB, objs):
-        cmd = [_nvcc(), "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB] + objs
+    if jobs or force or _stale(lib_path, objs):
+        cmd = [_nvcc(), "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", lib_path] + objs
         res = subprocess.run(cmd, capture_output=True, text=True)
         if res.returncode != 0:
             raise RuntimeError(f"link failed:\n{res.stdout}\n{res.stderr}")
-    return LIB
+    return lib_path
 
 
 if __name__ == "__main__":
-    path = build(force="--force" in sys.argv, verbose="--verbose" in sys.argv)
+    variant, flags = None, []
+    for arg in sys.argv[1:]:
+        if arg.startswith("--variant="):
+            variant = arg.split("=", 1)[1]
+        elif arg.startswith("-D"):
+            flags.append(arg)
+    path = build(force="--force" in sys.argv, verbose="--verbose" in sys.argv, variant=variant, extra_flags=flags)
     print(path)

@@ -206,10 +206,16 @@ __global__ void __launch_bounds__(kBlock, 5) fit_kernel_mono2_list(const __grid_
 // the warp is fitting earlier tiles, so the HBM latency that the plain kernel exposes at the top of every
 // CTA is hidden behind arithmetic.  Lanes read their two voxels of every echo as one conflict-free 8-byte
 // shared load.  No block-level synchronisation inside the loop.
+#ifndef DFIT_M2_MIN_CTAS
+#define DFIT_M2_MIN_CTAS 5
+#endif
 constexpr int kM2Warps = 4;
 constexpr int kM2Tile = 64;
 constexpr int kDeferCap = 96;  // per-warp queue of deferred voxels: at most 31 left over + 64 from one tile
-constexpr int m2_stages(int E) { return E <= 8 ? 4 : 2; }  // 32 KB of tiles per CTA
+#ifndef DFIT_M2_STAGES
+#define DFIT_M2_STAGES 4
+#endif
+constexpr int m2_stages(int E) { return E <= 8 ? DFIT_M2_STAGES : 2; }  // 32 KB of tiles per CTA
 
 // One voxel per lane over a warp's queue of deferred voxels (indices into the launch's voxel range): the
 // generic Newton loop of the fast path first, the LM from the caller's initial guess where that declines.
@@ -243,7 +249,7 @@ __device__ __forceinline__ void fit_deferred(const KernelArgs<float, EMAX>& a, c
 }
 
 template <class M, int EMAX, bool GATHER, typename S>
-__global__ void __launch_bounds__(kM2Warps * 32, 5)  // 5 CTAs/SM: 6 spills, 4 is slower (measured: 0.743 / 0.689 / 0.696 ms)
+__global__ void __launch_bounds__(kM2Warps * 32, DFIT_M2_MIN_CTAS)  // 5 CTAs/SM by default (measured in round 1: 4 / 5 / 6-with-spills = 0.696 / 0.689 / 0.743 ms)
     fit_kernel_mono2_tma(const __grid_constant__ KernelArgs<float, EMAX> a, const __grid_constant__ CUtensorMap tmap) {
   typedef float T;
   constexpr int P = 2;
@@ -252,7 +258,9 @@ __global__ void __launch_bounds__(kM2Warps * 32, 5)  // 5 CTAs/SM: 6 spills, 4 i
   __shared__ __align__(128) S tiles[kM2Warps][kStages][EMAX][kM2Tile];
   __shared__ __align__(8) uint64_t full[kM2Warps][kStages];
   __shared__ unsigned defer_q[kM2Warps][kDeferCap];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // (the warp index through a shuffle: provably warp-uniform, so that the tile bookkeeping and the TMA operands
+  // live in uniform registers)
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   // 32-bit indexing: the launcher admits fewer than 2^31 voxels
   const int n_vox = (int)a.n;
   const int n_tiles = (n_vox + kM2Tile - 1) / kM2Tile;
@@ -278,30 +286,38 @@ __global__ void __launch_bounds__(kM2Warps * 32, 5)  // 5 CTAs/SM: 6 spills, 4 i
   int n_def = 0;  // entries in this warp's queue (warp-uniform)
   // raw fp32 parameters into fp32 maps and nothing else to write: two vector stores per lane
   const bool plain = !a.po.enabled && a.out_dtype == DT_F32 && a.popt != nullptr && a.status == nullptr && a.niter == nullptr;
-  char* const popt_lane = reinterpret_cast<char*>(a.popt) + lane * (2 * P * sizeof(float));
-  char* const r2_lane = reinterpret_cast<char*>(a.r2) + lane * (2 * sizeof(float));
-  int k = 0;
-  for (int t = warp_global; t < n_tiles; t += warp_stride, ++k) {
-    const int s = k % kStages;
-    mbar_wait(&full[warp][s], (unsigned)(k / kStages) & 1u);
+  constexpr int64_t kPoptTile = (int64_t)kM2Tile * P * sizeof(float), kR2Tile = (int64_t)kM2Tile * sizeof(float);
+  char* popt_lane = reinterpret_cast<char*>(a.popt) + lane * (2 * P * sizeof(float)) + (int64_t)warp_global * kPoptTile;
+  char* r2_lane = reinterpret_cast<char*>(a.r2) + lane * (2 * sizeof(float)) + (int64_t)warp_global * kR2Tile;
+  int stage = 0;
+  unsigned phase = 0;
+  [[maybe_unused]] int k = 0;
+  for (int t = warp_global; t < n_tiles; t += warp_stride, ++k, popt_lane += warp_stride * kPoptTile, r2_lane += warp_stride * kR2Tile) {
+    mbar_wait(&full[warp][stage], phase);
     pair2<T> Y[EMAX], pa, pb, r2;
 #pragma unroll
     for (int e = 0; e < EMAX; ++e) {
-      const typename Vec2<S>::type v = *reinterpret_cast<const typename Vec2<S>::type*>(&tiles[warp][s][e][2 * lane]);
+      const typename Vec2<S>::type v = *reinterpret_cast<const typename Vec2<S>::type*>(&tiles[warp][stage][e][2 * lane]);
       Y[e] = p2_make<T>((T)v.x, (T)v.y);
-    }
-    __syncwarp();
-    if (lane == 0) {  // the stage is drained: refill it with the tile kStages trips ahead
-      const int tn = t + kStages * warp_stride;
-      if (tn < n_tiles) {
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        mbar_expect_tx(&full[warp][s], kTileBytes);
-        tma_load_2d(&tiles[warp][s][0][0], &tmap, tn * kM2Tile, 0, &full[warp][s]);
-      }
     }
     const int v0 = t * kM2Tile + 2 * lane;
     bool ok[2];
     fit_voxel_fast2s<M, T, EMAX, pair2<T>[EMAX]>(Y, a.xt, a.vo, pa, pb, r2, ok);
+    // The stage was drained long ago (every sample has been used): refill it with the tile kStages trips ahead.
+    // (Issued here rather than right after the shared loads so that the proxy fence finds nothing to wait for.)
+    __syncwarp();
+    if (lane == 0) {
+      const int tn = t + kStages * warp_stride;
+      if (tn < n_tiles) {
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        mbar_expect_tx(&full[warp][stage], kTileBytes);
+        tma_load_2d(&tiles[warp][stage][0][0], &tmap, tn * kM2Tile, 0, &full[warp][stage]);
+      }
+    }
+    if (++stage == kStages) {
+      stage = 0;
+      phase ^= 1u;
+    }
     bool defA = !ok[0], defB = !ok[1];
     if (t == n_tiles - 1) {  // the last tile may be ragged: voxels past the end are zero-filled and must go nowhere
       const bool validA = v0 < n_vox, validB = v0 + 1 < n_vox;
@@ -353,11 +369,11 @@ __global__ void __launch_bounds__(kM2Warps * 32, 5)  // 5 CTAs/SM: 6 spills, 4 i
     }
     if (plain) {
       if (ok[0] && ok[1]) {
-        __stcs(reinterpret_cast<float4*>(popt_lane + (int64_t)t * (kM2Tile * P * sizeof(float))), make_float4(pa.lo, pb.lo, pa.hi, pb.hi));
-        __stcs(reinterpret_cast<float2*>(r2_lane + (int64_t)t * (kM2Tile * sizeof(float))), make_float2(r2.lo, r2.hi));
+        __stcs(reinterpret_cast<float4*>(popt_lane), make_float4(pa.lo, pb.lo, pa.hi, pb.hi));
+        __stcs(reinterpret_cast<float2*>(r2_lane), make_float2(r2.lo, r2.hi));
       } else {
-        float2* pp = reinterpret_cast<float2*>(popt_lane + (int64_t)t * (kM2Tile * P * sizeof(float)));
-        float* pr = reinterpret_cast<float*>(r2_lane + (int64_t)t * (kM2Tile * sizeof(float)));
+        float2* pp = reinterpret_cast<float2*>(popt_lane);
+        float* pr = reinterpret_cast<float*>(r2_lane);
         if (ok[0]) { __stcs(pp, make_float2(pa.lo, pb.lo)); __stcs(pr, r2.lo); }
         if (ok[1]) { __stcs(pp + 1, make_float2(pa.hi, pb.hi)); __stcs(pr + 1, r2.hi); }
       }

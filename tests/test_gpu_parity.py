@@ -141,6 +141,53 @@ def test_biexp_noise_free(D, name):
     assert np.abs(r2[ok] - c["r2"][ok]).max() < 1e-7
 
 
+@pytest.mark.parametrize("name", sorted(G.BIEXP_F32_TOL))
+def test_biexp_fp32_golden(D, name):
+    """Bi-exponential fit in fp32 arithmetic (what BASELINE config 4 runs) against the reference's outputs on the
+    noise-free and the SNR-100 fixture: percentile tolerances on popt, r2 and the NaN set as stated in
+    tests/golden_util.py (the same bounds hold the host build of the solver in the CPU suite)."""
+    c = G.load(name)
+    popt, r2 = D.curve_fit(D.biexponential, c["x"], c["y"], p0=G.p0_of(c), compute_dtype="f32")
+    G.check_biexp_f32(name, popt, r2)
+
+
+def test_config4_sample_against_c_oracle(D):
+    """A config-4-shaped volume (16 echoes x 5 ms, bi-exponential, SNR 100, fp32) fitted on the GPU in fp32; a seeded
+    sample of voxels is compared with the MINPACK restatement (oracle/minpack_lmdif.c, pinned to SciPy on the
+    bi-exponential fixtures): same minimum (r2), parameters within the ftol slack of the reference."""
+    import torch
+
+    from dosma_b200 import device_api as A
+    from oracle import c_oracle
+
+    dev = torch.device("cuda", 0)
+    g = torch.Generator(device=dev).manual_seed(3)
+    x16 = [5.0 * i for i in range(1, 17)]
+    n = 256 * 256 * 128
+    xt = torch.tensor(x16, device=dev, dtype=torch.float32)[:, None]
+    amp = 500 + 1000 * torch.rand(n, device=dev, generator=g)
+    fs = 0.3 + 0.4 * torch.rand(n, device=dev, generator=g)
+    ts = 8 + 12 * torch.rand(n, device=dev, generator=g)
+    tl = 50 + 50 * torch.rand(n, device=dev, generator=g)
+    y = amp * fs * torch.exp(-xt / ts) + amp * (1 - fs) * torch.exp(-xt / tl) + 10 * torch.randn(16, n, device=dev, generator=g)
+    p0 = (500.0, -1 / 10, 500.0, -1 / 60)
+    o, P = A.make_opts(D.biexponential, p0=p0, compute_dtype="f32")
+    p, r = A.fit_device(o, P, x16, y)
+    torch.cuda.synchronize()
+    sel = torch.from_numpy(np.random.default_rng(4).choice(n, 4096, replace=False)).to(dev)
+    ys = y[:, sel].double().cpu().numpy()
+    ps, rs = p[sel].double().cpu().numpy(), r[sel].double().cpu().numpy()
+    pr, rr = c_oracle.curve_fit("biexponential", x16, ys, p0=p0)
+    nan, ref_nan = np.isnan(ps[:, 0]), np.isnan(pr[:, 0])
+    assert (nan ^ ref_nan).mean() < 0.03, ((nan ^ ref_nan).sum(), nan.sum(), ref_nan.sum())
+    ok = ~nan & ~ref_nan
+    assert np.abs(rs[ok] - rr[ok]).max() < 2e-6
+    rel = (np.abs(ps[ok] - pr[ok]) / np.abs(pr[ok])).max(axis=1)
+    q = np.percentile(rel, [50, 90])
+    assert q[0] < 3e-4 and q[1] < 5e-3, q
+    assert float(torch.isnan(p[:, 0]).float().mean()) < 0.05
+
+
 @pytest.mark.parametrize("name", G.names("monoexpfit_"))
 def test_monoexpfit_golden(D, name):
     c = G.load(name)
@@ -361,8 +408,16 @@ def test_two_voxel_fast_kernels_agree_with_lm(D):
             assert ok.float().mean() > 0.999
             rel = (pb_[ok] - pa_[ok]).abs() / pa_[ok].abs()
             assert rel.max() < 2e-3 and (rel > 1e-4).float().mean() < 1e-3 and (rb_[ok] - ra_[ok]).abs().max() < 1e-5
-            # the mask path runs the same per-voxel arithmetic: identical inside, NaN outside
-            assert torch.equal(pm_[mask].nan_to_num(-1), pb_[mask].nan_to_num(-1)) and torch.equal(rm_[mask], rb_[mask])
+            # the mask path (two-voxel list kernel) runs the same per-voxel arithmetic as the dense two-voxel kernel:
+            # identical inside, NaN outside; the dense one-voxel kernel (odd n) runs the loop form of the same
+            # iteration: equal to rounding
+            if n % 4 == 0:
+                assert torch.equal(pm_[mask].nan_to_num(-1), pb_[mask].nan_to_num(-1)) and torch.equal(rm_[mask], rb_[mask])
+            else:
+                okm = ~torch.isnan(pm_[mask][:, 0]) & ~torch.isnan(pb_[mask][:, 0])
+                assert okm.float().mean() > 0.999
+                assert ((pm_[mask][okm] - pb_[mask][okm]).abs() / pb_[mask][okm].abs()).max() < 2e-5
+                assert (rm_[mask][okm] - rb_[mask][okm]).abs().max() < 2e-6
             assert torch.isnan(pm_[~mask]).all()
     # y_bounds keep the voxel-skipping rules with the LM: identical results with and without the fast path
     xn = np.arange(1, 9) * 10.0

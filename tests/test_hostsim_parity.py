@@ -53,6 +53,15 @@ def test_noisy_percentiles(name, frac, fast):
     assert it[ok].mean() < 8
 
 
+@pytest.mark.parametrize("name", sorted(G.BIEXP_F32_TOL))
+def test_biexp_fp32_golden(name):
+    """Bi-exponential LM in fp32 (the arithmetic of BASELINE config 4) against the reference's outputs on both
+    bi-exponential fixtures -- tolerances stated in tests/golden_util.py."""
+    c = G.load(name)
+    popt, r2, st, it = H.fit("biexponential", c["x"], c["y"], p0=G.p0_of(c), dtype="f32", fast=0, init_linear=0)
+    G.check_biexp_f32(name, popt, r2)
+
+
 def test_degenerate_and_bounds():
     c = G.load("curvefit_mono8_degenerate_f32")
     popt, r2, st, it = H.fit("monoexponential", c["x"], c["y"], p0=(1.0, -1 / 30))
