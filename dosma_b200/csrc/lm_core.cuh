@@ -16,6 +16,7 @@
 
 #include <math.h>
 #include <stdint.h>
+#include <string.h>
 
 #if defined(__CUDACC__)
 #define DFIT_HD __host__ __device__ __forceinline__
@@ -812,6 +813,12 @@ struct PostOpts {
   // epilogue of such a parameter is exact in fp32.  Filled by set_post_scales().
   int simple[4];
   float lbf[4], ubf[4], r2_thresh_f, fill_f;
+  // fp32 plan for the MonoExponentialFit column (ufunc 1 / |v| with bounds, threshold, fill and rounding,
+  // fitting.py:725-737): `fastinv` set when every decision of the float64 evaluation can be reproduced from
+  // fp32 quantities -- x = |v| is in bounds exactly when xa <= x <= xb (the floats between which
+  // fl64(1 / x) lies inside [lb, ub]); the rounding is decided on a two-float quotient.  Filled by set_post_scales().
+  int fastinv[4];
+  float inv_xa[4], inv_xb[4], scale_f[4], inv_scale_f[4], fill_rounded_f[4];
 };
 
 // 1 / v in double.  On the device: MUFU.RCP of the fp32 image of v, refined by two Newton steps in fp64
@@ -859,6 +866,25 @@ inline float float_at_most(double v) {  // largest float <= v
   return f;
 }
 
+// Smallest non-negative float (by bit pattern, 0 .. +inf) for which `pred` holds; pred must be monotone
+// (false ... false true ... true).  Returns NaN when it never holds.
+template <class Pred>
+inline float first_float_where(Pred pred) {
+  uint32_t lo = 0u, hi = 0x7f800000u;  // +0 .. +inf
+  auto as_float = [](uint32_t u) {
+    float f;
+    memcpy(&f, &u, sizeof(f));
+    return f;
+  };
+  if (!pred(as_float(hi))) return NAN;
+  while (lo < hi) {
+    const uint32_t mid = lo + (hi - lo) / 2;
+    if (pred(as_float(mid))) hi = mid;
+    else lo = mid + 1;
+  }
+  return as_float(lo);
+}
+
 inline void set_post_scales(PostOpts& po) {
   po.fill_f = (float)po.fill;
   const bool fill_ok = !po.has_fill || (double)po.fill_f == po.fill;
@@ -869,6 +895,26 @@ inline void set_post_scales(PostOpts& po) {
     po.simple[i] = (po.ufunc[i] == UF_NONE && po.decimals[i] < 0 && fill_ok) ? 1 : 0;
     po.lbf[i] = float_at_least(po.lb[i]);
     po.ubf[i] = float_at_most(po.ub[i]);
+    // 1 / |v| in fp32 with the float64 evaluation's decisions
+    po.fastinv[i] = 0;
+    po.inv_xa[i] = po.inv_xb[i] = po.fill_rounded_f[i] = 0.f;
+    po.scale_f[i] = (float)po.scale[i];
+    po.inv_scale_f[i] = (float)po.inv_scale[i];
+    if (po.ufunc[i] == UF_INV_ABS && po.decimals[i] <= 10) {
+      const double lb = po.lb[i], ub = po.ub[i];
+      // fl64(1 / x) decreases with x: in bounds for xa <= x <= xb
+      const float xa = first_float_where([&](float x) { return !(1.0 / (double)x > ub); });
+      const float xb1 = first_float_where([&](float x) { return 1.0 / (double)x < lb; });  // first x out again
+      double fr = po.fill;
+      if (po.has_fill && po.decimals[i] >= 0 && fabs(fr) < 1e300) fr = nearbyint(fr * po.scale[i]) / po.scale[i];
+      const bool fr_ok = !po.has_fill || ((double)(float)fr == fr);
+      if (xa == xa && fr_ok) {
+        po.inv_xa[i] = xa;
+        po.inv_xb[i] = xb1 != xb1 ? INFINITY : nextafterf(xb1, -INFINITY);  // (never out again: up to +inf)
+        po.fill_rounded_f[i] = (float)fr;
+        po.fastinv[i] = 1;
+      }
+    }
   }
 }
 
@@ -906,6 +952,19 @@ DFIT_HD double post_param(const PostOpts& po, int i, double v, double r2) {
 
 // Epilogue of one fp32 parameter into an fp32 map: comparisons-only parameters stay in fp32 (exactly the
 // decisions the float64 evaluation takes, see PostOpts::simple); everything else goes through post_param.
+// 1 / x, x positive and finite, as two floats hi + lo (relative error ~2^-45): MUFU reciprocal, one Newton step,
+// quotient and exact remainder by fma.  `top` = 1 or a power of ten.
+DFIT_HD void quotient2(float top, float x, float& hi, float& lo) {
+  float r = num<float>::rcp_(x);
+  r = fmaf(r, fmaf(-x, r, 1.0f), r);
+  hi = top * r;
+  lo = fmaf(-hi, x, top) * r;
+}
+
+// Epilogue of one fp32 parameter into an fp32 map: comparisons-only parameters stay in fp32 (exactly the
+// decisions the float64 evaluation takes, see PostOpts::simple), and so does the MonoExponentialFit column
+// 1 / |v| with bounds, r2 threshold, fill and rounding (PostOpts::fastinv): the value returned is the float64
+// epilogue's result converted to float, bit for bit.  Everything else goes through post_param.
 DFIT_HD float post_param_f32(const PostOpts& po, int i, float v, float r2) {
   if (!po.enabled) return v;
   if (po.simple[i] && !(fabsf(v) > 3.4028234e38f)) {  // finite or NaN (+-inf takes the nan_to_num branch in double)
@@ -913,6 +972,39 @@ DFIT_HD float post_param_f32(const PostOpts& po, int i, float v, float r2) {
     if (bad) v = NAN;
     if (po.has_fill && v != v) v = po.fill_f;
     return v;
+  }
+  if (po.fastinv[i]) {
+    const float x = fabsf(v);
+    // fitting.py:130-141: outside the bounds (decided on x, see set_post_scales; false for NaN) or below the r2 threshold
+    const bool good = x >= po.inv_xa[i] && x <= po.inv_xb[i] && !(po.has_r2_thresh && r2 < po.r2_thresh_f);
+    if (!good) {
+      if (po.has_fill) return po.fill_rounded_f[i];  // fitting.py:143-144, then :736-737
+      if (x == x) return NAN;                        // (a NaN parameter keeps its payload through post_param)
+    } else if (x > 1e-30f && x < 1e30f) {
+      const float S = po.decimals[i] >= 0 ? po.scale_f[i] : 1.0f;
+      float hi, lo;
+      quotient2(S, x, hi, lo);
+      if (po.decimals[i] < 0) {
+        // fl32(fl64(1 / x)): hi is within an ulp, lo says on which side of hi the quotient lies
+        const float up = nextafterf(hi, INFINITY), dn = nextafterf(hi, -INFINITY);
+        const float h_up = 0.5f * (up - hi), h_dn = 0.5f * (hi - dn);
+        if (lo > h_up) return up;
+        if (-lo > h_dn) return dn;
+        if (lo != h_up && -lo != h_dn) return hi;
+      } else if (hi < 4.0e6f) {
+        // np.around(1 / x, d) = rint(S / x) / S: the integer is decided on hi + lo (a quotient that is not a tie
+        // is at least 2^-25 away from one, far more than either evaluation's error), ties go to post_param
+        float m = rintf(hi);
+        const float f = (hi - m) + lo;
+        if (fabsf(f) != 0.5f) {
+          if (f > 0.5f) m += 1.0f;
+          else if (f < -0.5f) m -= 1.0f;
+          // m / S correctly rounded (Markstein's correction): equals fl32(fl64(m / S))
+          const float q = m * po.inv_scale_f[i];
+          return fmaf(fmaf(-q, S, m), po.inv_scale_f[i], q);
+        }
+      }
+    }
   }
   return (float)post_param(po, i, (double)v, (double)r2);
 }

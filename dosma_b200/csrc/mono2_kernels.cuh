@@ -114,8 +114,15 @@ __global__ void __launch_bounds__(kBlock2, 5) fit_kernel_mono2(const __grid_cons
       st[1] = -1;
       iters[1] = 0;
     }
-    if (!a.po.enabled && a.out_dtype == DT_F32 && both) {
-      __stcs(reinterpret_cast<float4*>(reinterpret_cast<float*>(a.popt) + v0 * P), make_float4(pa.lo, pb.lo, pa.hi, pb.hi));
+    if (a.out_dtype == DT_F32 && both && a.popt != nullptr) {
+      float4 q = make_float4(pa.lo, pb.lo, pa.hi, pb.hi);
+      if (a.po.enabled) {  // fused epilogue, fp32 form (see post_param_f32)
+        q.x = post_param_f32(a.po, 0, pa.lo, r2.lo);
+        q.y = post_param_f32(a.po, 1, pb.lo, r2.lo);
+        q.z = post_param_f32(a.po, 0, pa.hi, r2.hi);
+        q.w = post_param_f32(a.po, 1, pb.hi, r2.hi);
+      }
+      __stcs(reinterpret_cast<float4*>(reinterpret_cast<float*>(a.popt) + v0 * P), q);
       __stcs(reinterpret_cast<float2*>(reinterpret_cast<float*>(a.r2) + v0), make_float2(r2.lo, r2.hi));
       if (a.status) {
         a.status[v0] = (uint8_t)st[0];
@@ -284,8 +291,8 @@ __global__ void __launch_bounds__(kM2Warps * 32, DFIT_M2_MIN_CTAS)  // 5 CTAs/SM
 
   unsigned n_fast = 0, n_fit = 0, n_fail = 0, n_nf = 0, n_oob = 0, it_sum = 0, it_max = 0;
   int n_def = 0;  // entries in this warp's queue (warp-uniform)
-  // raw fp32 parameters into fp32 maps and nothing else to write: two vector stores per lane
-  const bool plain = !a.po.enabled && a.out_dtype == DT_F32 && a.popt != nullptr && a.status == nullptr && a.niter == nullptr;
+  // fp32 maps (raw parameters or the fp32 form of the fused epilogue) and nothing else to write: two vector stores per lane
+  const bool plain = a.out_dtype == DT_F32 && a.popt != nullptr && a.status == nullptr && a.niter == nullptr;
   constexpr int64_t kPoptTile = (int64_t)kM2Tile * P * sizeof(float), kR2Tile = (int64_t)kM2Tile * sizeof(float);
   char* popt_lane = reinterpret_cast<char*>(a.popt) + lane * (2 * P * sizeof(float)) + (int64_t)warp_global * kPoptTile;
   char* r2_lane = reinterpret_cast<char*>(a.r2) + lane * (2 * sizeof(float)) + (int64_t)warp_global * kR2Tile;
@@ -368,14 +375,21 @@ __global__ void __launch_bounds__(kM2Warps * 32, DFIT_M2_MIN_CTAS)  // 5 CTAs/SM
       }
     }
     if (plain) {
+      float4 q = make_float4(pa.lo, pb.lo, pa.hi, pb.hi);
+      if (a.po.enabled) {  // fused _process_params + rounding (fitting.py:109-146, 734-737), fp32 form
+        q.x = post_param_f32(a.po, 0, pa.lo, r2.lo);
+        q.y = post_param_f32(a.po, 1, pb.lo, r2.lo);
+        q.z = post_param_f32(a.po, 0, pa.hi, r2.hi);
+        q.w = post_param_f32(a.po, 1, pb.hi, r2.hi);
+      }
       if (ok[0] && ok[1]) {
-        __stcs(reinterpret_cast<float4*>(popt_lane), make_float4(pa.lo, pb.lo, pa.hi, pb.hi));
+        __stcs(reinterpret_cast<float4*>(popt_lane), q);
         __stcs(reinterpret_cast<float2*>(r2_lane), make_float2(r2.lo, r2.hi));
       } else {
         float2* pp = reinterpret_cast<float2*>(popt_lane);
         float* pr = reinterpret_cast<float*>(r2_lane);
-        if (ok[0]) { __stcs(pp, make_float2(pa.lo, pb.lo)); __stcs(pr, r2.lo); }
-        if (ok[1]) { __stcs(pp + 1, make_float2(pa.hi, pb.hi)); __stcs(pr + 1, r2.hi); }
+        if (ok[0]) { __stcs(pp, make_float2(q.x, q.y)); __stcs(pr, r2.lo); }
+        if (ok[1]) { __stcs(pp + 1, make_float2(q.z, q.w)); __stcs(pr + 1, r2.hi); }
       }
     } else if (!(GATHER && a.popt == nullptr)) {  // (with the fused gather the maps may be the only output)
       const T p0_[P] = {pa.lo, pb.lo}, p1_[P] = {pa.hi, pb.hi};

@@ -503,14 +503,18 @@ constexpr float kSsTotCond = 0.04f;
 template <typename T, int E, class YS>
 DFIT_HD pair2<T> ss_total2_fast(const YS& Y, pair2<T> ysq, pair2<T> S) {
   pair2<T> t = p2_fma<T>(p2_mul<T>(S, p2_bcast<T>((T)(-1.0 / E))), S, ysq);
-  if (t.lo < (T)kSsTotCond * ysq.lo || t.hi < (T)kSsTotCond * ysq.hi) {  // rare: nearly constant signals
+  const bool ill_lo = t.lo < (T)kSsTotCond * ysq.lo, ill_hi = t.hi < (T)kSsTotCond * ysq.hi;
+  if (ill_lo || ill_hi) {  // rare: nearly constant signals
     const pair2<T> nmean = p2_mul<T>(S, p2_bcast<T>((T)(-1.0 / E)));
-    t = p2_bcast<T>((T)0);
+    pair2<T> u = p2_bcast<T>((T)0);
 #pragma unroll
     for (int e = 0; e < E; ++e) {
       const pair2<T> d = p2_add<T>(Y[e], nmean);
-      t = p2_fma<T>(d, d, t);
+      u = p2_fma<T>(d, d, u);
     }
+    // per voxel: a voxel's result must not depend on its neighbour in the pair
+    if (ill_lo) t.lo = u.lo;
+    if (ill_hi) t.hi = u.hi;
   }
   return t;
 }

@@ -558,6 +558,33 @@ def test_config4_biexp_full_size_round_trip(D):
     assert rel32.median() < 1e-3 and (r32[ok32] > 1 - 1e-5).all()
 
 
+def test_fp32_fused_epilogue_equals_float64_epilogue(D):
+    """The fused MonoExponentialFit epilogue (1/|b|, bounds, r2 threshold, fill, rounding) computed in fp32 by the
+    kernels (float32 maps) must be, bit for bit, the float64 epilogue's result converted to float32 -- on a million
+    voxels whose time constants straddle the bounds and the rounding ties, for every kernel variant."""
+    import torch
+
+    from dosma_b200 import device_api as A
+
+    g = torch.Generator(device="cuda").manual_seed(21)
+    x = np.arange(1, 9) * 10.0
+    xt = torch.tensor(x, device="cuda", dtype=torch.float32)[:, None]
+    n = 1_000_000
+    t2 = 5 + 120 * torch.rand(n, device="cuda", generator=g)  # beyond the upper bound of 100 as well
+    y = (500 + 1000 * torch.rand(n, device="cuda", generator=g)) * torch.exp(-xt / t2) + 10 * torch.randn(8, n, device="cuda", generator=g)
+    for decimals in (1, 3, -1):
+        post = dict(ufunc=[0, 1], lb=[-np.inf, 0.0], ub=[np.inf, 100.0], decimals=[-1, decimals], r2_threshold=0.9, nan_to_num=0.0)
+        for kw in (dict(), dict(use_tma=0), dict(fast_path=2, use_tma=0), dict(fast_path=0, use_tma=0)):
+            o, P = A.make_opts(D.monoexponential, p0=(1.0, -1 / 30), post=post, **kw)
+            p32, r32 = A.fit_device(o, P, x, y, out_dtype=torch.float32)
+            p64, r64 = A.fit_device(o, P, x, y, out_dtype=torch.float64)
+            torch.cuda.synchronize()
+            assert torch.equal(p32, p64.float()) and torch.equal(r32, r64.float()), (decimals, kw)
+            if decimals >= 0:  # on the decimal grid, filled voxels are 0
+                assert torch.equal(torch.round(p64[:, 1] * 10 ** decimals) / 10 ** decimals, p64[:, 1])
+            assert float((p32[:, 1] == 0).float().mean()) > 0.05 and float((p32[:, 1] > 0).float().mean()) > 0.5
+
+
 def test_nonfinite_input_raises(D):
     x = np.arange(1, 5) * 10.0
     y = np.ones((4, 100), dtype=np.float32)

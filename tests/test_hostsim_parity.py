@@ -138,6 +138,48 @@ def test_fp32_epilogue_takes_the_float64_decisions():
         assert np.array_equal(a, b, equal_nan=True), (ufunc, decimals, fill)
 
 
+@pytest.mark.parametrize("decimals", [-1, 0, 1, 3, 6])
+@pytest.mark.parametrize("fill", [None, 0.0, 0.05])
+def test_fp32_inverse_epilogue_is_the_float64_one(decimals, fill):
+    """The MonoExponentialFit column in fp32 (1 / |v|, bounds, r2 threshold, fill, rounding: post_param_f32's
+    `fastinv` plan) against the float64 epilogue converted to float, bit for bit -- on random values and on
+    adversarial ones: |v| whose reciprocal sits next to a rounding tie (10^d / (k + 1/2) and its float
+    neighbours), next to the bounds, exact ties, zeros, infinities, NaN, tiny and huge magnitudes."""
+    lib = H._load()
+    rng = np.random.default_rng(1)
+    S = 10.0 ** max(decimals, 0)
+    lb, ub, thr = 0.0, 100.0, 0.9
+    parts = [rng.uniform(-0.3, 0.3, 100000), rng.uniform(0.005, 0.02, 50000) * rng.choice([-1, 1], 50000),
+             10.0 ** rng.uniform(-38, 38, 20000)]
+    k = np.arange(0, 20000, dtype=np.float64)
+    ties = (S / (k + 0.5)).astype(np.float32)
+    for d in (-2, -1, 0, 1, 2):
+        t = ties.copy()
+        for _ in range(abs(d)):
+            t = np.nextafter(t, np.float32(np.inf if d > 0 else -np.inf))
+        parts.append(t.astype(np.float64))
+    for edge in (1.0 / ub, 20.0, 4.0, 2000.0, 16.0, 0.25):
+        f = np.float32(edge)
+        parts.append(np.array([np.nextafter(f, np.float32(0)), f, np.nextafter(f, np.float32(np.inf))], dtype=np.float64))
+    parts.append(np.array([0.0, -0.0, np.inf, -np.inf, np.nan, 1e-45, 3e38, -3e38]))
+    v = np.concatenate(parts).astype(np.float32)
+    n = v.size
+    r2 = rng.uniform(0.8, 1.0, n).astype(np.float32)
+    fp = ctypes.POINTER(ctypes.c_float)
+    uf = (ctypes.c_int * 4)(1, 1, 0, 0)
+    dec = (ctypes.c_int * 4)(decimals, decimals, -1, -1)
+    for lbs_, ubs_ in (((lb,) * 2, (ub,) * 2), ((-np.inf,) * 2, (np.inf,) * 2), ((0.1,) * 2, (37.123456789,) * 2)):
+        lbs = (ctypes.c_double * 4)(*lbs_, -np.inf, -np.inf)
+        ubs = (ctypes.c_double * 4)(*ubs_, np.inf, np.inf)
+        a = np.empty(n, np.float32)
+        b = np.empty(n, np.float32)
+        lib.hostsim_post_param_f32(1, uf, lbs, ubs, 1, ctypes.c_double(thr), int(fill is not None),
+                                   ctypes.c_double(fill or 0.0), dec, 1, ctypes.c_int64(n), v.ctypes.data_as(fp),
+                                   r2.ctypes.data_as(fp), a.ctypes.data_as(fp), b.ctypes.data_as(fp))
+        bad = ~((a == b) | (np.isnan(a) & np.isnan(b)))
+        assert not bad.any(), (decimals, fill, lbs_, v[bad][:5], a[bad][:5], b[bad][:5])
+
+
 @pytest.mark.parametrize("name", G.names("monoexpfit_"))
 @pytest.mark.parametrize("fast", [0, 2])
 def test_monoexpfit_chain_on_the_host_build(name, fast):
