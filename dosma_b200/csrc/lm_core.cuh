@@ -181,6 +181,24 @@ __device__ __forceinline__ pair2<float> p2_add<float>(pair2<float> a, pair2<floa
   return d;
 }
 #endif
+// Packed add / multiply that are guaranteed not to be contracted with neighbouring operations (the device versions
+// above are inline asm already; the host versions go through volatile temporaries).
+DFIT_HD pair2<float> p2_add_rn(pair2<float> a, pair2<float> b) {
+#if defined(__CUDA_ARCH__)
+  return p2_add<float>(a, b);
+#else
+  volatile float lo = a.lo + b.lo, hi = a.hi + b.hi;
+  return p2_make<float>(lo, hi);
+#endif
+}
+DFIT_HD pair2<float> p2_mul_rn(pair2<float> a, pair2<float> b) {
+#if defined(__CUDA_ARCH__)
+  return p2_mul<float>(a, b);
+#else
+  volatile float lo = a.lo * b.lo, hi = a.hi * b.hi;
+  return p2_make<float>(lo, hi);
+#endif
+}
 template <typename T>
 DFIT_HD pair2<T> p2_expbx(T b, pair2<T> x, pair2<T> xs) {
   return p2_make<T>(num<T>::expbx(b, x.lo, xs.lo), num<T>::expbx(b, x.hi, xs.hi));
@@ -866,6 +884,8 @@ inline float float_at_most(double v) {  // largest float <= v
   return f;
 }
 
+constexpr float kInvXMax = 1e30f;  // largest |v| the fp32 form of the 1 / |v| epilogue handles itself
+
 // Smallest non-negative float (by bit pattern, 0 .. +inf) for which `pred` holds; pred must be monotone
 // (false ... false true ... true).  Returns NaN when it never holds.
 template <class Pred>
@@ -908,7 +928,11 @@ inline void set_post_scales(PostOpts& po) {
       double fr = po.fill;
       if (po.has_fill && po.decimals[i] >= 0 && fabs(fr) < 1e300) fr = nearbyint(fr * po.scale[i]) / po.scale[i];
       const bool fr_ok = !po.has_fill || ((double)(float)fr == fr);
-      if (xa == xa && fr_ok) {
+      // (x stays a normal, finite float and 10^d / x below 2^22 for every x in bounds: no per-voxel range checks)
+      // (bounds-wise the upper end may be anything up to +inf; the fp32 arithmetic is used up to kInvXMax and the
+      // float64 form beyond it)
+      const bool range_ok = xa == xa && xa >= 1e-30f && xa < kInvXMax && po.scale[i] / (double)xa < 4.0e6;
+      if (range_ok && fr_ok) {
         po.inv_xa[i] = xa;
         po.inv_xb[i] = xb1 != xb1 ? INFINITY : nextafterf(xb1, -INFINITY);  // (never out again: up to +inf)
         po.fill_rounded_f[i] = (float)fr;
@@ -950,15 +974,24 @@ DFIT_HD double post_param(const PostOpts& po, int i, double v, double r2) {
 }
 
 
-// Epilogue of one fp32 parameter into an fp32 map: comparisons-only parameters stay in fp32 (exactly the
-// decisions the float64 evaluation takes, see PostOpts::simple); everything else goes through post_param.
-// 1 / x, x positive and finite, as two floats hi + lo (relative error ~2^-45): MUFU reciprocal, one Newton step,
+// a * b rounded to float and never contracted into a following add (the two-float arithmetic below relies on
+// the ROUNDED product: its companion term compensates exactly that rounding)
+DFIT_HD float mul_rn(float a, float b) {
+#if defined(__CUDA_ARCH__)
+  return __fmul_rn(a, b);
+#else
+  volatile float t = a * b;
+  return t;
+#endif
+}
+
+// top / x, x positive and finite, as two floats hi + lo (relative error ~2^-45): MUFU reciprocal, one Newton step,
 // quotient and exact remainder by fma.  `top` = 1 or a power of ten.
 DFIT_HD void quotient2(float top, float x, float& hi, float& lo) {
   float r = num<float>::rcp_(x);
   r = fmaf(r, fmaf(-x, r, 1.0f), r);
-  hi = top * r;
-  lo = fmaf(-hi, x, top) * r;
+  hi = mul_rn(top, r);
+  lo = mul_rn(fmaf(-hi, x, top), r);
 }
 
 // Epilogue of one fp32 parameter into an fp32 map: comparisons-only parameters stay in fp32 (exactly the
@@ -980,7 +1013,7 @@ DFIT_HD float post_param_f32(const PostOpts& po, int i, float v, float r2) {
     if (!good) {
       if (po.has_fill) return po.fill_rounded_f[i];  // fitting.py:143-144, then :736-737
       if (x == x) return NAN;                        // (a NaN parameter keeps its payload through post_param)
-    } else if (x > 1e-30f && x < 1e30f) {
+    } else if (x <= kInvXMax) {
       const float S = po.decimals[i] >= 0 ? po.scale_f[i] : 1.0f;
       float hi, lo;
       quotient2(S, x, hi, lo);
@@ -991,7 +1024,7 @@ DFIT_HD float post_param_f32(const PostOpts& po, int i, float v, float r2) {
         if (lo > h_up) return up;
         if (-lo > h_dn) return dn;
         if (lo != h_up && -lo != h_dn) return hi;
-      } else if (hi < 4.0e6f) {
+      } else {
         // np.around(1 / x, d) = rint(S / x) / S: the integer is decided on hi + lo (a quotient that is not a tie
         // is at least 2^-25 away from one, far more than either evaluation's error), ties go to post_param
         float m = rintf(hi);
@@ -1000,13 +1033,44 @@ DFIT_HD float post_param_f32(const PostOpts& po, int i, float v, float r2) {
           if (f > 0.5f) m += 1.0f;
           else if (f < -0.5f) m -= 1.0f;
           // m / S correctly rounded (Markstein's correction): equals fl32(fl64(m / S))
-          const float q = m * po.inv_scale_f[i];
+          const float q = mul_rn(m, po.inv_scale_f[i]);
           return fmaf(fmaf(-q, S, m), po.inv_scale_f[i], q);
         }
       }
     }
   }
   return (float)post_param(po, i, (double)v, (double)r2);
+}
+
+// The same epilogue for the two voxels of a lane (parameter i of both): for the rounded 1 / |v| column the
+// two-float quotient, the rounding (round-to-nearest-even by adding and subtracting 1.5 * 2^23) and the division by
+// 10^d run on packed pairs; only the comparisons are per voxel.  Bit-identical to post_param_f32 on each half.
+DFIT_HD pair2<float> post_pair_f32(const PostOpts& po, int i, pair2<float> v, pair2<float> r2) {
+  if (!po.enabled) return v;
+  if (po.fastinv[i] && po.decimals[i] >= 0) {
+    typedef pair2<float> V;
+    const V x = p2_make<float>(fabsf(v.lo), fabsf(v.hi));
+    const bool good_lo = x.lo >= po.inv_xa[i] && x.lo <= po.inv_xb[i] && !(po.has_r2_thresh && r2.lo < po.r2_thresh_f);
+    const bool good_hi = x.hi >= po.inv_xa[i] && x.hi <= po.inv_xb[i] && !(po.has_r2_thresh && r2.hi < po.r2_thresh_f);
+    const V S = p2_bcast<float>(po.scale_f[i]), rS = p2_bcast<float>(po.inv_scale_f[i]);
+    const V nx = p2_mul<float>(x, p2_bcast<float>(-1.0f));
+    V r = p2_make<float>(num<float>::rcp_(x.lo), num<float>::rcp_(x.hi));
+    r = p2_fma<float>(r, p2_fma<float>(nx, r, p2_bcast<float>(1.0f)), r);
+    const V hi = p2_mul_rn(S, r);
+    const V lo = p2_mul_rn(p2_fma<float>(p2_mul<float>(hi, p2_bcast<float>(-1.0f)), x, S), r);
+    const V C = p2_bcast<float>(12582912.0f), nC = p2_bcast<float>(-12582912.0f);  // 1.5 * 2^23: rint for |t| < 2^22
+    V m = p2_add_rn(p2_add_rn(hi, C), nC);
+    const V f = p2_add_rn(p2_add_rn(hi, p2_mul<float>(m, p2_bcast<float>(-1.0f))), lo);
+    const bool tie = fabsf(f.lo) == 0.5f || fabsf(f.hi) == 0.5f || x.lo > kInvXMax || x.hi > kInvXMax;  // (or out of the fp32 form's range)
+    m = p2_add_rn(m, p2_add_rn(p2_add_rn(f, C), nC));  // + rint(f): +-1 when the low part carries over a half
+    const V q = p2_mul_rn(m, rS);
+    const V out = p2_fma<float>(p2_fma<float>(p2_mul<float>(q, p2_bcast<float>(-1.0f)), S, m), rS, q);
+    // (out of bounds without a fill value: NaN, through the one-voxel form so that a NaN parameter keeps its payload)
+    if (!tie && (good_lo || po.has_fill) && (good_hi || po.has_fill)) {
+      return p2_make<float>(good_lo ? out.lo : po.fill_rounded_f[i], good_hi ? out.hi : po.fill_rounded_f[i]);
+    }
+  }
+  return p2_make<float>(post_param_f32(po, i, v.lo, r2.lo), post_param_f32(po, i, v.hi, r2.hi));
 }
 
 }  // namespace dfit

@@ -116,11 +116,9 @@ __global__ void __launch_bounds__(kBlock2, 5) fit_kernel_mono2(const __grid_cons
     }
     if (a.out_dtype == DT_F32 && both && a.popt != nullptr) {
       float4 q = make_float4(pa.lo, pb.lo, pa.hi, pb.hi);
-      if (a.po.enabled) {  // fused epilogue, fp32 form (see post_param_f32)
-        q.x = post_param_f32(a.po, 0, pa.lo, r2.lo);
-        q.y = post_param_f32(a.po, 1, pb.lo, r2.lo);
-        q.z = post_param_f32(a.po, 0, pa.hi, r2.hi);
-        q.w = post_param_f32(a.po, 1, pb.hi, r2.hi);
+      if (a.po.enabled) {  // fused epilogue, fp32 form (see post_pair_f32)
+        const pair2<float> qa = post_pair_f32(a.po, 0, pa, r2), qb = post_pair_f32(a.po, 1, pb, r2);
+        q = make_float4(qa.lo, qb.lo, qa.hi, qb.hi);
       }
       __stcs(reinterpret_cast<float4*>(reinterpret_cast<float*>(a.popt) + v0 * P), q);
       __stcs(reinterpret_cast<float2*>(reinterpret_cast<float*>(a.r2) + v0), make_float2(r2.lo, r2.hi));
@@ -213,16 +211,21 @@ __global__ void __launch_bounds__(kBlock, 5) fit_kernel_mono2_list(const __grid_
 // the warp is fitting earlier tiles, so the HBM latency that the plain kernel exposes at the top of every
 // CTA is hidden behind arithmetic.  Lanes read their two voxels of every echo as one conflict-free 8-byte
 // shared load.  No block-level synchronisation inside the loop.
+// Resident CTAs per SM the compiler is asked to make room for (register cap) and depth of each warp's tile ring.
+// Measured on the benchmark volume (8 echoes; ms per 56.6 M voxels): 5 CTAs x 4 stages 0.525, 6 x 4 0.543,
+// 7 x 3 0.505 (72 registers, no spills), 8 x 3 0.579 (64 registers, spills).  Above 8 echoes the samples alone
+// take up to 32 registers: 4 CTAs.
 #ifndef DFIT_M2_MIN_CTAS
-#define DFIT_M2_MIN_CTAS 5
+#define DFIT_M2_MIN_CTAS 7
 #endif
+#ifndef DFIT_M2_STAGES
+#define DFIT_M2_STAGES 3
+#endif
+constexpr int m2_min_ctas(int E) { return E <= 8 ? DFIT_M2_MIN_CTAS : 4; }
 constexpr int kM2Warps = 4;
 constexpr int kM2Tile = 64;
 constexpr int kDeferCap = 96;  // per-warp queue of deferred voxels: at most 31 left over + 64 from one tile
-#ifndef DFIT_M2_STAGES
-#define DFIT_M2_STAGES 4
-#endif
-constexpr int m2_stages(int E) { return E <= 8 ? DFIT_M2_STAGES : 2; }  // 32 KB of tiles per CTA
+constexpr int m2_stages(int E) { return E <= 8 ? DFIT_M2_STAGES : 2; }  // <= 24 KB (32 KB above 8 echoes) of tiles per CTA
 
 // One voxel per lane over a warp's queue of deferred voxels (indices into the launch's voxel range): the
 // generic Newton loop of the fast path first, the LM from the caller's initial guess where that declines.
@@ -256,7 +259,7 @@ __device__ __forceinline__ void fit_deferred(const KernelArgs<float, EMAX>& a, c
 }
 
 template <class M, int EMAX, bool GATHER, typename S>
-__global__ void __launch_bounds__(kM2Warps * 32, DFIT_M2_MIN_CTAS)  // 5 CTAs/SM by default (measured in round 1: 4 / 5 / 6-with-spills = 0.696 / 0.689 / 0.743 ms)
+__global__ void __launch_bounds__(kM2Warps * 32, m2_min_ctas(EMAX))
     fit_kernel_mono2_tma(const __grid_constant__ KernelArgs<float, EMAX> a, const __grid_constant__ CUtensorMap tmap) {
   typedef float T;
   constexpr int P = 2;
@@ -377,10 +380,8 @@ __global__ void __launch_bounds__(kM2Warps * 32, DFIT_M2_MIN_CTAS)  // 5 CTAs/SM
     if (plain) {
       float4 q = make_float4(pa.lo, pb.lo, pa.hi, pb.hi);
       if (a.po.enabled) {  // fused _process_params + rounding (fitting.py:109-146, 734-737), fp32 form
-        q.x = post_param_f32(a.po, 0, pa.lo, r2.lo);
-        q.y = post_param_f32(a.po, 1, pb.lo, r2.lo);
-        q.z = post_param_f32(a.po, 0, pa.hi, r2.hi);
-        q.w = post_param_f32(a.po, 1, pb.hi, r2.hi);
+        const pair2<float> qa = post_pair_f32(a.po, 0, pa, r2), qb = post_pair_f32(a.po, 1, pb, r2);
+        q = make_float4(qa.lo, qb.lo, qa.hi, qb.hi);
       }
       if (ok[0] && ok[1]) {
         __stcs(reinterpret_cast<float4*>(popt_lane), q);

@@ -179,3 +179,87 @@ def load_reference_fitting():
         sys.path.remove(scratch)
     _CACHE["F"], _CACHE["MV"], _CACHE["scratch"] = F, MV, scratch
     return F, MV
+
+
+def load_reference_quant_vals():
+    """The real ``dosma/core/quant_vals.py`` (``QuantitativeValue.to_metrics``, :145-229).  Its two I/O imports
+    (``dosma.core.io.format_io[_utils]``, which pull in natsort / nibabel / pydicom / h5py for load / save) are
+    replaced by empty stand-ins; the module itself runs verbatim on the real ``MedicalVolume``."""
+    if "Q" in _CACHE:
+        return _CACHE["Q"]
+    load_reference_fitting()
+    import enum
+
+    class ImageDataFormat(enum.Enum):
+        nifti = 1
+        dicom = 2
+
+    for name, attrs in (("dosma.core.io.format_io", {"ImageDataFormat": ImageDataFormat}),
+                        ("dosma.core.io.format_io_utils", {})):
+        if name not in sys.modules:
+            sys.modules[name] = _stub(name, **attrs)
+    sys.modules["dosma.core.io"].format_io_utils = sys.modules["dosma.core.io.format_io_utils"]
+    sys.path.insert(0, _CACHE["scratch"])
+    try:
+        Q = importlib.import_module("dosma.core.quant_vals")
+    finally:
+        sys.path.remove(_CACHE["scratch"])
+    _CACHE["Q"] = Q
+    return Q
+
+
+def load_reference_qdess():
+    """The real ``dosma/scan_sequences/mri/qdess.py`` (``QDess.generate_t2_map``, :100-258).  What the module imports
+    besides numpy -- pydicom, the Keras segmentation models, the scan base class, the tissue classes, the CLI
+    helpers -- is replaced by minimal stand-ins that provide exactly the members ``generate_t2_map`` touches
+    (``ScanSequence.__init__ / get_metadata``, ``pydicom.Dataset``, ``Tag``); the method itself runs verbatim on
+    the real ``MedicalVolume`` and wraps its result in the real ``quant_vals.T2``."""
+    if "QD" in _CACHE:
+        return _CACHE["QD"]
+    load_reference_quant_vals()
+
+    class Dataset(dict):
+        pass
+
+    class ScanSequence:
+        def __init__(self, volumes):
+            self.volumes = volumes
+            self.ref_dicom = None
+            self._metadata = {}
+
+        def get_metadata(self, key, default=None):  # scans.py:88-116
+            metadata = self._metadata.get(key, None)
+            if metadata is None and self.ref_dicom is not None:
+                metadata = self.ref_dicom[key].value if key in self.ref_dicom else None
+            if metadata is None and default is False:
+                raise KeyError(f"Metadata '{key}' not found")
+            return default if metadata is None else metadata
+
+    pyd = sys.modules.get("pydicom")
+    if not hasattr(pyd, "Dataset"):
+        pyd.Dataset = Dataset
+    if "pydicom.tag" not in sys.modules:
+        sys.modules["pydicom.tag"] = _stub("pydicom.tag", Tag=lambda v: v)
+        pyd.tag = sys.modules["pydicom.tag"]
+    for name, attrs in (
+        ("dosma.models", {}),
+        ("dosma.models.seg_model", {"SegModel": type("SegModel", (), {})}),
+        ("dosma.scan_sequences", {}),
+        ("dosma.scan_sequences.scans", {"ScanSequence": ScanSequence}),
+        ("dosma.scan_sequences.mri", {}),
+        ("dosma.tissues", {}),
+        ("dosma.tissues.tissue", {"Tissue": type("Tissue", (), {})}),
+        ("dosma.utils.cmd_line_utils", {"ActionWrapper": type("ActionWrapper", (), {"__init__": lambda self, *a, **k: None})}),
+    ):
+        if name not in sys.modules:
+            mod = _stub(name, **attrs)
+            sys.modules[name] = mod
+    scratch = _CACHE["scratch"]
+    sys.modules["dosma.scan_sequences.mri"].__path__ = [os.path.join(scratch, "dosma", "scan_sequences", "mri")]
+    sys.path.insert(0, scratch)
+    try:
+        QD = importlib.import_module("dosma.scan_sequences.mri.qdess")
+    finally:
+        sys.path.remove(scratch)
+    _CACHE["QD"] = QD
+    return QD

@@ -139,6 +139,8 @@ extern "C" double hostsim_post_param(int enabled, const int* ufunc, const double
   return post_param(po, i, v, r2);
 }
 
+static int g_pairs = 0;
+
 // fp32 epilogue (post_param_f32) next to the float64 one (post_param) on the same inputs: returns both
 extern "C" void hostsim_post_param_f32(int enabled, const int* ufunc, const double* lb, const double* ub, int has_thr,
                                        double thr, int has_fill, double fill, const int* decimals, int i, int64_t n,
@@ -156,11 +158,20 @@ extern "C" void hostsim_post_param_f32(int enabled, const int* ufunc, const doub
   po.has_fill = has_fill;
   po.fill = fill;
   set_post_scales(po);
-  for (int64_t k = 0; k < n; ++k) {
-    out_f32[k] = post_param_f32(po, i, v[k], r2[k]);
-    out_f64path[k] = (float)post_param(po, i, (double)v[k], (double)r2[k]);
-  }
+  // even n: through the packed two-voxel form (what the two-voxel kernels run), pairs (k, k + 1); the last of an odd n
+  // and everything when `pairs` is off: the one-voxel form
+  for (int64_t k = 0; k < n; ++k) out_f64path[k] = (float)post_param(po, i, (double)v[k], (double)r2[k]);
+  int64_t k = 0;
+  if (g_pairs)
+    for (; k + 1 < n; k += 2) {
+      const pair2<float> o = post_pair_f32(po, i, p2_make<float>(v[k], v[k + 1]), p2_make<float>(r2[k], r2[k + 1]));
+      out_f32[k] = o.lo;
+      out_f32[k + 1] = o.hi;
+    }
+  for (; k < n; ++k) out_f32[k] = post_param_f32(po, i, v[k], r2[k]);
 }
+
+extern "C" void hostsim_set_pairs(int on) { g_pairs = on; }
 
 // echo-table classification the launcher relies on: bit 0 uniform spacing, bit 1 descending (backward Prony)
 extern "C" int hostsim_xtab_flags(int dtype, int E, const double* x) {
@@ -173,4 +184,23 @@ extern "C" int hostsim_xtab_flags(int dtype, int E, const double* x) {
   XTab<double, 16> xt;
   fill_xtab<double, 16>(xt, x, E);
   return xt.uniform | (xt.backward << 1);
+}
+
+// which plan set_post_scales chose for parameter i: bit 0 simple (comparisons only), bit 1 fastinv (fp32 1 / |v| form)
+extern "C" int hostsim_post_plan(const int* ufunc, const double* lb, const double* ub, int has_fill, double fill,
+                                 const int* decimals, int i) {
+  PostOpts po;
+  po.enabled = 1;
+  for (int k = 0; k < 4; ++k) {
+    po.ufunc[k] = ufunc[k];
+    po.lb[k] = lb[k];
+    po.ub[k] = ub[k];
+    po.decimals[k] = decimals[k];
+  }
+  po.has_r2_thresh = 0;
+  po.r2_thresh = 0;
+  po.has_fill = has_fill;
+  po.fill = fill;
+  set_post_scales(po);
+  return po.simple[i] | (po.fastinv[i] << 1);
 }

@@ -140,12 +140,14 @@ def test_fp32_epilogue_takes_the_float64_decisions():
 
 @pytest.mark.parametrize("decimals", [-1, 0, 1, 3, 6])
 @pytest.mark.parametrize("fill", [None, 0.0, 0.05])
-def test_fp32_inverse_epilogue_is_the_float64_one(decimals, fill):
+@pytest.mark.parametrize("pairs", [0, 1])  # one-voxel form (post_param_f32) / packed two-voxel form (post_pair_f32)
+def test_fp32_inverse_epilogue_is_the_float64_one(decimals, fill, pairs):
     """The MonoExponentialFit column in fp32 (1 / |v|, bounds, r2 threshold, fill, rounding: post_param_f32's
     `fastinv` plan) against the float64 epilogue converted to float, bit for bit -- on random values and on
     adversarial ones: |v| whose reciprocal sits next to a rounding tie (10^d / (k + 1/2) and its float
     neighbours), next to the bounds, exact ties, zeros, infinities, NaN, tiny and huge magnitudes."""
     lib = H._load()
+    lib.hostsim_set_pairs(pairs)
     rng = np.random.default_rng(1)
     S = 10.0 ** max(decimals, 0)
     lb, ub, thr = 0.0, 100.0, 0.9
@@ -178,6 +180,20 @@ def test_fp32_inverse_epilogue_is_the_float64_one(decimals, fill):
                                    r2.ctypes.data_as(fp), a.ctypes.data_as(fp), b.ctypes.data_as(fp))
         bad = ~((a == b) | (np.isnan(a) & np.isnan(b)))
         assert not bad.any(), (decimals, fill, lbs_, v[bad][:5], a[bad][:5], b[bad][:5])
+    lib.hostsim_set_pairs(0)
+
+
+def test_monoexpfit_epilogue_gets_the_fp32_plan():
+    """The epilogue MonoExponentialFit asks for (fitting.py:722-737: 1/|b| within (0, 100), fill 0, one decimal) must
+    be served by the fp32 forms, not by the float64 fallback."""
+    lib = H._load()
+    I4, D4 = ctypes.c_int * 4, ctypes.c_double * 4
+    uf, dec = I4(0, 1, 0, 0), I4(-1, 1, -1, -1)
+    lb, ub = D4(-np.inf, 0.0, -np.inf, -np.inf), D4(np.inf, 100.0, np.inf, np.inf)
+    assert lib.hostsim_post_plan(uf, lb, ub, 1, ctypes.c_double(0.0), dec, 0) == 1  # a: comparisons only
+    assert lib.hostsim_post_plan(uf, lb, ub, 1, ctypes.c_double(0.0), dec, 1) == 2  # tc: fp32 two-float form
+    ub2 = D4(np.inf, np.inf, np.inf, np.inf)  # unbounded tc: 10^d / x is unbounded too -> float64 form
+    assert lib.hostsim_post_plan(uf, lb, ub2, 1, ctypes.c_double(0.0), dec, 1) == 0
 
 
 @pytest.mark.parametrize("name", G.names("monoexpfit_"))
