@@ -181,11 +181,11 @@ void make_desc(const dfit_opts* o, int n_echo, int64_t n_vox, const double* x, L
     d.po.ub[i] = o->ub[i];
     d.po.decimals[i] = o->decimals[i];
   }
-  set_post_scales(d.po);
   d.po.has_r2_thresh = o->has_r2_threshold;
   d.po.r2_thresh = o->r2_threshold;
   d.po.has_fill = o->has_nan_fill;
   d.po.fill = o->nan_fill;
+  set_post_scales(d.po);  // (derived fp32 thresholds / plans: after every field they are derived from)
   d.mask_fill = o->has_nan_fill ? o->nan_fill : std::numeric_limits<double>::quiet_NaN();
   d.use_tma = o->use_tma;
   d.tmap = nullptr;
@@ -461,10 +461,34 @@ int dfit_fit_device(dfit_handle* h, const dfit_opts* opts, int n_echo, int64_t n
   return DFIT_OK;
 }
 
+static int fit_host_impl(dfit_handle* h, const dfit_opts* opts, int n_echo, int64_t n_vox, const double* x,
+                         const void* const* y_planes, int y_dtype, const uint8_t* mask, const void* p0_voxel, int p0_dtype,
+                         void* popt, void* r2, int out_dtype, uint8_t* status, uint8_t* niter);
+
 int dfit_fit_host(dfit_handle* h, const dfit_opts* opts, int n_echo, int64_t n_vox, const double* x,
                   const void* const* y_planes, int y_dtype, const uint8_t* mask, const void* p0_voxel, int p0_dtype,
                   void* popt, void* r2, int out_dtype, uint8_t* status, uint8_t* niter) {
   if (!h) return fail(DFIT_ERR_BAD_ARG, "handle is NULL");
+  const int rc = fit_host_impl(h, opts, n_echo, n_vox, x, y_planes, y_dtype, mask, p0_voxel, p0_dtype, popt, r2, out_dtype,
+                               status, niter);
+  if (rc != DFIT_OK) {
+    // An error in the middle of the chunk loop leaves earlier chunks in flight, with asynchronous copies still
+    // writing into the caller's buffers: nothing may be pending on this handle when the error is returned.
+    // (The error detail of the failure itself is kept.)
+    char detail[sizeof(dfit::g_err)];
+    std::memcpy(detail, dfit::g_err, sizeof(detail));
+    if (cudaSetDevice(h->device) == cudaSuccess)
+      for (int s = 0; s < kSlots; ++s) cudaStreamSynchronize(h->slots[s].stream);
+    cudaGetLastError();
+    std::memcpy(dfit::g_err, detail, sizeof(detail));
+    h->ev_valid = false;
+  }
+  return rc;
+}
+
+static int fit_host_impl(dfit_handle* h, const dfit_opts* opts, int n_echo, int64_t n_vox, const double* x,
+                         const void* const* y_planes, int y_dtype, const uint8_t* mask, const void* p0_voxel, int p0_dtype,
+                         void* popt, void* r2, int out_dtype, uint8_t* status, uint8_t* niter) {
   int rc = validate(opts, n_echo, n_vox, x, y_dtype, p0_dtype, out_dtype, p0_voxel != nullptr);
   if (rc != DFIT_OK) return rc;
   if (n_vox > 0 && (!y_planes || !popt || !r2)) return fail(DFIT_ERR_BAD_ARG, "y_planes/popt/r2 must not be NULL");

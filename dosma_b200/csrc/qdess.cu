@@ -33,7 +33,8 @@ struct QdessArgs {
   int decimals;
   int suppress_fat, suppress_fluid;
   double beta;
-  const float* maxima;  // [0] max(S1), [1] max(S1 - beta S2)  (device)
+  const double* maxima;  // [0] max(S1), [1] max(S1 - beta S2)  (device)
+  int wide_masks;        // suppression masks compared in float64 (any sample type but float32, see qdess_voxel)
 };
 
 template <typename T>
@@ -47,20 +48,29 @@ __device__ __forceinline__ T nan_to_num_t(T v) {
 
 // Exact path (T = double): the reference's own arithmetic -- its `mask = ones(...)` promotes every
 // volume to float64 (qdess.py:226-228) -- so results are bit-comparable with numpy.
-__device__ __forceinline__ double qdess_voxel(const QdessArgs& a, double s1, double s2, float max1, float maxnf) {
+// The suppression masks (:250-255) are compared in the arithmetic numpy uses for them: float32 echoes stay float32
+// (`0.15 * np.float32` is a float32 under numpy >= 2 scalar promotion, and so is `echo_1 - beta * echo_2`), every
+// other sample type (int16 DICOM pixels, float64) is promoted to float64.
+__device__ __forceinline__ double qdess_voxel(const QdessArgs& a, double s1, double s2, double max1, double maxnf) {
   double ratio = nan_to_num_t<double>(s2 / s1);
   double v = nan_to_num_t<double>(a.scale / (log(fabs(ratio) / a.k) + a.c1));
   if (a.has_bounds && (v < a.lb || v > a.ub)) v = NAN;
   if (a.has_fill && v != v) v = a.fill;
   if (a.decimals >= 0) v = rint(v * a.round_scale) / a.round_scale;
-  if (a.suppress_fat) v = v * (double)((float)s1 > 0.15f * max1);
-  if (a.suppress_fluid) v = v * (double)(((float)s1 - (float)a.beta * (float)s2) > 0.1f * maxnf);
+  if (a.wide_masks) {
+    if (a.suppress_fat) v = v * (double)(s1 > 0.15 * max1);
+    if (a.suppress_fluid) v = v * (double)((s1 - a.beta * s2) > 0.1 * maxnf);
+  } else {
+    if (a.suppress_fat) v = v * (double)((float)s1 > 0.15f * (float)max1);
+    if (a.suppress_fluid) v = v * (double)(((float)s1 - (float)a.beta * (float)s2) > 0.1f * (float)maxnf);
+  }
   return v;
 }
 
 // Fast path (T = float): fp32 with MUFU reciprocal / log2, ~2e-6 relative before rounding; only the
 // final rounding divide is IEEE so that rounded values are the nearest float to the decimal.
-__device__ __forceinline__ float qdess_voxel(const QdessArgs& a, float s1, float s2, float max1, float maxnf) {
+__device__ __forceinline__ float qdess_voxel(const QdessArgs& a, float s1, float s2, double max1d, double maxnfd) {
+  const float max1 = (float)max1d, maxnf = (float)maxnfd;
   float ratio = nan_to_num_t<float>(__fdividef(s2, s1));
   if (s1 == 0.f) ratio = s2 == 0.f ? 0.f : (s2 > 0.f ? FLT_MAX : -FLT_MAX);  // __fdividef(x, 0) is not IEEE
   float v = nan_to_num_t<float>(__fdividef((float)a.scale, __logf(fabsf(ratio) * (float)a.inv_k) + (float)a.c1));
@@ -74,7 +84,7 @@ __device__ __forceinline__ float qdess_voxel(const QdessArgs& a, float s1, float
 
 template <typename T>
 __global__ void __launch_bounds__(256) qdess_kernel(const __grid_constant__ QdessArgs a) {
-  const float max1 = a.maxima ? a.maxima[0] : 0.f, maxnf = a.maxima ? a.maxima[1] : 0.f;
+  const double max1 = a.maxima ? a.maxima[0] : 0.0, maxnf = a.maxima ? a.maxima[1] : 0.0;
   const int64_t n4 = a.n / 4;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   const bool vec_in = a.in_dtype == DT_F32 &&
@@ -103,50 +113,58 @@ __global__ void __launch_bounds__(256) qdess_kernel(const __grid_constant__ Qdes
   }
 }
 
-// Global maxima for the suppression masks: max(S1) and max(S1 - beta S2), as ordered ints.
-__device__ __forceinline__ int float_to_ordered(float f) {
-  const int i = __float_as_int(f);
-  return i >= 0 ? i : i ^ 0x7fffffff;
+// Global maxima for the suppression masks: max(S1) and max(S1 - beta S2), reduced as order-preserving integers
+// (in float32 arithmetic for float32 echoes, float64 otherwise -- see qdess_voxel).
+__device__ __forceinline__ long long double_to_ordered(double f) {
+  const long long i = __double_as_longlong(f);
+  return i >= 0 ? i : i ^ 0x7fffffffffffffffll;
 }
-__device__ __forceinline__ float ordered_to_float(int i) { return __int_as_float(i >= 0 ? i : i ^ 0x7fffffff); }
+__device__ __forceinline__ double ordered_to_double(long long i) { return __longlong_as_double(i >= 0 ? i : i ^ 0x7fffffffffffffffll); }
 
-__global__ void __launch_bounds__(256) qdess_max_kernel(const void* e1, const void* e2, int dtype, int64_t n, float beta,
-                                                        int* ordered /*[2]*/) {
-  float m1 = -FLT_MAX, m2 = -FLT_MAX;
+__global__ void __launch_bounds__(256) qdess_max_kernel(const void* e1, const void* e2, int dtype, int64_t n, double beta,
+                                                        int wide, long long* ordered /*[2]*/) {
+  double m1 = -DBL_MAX, m2 = -DBL_MAX;
   for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < n; v += (int64_t)gridDim.x * blockDim.x) {
-    const float s1 = load_as<float>(e1, dtype, v), s2 = load_as<float>(e2, dtype, v);
-    m1 = fmaxf(m1, s1);  // fmaxf ignores NaN like np.max would not; volumes are finite by construction
-    m2 = fmaxf(m2, s1 - beta * s2);
+    if (wide) {
+      const double s1 = load_as<double>(e1, dtype, v), s2 = load_as<double>(e2, dtype, v);
+      m1 = fmax(m1, s1);  // (fmax ignores NaN like np.max would not; volumes are finite by construction)
+      m2 = fmax(m2, s1 - beta * s2);
+    } else {
+      const float s1 = load_as<float>(e1, dtype, v), s2 = load_as<float>(e2, dtype, v);
+      m1 = fmax(m1, (double)s1);
+      m2 = fmax(m2, (double)(s1 - (float)beta * s2));
+    }
   }
   for (int o = 16; o > 0; o >>= 1) {
-    m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, o));
-    m2 = fmaxf(m2, __shfl_xor_sync(0xffffffffu, m2, o));
+    m1 = fmax(m1, __shfl_xor_sync(0xffffffffu, m1, o));
+    m2 = fmax(m2, __shfl_xor_sync(0xffffffffu, m2, o));
   }
   if ((threadIdx.x & 31) == 0) {
-    atomicMax(ordered + 0, float_to_ordered(m1));
-    atomicMax(ordered + 1, float_to_ordered(m2));
+    atomicMax(ordered + 0, double_to_ordered(m1));
+    atomicMax(ordered + 1, double_to_ordered(m2));
   }
 }
 
-__global__ void qdess_max_finish(int* ordered, float* maxima) {
-  maxima[0] = ordered_to_float(ordered[0]);
-  maxima[1] = ordered_to_float(ordered[1]);
+__global__ void qdess_max_finish(long long* ordered, double* maxima) {
+  maxima[0] = ordered_to_double(ordered[0]);
+  maxima[1] = ordered_to_double(ordered[1]);
 }
 
-static inline int float_to_ordered_host(float f) {
-  int i;
+static inline long long double_to_ordered_host(double f) {
+  long long i;
   memcpy(&i, &f, sizeof(i));
-  return i >= 0 ? i : i ^ 0x7fffffff;
+  return i >= 0 ? i : i ^ 0x7fffffffffffffffll;
 }
 
-cudaError_t launch_qdess(const QdessArgs& a, int compute_f64, int sm_count, int* ordered, float* maxima,
+cudaError_t launch_qdess(const QdessArgs& a, int compute_f64, int sm_count, long long* ordered, double* maxima,
                          cudaStream_t stream) {
   QdessArgs args = a;
+  args.wide_masks = (compute_f64 && a.in_dtype != DT_F32) ? 1 : 0;
   if (a.suppress_fat || a.suppress_fluid) {
-    const int init[2] = {float_to_ordered_host(-FLT_MAX), float_to_ordered_host(-FLT_MAX)};
+    const long long init[2] = {double_to_ordered_host(-DBL_MAX), double_to_ordered_host(-DBL_MAX)};
     cudaError_t e = cudaMemcpyAsync(ordered, init, sizeof(init), cudaMemcpyHostToDevice, stream);
     if (e != cudaSuccess) return e;
-    qdess_max_kernel<<<sm_count * 8, 256, 0, stream>>>(a.e1, a.e2, a.in_dtype, a.n, (float)a.beta, ordered);
+    qdess_max_kernel<<<sm_count * 8, 256, 0, stream>>>(a.e1, a.e2, a.in_dtype, a.n, a.beta, args.wide_masks, ordered);
     qdess_max_finish<<<1, 1, 0, stream>>>(ordered, maxima);
     args.maxima = maxima;
   } else {
@@ -209,6 +227,7 @@ static int qdess_args(const dfit_qdess_opts* o, int64_t n, int in_dtype, int out
   a.suppress_fluid = o->suppress_fluid;
   a.beta = o->beta;
   a.maxima = nullptr;
+  a.wide_masks = 0;
   // default: the reference's float64 arithmetic (exact parity); DFIT_F32 selects the HBM-bound fast path
   f64 = o->compute_dtype != DFIT_F32;
   return DFIT_OK;
@@ -228,8 +247,8 @@ int dfit_qdess_t2_device(dfit_handle* h, const dfit_qdess_opts* opts, int64_t n_
   a.e1 = echo1;
   a.e2 = echo2;
   a.out = t2;
-  CUDA_TRY(launch_qdess(a, f64, h->sm_count, reinterpret_cast<int*>(h->scratch.p),
-                        reinterpret_cast<float*>(h->scratch.p) + 4, (cudaStream_t)stream));
+  CUDA_TRY(launch_qdess(a, f64, h->sm_count, reinterpret_cast<long long*>(h->scratch.p),
+                        reinterpret_cast<double*>(h->scratch.p) + 4, (cudaStream_t)stream));
   return DFIT_OK;
 }
 
@@ -256,8 +275,8 @@ int dfit_qdess_t2_host(dfit_handle* h, const dfit_qdess_opts* opts, int64_t n_vo
   a.e1 = d1;
   a.e2 = d2;
   a.out = sl.popt.p;
-  CUDA_TRY(launch_qdess(a, f64, h->sm_count, reinterpret_cast<int*>(h->scratch.p),
-                        reinterpret_cast<float*>(h->scratch.p) + 4, st));
+  CUDA_TRY(launch_qdess(a, f64, h->sm_count, reinterpret_cast<long long*>(h->scratch.p),
+                        reinterpret_cast<double*>(h->scratch.p) + 4, st));
   CUDA_TRY(cudaMemcpyAsync(t2, sl.popt.p, (size_t)n_vox * osz, cudaMemcpyDeviceToHost, st));
   CUDA_TRY(cudaStreamSynchronize(st));
   return DFIT_OK;

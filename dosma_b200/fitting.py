@@ -21,7 +21,7 @@ import numpy as np
 
 from . import _cabi
 from .med_volume import MedicalVolume, is_volume
-from .models import biexponential, monoexponential, param_names, resolve_model, resolve_ufunc
+from .models import biexponential, inv_abs, monoexponential, param_names, resolve_model, resolve_ufunc
 
 __all__ = ["CurveFitter", "MonoExponentialFit", "curve_fit", "monoexponential", "biexponential"]
 
@@ -468,9 +468,11 @@ class CurveFitter:
         cols = _split_p0(p0, self._param_names, N)
 
         planes = [np.asarray(_y.volume).reshape(-1) for _y in y]
-        if self.y_bounds is not None and any(
-                (p < self.y_bounds[0]).any() or (p > self.y_bounds[1]).any() for p in planes):
-            warnings.warn("Out of bounds values found. Failure in fit will result in np.nan")
+        if self.y_bounds is not None:
+            # (the reference tests the samples `curve_fit` receives, i.e. the masked ones: fitting.py:199-200, 845-847)
+            sel = slice(None) if mask_flat is None else mask_flat
+            if any((p[sel] < self.y_bounds[0]).any() or (p[sel] > self.y_bounds[1]).any() for p in planes):
+                warnings.warn("Out of bounds values found. Failure in fit will result in np.nan")
 
         post = self._plan_post(nparams)
         engine = {k: v for k, v in self.kwargs.items() if k in _ENGINE_KWARGS and k != "return_stats"}
@@ -565,7 +567,7 @@ class MonoExponentialFit:
         fitter = CurveFitter(
             monoexponential,
             y_bounds=None,
-            out_ufuncs=(None, lambda _x: 1 / np.abs(_x)),
+            out_ufuncs=(None, inv_abs),  # 1 / |b| (fitting.py:725)
             out_bounds=((-np.inf, np.inf), self.bounds),
             r2_threshold=self.r2_threshold,
             num_workers=self.num_workers,

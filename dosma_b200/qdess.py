@@ -9,6 +9,7 @@ constants `k` and `c1` are computed here exactly as at qdess.py:204-223; the per
 """
 import ctypes
 import math
+import numbers
 import warnings
 
 import numpy as np
@@ -52,7 +53,7 @@ def qdess_t2_map(echo1, echo2, *, tr, te, tg, gl_area, alpha, t1, diffusivity=1.
     """
     if precision not in ("exact", "fast"):
         raise ValueError("precision must be 'exact' or 'fast'")
-    if not all(isinstance(v, (int, float)) for v in (alpha, t1, diffusivity)):
+    if not all(isinstance(v, numbers.Real) for v in (alpha, t1, diffusivity)):  # (numpy scalars included)
         raise NotImplementedError("array-valued alpha / t1 / diffusivity are not supported by the CUDA path")
     vol = echo1 if is_volume(echo1) else None
     a1 = np.asarray(echo1.volume if is_volume(echo1) else echo1)

@@ -1,8 +1,10 @@
 """CPU ORACLE for region statistics -- test infrastructure, NOT product code.
 
 numpy restatement of `QuantitativeValue.to_metrics` (dosma/core/quant_vals.py:181-229) at array
-level.  Parity status: pinned against the real reference method in tests/test_metrics_oracle.py
-(build container only; `quant_vals.py` loads through the stub loader) and by closed-form checks.
+level.  Parity status: PINNED -- tests/test_metrics_oracle.py checks it, bit for bit, against
+tests/golden/metrics_*.npz, the tables of the real reference method (tests/golden/make_golden_next.py loads
+quant_vals.py verbatim through tests/golden/ref_loader.py::load_reference_quant_vals), and in the build container
+against the live reference on fresh seeds.
 """
 import warnings
 

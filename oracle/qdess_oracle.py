@@ -1,10 +1,10 @@
 """CPU ORACLE for the qDESS analytic T2 map -- test infrastructure, NOT product code.
 
 numpy restatement of dosma/scan_sequences/mri/qdess.py:193-255 (the arithmetic of
-`QDess.generate_t2_map`).  Parity status: UNPINNED by reference outputs -- `QDess` cannot be
-instantiated in this container (its module imports pydicom, the Keras models and the tissue
-classes); the restatement below follows the reference line by line and is checked against
-closed-form values in tests/test_qdess_oracle.py.
+`QDess.generate_t2_map`).  Parity status: PINNED -- tests/test_qdess_oracle.py checks it, bit for bit, against
+tests/golden/qdess_*.npz, the outputs of the real reference method (tests/golden/make_golden_next.py loads qdess.py
+verbatim through tests/golden/ref_loader.py::load_reference_qdess), and in the build container against the live
+reference on fresh seeds.
 """
 import math
 

@@ -204,3 +204,25 @@ extern "C" int hostsim_post_plan(const int* ufunc, const double* lb, const doubl
   set_post_scales(po);
   return po.simple[i] | (po.fastinv[i] << 1);
 }
+
+// The fused epilogue over arrays (what store_voxel applies per voxel), for the test-only host engine:
+// popt (n, P) in place, double arithmetic like the float64 maps of the device path.
+extern "C" void hostsim_post_params(int64_t n, int P, double* popt, const double* r2, const int* ufunc, const double* lb,
+                                    const double* ub, int has_thr, double thr, int has_fill, double fill,
+                                    const int* decimals) {
+  PostOpts po;
+  po.enabled = 1;
+  for (int k = 0; k < 4; ++k) {
+    po.ufunc[k] = ufunc[k];
+    po.lb[k] = lb[k];
+    po.ub[k] = ub[k];
+    po.decimals[k] = decimals[k];
+  }
+  po.has_r2_thresh = has_thr;
+  po.r2_thresh = thr;
+  po.has_fill = has_fill;
+  po.fill = fill;
+  set_post_scales(po);
+  for (int64_t v = 0; v < n; ++v)
+    for (int i = 0; i < P; ++i) popt[v * P + i] = post_param(po, i, popt[v * P + i], r2[v]);
+}

@@ -2,6 +2,8 @@
 import numpy as np
 import pytest
 
+from tests import golden_util as G
+
 pytestmark = pytest.mark.gpu
 
 
@@ -57,3 +59,16 @@ def test_metrics_full_size_properties():
     assert abs(got["Mean"][0] - vol.mean()) < 1e-9 and abs(got["Std"][0] - vol.std()) < 1e-9
     got = region_metrics(vol[:-1], as_frame=False)
     assert got["Median"][0] == float(np.median(vol[:-1]))
+
+
+@pytest.mark.parametrize("name", G.names("metrics_"))
+def test_metrics_golden_reference_outputs(name):
+    """The CUDA reductions against the tables of the REAL `QuantitativeValue.to_metrics` (tests/golden/metrics_*.npz):
+    categories, voxel counts and medians exactly; mean / std to float64 summation-order accuracy (a float32 map is
+    reduced in float32 by numpy and in float64 by the kernel: 2e-6 there)."""
+    from dosma_b200.metrics import region_metrics
+    from tests.test_metrics_oracle import check_against_golden, run_case
+
+    c = G.load(name)
+    got = run_case(lambda vol, **kw: region_metrics(vol, as_frame=False, **kw), c)
+    check_against_golden(got, c, rtol=1e-11 if c["volume"].dtype == np.float64 else 2e-6)

@@ -585,6 +585,98 @@ def test_fp32_fused_epilogue_equals_float64_epilogue(D):
             assert float((p32[:, 1] == 0).float().mean()) > 0.05 and float((p32[:, 1] > 0).float().mean()) > 0.5
 
 
+class _Hdr(dict):
+    """Header stand-in (pydicom is not installed): `.get` access, deep-copyable."""
+
+
+def _hdrs(shape, **fields):
+    arr = np.empty(int(np.prod(shape)), dtype=object)
+    for i in range(arr.size):
+        arr[i] = _Hdr(fields)
+    return arr.reshape(shape)
+
+
+def test_fit_marshalling_headers_4d_copy_headers(D):
+    """`_Fitter.fit` marshalling on the real engine (fitting.py:157-235; the reference's TestCurveFitter.test_headers
+    :433-477 and TestMonoExponentialFit.test_headers :220-236): 4-D inputs give 5-D parameter maps, headers of y[0]
+    are deep-copied and get a trailing axis, `copy_headers=False` drops them, a one-parameter model works, the
+    time-constant map of MonoExponentialFit keeps (1, 1, Z) headers, reoriented inputs come back in y[0]'s frame."""
+    rng = np.random.default_rng(8)
+    x = np.asarray([0.5, 1.0, 2.0, 4.0])
+    b = rng.random((10, 10, 20, 4)) + 0.1
+    y = [D.MedicalVolume(D.monoexponential(t, 1.0, b), np.eye(4), headers=_hdrs((1, 1, 20, 4), EchoNumbers=i))
+         for i, t in enumerate(x)]
+    popt, r2 = D.CurveFitter(D.monoexponential).fit(x, y)
+    assert popt.shape == (10, 10, 20, 4, 2) and r2.shape == (10, 10, 20, 4) and popt.volume.dtype == np.float64
+    assert np.allclose(popt.volume[..., 0], 1.0) and np.allclose(popt.volume[..., 1], b)
+    assert popt.headers().shape == (1, 1, 20, 4, 1) and r2.headers().shape == (1, 1, 20, 4)
+    assert all(h.get("EchoNumbers") == 0 for h in popt.headers().flatten())
+    assert popt.headers().flatten()[0] is not y[0].headers().flatten()[0]  # deep copy (fitting.py:225)
+    a_hat, b_hat = popt[..., 0], popt[..., 1]  # the reference test's own indexing
+    assert np.allclose(b_hat.volume, b) and b_hat.headers().shape == (1, 1, 20, 4) and a_hat.shape == b.shape
+    popt, r2 = D.CurveFitter(D.monoexponential).fit(x, y, copy_headers=False)
+    assert np.allclose(popt.volume[..., 1], b) and popt.headers() is None and r2.headers() is None
+    a = rng.random((10, 10, 20, 4)) + 0.1
+    yl = [D.MedicalVolume(a * t, np.eye(4), headers=_hdrs((1, 1, 20, 4), EchoNumbers=i)) for i, t in enumerate(x)]
+    popt, _ = D.CurveFitter(D.linear).fit(x, yl)
+    assert popt.shape == (10, 10, 20, 4, 1) and np.allclose(popt.volume[..., 0], a)
+    # MonoExponentialFit (3-D, headers): TestMonoExponentialFit.test_headers
+    b3 = rng.random((10, 10, 20)) + 0.1
+    y3 = [D.MedicalVolume(D.monoexponential(t, 1.0, b3), np.eye(4),
+                          headers=_hdrs((1, 1, 20), StudyDescription="Sample study", EchoNumbers=i)) for i, t in enumerate(x)]
+    t_hat = D.MonoExponentialFit(decimal_precision=8).fit(x, y3)[0]
+    assert np.allclose(t_hat.volume, 1 / np.abs(b3)) and t_hat.headers().shape == (1, 1, 20)
+    assert all(h.get("StudyDescription") == "Sample study" for h in t_hat.headers().flatten())
+    # echoes stored in another orientation are brought to y[0]'s frame (fitting.py:189-190)
+    y3r = [y3[0]] + [v.reformat(("SI", "AP", "LR")) for v in y3[1:]]
+    assert y3r[1].orientation != y3r[0].orientation
+    t_hat2 = D.MonoExponentialFit(decimal_precision=8).fit(x, y3r)[0]
+    assert t_hat2.orientation == y3[0].orientation and np.allclose(t_hat2.volume, t_hat.volume)
+
+
+def test_patch_dosma_swaps_the_engine_in(D):
+    """`dosma_b200.patch_dosma()` rebinds the three names in every DOSMA module that holds them
+    (fitting.py:24-32 and the scan pipelines that bind them at import, cube_quant.py:9 / mapss.py:10 / cones.py:10):
+    checked on stand-in modules (DOSMA itself is not importable on the GPU box), and a pipeline-style call through the
+    patched module runs on the GPU."""
+    import sys
+    import types
+
+    names = ["dosma", "dosma.core", "dosma.core.fitting", "dosma.scan_sequences", "dosma.scan_sequences.mri",
+             "dosma.scan_sequences.mri.cube_quant", "dosma.scan_sequences.mri.mapss", "dosma.scan_sequences.mri.cones"]
+    saved = {n: sys.modules.get(n) for n in names}
+    try:
+        for n in names:
+            mod = types.ModuleType(n)
+            mod.__path__ = []
+            sys.modules[n] = mod
+        sentinel = object()
+        for n in ("dosma", "dosma.core", "dosma.core.fitting"):
+            sys.modules[n].CurveFitter = sys.modules[n].MonoExponentialFit = sys.modules[n].curve_fit = sentinel
+        for n in names[5:]:
+            sys.modules[n].MonoExponentialFit = sentinel  # `from dosma.core.fitting import MonoExponentialFit`
+        patched = D.patch_dosma()
+        assert len(patched) == 12, patched
+        F = sys.modules["dosma.core.fitting"]
+        assert F.CurveFitter is D.CurveFitter and F.curve_fit is D.curve_fit
+        for n in names[5:]:
+            assert sys.modules[n].MonoExponentialFit is D.MonoExponentialFit and not hasattr(sys.modules[n], "CurveFitter")
+        # what cube_quant.generate_t1_rho_map does (cube_quant.py:170-178), through the patched module global
+        x = [10.0, 20.0, 40.0, 80.0]
+        t = np.random.default_rng(3).uniform(10, 80, (16, 16, 4))
+        vols = [D.MedicalVolume((1000 * np.exp(-xi / t)).astype(np.float32), np.eye(4)) for xi in x]
+        fitter = sys.modules["dosma.scan_sequences.mri.cube_quant"].MonoExponentialFit(
+            bounds=(0, 100), tc0="polyfit", decimal_precision=1, num_workers=4)
+        tc, r2 = fitter.fit(x, vols)
+        assert np.abs(tc.volume - np.around(t, 1)).max() < 0.11 and fitter.last_stats["n_launches"] >= 1
+    finally:
+        for n, m in saved.items():
+            if m is None:
+                sys.modules.pop(n, None)
+            else:
+                sys.modules[n] = m
+
+
 def test_nonfinite_input_raises(D):
     x = np.arange(1, 5) * 10.0
     y = np.ones((4, 100), dtype=np.float32)

@@ -1,7 +1,42 @@
-"""CPU checks of the qDESS oracle restatement against closed-form values."""
+"""Pins oracle/qdess_oracle.py (numpy restatement of `QDess.generate_t2_map`, dosma/scan_sequences/mri/qdess.py:193-255):
+against the outputs of the REAL reference method -- the golden fixtures tests/golden/qdess_*.npz written by
+tests/golden/make_golden_next.py, which loads qdess.py verbatim -- and against closed-form values."""
 import numpy as np
+import pytest
 
 from oracle import qdess_oracle as Q
+from tests import golden_util as G
+
+
+def golden_kwargs(c):
+    kw = dict(c["meta"]["params"])
+    kw.update({k: (tuple(v) if isinstance(v, list) else v) for k, v in c["meta"]["kwargs"].items()})
+    return kw
+
+
+@pytest.mark.parametrize("name", G.names("qdess_"))
+def test_qdess_oracle_matches_reference(name):
+    """Same numpy calls in the same order as the reference: bit-identical, NaN for NaN."""
+    c = G.load(name)
+    got = Q.t2_map(c["echo1"], c["echo2"], **golden_kwargs(c))
+    assert got.dtype == c["t2"].dtype and got.shape == c["t2"].shape
+    assert np.array_equal(got, c["t2"], equal_nan=True)
+
+
+@pytest.mark.needs_reference
+def test_qdess_oracle_matches_live_reference():
+    """Fresh seeds against the reference method itself (build container only)."""
+    from tests.golden import ref_loader as R
+
+    F, MV = R.load_reference_fitting()
+    QD = R.load_reference_qdess()
+    rng = np.random.default_rng(77)
+    s1 = rng.uniform(100, 1000, (10, 9, 4))
+    s2 = s1 * rng.uniform(0.02, 0.5, s1.shape)
+    for kw in (dict(), dict(suppress_fat=True, suppress_fluid=True, beta=1.1), dict(nan_bounds=(1, 40), decimals=None)):
+        ref = QD.QDess([MV(s1, np.eye(4)), MV(s2, np.eye(4))]).generate_t2_map(**PARAMS, **kw).volumetric_map.volume
+        assert np.array_equal(Q.t2_map(s1, s2, **PARAMS, **kw), ref, equal_nan=True)
+
 
 PARAMS = dict(tr=20.36, te=6.43, tg=3400.0, gl_area=3132.0, alpha=20.0, t1=1200.0)
 
