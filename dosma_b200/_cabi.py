@@ -31,7 +31,7 @@ NP_TO_DTYPE = {
 EXPORTED_SYMBOLS = (
     "dfit_version", "dfit_device_count", "dfit_strerror", "dfit_last_error", "dfit_default_opts",
     "dfit_model_nparams", "dfit_create", "dfit_destroy", "dfit_fit_device", "dfit_fit_host", "dfit_get_stats",
-    "dfit_set_gather", "dfit_ipc_alloc", "dfit_ipc_open", "dfit_ipc_close", "dfit_ipc_free",
+    "dfit_set_gather", "dfit_set_gather_ex", "dfit_ipc_alloc", "dfit_ipc_open", "dfit_ipc_close", "dfit_ipc_free",
     "dfit_default_qdess_opts", "dfit_qdess_t2_device", "dfit_qdess_t2_host", "dfit_region_metrics_host",
 )
 
@@ -63,6 +63,7 @@ class DfitOpts(ctypes.Structure):
         ("decimals", ctypes.c_int32 * MAX_PARAMS),
         ("fast_path", ctypes.c_int32),
         ("use_tma", ctypes.c_int32),
+        ("out_param", ctypes.c_int32),
     ]
 
 
@@ -82,6 +83,21 @@ class DfitQdessOpts(ctypes.Structure):
         ("suppress_fluid", ctypes.c_int32),
         ("beta", ctypes.c_double),
         ("compute_dtype", ctypes.c_int32),
+    ]
+
+
+class DfitGatherDesc(ctypes.Structure):
+    _fields_ = [
+        ("struct_size", ctypes.c_int32),
+        ("world", ctypes.c_int32),
+        ("rank", ctypes.c_int32),
+        ("maps", ctypes.c_void_p),
+        ("multicast", ctypes.c_void_p),
+        ("rows", ctypes.c_int64),
+        ("row0", ctypes.c_int64),
+        ("param_mask", ctypes.c_uint32),
+        ("split_list", ctypes.c_int32),
+        ("y_voxel0", ctypes.c_int64),
     ]
 
 

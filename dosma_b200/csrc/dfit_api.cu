@@ -6,6 +6,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <limits>
 #include <new>
@@ -93,6 +94,48 @@ void par_copy(const CopySeg* segs, int count) {
   for (auto& x : th) x.join();
 }
 
+// Generic static partition of [0, n) over a few host threads.
+template <class F>
+void par_for(int64_t n, int64_t grain, F fn) {
+  unsigned hw = std::thread::hardware_concurrency();
+  int nt = (int)(hw == 0 ? 4 : (hw > 16 ? 16 : hw));
+  const int64_t nb = (n + grain - 1) / grain;
+  if (nt > nb) nt = (int)nb;
+  if (nt <= 1) {
+    if (n > 0) fn(0, n);
+    return;
+  }
+  auto work = [&](int t) {
+    const int64_t b0 = nb * t / nt, b1 = nb * (t + 1) / nt;
+    const int64_t lo = b0 * grain, hi = b1 * grain < n ? b1 * grain : n;
+    if (lo < hi) fn(lo, hi);
+  };
+  std::vector<std::thread> th;
+  th.reserve(nt - 1);
+  for (int t = 1; t < nt; ++t) th.emplace_back(work, t);
+  work(0);
+  for (auto& x : th) x.join();
+}
+
+// float32 staging [n, ncols] -> the caller's float64 map.  scale[c] > 0: column c was rounded to a decimal grid on the
+// device (v = fl32(m / scale), m an integer below 2^22): it is put back onto the float64 grid with numpy.around's own
+// formula, rint(v scale) / scale, which recovers m exactly; other columns (and NaN / inf) are widened as they are.
+void par_widen(double* dst, const float* src, int64_t n, int ncols, const double* scale) {
+  par_for(n, (int64_t)1 << 17, [&](int64_t lo, int64_t hi) {
+    if (ncols == 1) {
+      const double s = scale[0];
+      if (s > 0) for (int64_t i = lo; i < hi; ++i) dst[i] = std::nearbyint((double)src[i] * s) / s;
+      else for (int64_t i = lo; i < hi; ++i) dst[i] = (double)src[i];
+      return;
+    }
+    for (int64_t i = lo; i < hi; ++i)
+      for (int c = 0; c < ncols; ++c) {
+        const double v = (double)src[i * ncols + c], s = scale[c];
+        dst[i * ncols + c] = s > 0 ? std::nearbyint(v * s) / s : v;
+      }
+  });
+}
+
 int model_nparams(int model) {
   switch (model) {
     case DFIT_MODEL_MONOEXP: return 2;
@@ -132,6 +175,7 @@ int validate(const dfit_opts* o, int n_echo, int64_t n_vox, const double* x, int
     if (std::isnan(o->p0[i]) && !have_p0v && o->init_mode == DFIT_INIT_GIVEN)
       return fail(DFIT_ERR_BAD_ARG, "p0[%d] is NaN (per-voxel) but p0_voxel is NULL", i);
   if (o->maxfev < 1) return fail(DFIT_ERR_BAD_ARG, "maxfev < 1");
+  if (o->out_param >= P) return fail(DFIT_ERR_BAD_ARG, "out_param=%d but the model has %d parameters", o->out_param, P);
   return DFIT_OK;
 }
 
@@ -188,14 +232,37 @@ void make_desc(const dfit_opts* o, int n_echo, int64_t n_vox, const double* x, L
   set_post_scales(d.po);  // (derived fp32 thresholds / plans: after every field they are derived from)
   d.mask_fill = o->has_nan_fill ? o->nan_fill : std::numeric_limits<double>::quiet_NaN();
   d.use_tma = o->use_tma;
+  d.sel = o->out_param < 0 ? -1 : o->out_param;
   d.tmap = nullptr;
   d.tmap2 = nullptr;
   d.sm_count = 148;
   d.index = nullptr;
   d.index_count = nullptr;
-  for (int r = 0; r < kMaxPeers; ++r) d.gather[r] = nullptr;
-  d.gather_world = 0;
-  d.gather_row0 = 0;
+  d.g = GatherArgs{};
+}
+
+// May the result maps of this fit cross PCIe as float32 and be widened on the host?  Yes for fp32 arithmetic into
+// float64 maps, unless a rounded parameter could exceed what a float32 carries exactly on its decimal grid
+// (|value| 10^d < 2^22 needs finite bounds).  scale[i] = 10^decimals[i] for rounded parameters, else 0.
+bool widen_plan(const dfit_opts* o, int out_dtype, double (&scale)[DFIT_MAX_PARAMS]) {
+  for (int i = 0; i < DFIT_MAX_PARAMS; ++i) scale[i] = 0.0;
+  if (out_dtype != DFIT_F64 || o->compute_dtype != DFIT_F32) return false;
+  if (const char* e = std::getenv("DFIT_HOST_WIDEN")) {
+    if (e[0] == '0') return false;
+  }
+  if (!o->post_enabled) return true;
+  const int P = model_nparams(o->model);
+  for (int i = 0; i < P; ++i) {
+    if (o->decimals[i] < 0) continue;
+    if (o->decimals[i] > 10) return false;
+    double s = 1.0;
+    for (int k = 0; k < o->decimals[i]; ++k) s *= 10.0;
+    const double m = std::fmax(std::fabs(o->lb[i]), std::fabs(o->ub[i]));
+    if (!(m * s < 4.0e6)) return false;
+    if (o->has_nan_fill && !(std::fabs(o->nan_fill) * s < 4.0e6)) return false;
+    scale[i] = s;
+  }
+  return true;
 }
 
 // cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time dependency on libcuda).
@@ -326,6 +393,7 @@ int dfit_default_opts(dfit_opts* o, int model) {
   }
   o->fast_path = -1;
   o->use_tma = -1;
+  o->out_param = -1;
   return DFIT_OK;
 }
 
@@ -394,13 +462,17 @@ int dfit_fit_device(dfit_handle* h, const dfit_opts* opts, int n_echo, int64_t n
   int rc = validate(opts, n_echo, n_vox, x, y_dtype, p0_dtype, out_dtype, p0_voxel != nullptr);
   if (rc != DFIT_OK) return rc;
   if (y_layout != DFIT_PLANAR && y_layout != DFIT_ECHO_FASTEST) return fail(DFIT_ERR_BAD_ARG, "bad layout");
-  const bool gathering = h->gather_world > 0;
+  const bool gathering = h->g.world > 0;
   if (n_vox > 0 && !y) return fail(DFIT_ERR_BAD_ARG, "y must not be NULL");
   if (n_vox > 0 && (!popt != !r2)) return fail(DFIT_ERR_BAD_ARG, "popt and r2 must both be given or both be NULL");
   if (n_vox > 0 && !popt && !gathering) return fail(DFIT_ERR_BAD_ARG, "popt/r2 may only be NULL with dfit_set_gather");
-  if (gathering && n_vox > h->gather_rows_per_rank) return fail(DFIT_ERR_BAD_ARG, "n_vox exceeds gather rows_per_rank");
+  if (gathering && h->g.row0 + n_vox > h->gather_rows) return fail(DFIT_ERR_BAD_ARG, "row0 + n_vox exceeds the rows of the gather maps");
   if (gathering && opts->compute_dtype != DFIT_F32)
     return fail(DFIT_ERR_UNSUPPORTED, "the fused all-gather map is fp32: use compute_dtype = DFIT_F32 with dfit_set_gather");
+  if (gathering && h->g.split_list && (!mask || p0_voxel))
+    return fail(DFIT_ERR_BAD_ARG, "split_list gathers need a mask (of the whole volume) and a scalar initial guess");
+  if (gathering && (h->g.cols >> model_nparams(opts->model)) != 0u)
+    return fail(DFIT_ERR_BAD_ARG, "gather param_mask names a parameter the model does not have");
   if (ld < (y_layout == DFIT_PLANAR ? n_vox : (int64_t)n_echo)) return fail(DFIT_ERR_BAD_ARG, "ld too small");
   CUDA_TRY(cudaSetDevice(h->device));
   cudaStream_t st = (cudaStream_t)stream;  // NULL is the legacy default stream (what torch calls its default stream)
@@ -422,9 +494,9 @@ int dfit_fit_device(dfit_handle* h, const dfit_opts* opts, int n_echo, int64_t n
   d.counters = h->counters;
   d.stream = st;
   if (gathering) {
-    for (int r = 0; r < h->gather_world; ++r) d.gather[r] = h->gather[r];
-    d.gather_world = h->gather_world;
-    d.gather_row0 = (int64_t)h->gather_rank * h->gather_rows_per_rank;
+    d.g = h->g;
+    if (d.g.cols == 0u) d.g.cols = (1u << model_nparams(opts->model)) - 1u;  // all parameters
+    d.g.ncols = __builtin_popcount(d.g.cols) + 1;
   }
   CUDA_TRY(cudaMemsetAsync(h->counters, 0, kStatSlots * CNT_COUNT * sizeof(unsigned long long), st));
   CUDA_TRY(cudaEventRecord(h->ev_start, st));
@@ -497,7 +569,15 @@ static int fit_host_impl(dfit_handle* h, const dfit_opts* opts, int n_echo, int6
   CUDA_TRY(cudaSetDevice(h->device));
   const auto t0 = std::chrono::steady_clock::now();
   const int P = model_nparams(opts->model);
-  const size_t ysz = dtype_size(y_dtype), osz = out_dtype == DFIT_F32 ? 4 : 8, psz = p0_dtype == DFIT_F32 ? 4 : 8;
+  const int PW = opts->out_param >= 0 ? 1 : P;  // parameters written per voxel
+  // fp32 arithmetic with float64 result maps (the reference's dtype, fitting.py:870): the maps cross PCIe as float32 --
+  // half the device-to-host bytes -- and are widened by the host threads that drain the staging blocks.  Rounded
+  // parameters come back onto their decimal grid in float64 there (rint(v 10^d) / 10^d, numpy.around's own formula).
+  double wscale[DFIT_MAX_PARAMS];
+  const bool widen = widen_plan(opts, out_dtype, wscale);
+  const int dev_out = widen ? DFIT_F32 : out_dtype;
+  const size_t ysz = dtype_size(y_dtype), osz = dev_out == DFIT_F32 ? 4 : 8, psz = p0_dtype == DFIT_F32 ? 4 : 8;
+  const size_t hosz = out_dtype == DFIT_F32 ? 4 : 8;  // element size of the caller's maps
 
   // Chunks of voxels flow through kSlots stream slots: H2D(chunk i+1) overlaps fit(chunk i) and
   // D2H(chunk i-1).  Chunk size keeps every copy large enough to run PCIe at full rate.
@@ -517,7 +597,7 @@ static int fit_host_impl(dfit_handle* h, const dfit_opts* opts, int n_echo, int6
   d.layout = DFIT_PLANAR;
   d.ld = chunk;
   d.p0_dtype = p0_dtype;
-  d.out_dtype = out_dtype;
+  d.out_dtype = dev_out;
   d.counters = h->counters;
 
   // the E planes of one contiguous (E, N) host array are equidistant: detect it once
@@ -534,7 +614,8 @@ static int fit_host_impl(dfit_handle* h, const dfit_opts* opts, int n_echo, int6
   // out: device -> slot.hpopt / hr2 (DMA)    -> caller's arrays (host threads), one chunk behind the GPU
   bool in_pageable = false;
   for (int e = 0; e < n_echo && n_vox > 0; ++e) in_pageable = in_pageable || !is_pinned_or_device(y_planes[e]);
-  const bool out_pageable = n_vox > 0 && (!is_pinned_or_device(popt) || !is_pinned_or_device(r2));
+  // results go through the page-locked staging blocks when the caller's arrays are pageable or have to be widened
+  const bool out_pageable = n_vox > 0 && (widen || !is_pinned_or_device(popt) || !is_pinned_or_device(r2));
   struct Pending {
     int64_t v0, n;
   } pending[kSlots];
@@ -542,8 +623,16 @@ static int fit_host_impl(dfit_handle* h, const dfit_opts* opts, int n_echo, int6
     Slot& sj = h->slots[j % kSlots];
     CUDA_TRY(cudaEventSynchronize(sj.ev_out));
     const Pending& pj = pending[j % kSlots];
-    const CopySeg segs[2] = {{(char*)popt + (size_t)pj.v0 * P * osz, sj.hpopt.p, (size_t)pj.n * P * osz},
-                             {(char*)r2 + (size_t)pj.v0 * osz, sj.hr2.p, (size_t)pj.n * osz}};
+    if (widen) {
+      double sc[DFIT_MAX_PARAMS];
+      for (int i = 0; i < PW; ++i) sc[i] = wscale[opts->out_param >= 0 ? opts->out_param : i];
+      par_widen((double*)popt + (size_t)pj.v0 * PW, (const float*)sj.hpopt.p, pj.n, PW, sc);
+      const double none[1] = {0.0};
+      par_widen((double*)r2 + (size_t)pj.v0, (const float*)sj.hr2.p, pj.n, 1, none);
+      return DFIT_OK;
+    }
+    const CopySeg segs[2] = {{(char*)popt + (size_t)pj.v0 * PW * hosz, sj.hpopt.p, (size_t)pj.n * PW * hosz},
+                             {(char*)r2 + (size_t)pj.v0 * hosz, sj.hr2.p, (size_t)pj.n * hosz}};
     par_copy(segs, 2);
     return DFIT_OK;
   };
@@ -552,7 +641,7 @@ static int fit_host_impl(dfit_handle* h, const dfit_opts* opts, int n_echo, int6
     const int64_t n = n_vox - v0 < chunk ? n_vox - v0 : chunk;
     Slot& sl = h->slots[idx % kSlots];
     if ((rc = ensure(sl.y, (size_t)n_echo * chunk * ysz)) != DFIT_OK) return rc;
-    if ((rc = ensure(sl.popt, (size_t)chunk * P * osz)) != DFIT_OK) return rc;
+    if ((rc = ensure(sl.popt, (size_t)chunk * PW * osz)) != DFIT_OK) return rc;
     if ((rc = ensure(sl.r2, (size_t)chunk * osz)) != DFIT_OK) return rc;
     if (mask && (rc = ensure(sl.mask, (size_t)chunk)) != DFIT_OK) return rc;
     if (mask && (rc = ensure(sl.index, (size_t)chunk * sizeof(unsigned) + 16)) != DFIT_OK) return rc;
@@ -607,16 +696,16 @@ static int fit_host_impl(dfit_handle* h, const dfit_opts* opts, int n_echo, int6
     CUDA_TRY(dispatch(d));
     h->last_launches += mask && d.tmap == nullptr ? 2 : 1;
     if (out_pageable) {
-      if ((rc = ensure_host(sl.hpopt, (size_t)chunk * P * osz)) != DFIT_OK) return rc;
+      if ((rc = ensure_host(sl.hpopt, (size_t)chunk * PW * osz)) != DFIT_OK) return rc;
       if ((rc = ensure_host(sl.hr2, (size_t)chunk * osz)) != DFIT_OK) return rc;
-      CUDA_TRY(cudaMemcpyAsync(sl.hpopt.p, sl.popt.p, (size_t)n * P * osz, cudaMemcpyDeviceToHost, st));
+      CUDA_TRY(cudaMemcpyAsync(sl.hpopt.p, sl.popt.p, (size_t)n * PW * osz, cudaMemcpyDeviceToHost, st));
       CUDA_TRY(cudaMemcpyAsync(sl.hr2.p, sl.r2.p, (size_t)n * osz, cudaMemcpyDeviceToHost, st));
       CUDA_TRY(cudaEventRecord(sl.ev_out, st));
       pending[idx % kSlots] = Pending{v0, n};
       // the staging blocks of a slot are emptied before the slot is used again: drain the oldest chunk in flight
       if (idx >= kSlots - 1 && (rc = drain(idx - (kSlots - 1))) != DFIT_OK) return rc;
     } else {
-      CUDA_TRY(cudaMemcpyAsync((char*)popt + (size_t)v0 * P * osz, sl.popt.p, (size_t)n * P * osz, cudaMemcpyDeviceToHost, st));
+      CUDA_TRY(cudaMemcpyAsync((char*)popt + (size_t)v0 * PW * osz, sl.popt.p, (size_t)n * PW * osz, cudaMemcpyDeviceToHost, st));
       CUDA_TRY(cudaMemcpyAsync((char*)r2 + (size_t)v0 * osz, sl.r2.p, (size_t)n * osz, cudaMemcpyDeviceToHost, st));
     }
     if (status) CUDA_TRY(cudaMemcpyAsync(status + v0, sl.status.p, (size_t)n, cudaMemcpyDeviceToHost, st));
@@ -633,31 +722,54 @@ static int fit_host_impl(dfit_handle* h, const dfit_opts* opts, int n_echo, int6
   return DFIT_OK;
 }
 
-int dfit_set_gather(dfit_handle* h, int world, int rank, void* const* maps, int64_t rows_per_rank) {
+int dfit_set_gather_ex(dfit_handle* h, const dfit_gather_desc* gd) {
   if (!h) return fail(DFIT_ERR_BAD_ARG, "handle is NULL");
-  if (world == 0) {
-    h->gather_world = 0;
+  if (!gd || gd->world == 0) {
+    h->g = GatherArgs{};
     return DFIT_OK;
   }
-  if (world < 1 || world > kMaxPeers || rank < 0 || rank >= world || !maps || rows_per_rank < 0)
-    return fail(DFIT_ERR_BAD_ARG, "bad gather specification (world=%d rank=%d, at most %d peers)", world, rank, kMaxPeers);
+  if (gd->struct_size != (int32_t)sizeof(dfit_gather_desc))
+    return fail(DFIT_ERR_BAD_ARG, "dfit_gather_desc.struct_size=%d, expected %d", gd->struct_size, (int)sizeof(dfit_gather_desc));
+  if (gd->world < 1 || gd->world > kMaxPeers || gd->rank < 0 || gd->rank >= gd->world || !gd->maps || gd->rows < 0 || gd->row0 < 0)
+    return fail(DFIT_ERR_BAD_ARG, "bad gather specification (world=%d rank=%d, at most %d peers)", gd->world, gd->rank, kMaxPeers);
   CUDA_TRY(cudaSetDevice(h->device));
-  for (int r = 0; r < world; ++r) {
-    if (!maps[r]) return fail(DFIT_ERR_BAD_ARG, "maps[%d] is NULL", r);
+  GatherArgs g{};
+  for (int r = 0; r < gd->world; ++r) {
+    if (!gd->maps[r]) return fail(DFIT_ERR_BAD_ARG, "maps[%d] is NULL", r);
     cudaPointerAttributes at;
-    CUDA_TRY(cudaPointerGetAttributes(&at, maps[r]));
+    CUDA_TRY(cudaPointerGetAttributes(&at, gd->maps[r]));
     if (at.type != cudaMemoryTypeDevice) return fail(DFIT_ERR_BAD_ARG, "maps[%d] is not device memory", r);
     if (at.device != h->device) {  // a peer's map: this device must be allowed to store into it
       int can = 0;
       CUDA_TRY(cudaDeviceCanAccessPeer(&can, h->device, at.device));
       if (!can) return fail(DFIT_ERR_UNSUPPORTED, "device %d cannot access peer device %d", h->device, at.device);
     }
-    h->gather[r] = static_cast<float*>(maps[r]);
+    g.maps[r] = static_cast<float*>(gd->maps[r]);
   }
-  h->gather_world = world;
-  h->gather_rank = rank;
-  h->gather_rows_per_rank = rows_per_rank;
+  g.mc = static_cast<float*>(gd->multicast);
+  g.world = gd->world;
+  g.self = gd->rank;
+  g.cols = gd->param_mask;
+  g.ncols = 0;  // (set per launch: depends on the model)
+  g.row0 = gd->row0;
+  g.split_list = gd->split_list ? 1 : 0;
+  g.y_voxel0 = gd->y_voxel0;
+  h->g = g;
+  h->gather_rows = gd->rows;
   return DFIT_OK;
+}
+
+int dfit_set_gather(dfit_handle* h, int world, int rank, void* const* maps, int64_t rows_per_rank) {
+  if (world == 0) return dfit_set_gather_ex(h, nullptr);
+  dfit_gather_desc gd;
+  std::memset(&gd, 0, sizeof(gd));
+  gd.struct_size = (int32_t)sizeof(gd);
+  gd.world = world;
+  gd.rank = rank;
+  gd.maps = maps;
+  gd.rows = (int64_t)world * rows_per_rank;
+  gd.row0 = (int64_t)rank * rows_per_rank;
+  return dfit_set_gather_ex(h, &gd);
 }
 
 int dfit_ipc_alloc(dfit_handle* h, size_t bytes, void** dev_ptr, unsigned char* handle_out) {

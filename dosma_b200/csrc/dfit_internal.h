@@ -63,9 +63,8 @@ struct dfit_handle {
   int last_launches = 0;
   float last_total_ms = 0.f;
   float host_kernel_ms = -1.f;
-  float* gather[dfit::kMaxPeers] = {nullptr};
-  int gather_world = 0, gather_rank = 0;
-  int64_t gather_rows_per_rank = 0;
+  dfit::GatherArgs g = {};     // fused all-gather (dfit_set_gather / dfit_set_gather_ex); g.world == 0: off
+  int64_t gather_rows = 0;     // rows in every map
   dfit::DevBuf scratch;    // small device scratch (qDESS maxima, metrics partials)
   dfit::DevBuf index_buf;  // compacted voxel list of the masked device path
 };

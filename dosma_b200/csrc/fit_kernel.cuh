@@ -27,17 +27,16 @@ inline cudaError_t launch_one(const LaunchDesc& d) {
     // dense fast path, two voxels per lane (see fit_kernel_mono2 for what it needs)
     const bool dt_ok = d.y_dtype == DT_F32 || d.y_dtype == DT_I16 || d.y_dtype == DT_U16;
     const size_t pair_bytes = 2 * dtype_size(d.y_dtype);
-    // with the fused all-gather only the TMA kernel qualifies (raw parameters, 16-byte-aligned rank blocks)
-    // Measured (weak scaling, 384^3 x 8 echoes per GPU): the one-voxel kernel's warp-transposed peer stores reach
-    // 696 / 680 GB/s of NVLink egress at 4 / 8 GPUs, the TMA bulk stores of this kernel 652 / 657 GB/s (equal at 2),
-    // and the step is NVLink-bound there -- so the bulk-store gather is opt-in (use_tma = 1).
-    const bool gather_ok = d.gather_world == 0 || (d.use_tma == 1 && d.tmap2 != nullptr && d.y_dtype == DT_F32 &&
-                                                   !d.po.enabled && d.gather_row0 % 4 == 0);
+    // With the fused all-gather only the TMA kernel qualifies, for the two row formats it stores as vectors: one
+    // parameter + r2 (8-byte rows, the T2 map) or all three columns; the rows of a lane's voxel pair must be 8 / 16-byte
+    // aligned (even first row).  Everything else gathers through the one-voxel kernel below.
+    const bool gather_ok = d.g.world == 0 || (d.tmap2 != nullptr && d.y_dtype == DT_F32 && (d.g.ncols == 2 || d.g.ncols == 3) &&
+                                              d.g.row0 % 2 == 0);
     if (d.fast_path == 1 && !a.vo.has_bounds && d.mask == nullptr && gather_ok && dt_ok && d.layout == LAYOUT_PLANAR &&
-        (d.popt != nullptr || d.gather_world > 0) && reinterpret_cast<uintptr_t>(d.y) % pair_bytes == 0 && d.ld % 2 == 0 &&
+        (d.popt != nullptr || d.g.world > 0) && reinterpret_cast<uintptr_t>(d.y) % pair_bytes == 0 && d.ld % 2 == 0 &&
         reinterpret_cast<uintptr_t>(d.popt) % 16 == 0 && reinterpret_cast<uintptr_t>(d.r2) % 8 == 0) {
       if (d.tmap2 != nullptr) {  // persistent, tiles staged through shared memory by TMA
-        auto kfn = d.gather_world > 0    ? fit_kernel_mono2_tma<M, EMAX, true, float>
+        auto kfn = d.g.world > 0         ? fit_kernel_mono2_tma<M, EMAX, true, float>
                    : d.y_dtype == DT_I16 ? fit_kernel_mono2_tma<M, EMAX, false, short>
                    : d.y_dtype == DT_U16 ? fit_kernel_mono2_tma<M, EMAX, false, unsigned short>
                                          : fit_kernel_mono2_tma<M, EMAX, false, float>;
@@ -84,12 +83,13 @@ inline cudaError_t launch_one(const LaunchDesc& d) {
     int64_t g = (int64_t)d.sm_count * 16;
     if (g > blocks) g = blocks;
     if constexpr (M::MONO && EXACT && sizeof(T) == 4 && EMAX >= 3) {
-      if (d.fast_path == 1 && !a.vo.has_bounds && d.gather_world == 0) {  // two voxels per lane over the list
-        fit_kernel_mono2_list<M, EMAX><<<(unsigned)g, kBlock, 0, d.stream>>>(a);
+      if (d.fast_path == 1 && !a.vo.has_bounds) {  // two voxels per lane over the list
+        if (d.g.world > 0) fit_kernel_mono2_list<M, EMAX, true><<<(unsigned)g, kBlock, 0, d.stream>>>(a);
+        else fit_kernel_mono2_list<M, EMAX, false><<<(unsigned)g, kBlock, 0, d.stream>>>(a);
         return cudaGetLastError();
       }
     }
-    if (d.gather_world > 0) {
+    if (d.g.world > 0) {
       if constexpr (sizeof(T) == 4) fit_kernel<M, T, EMAX, EXACT, true><<<(unsigned)g, kBlock, 0, d.stream>>>(a);
       else return cudaErrorNotSupported;
     } else {
@@ -98,7 +98,7 @@ inline cudaError_t launch_one(const LaunchDesc& d) {
     return cudaGetLastError();
   }
   // the fused all-gather epilogue is a separate instance so that single-GPU launches do not pay its registers
-  if (d.gather_world > 0) {
+  if (d.g.world > 0) {
     if constexpr (sizeof(T) == 4) fit_kernel<M, T, EMAX, EXACT, true><<<(unsigned)blocks, kBlock, 0, d.stream>>>(a);
     else return cudaErrorNotSupported;  // the gathered map is fp32 (the C-ABI layer rejects this earlier)
   } else {

@@ -72,15 +72,16 @@ __global__ void __launch_bounds__(kBlock, sizeof(T) == 4 ? (EMAX <= 8 ? 8 : 3) :
     return;
   } else {
     // compacted mask path: grid-stride over the index list (its length is only known on the device)
-    const unsigned count = *a.index_count;
+    unsigned first = 0, count = *a.index_count;
+    if (GATHER && a.g.split_list) list_share(a.g, first, count);  // multi-GPU: this rank's share of the list
     int it_sum = 0;
     unsigned n_fit = 0, n_fail = 0, n_nf = 0, n_oob = 0;
     for (unsigned i = blockIdx.x * kBlock + threadIdx.x; i < count; i += gridDim.x * kBlock) {
-      const int64_t v = (int64_t)a.index[i];
+      const int64_t v = (int64_t)a.index[first + i];
       T p[P], r2 = 0, y[EMAX];
       int it = 0;
       unsigned fl = 0;
-      load_samples<T, EMAX, EXACT>(a, v, y);
+      load_samples<T, EMAX, EXACT>(a, v - a.g.y_voxel0, y);
       int s = fit_voxel_fast<M, T, EMAX, EXACT>(y, a.xt, a.vo, p, r2, it);
       if (s < 0) {
         load_p0<P, T, EMAX>(a, v, p);

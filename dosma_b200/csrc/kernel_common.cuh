@@ -21,6 +21,22 @@ enum Counter : int { CNT_FITTED = 0, CNT_FAILED, CNT_NONFINITE, CNT_OOB, CNT_ITE
 constexpr int kStatSlots = 1024;  // power of two
 constexpr int kMaxPeers = 8;
 
+// Fused all-gather epilogue (multi-GPU, one process per GPU): while world > 0 the kernels store each voxel's packed
+// fp32 row [selected parameters..., r2] straight into the reassembled map of EVERY rank at row `row0 + v` -- peer-mapped
+// over NVLink, or with one multicast store that the NVSwitch replicates (NVLS) -- so the collective overlaps the fit
+// instead of following it.
+struct GatherArgs {
+  float* maps[kMaxPeers];  // rank r's map as THIS process addresses it (own allocation for r == self)
+  float* mc;               // multicast address of the same buffers (every rank's copy is written by one store) or null
+  int world, self;         // world == 0: no gather
+  unsigned cols;           // bit i: parameter i is carried in the row (r2 always is, last)
+  int ncols;               // floats per row = popcount(cols) + 1
+  int64_t row0;            // row of this launch's voxel 0
+  int split_list;          // masked fits: this rank fits entries [count self / world, count (self + 1) / world) of the
+                           // compacted voxel list (every rank compacts the same whole-volume mask)
+  int64_t y_voxel0;        // voxel index of the first sample of `y` (split_list: a rank holds only its span of samples)
+};
+
 template <typename T, int EMAX>
 struct KernelArgs {
   XTab<T, EMAX> xt;
@@ -40,16 +56,12 @@ struct KernelArgs {
   void* popt;
   void* r2;
   int out_dtype;
+  int sel;  // >= 0: only this parameter is written, popt is [N] (dfit_opts.out_param); -1: all, popt is [N, P]
   uint8_t* status;
   uint8_t* niter;
   double mask_fill;  // value written outside the mask: NaN or nan_to_num (fitting.py:207-212)
   unsigned long long* counters;
-  // Fused all-gather epilogue: when gather_world > 0 every voxel's packed row [popt..., r2] (fp32) is
-  // also stored straight into the reassembled map of EVERY rank (peer-mapped over NVLink) at row
-  // gather_row0 + v -- the collective overlaps the fit instead of following it.
-  float* gather[kMaxPeers];
-  int gather_world;
-  int64_t gather_row0;
+  GatherArgs g;
 };
 
 static inline size_t dtype_size(int dt) {
@@ -140,6 +152,54 @@ __device__ __forceinline__ void store_vec(TO* __restrict__ dst, const double (&q
   }
 }
 
+// N consecutive floats (N = 1, 2 or 4; the address aligned to N floats) into every rank's map at float offset `off`:
+// one multicast store when the maps are bound to an NVLS multicast object, else one store per rank (local HBM for
+// the own rank, NVLink for the peers).
+template <int N>
+__device__ __forceinline__ void gather_store(const GatherArgs& g, int64_t off, const float (&w)[N]) {
+  static_assert(N == 1 || N == 2 || N == 4, "vector width");
+  if (g.mc != nullptr) {
+    float* dst = g.mc + off;
+    if constexpr (N == 4)
+      asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(w[0]), "f"(w[1]), "f"(w[2]), "f"(w[3]) : "memory");
+    else if constexpr (N == 2)
+      asm volatile("multimem.st.relaxed.sys.global.v2.f32 [%0], {%1, %2};" ::"l"(dst), "f"(w[0]), "f"(w[1]) : "memory");
+    else
+      asm volatile("multimem.st.relaxed.sys.global.f32 [%0], %1;" ::"l"(dst), "f"(w[0]) : "memory");
+    return;
+  }
+#pragma unroll
+  for (int r = 0; r < kMaxPeers; ++r) {
+    if (r < g.world) {
+      float* dst = g.maps[r] + off;
+      if constexpr (N == 4) *reinterpret_cast<float4*>(dst) = make_float4(w[0], w[1], w[2], w[3]);
+      else if constexpr (N == 2) *reinterpret_cast<float2*>(dst) = make_float2(w[0], w[1]);
+      else *dst = w[0];
+    }
+  }
+}
+
+// Split-list mode: this rank's share [first, first + count) of a compacted list of `count` entries (on entry).
+// (The same integer formula as dosma_b200.sharding.voxel_ranges, so that the host knows each rank's voxel span.)
+__device__ __forceinline__ void list_share(const GatherArgs& g, unsigned& first, unsigned& count) {
+  const unsigned long long n = count;
+  const unsigned lo = (unsigned)(n * (unsigned)g.self / (unsigned)g.world);
+  const unsigned hi = (unsigned)(n * ((unsigned)g.self + 1u) / (unsigned)g.world);
+  first = lo;
+  count = hi - lo;
+}
+
+// The row of one voxel: the selected parameters, then r2.  Returns the number of floats.
+template <int P>
+__device__ __forceinline__ int gather_row(const GatherArgs& g, const float (&q)[P], float r2, float (&row)[P + 1]) {
+  int n = 0;
+#pragma unroll
+  for (int i = 0; i < P; ++i)
+    if ((g.cols >> i) & 1u) row[n++] = q[i];
+  row[n++] = r2;
+  return n;
+}
+
 // Epilogue + stores for one voxel.  `fitted` false: voxel outside the mask.
 template <int P, typename T, int EMAX, bool GATHER = true>
 __device__ __forceinline__ void store_voxel(const KernelArgs<T, EMAX>& a, int64_t v, const T (&p)[P], T r2, bool fitted,
@@ -147,12 +207,18 @@ __device__ __forceinline__ void store_voxel(const KernelArgs<T, EMAX>& a, int64_
   if constexpr (sizeof(T) == 4) {
     // fp32 parameters into fp32 maps: raw (curve_fit without an epilogue) or through the fp32-where-exact
     // epilogue -- no trip through double for r2 and the comparisons-only parameters.
-    if (fitted && a.out_dtype == DT_F32 && a.popt != nullptr && !(GATHER && a.gather_world > 0)) {
+    if (fitted && a.out_dtype == DT_F32 && a.popt != nullptr && !(GATHER && a.g.world > 0)) {
       float q[P];
 #pragma unroll
       for (int i = 0; i < P; ++i) q[i] = post_param_f32(a.po, i, p[i], r2);
       float* dst = reinterpret_cast<float*>(a.popt) + v * P;
-      if constexpr (P == 2) __stcs(reinterpret_cast<float2*>(dst), make_float2(q[0], q[1]));
+      if (a.sel >= 0) {  // one selected parameter: popt is [N]
+        float qs = q[0];
+#pragma unroll
+        for (int i = 1; i < P; ++i)
+          if (i == a.sel) qs = q[i];
+        __stcs(reinterpret_cast<float*>(a.popt) + v, qs);
+      } else if constexpr (P == 2) __stcs(reinterpret_cast<float2*>(dst), make_float2(q[0], q[1]));
       else if constexpr (P == 4) __stcs(reinterpret_cast<float4*>(dst), make_float4(q[0], q[1], q[2], q[3]));
       else {
 #pragma unroll
@@ -179,7 +245,19 @@ __device__ __forceinline__ void store_voxel(const KernelArgs<T, EMAX>& a, int64_
     }
   }
   if (a.popt != nullptr) {
-    if (a.out_dtype == DT_F32) {
+    if (a.sel >= 0) {  // one selected parameter: popt is [N]
+      double qs = q[0];
+#pragma unroll
+      for (int i = 1; i < P; ++i)
+        if (i == a.sel) qs = q[i];
+      if (a.out_dtype == DT_F32) {
+        __stcs(reinterpret_cast<float*>(a.popt) + v, (float)qs);
+        __stcs(reinterpret_cast<float*>(a.r2) + v, (float)r2o);
+      } else {
+        __stcs(reinterpret_cast<double*>(a.popt) + v, qs);
+        __stcs(reinterpret_cast<double*>(a.r2) + v, r2o);
+      }
+    } else if (a.out_dtype == DT_F32) {
       store_vec<P, float>(reinterpret_cast<float*>(a.popt) + v * P, q);
       __stcs(reinterpret_cast<float*>(a.r2) + v, (float)r2o);
     } else {
@@ -187,17 +265,25 @@ __device__ __forceinline__ void store_voxel(const KernelArgs<T, EMAX>& a, int64_
       __stcs(reinterpret_cast<double*>(a.r2) + v, r2o);
     }
   }
-  if (GATHER && a.gather_world > 0) {
+  if (GATHER && a.g.world > 0) {
     constexpr int C = P + 1;
-    float row[C];
+    float qf[P], row[C];
 #pragma unroll
-    for (int i = 0; i < P; ++i) row[i] = (float)q[i];
-    row[P] = (float)r2o;
-    if (warp_rows) {
-      // The warp's 32 rows are one contiguous block of 32*C floats in every map.  Transpose it through
-      // shuffles so that each of the C store instructions writes 128 contiguous bytes per warp: NVLink
+    for (int i = 0; i < P; ++i) qf[i] = (float)q[i];
+    if (!fitted && a.g.split_list) {
+      // split-list mode, outside the mask: the fill value goes into the OWN map only -- every rank compacts the same
+      // whole-volume mask and fills its own copy, so nothing of it crosses NVLink
+      const int n = gather_row<P>(a.g, qf, (float)r2o, row);
+      float* dst = a.g.maps[a.g.self] + (a.g.row0 + v) * n;
+      for (int i = 0; i < n; ++i) dst[i] = row[i];
+    } else if (warp_rows && a.g.ncols == C && a.g.mc == nullptr) {
+      // All columns, whole warp: the warp's 32 rows are one contiguous block of 32*C floats in every map.  Transpose it
+      // through shuffles so that each of the C store instructions writes 128 contiguous bytes per warp: NVLink
       // carries full write packets instead of 4-byte fragments at a 4*C-byte stride.
       const int lane = threadIdx.x & 31;
+#pragma unroll
+      for (int i = 0; i < P; ++i) row[i] = qf[i];
+      row[P] = (float)r2o;
       float word[C];
 #pragma unroll
       for (int k = 0; k < C; ++k) {
@@ -211,23 +297,25 @@ __device__ __forceinline__ void store_voxel(const KernelArgs<T, EMAX>& a, int64_
         }
         word[k] = val;
       }
-      const int64_t block0 = (a.gather_row0 + (v - lane)) * C;
+      const int64_t block0 = (a.g.row0 + (v - lane)) * C;
 #pragma unroll
       for (int r = 0; r < kMaxPeers; ++r) {
-        if (r < a.gather_world) {
-          float* dst = a.gather[r] + block0 + lane;  // local HBM for r == own rank, a peer's over NVLink otherwise
+        if (r < a.g.world) {
+          float* dst = a.g.maps[r] + block0 + lane;  // local HBM for r == own rank, a peer's over NVLink otherwise
 #pragma unroll
           for (int k = 0; k < C; ++k) dst[k * 32] = word[k];
         }
       }
     } else {
-      const int64_t off = (a.gather_row0 + v) * C;
-#pragma unroll
-      for (int r = 0; r < kMaxPeers; ++r) {
-        if (r < a.gather_world) {
-          float* dst = a.gather[r] + off;
-#pragma unroll
-          for (int i = 0; i < C; ++i) dst[i] = row[i];
+      const int n = gather_row<P>(a.g, qf, (float)r2o, row);
+      const int64_t off = (a.g.row0 + v) * n;
+      if (n == 2) {  // one parameter + r2 (the T2 map): 8-byte rows, a warp's rows are contiguous
+        const float w2[2] = {row[0], row[1]};
+        gather_store<2>(a.g, off, w2);
+      } else {
+        for (int i = 0; i < n; ++i) {
+          const float w1[1] = {row[i]};
+          gather_store<1>(a.g, off + i, w1);
         }
       }
     }
@@ -355,6 +443,7 @@ struct LaunchDesc {
   void* popt;
   void* r2;
   int out_dtype;
+  int sel;
   uint8_t* status;
   uint8_t* niter;
   unsigned long long* counters;
@@ -365,9 +454,7 @@ struct LaunchDesc {
   double mask_fill;
   int use_tma;
   cudaStream_t stream;
-  float* gather[kMaxPeers];
-  int gather_world;
-  int64_t gather_row0;
+  GatherArgs g;
   const CUtensorMap* tmap;   // host pointer to an encoded 2-D map of the planar fp32 samples (box 32 x E), or null
   const CUtensorMap* tmap2;  // the same with a 64-voxel box, for the two-voxels-per-lane kernel, or null
   int sm_count;
@@ -405,13 +492,12 @@ inline void fill_args(const LaunchDesc& d, KernelArgs<T, EMAX>& a) {
   a.popt = d.popt;
   a.r2 = d.r2;
   a.out_dtype = d.out_dtype;
+  a.sel = d.sel;
   a.status = d.status;
   a.niter = d.niter;
   a.mask_fill = d.mask_fill;
   a.counters = d.counters;
-  for (int r = 0; r < kMaxPeers; ++r) a.gather[r] = d.gather[r];
-  a.gather_world = d.gather_world;
-  a.gather_row0 = d.gather_row0;
+  a.g = d.g;
 }
 
 }  // namespace dfit

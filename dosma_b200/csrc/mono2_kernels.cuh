@@ -120,7 +120,8 @@ __global__ void __launch_bounds__(kBlock2, 5) fit_kernel_mono2(const __grid_cons
         const pair2<float> qa = post_pair_f32(a.po, 0, pa, r2), qb = post_pair_f32(a.po, 1, pb, r2);
         q = make_float4(qa.lo, qb.lo, qa.hi, qb.hi);
       }
-      __stcs(reinterpret_cast<float4*>(reinterpret_cast<float*>(a.popt) + v0 * P), q);
+      if (a.sel >= 0) __stcs(reinterpret_cast<float2*>(reinterpret_cast<float*>(a.popt) + v0), a.sel == 0 ? make_float2(q.x, q.z) : make_float2(q.y, q.w));
+      else __stcs(reinterpret_cast<float4*>(reinterpret_cast<float*>(a.popt) + v0 * P), q);
       __stcs(reinterpret_cast<float2*>(reinterpret_cast<float*>(a.r2) + v0), make_float2(r2.lo, r2.hi));
       if (a.status) {
         a.status[v0] = (uint8_t)st[0];
@@ -143,20 +144,23 @@ __global__ void __launch_bounds__(kBlock2, 5) fit_kernel_mono2(const __grid_cons
 // Two voxels per lane over the compacted voxel list of the mask path (any echo spacing, any sample type):
 // lane i takes list entries 2i and 2i+1, gathers their samples and runs the same packed fast path; voxels
 // it declines run the LM.  Grid-stride, because the list length is only known on the device.
-template <class M, int EMAX>
+template <class M, int EMAX, bool GATHER = false>
 __global__ void __launch_bounds__(kBlock, 5) fit_kernel_mono2_list(const __grid_constant__ KernelArgs<float, EMAX> a) {
   typedef float T;
   constexpr int P = 2;
-  const unsigned count = *a.index_count;
+  // the list entries this launch fits: all of them, or -- multi-GPU split-list mode -- this rank's share
+  unsigned first = 0, count = *a.index_count;
+  if (GATHER && a.g.split_list) list_share(a.g, first, count);
   const unsigned npairs = (count + 1u) >> 1;
+  const unsigned* __restrict__ list = a.index + first;
   int it_sum = 0, it_max = 0;
   unsigned n_fit = 0, n_fail = 0, n_nf = 0, n_oob = 0;
   for (unsigned i = blockIdx.x * kBlock + threadIdx.x; i < npairs; i += gridDim.x * kBlock) {
     const bool both = 2u * i + 1u < count;
-    const int64_t vA = (int64_t)a.index[2u * i], vB = both ? (int64_t)a.index[2u * i + 1u] : vA;
+    const int64_t vA = (int64_t)list[2u * i], vB = both ? (int64_t)list[2u * i + 1u] : vA;
     T yA[EMAX], yB[EMAX];
-    load_samples<T, EMAX, true>(a, vA, yA);
-    load_samples<T, EMAX, true>(a, vB, yB);
+    load_samples<T, EMAX, true>(a, vA - a.g.y_voxel0, yA);
+    load_samples<T, EMAX, true>(a, vB - a.g.y_voxel0, yB);
     pair2<T> Y[EMAX], pa, pb, r2;
 #pragma unroll
     for (int e = 0; e < EMAX; ++e) Y[e] = p2_make<T>(yA[e], yB[e]);
@@ -192,8 +196,8 @@ __global__ void __launch_bounds__(kBlock, 5) fit_kernel_mono2_list(const __grid_
       }
     }
     const T p0_[P] = {pa.lo, pb.lo}, p1_[P] = {pa.hi, pb.hi};
-    store_voxel<P, T, EMAX, false>(a, vA, p0_, r2.lo, true, st[0], iters[0]);
-    if (both) store_voxel<P, T, EMAX, false>(a, vB, p1_, r2.hi, true, st[1], iters[1]);
+    store_voxel<P, T, EMAX, GATHER>(a, vA, p0_, r2.lo, true, st[0], iters[0]);
+    if (both) store_voxel<P, T, EMAX, GATHER>(a, vB, p1_, r2.hi, true, st[1], iters[1]);
     else { st[1] = -1; iters[1] = 0; }
     it_sum += iters[0] + iters[1];
     it_max = iters[0] > it_max ? iters[0] : it_max;
@@ -296,8 +300,10 @@ __global__ void __launch_bounds__(kM2Warps * 32, m2_min_ctas(EMAX))
   int n_def = 0;  // entries in this warp's queue (warp-uniform)
   // fp32 maps (raw parameters or the fp32 form of the fused epilogue) and nothing else to write: two vector stores per lane
   const bool plain = a.out_dtype == DT_F32 && a.popt != nullptr && a.status == nullptr && a.niter == nullptr;
-  constexpr int64_t kPoptTile = (int64_t)kM2Tile * P * sizeof(float), kR2Tile = (int64_t)kM2Tile * sizeof(float);
-  char* popt_lane = reinterpret_cast<char*>(a.popt) + lane * (2 * P * sizeof(float)) + (int64_t)warp_global * kPoptTile;
+  const int pw = a.sel >= 0 ? 1 : P;  // floats per voxel in popt (one selected parameter, or all)
+  const int64_t kPoptTile = (int64_t)kM2Tile * pw * sizeof(float);
+  constexpr int64_t kR2Tile = (int64_t)kM2Tile * sizeof(float);
+  char* popt_lane = reinterpret_cast<char*>(a.popt) + lane * (2 * pw * (int)sizeof(float)) + (int64_t)warp_global * kPoptTile;
   char* r2_lane = reinterpret_cast<char*>(a.r2) + lane * (2 * sizeof(float)) + (int64_t)warp_global * kR2Tile;
   int stage = 0;
   unsigned phase = 0;
@@ -337,42 +343,38 @@ __global__ void __launch_bounds__(kM2Warps * 32, m2_min_ctas(EMAX))
       defB = defB && validB;
     }
     if constexpr (GATHER) {
-      // Fused all-gather: the tile's 64 rows [a, b, r2] are one contiguous 768-byte block in every rank's map.
-      // Stage them in shared memory (double-buffered) and let the TMA push the block to every rank with one
-      // bulk store each (cp.async.bulk global <- shared): the SM's load/store path never waits on NVLink.  The
-      // launcher admits this kernel only without the epilogue and with 16-byte-aligned rank blocks.  Rows of
-      // deferred voxels are overwritten when their queue is run (after the bulk stores have completed).
-      __shared__ __align__(128) float rows[kM2Warps][2][kM2Tile * 3];
-      float* sg = rows[warp][k & 1];
-      if (t * kM2Tile + kM2Tile <= n_vox) {
-        // the staging buffer used two tiles ago must have been read by its bulk copies
-        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-        __syncwarp();
-        *reinterpret_cast<float2*>(sg + 6 * lane) = make_float2(pa.lo, pb.lo);
-        *reinterpret_cast<float2*>(sg + 6 * lane + 2) = make_float2(r2.lo, pa.hi);
-        *reinterpret_cast<float2*>(sg + 6 * lane + 4) = make_float2(pb.hi, r2.hi);
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        __syncwarp();
-        if (lane == 0) {
-          // one TMA bulk store of the 768-byte block per rank: local HBM for the own rank, NVLink otherwise
-          const int64_t base = (a.gather_row0 + (int64_t)t * kM2Tile) * 3;
-#pragma unroll
-          for (int r = 0; r < kMaxPeers; ++r) {
-            if (r < a.gather_world) {
-              asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(a.gather[r] + base),
-                           "r"(smem_u32(sg)), "n"(kM2Tile * 3 * 4)
-                           : "memory");
-            }
-          }
-          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      // Fused all-gather: the lane's two rows are adjacent in every rank's map.  With one parameter + r2 per row (the
+      // T2 map: 8-byte rows) they are ONE 16-byte store per rank -- a warp writes 512 contiguous bytes -- or one
+      // multicast store that the NVSwitch replicates; with all three columns, three 8-byte stores.  Rows of deferred
+      // voxels are written when their queue is run.  (The launcher admits this kernel for these two row formats.)
+      pair2<float> ga = pa, gb = pb;
+      if (a.po.enabled) {
+        ga = post_pair_f32(a.po, 0, pa, r2);
+        gb = post_pair_f32(a.po, 1, pb, r2);
+      }
+      const int64_t row = a.g.row0 + v0;
+      if (a.g.ncols == 2) {
+        const pair2<float> gp = (a.g.cols & 1u) ? ga : gb;
+        if (ok[0] && ok[1]) {
+          const float w[4] = {gp.lo, r2.lo, gp.hi, r2.hi};
+          gather_store<4>(a.g, row * 2, w);
+        } else {
+          const float w0[2] = {gp.lo, r2.lo}, w1[2] = {gp.hi, r2.hi};
+          if (ok[0]) gather_store<2>(a.g, row * 2, w0);
+          if (ok[1]) gather_store<2>(a.g, row * 2 + 2, w1);
         }
-      } else {  // ragged last tile: row by row
+      } else {
+        const float w0[2] = {ga.lo, gb.lo}, w1[2] = {r2.lo, ga.hi}, w2[2] = {gb.hi, r2.hi};
+        if (ok[0] && ok[1]) {
+          gather_store<2>(a.g, row * 3, w0);
+          gather_store<2>(a.g, row * 3 + 2, w1);
+          gather_store<2>(a.g, row * 3 + 4, w2);
+        } else {
+          const float s[6] = {ga.lo, gb.lo, r2.lo, ga.hi, gb.hi, r2.hi};
 #pragma unroll
-        for (int r = 0; r < kMaxPeers; ++r) {
-          if (r < a.gather_world) {
-            float* dst = a.gather[r] + (a.gather_row0 + v0) * 3;
-            if (ok[0]) { dst[0] = pa.lo; dst[1] = pb.lo; dst[2] = r2.lo; }
-            if (ok[1]) { dst[3] = pa.hi; dst[4] = pb.hi; dst[5] = r2.hi; }
+          for (int i = 0; i < 6; ++i) {
+            const float w[1] = {s[i]};
+            if (i < 3 ? ok[0] : ok[1]) gather_store<1>(a.g, row * 3 + i, w);
           }
         }
       }
@@ -383,7 +385,18 @@ __global__ void __launch_bounds__(kM2Warps * 32, m2_min_ctas(EMAX))
         const pair2<float> qa = post_pair_f32(a.po, 0, pa, r2), qb = post_pair_f32(a.po, 1, pb, r2);
         q = make_float4(qa.lo, qb.lo, qa.hi, qb.hi);
       }
-      if (ok[0] && ok[1]) {
+      if (a.sel >= 0) {  // one selected parameter (the time-constant map): popt is [N]
+        const float2 qs = a.sel == 0 ? make_float2(q.x, q.z) : make_float2(q.y, q.w);
+        float* pp = reinterpret_cast<float*>(popt_lane);
+        float* pr = reinterpret_cast<float*>(r2_lane);
+        if (ok[0] && ok[1]) {
+          __stcs(reinterpret_cast<float2*>(pp), qs);
+          __stcs(reinterpret_cast<float2*>(pr), make_float2(r2.lo, r2.hi));
+        } else {
+          if (ok[0]) { __stcs(pp, qs.x); __stcs(pr, r2.lo); }
+          if (ok[1]) { __stcs(pp + 1, qs.y); __stcs(pr + 1, r2.hi); }
+        }
+      } else if (ok[0] && ok[1]) {
         __stcs(reinterpret_cast<float4*>(popt_lane), q);
         __stcs(reinterpret_cast<float2*>(r2_lane), make_float2(r2.lo, r2.hi));
       } else {
@@ -408,10 +421,6 @@ __global__ void __launch_bounds__(kM2Warps * 32, m2_min_ctas(EMAX))
       n_def += nA + __popc(mB);
       __syncwarp();
       if (n_def >= 32) {
-        if constexpr (GATHER) {  // their rows must land after the tile blocks that contain them
-          if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
-          __syncwarp();
-        }
         do {
           n_def -= 32;
           fit_deferred<M, EMAX, GATHER>(a, &defer_q[warp][n_def], 32, lane, n_fit, n_fail, n_nf, n_oob, it_sum, it_max);
@@ -419,10 +428,6 @@ __global__ void __launch_bounds__(kM2Warps * 32, m2_min_ctas(EMAX))
         __syncwarp();
       }
     }
-  }
-  if constexpr (GATHER) {
-    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // all bulk stores of this warp are done
-    __syncwarp();
   }
   if (n_def > 0) fit_deferred<M, EMAX, GATHER>(a, &defer_q[warp][0], n_def, lane, n_fit, n_fail, n_nf, n_oob, it_sum, it_max);
   // statistics: per-thread accumulators -> one reduction per warp at the end of the kernel

@@ -80,11 +80,12 @@ def _as_plane(arr):
 
 
 def _engine_fit(model_id, nparams, x, planes, mask, p0_cols, *, init_mode=_cabi.INIT_GIVEN, y_bounds=None,
-                maxfev=100, ftol=1e-5, eps=1e-8, post=None, engine=None):
+                maxfev=100, ftol=1e-5, eps=1e-8, post=None, engine=None, out_param=None):
     """Run the CUDA engine on host buffers.
 
     planes: list of E arrays (one per echo), each flattened to [N]; mask: None or [N] (truthy =
     fit); p0_cols: length-P list of scalars or [N] arrays.  post: dict for the fused epilogue.
+    out_param: None, or the index of the one parameter to return (popt is then (N,): `dfit_opts.out_param`).
     Returns popt (N, P) float64, r2 (N,) float64, stats dict.
     """
     engine = dict(engine or {})
@@ -156,7 +157,9 @@ def _engine_fit(model_id, nparams, x, planes, mask, p0_cols, *, init_mode=_cabi.
     out_dt = {"f64": np.float64, "f32": np.float32}.get(engine.get("out_dtype") or "f64")
     if out_dt is None:
         raise ValueError("out_dtype must be 'f64' or 'f32'")
-    popt = np.empty((N, nparams), dtype=out_dt)
+    if out_param is not None:
+        o.out_param = int(out_param)
+    popt = np.empty((N, nparams) if out_param is None else (N,), dtype=out_dt)
     r2 = np.empty(N, dtype=out_dt)
     plane_ptrs = (ctypes.c_void_p * E)(*[p.ctypes.data for p in planes])
     h = _cabi.get_handle(engine.get("device", _default_device()))
@@ -377,16 +380,6 @@ def _format_p0_volumes(p0, ref, mask_flat, depth=0):
     raise ValueError(f"p0={p0} not supported")
 
 
-def _slice_param(popt, index):
-    """`popt[..., index]` without going through `MedicalVolume.__getitem__` (which breaks on
-    header-bearing volumes with numpy >= 1.23 in the reference)."""
-    vol = np.ascontiguousarray(np.asarray(popt.volume)[..., index])
-    hdr = popt.headers()
-    if hdr is not None:
-        hdr = hdr[..., 0]
-    return popt._partial_clone(volume=vol, headers=hdr)
-
-
 class CurveFitter:
     """Non-linear least squares over MedicalVolumes -- `dosma.core.fitting.CurveFitter`
     (fitting.py:238-458) on the CUDA engine.
@@ -417,6 +410,7 @@ class CurveFitter:
         self.verbose = verbose
         self.kwargs = kwargs
         self._decimals = None  # set by MonoExponentialFit to fuse its rounding
+        self._out_param = None  # set by MonoExponentialFit: the one parameter it keeps (fitting.py:734)
 
     # -- epilogue planning -----------------------------------------------------------------------
     def _plan_post(self, nparams):
@@ -483,8 +477,11 @@ class CurveFitter:
         fused = post if post is not None else {
             "ufunc": [0] * nparams, "lb": [-np.inf] * nparams, "ub": [np.inf] * nparams, "decimals": [-1] * nparams,
             "r2_threshold": None, "nan_to_num": None}
+        # (a single kept parameter is selected on the device when the whole epilogue is fused: a third less to write
+        # and to bring back over PCIe, and no host pass to slice the column out)
+        only = self._out_param if post is not None else None
         popt, r2, stats = _engine_fit(model_id, nparams, x, planes, mask_flat, cols, init_mode=_init_mode,
-                                      y_bounds=self.y_bounds, post=fused, engine=engine, **fit_kwargs)
+                                      y_bounds=self.y_bounds, post=fused, engine=engine, out_param=only, **fit_kwargs)
         self.last_stats = stats
         if post is None:
             # arbitrary Python ufunc: finish `_process_params` on the host, then redo the mask fill
@@ -500,12 +497,17 @@ class CurveFitter:
                 for i, d in self._decimals.items():
                     popt[:, i] = np.around(popt[:, i], d)
 
-        popt = popt.reshape(original_shape + (nparams,))
+        if self._out_param is not None and only is None:  # (host epilogue: the column is sliced here)
+            popt = np.ascontiguousarray(popt[:, self._out_param])
+        one = self._out_param is not None
+        popt = popt.reshape(original_shape if one else original_shape + (nparams,))
         r2 = r2.reshape(original_shape)
         if copy_headers:
             headers = y0.headers()
             if headers is not None:
-                headers = np.expand_dims(deepcopy(headers), axis=-1)
+                # (parameter maps get a trailing axis, fitting.py:503-507; a single parameter -- what `popt[..., i]`
+                # leaves, :734 -- keeps the shape of the inputs' headers)
+                headers = deepcopy(headers) if one else np.expand_dims(deepcopy(headers), axis=-1)
             popt_headers, r2_headers = headers, True
         else:
             popt_headers, r2_headers = None, None
@@ -578,11 +580,12 @@ class MonoExponentialFit:
         )
         if self.decimal_precision is not None:
             fitter._decimals = {1: self.decimal_precision}
+        fitter._out_param = 1  # `popt[..., 1]` (fitting.py:734), selected on the device
         p0 = None if polyfit else {"a": 1.0, "b": -1 / self.tc0}
         popt, r_squared = fitter.fit(
             x, y, mask=mask, p0=p0, _init_mode=_cabi.INIT_LOGLINEAR if polyfit else _cabi.INIT_GIVEN)
         self.last_stats = fitter.last_stats
-        return _slice_param(popt, 1), r_squared
+        return popt, r_squared
 
     def _check_y(self, x, y):
         """fitting.py:741-749."""

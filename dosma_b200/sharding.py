@@ -7,7 +7,7 @@ padded to the largest slab so that the reassembly stays a single `all_gather_int
 """
 import numpy as np
 
-__all__ = ["slab_bounds", "voxel_ranges", "gather_maps", "fit_sharded", "PeerMaps"]
+__all__ = ["slab_bounds", "voxel_ranges", "list_shares", "gather_maps", "fit_sharded", "PeerMaps"]
 
 
 def slab_bounds(n_slices, world_size):
@@ -24,6 +24,13 @@ def voxel_ranges(n_vox, world_size, align=1):
     b = slab_bounds(n_units, world_size) * align
     b[-1] = n_vox
     return np.minimum(b, n_vox)
+
+
+def list_shares(count, world_size):
+    """Boundaries of the ranks' shares of a compacted voxel list of `count` entries: rank r fits entries
+    [b[r], b[r + 1]).  The integer formula of the kernels' split-list mode (`list_share` in csrc/kernel_common.cuh),
+    so that the host can tell which voxel span -- hence which samples -- each rank needs."""
+    return np.asarray([int(count) * r // int(world_size) for r in range(int(world_size) + 1)], dtype=np.int64)
 
 
 def gather_maps(local, counts, group=None):
@@ -71,14 +78,24 @@ class _DevArray:
 class PeerMaps:
     """Reassembled parameter maps that every rank's fit kernel stores into directly (fused all-gather).
 
-    Each rank allocates its own full map `[world * rows_per_rank, P + 1]` (fp32) through the C-ABI
-    (`dfit_ipc_alloc`) and publishes the CUDA IPC handle; every rank maps all peers' allocations with
-    ITS device current (`dfit_ipc_open`: lazy peer access over NVLink) and hands the `world` device
-    pointers to `dfit_set_gather`, after which `fit_device` stores each voxel's row into all maps
-    while the fit is running.  `synchronize()` (stream drain + barrier) makes the local map complete.
+    Every rank owns one full map `[rows, ncols]` (fp32; `ncols` = parameters carried + r2) and can store into all of
+    them.  Two ways to get there, tried in this order:
+
+    * torch symmetric memory (`torch.distributed._symmetric_memory`: plumbing, like `torch.distributed` itself): the
+      buffers are exchanged by the runtime and, where the fabric offers it, bound to an NVLS multicast object -- one
+      `multimem.st` per row leaves the GPU and the NVSwitch replicates it to all ranks;
+    * CUDA IPC through the C-ABI (`dfit_ipc_alloc` / `dfit_ipc_open`, lazy peer access over NVLink): one store per rank.
+
+    `dfit_set_gather_ex` then hands the pointers to the kernels, after which `fit_device` stores each voxel's row into
+    all maps while the fit is running.  `synchronize()` (stream drain + barrier) makes the local map complete.
+
+    rows_per_rank, ncols: the dense layout (rank r's voxels are rows [r rows_per_rank, (r + 1) rows_per_rank)).
+    total_rows / row0: any other layout (e.g. the split-list mode: every rank addresses the whole volume, row0 = 0).
+    param_mask: parameters carried per row (bit i = parameter i, 0 = all); ncols must equal their number + 1.
     """
 
-    def __init__(self, rows_per_rank, ncols, device, group=None):
+    def __init__(self, rows_per_rank, ncols, device, group=None, *, total_rows=None, row0=None, param_mask=0,
+                 split_list=False, y_voxel0=0, multicast="auto"):
         import ctypes
 
         import torch
@@ -93,31 +110,89 @@ class PeerMaps:
         self.rows_per_rank = int(rows_per_rank)
         self.device = device
         self._handle = _cabi.get_handle(device.index)
-        shape = (self.world * self.rows_per_rank, int(ncols))
-        nbytes = shape[0] * shape[1] * 4
-        own = ctypes.c_void_p()
-        hbuf = ctypes.create_string_buffer(64)
-        _cabi.check(lib.dfit_ipc_alloc(self._handle.ptr, nbytes, ctypes.byref(own), hbuf))
-        self._own = own
-        handles = [None] * self.world
-        dist.all_gather_object(handles, bytes(hbuf.raw), group=group)
-        self._peer_ptrs = []
-        ptrs = []
-        for r in range(self.world):
-            if r == self.rank:
-                ptrs.append(own.value)
-            else:
-                p = ctypes.c_void_p()
-                _cabi.check(lib.dfit_ipc_open(self._handle.ptr, handles[r], ctypes.byref(p)))
-                self._peer_ptrs.append(p)
-                ptrs.append(p.value)
+        rows = int(total_rows) if total_rows is not None else self.world * self.rows_per_rank
+        row0 = int(row0) if row0 is not None else self.rank * self.rows_per_rank
+        shape = (rows, int(ncols))
+        self._own, self._peer_ptrs, self._symm = None, [], None
+        self.transport = None
+        mc_ptr = 0
+        ptrs = None
+        if multicast != "off":
+            ptrs, mc_ptr = self._try_symmetric(shape, device, group)
+        if ptrs is None:
+            nbytes = shape[0] * shape[1] * 4
+            own = ctypes.c_void_p()
+            hbuf = ctypes.create_string_buffer(64)
+            _cabi.check(lib.dfit_ipc_alloc(self._handle.ptr, nbytes, ctypes.byref(own), hbuf))
+            self._own = own
+            handles = [None] * self.world
+            dist.all_gather_object(handles, bytes(hbuf.raw), group=group)
+            ptrs = []
+            for r in range(self.world):
+                if r == self.rank:
+                    ptrs.append(own.value)
+                else:
+                    p = ctypes.c_void_p()
+                    _cabi.check(lib.dfit_ipc_open(self._handle.ptr, handles[r], ctypes.byref(p)))
+                    self._peer_ptrs.append(p)
+                    ptrs.append(p.value)
+            self.transport = "cuda-ipc peer stores"
+        if multicast == "require" and not mc_ptr:
+            raise RuntimeError("NVLS multicast was required but is not available")
+        self.multicast_ptr = int(mc_ptr or 0)
         with torch.cuda.device(device):
             self.maps = [torch.as_tensor(_DevArray(p, shape), device=device) for p in ptrs]
         self.local = self.maps[self.rank]
         self._ptrs = (ctypes.c_void_p * self.world)(*ptrs)
-        _cabi.check(lib.dfit_set_gather(self._handle.ptr, self.world, self.rank,
-                                        ctypes.cast(self._ptrs, ctypes.c_void_p), self.rows_per_rank))
+        gd = _cabi.DfitGatherDesc()
+        gd.struct_size = ctypes.sizeof(gd)
+        gd.world, gd.rank = self.world, self.rank
+        gd.maps = ctypes.cast(self._ptrs, ctypes.c_void_p)
+        gd.multicast = self.multicast_ptr or None
+        gd.rows, gd.row0 = rows, row0
+        gd.param_mask = int(param_mask)
+        gd.split_list = int(bool(split_list))
+        gd.y_voxel0 = int(y_voxel0)
+        self._desc = gd
+        _cabi.check(lib.dfit_set_gather_ex(self._handle.ptr, ctypes.byref(gd)))
         dist.barrier(group=group)
+
+    def _try_symmetric(self, shape, device, group):
+        """Allocate the maps as torch symmetric memory; returns (pointers, multicast pointer) or (None, 0).  All
+        ranks take the same branch (the outcome is agreed on with an all-reduce)."""
+        import torch
+        import torch.distributed as dist
+
+        ok, ptrs, mc = 1, None, 0
+        try:
+            import torch.distributed._symmetric_memory as symm
+
+            t = symm.empty(shape, dtype=torch.float32, device=device)
+            hdl = symm.rendezvous(t, group=group if group is not None else dist.group.WORLD)
+            t.zero_()
+            ptrs = [int(p) for p in hdl.buffer_ptrs]
+            mc = int(getattr(hdl, "multicast_ptr", 0) or 0)
+            self._symm = (t, hdl)
+        except Exception:  # not built / not permitted / no fabric support: the IPC path does the same job
+            ok = 0
+        flag = torch.tensor([ok, 1 if mc else 0], device=device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+        torch.cuda.synchronize(device)
+        if int(flag[0]) == 0:
+            self._symm = None
+            return None, 0
+        self.transport = "symmetric memory, NVLS multicast stores" if int(flag[1]) else "symmetric memory, peer stores"
+        return ptrs, (mc if int(flag[1]) else 0)
+
+    def reconfigure(self, **kw):
+        """Change row0 / param_mask / split_list / y_voxel0 of the gather without re-allocating the maps."""
+        import ctypes
+
+        from . import _cabi
+
+        for k, v in kw.items():
+            setattr(self._desc, k, int(v))
+        _cabi.check(_cabi.load().dfit_set_gather_ex(self._handle.ptr, ctypes.byref(self._desc)))
 
     def synchronize(self):
         """All ranks' peer stores into this rank's map are complete after this returns."""
@@ -135,7 +210,7 @@ class PeerMaps:
 
         lib = _cabi.load()
         torch.cuda.synchronize(self.device)
-        _cabi.check(lib.dfit_set_gather(self._handle.ptr, 0, 0, None, 0))
+        _cabi.check(lib.dfit_set_gather_ex(self._handle.ptr, None))
         self.maps = []
         self.local = None
         dist.barrier(group=self.group)  # nobody stores into a map that is about to go away
@@ -146,3 +221,4 @@ class PeerMaps:
         if self._own is not None:
             _cabi.check(lib.dfit_ipc_free(self._handle.ptr, self._own))
             self._own = None
+        self._symm = None

@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define DFIT_VERSION 200 /* major*10000 + minor*100 + patch */
+#define DFIT_VERSION 300 /* major*10000 + minor*100 + patch */
 #define DFIT_MAX_PARAMS 4
 #define DFIT_MAX_ECHOES 32
 
@@ -121,6 +121,9 @@ typedef struct dfit_opts {
                             from p0 whenever it declines.  -1 auto (on), 0 off (always LM from p0), 1 on, 2 on but never
                             with the two-voxels-per-lane kernel (diagnostic) */
   int32_t use_tma;         /* -1 auto, 0 plain coalesced loads, 1 TMA-staged tiles */
+  int32_t out_param;       /* -1 (default): popt is [N, P].  i >= 0: only parameter i is written and popt is [N] --
+                              what MonoExponentialFit keeps of its fit (fitting.py:734): a third less to write and to
+                              bring back over PCIe */
 } dfit_opts;
 
 /* Aggregate counters of the last fit on a handle (device-accumulated). */
@@ -172,6 +175,29 @@ int dfit_fit_device(dfit_handle* h, const dfit_opts* opts, int n_echo, int64_t n
  * still running; popt / r2 may then be NULL.  Peer stores are complete when the launching stream has
  * drained; ranks synchronise with each other before reading their maps.  world = 0 clears. */
 int dfit_set_gather(dfit_handle* h, int world, int rank, void* const* maps, int64_t rows_per_rank);
+
+/* The general form.  Rows carry the parameters named in `param_mask` (bit i = parameter i; 0 = all) followed by r2:
+ * a T2 / T1rho map needs [b or tc, r2] -- 8-byte rows instead of 12, and the reassembly is bound by the bytes every
+ * GPU must receive.  `multicast`: an NVLS multicast address bound to the same `world` buffers (e.g. from
+ * torch.distributed._symmetric_memory): every row then leaves the GPU once (multimem.st) and the NVSwitch replicates
+ * it, instead of `world - 1` peer stores.
+ * `split_list` (masked fits, SURVEY.md section 8e: "shard the mask-compacted voxel list"): every rank passes the mask of the WHOLE
+ * volume (n_vox = whole volume, the same on all ranks), fills its own map outside the mask and fits only its share
+ * [count rank / world, count (rank + 1) / world) of the compacted voxel list -- balanced however the tissue is
+ * distributed over the slabs; `y` then holds only the samples of that share's voxel span, y_voxel0 being the voxel
+ * index of its first column (dosma_b200.sharding.list_shares computes the spans). */
+typedef struct dfit_gather_desc {
+  int32_t struct_size; /* sizeof(dfit_gather_desc) */
+  int32_t world, rank;
+  void* const* maps;   /* world device pointers this process can store to */
+  void* multicast;     /* or NULL */
+  int64_t rows;        /* rows in every map */
+  int64_t row0;        /* row of voxel 0 of this rank's dfit_fit_device calls */
+  uint32_t param_mask;
+  int32_t split_list;
+  int64_t y_voxel0;
+} dfit_gather_desc;
+int dfit_set_gather_ex(dfit_handle* h, const dfit_gather_desc* g); /* g == NULL or g->world == 0 clears */
 
 /* Plumbing for the maps above: allocate a zeroed device buffer and export its CUDA IPC handle
  * (DFIT_IPC_HANDLE_BYTES bytes, to be sent to the peer processes by any means), and map a peer's

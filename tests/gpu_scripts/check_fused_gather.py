@@ -1,8 +1,10 @@
-"""Multi-GPU check (run under torchrun on >= 2 GPUs): the fused in-kernel all-gather (peer stores over
-NVLink, dosma_b200.sharding.PeerMaps) must equal a plain NCCL all-gather of the per-rank results.
+"""Multi-GPU check (run under torchrun on >= 2 GPUs): the fused in-kernel all-gather (dosma_b200.sharding.PeerMaps:
+peer stores over NVLink or NVLS multicast stores) must equal a plain NCCL all-gather of the per-rank results --
+all columns and the 8-byte [b or tc, r2] rows, raw parameters and the fused MonoExponentialFit epilogue, the one-voxel
+and the two-voxel TMA kernel, ragged sizes; and the masked split-list mode must equal the single-GPU masked fit.
 
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 \
-        --master-port 29512 tests/gpu_scripts/check_fused_gather.py [n_voxels]
+        --master-port 29512 tests/gpu_scripts/check_fused_gather.py [n_voxels ...]
 """
 import os
 import sys
@@ -17,6 +19,17 @@ sys.path.insert(0, ROOT)
 import dosma_b200 as D  # noqa: E402
 from dosma_b200 import device_api as A, sharding  # noqa: E402
 
+POST = dict(ufunc=[0, 1], lb=[-np.inf, 0.0], ub=[np.inf, 100.0], decimals=[-1, 1], r2_threshold=0.9, nan_to_num=0.0)
+X = np.arange(1, 9) * 10.0
+
+
+def synth(n, dev, seed):
+    g = torch.Generator(device=dev).manual_seed(seed)
+    xt = torch.tensor(X, device=dev, dtype=torch.float32)[:, None]
+    a = 500 + 1000 * torch.rand(n, device=dev, generator=g)
+    t2 = 10 + 70 * torch.rand(n, device=dev, generator=g)
+    return a * torch.exp(-xt / t2) + 10 * torch.randn(8, n, device=dev, generator=g)
+
 
 def main():
     sizes = [int(v) for v in sys.argv[1:]] or [100_000]
@@ -25,54 +38,79 @@ def main():
     dev = torch.device("cuda", local)
     dist.init_process_group("nccl", device_id=dev)
     ok = True
-    for n in sizes:  # odd sizes take the one-voxel kernel, multiples of 4 the two-voxel TMA kernel (ragged or not)
-        ok = check(n, rank, world, dev) and ok
+    for mc in ("auto", "off"):  # NVLS multicast / symmetric memory where available, and the CUDA-IPC peer-store path
+        for n in sizes:  # odd sizes take the one-voxel kernel, multiples of 4 the two-voxel TMA kernel (ragged or not)
+            ok = check_dense(n, rank, world, dev, mc) and ok
+        ok = check_split_list(rank, world, dev, mc) and ok
     dist.barrier()
     dist.destroy_process_group()
     if not ok:
         sys.exit(1)
 
 
-def check(n, rank, world, dev):
-    g = torch.Generator(device=dev).manual_seed(100 + rank)
-    x = np.arange(1, 9) * 10.0
-    xt = torch.tensor(x, device=dev, dtype=torch.float32)[:, None]
-    a = 500 + 1000 * torch.rand(n, device=dev, generator=g)
-    t2 = 10 + 70 * torch.rand(n, device=dev, generator=g)
-    y = a * torch.exp(-xt / t2) + 10 * torch.randn(8, n, device=dev, generator=g)
+def check_dense(n, rank, world, dev, mc):
+    y = synth(n, dev, 100 + rank)
     ok = True
-    # default: the one-voxel kernel's warp-transposed peer stores; use_tma=1 (16-byte-aligned pitch only): the
-    # two-voxel TMA kernel with bulk stores of 768-byte row blocks
-    for kw in [dict()] + ([dict(use_tma=1)] if n % 4 == 0 else []):
-        ok = check_one(n, rank, world, dev, x, y, kw) and ok
+    for post in (None, POST):
+        for mask_bits, cols in ((0, [0, 1, 2]), (0b10, [1, 2])):  # all columns / [b or tc, r2]
+            opts, P = A.make_opts(D.monoexponential, p0=(1.0, -1 / 30), post=post)
+            # the NCCL reference must come from the kernel the fused run uses: the two-voxel TMA kernel when the pitch
+            # allows it (n % 4 == 0), else the one-voxel kernel (which a plain fit only uses with fast_path=2)
+            ref_opts, _ = A.make_opts(D.monoexponential, p0=(1.0, -1 / 30), post=post, **({} if n % 4 == 0 else dict(fast_path=2)))
+            popt, r2 = A.fit_device(ref_opts, P, X, y)
+            torch.cuda.synchronize()
+            ref = sharding.gather_maps(torch.cat([popt, r2[:, None]], dim=1)[:, cols].contiguous(), [n] * world)
+            peer = sharding.PeerMaps(n, len(cols), dev, param_mask=mask_bits, multicast=mc)
+            A.fit_device(opts, P, X, y, popt=popt, r2=r2)
+            peer.synchronize()
+            same = torch.equal(peer.local.nan_to_num(-1.0), ref.nan_to_num(-1.0))
+            print(f"[rank {rank}] n={n} cols={cols} post={post is not None} via {peer.transport}: "
+                  f"fused gather == nccl all_gather: {same}", flush=True)
+            peer.close()
+            dist.barrier()
+            ok = ok and same
     return ok
 
 
-def check_one(n, rank, world, dev, x, y, kw):
-    opts, P = A.make_opts(D.monoexponential, p0=(1.0, -1 / 30), **kw)
-    # the NCCL reference must come from the same kernel arithmetic as the fused run: without use_tma=1 the
-    # gather runs in the one-voxel kernel, which a plain fit only uses with fast_path=2 (or an odd pitch)
-    ref_opts, _ = A.make_opts(D.monoexponential, p0=(1.0, -1 / 30), **(kw or dict(fast_path=2)))
+def check_split_list(rank, world, dev, mc):
+    """Masked fit of one volume by all ranks: everyone holds the whole mask, each fits its share of the compacted voxel
+    list from the samples of that share's voxel span only, every rank ends with the complete map."""
+    n = 300_032
+    y_full = synth(n, dev, 7)  # the same volume on every rank (only the rank's span is handed to the fit)
+    g = torch.Generator(device=dev).manual_seed(9)
+    zz = torch.arange(n, device=dev, dtype=torch.float32) / n
+    mask = (torch.rand(n, device=dev, generator=g) < 0.25 * torch.exp(-((zz - 0.3) / 0.1) ** 2)).to(torch.uint8)  # clustered
+    ok = True
+    for post, fill in ((None, float("nan")), (POST, 0.0)):
+        opts, P = A.make_opts(D.monoexponential, p0=(1.0, -1 / 30), post=post)
+        p1, r1 = A.fit_device(opts, P, X, y_full, mask=mask)  # single-GPU masked fit: the expected map
+        torch.cuda.synchronize()
+        expect = torch.stack([p1[:, 1], r1], dim=1)
+        idx = torch.nonzero(mask)[:, 0]
+        b = sharding.list_shares(idx.numel(), world)
+        lo, hi = int(b[rank]), int(b[rank + 1])
+        v_lo = int(idx[lo]) // 4 * 4 if hi > lo else 0  # (span start kept 16-byte aligned)
+        v_hi = int(idx[hi - 1]) + 1 if hi > lo else 0
+        y_span = y_full[:, v_lo:v_hi].contiguous()
+        peer = sharding.PeerMaps(n, 2, dev, total_rows=n, row0=0, param_mask=0b10, split_list=True, y_voxel0=v_lo, multicast=mc)
+        import ctypes
 
-    popt, r2 = A.fit_device(ref_opts, P, x, y)
-    torch.cuda.synchronize()
-    ref = sharding.gather_maps(torch.cat([popt, r2[:, None]], dim=1), [n] * world)
-
-    peer = sharding.PeerMaps(n, P + 1, dev)
-    # plumbing check first: a torch copy into every peer's map
-    for r in range(world):
-        peer.maps[r][rank * n: rank * n + 4, :] = float(rank + 1)
-    peer.synchronize()
-    for r in range(world):
-        assert torch.all(peer.local[r * n: r * n + 4] == float(r + 1)), "peer mapping broken"
-    print(f"[rank {rank}] peer mapping ok", flush=True)
-    A.fit_device(opts, P, x, y, popt=popt, r2=r2)
-    peer.synchronize()
-    same = torch.equal(peer.local.nan_to_num(-1.0), ref.nan_to_num(-1.0))
-    print(f"[rank {rank}] n={n} {kw} fused gather == nccl all_gather: {same}", flush=True)
-    peer.close()
-    dist.barrier()
-    return same
+        from dosma_b200 import _cabi
+        lib, h = _cabi.load(), _cabi.get_handle(dev.index)
+        xs = np.ascontiguousarray(X, dtype=np.float64)
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        _cabi.check(lib.dfit_fit_device(h.ptr, ctypes.byref(opts), 8, n, xs.ctypes.data, y_span.data_ptr(), _cabi.F32,
+                                        _cabi.PLANAR, y_span.stride(0), mask.data_ptr(), None, _cabi.F32, None, None, _cabi.F32,
+                                        None, None, ctypes.c_void_p(stream)))
+        peer.synchronize()
+        same = torch.equal(peer.local.nan_to_num(-7.0), expect.nan_to_num(-7.0))
+        fitted = h.stats()["n_fitted"]
+        print(f"[rank {rank}] split list post={post is not None} via {peer.transport}: share {hi - lo} of {idx.numel()} voxels "
+              f"(fitted {fitted}), span [{v_lo}, {v_hi}); complete map == single-GPU masked fit: {same}", flush=True)
+        peer.close()
+        dist.barrier()
+        ok = ok and same and fitted <= hi - lo
+    return ok
 
 
 if __name__ == "__main__":

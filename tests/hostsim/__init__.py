@@ -57,7 +57,7 @@ def fit(model, x, y, p0=None, dtype="f32", acc64=False, init_mode=0, init_linear
 
 
 def engine_fit(model_id, nparams, x, planes, mask, p0_cols, *, init_mode=0, y_bounds=None, maxfev=100, ftol=1e-5,
-               eps=1e-8, post=None, engine=None):
+               eps=1e-8, post=None, engine=None, out_param=None):
     """TEST-ONLY stand-in for `dosma_b200.fitting._engine_fit` with the same signature and return values: the device
     solver headers compiled by g++ run the fit, the fused epilogue and the mask fill on the host.  It lets the CPU
     suite drive the drop-in's Python layer (argument handling, marshalling, headers) end to end -- e.g. through
@@ -122,4 +122,6 @@ def engine_fit(model_id, nparams, x, planes, mask, p0_cols, *, init_mode=0, y_bo
     stats = {"n_voxels": N, "n_fitted": int(((st >= 1) & (st <= 4)).sum()), "n_failed": int((st >= 5).sum()),
              "n_nonfinite": 0, "n_oob": 0, "sum_iters": int(it.sum()), "max_iters": int(it.max()) if it.size else 0,
              "n_launches": 0, "kernel_ms": -1.0, "total_ms": -1.0}
+    if out_param is not None:
+        popt = np.ascontiguousarray(popt[:, out_param])
     return popt.astype(out_dt), r2.astype(out_dt), stats

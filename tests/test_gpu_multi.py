@@ -19,6 +19,8 @@ def test_fused_gather_matches_nccl():
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
            "--master-addr", "127.0.0.1", "--master-port", "29533",
            os.path.join(ROOT, "tests", "gpu_scripts", "check_fused_gather.py"), "200003", "200192", "200068"]
-    res = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
-    assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
-    assert res.stdout.count("fused gather == nccl all_gather: True") == 5 * world  # 3 sizes, 2 of them also with use_tma=1
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
+    assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]
+    # 2 transports x 3 sizes x (raw, fused epilogue) x (all columns, 8-byte rows); 2 transports x 2 split-list runs
+    assert res.stdout.count("fused gather == nccl all_gather: True") == 2 * 3 * 4 * world, res.stdout[-3000:]
+    assert res.stdout.count("complete map == single-GPU masked fit: True") == 2 * 2 * world, res.stdout[-3000:]
