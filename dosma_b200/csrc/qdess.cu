@@ -59,10 +59,12 @@ __device__ __forceinline__ double qdess_voxel(const QdessArgs& a, double s1, dou
   if (a.decimals >= 0) v = rint(v * a.round_scale) / a.round_scale;
   if (a.wide_masks) {
     if (a.suppress_fat) v = v * (double)(s1 > 0.15 * max1);
-    if (a.suppress_fluid) v = v * (double)((s1 - a.beta * s2) > 0.1 * maxnf);
+    // (numpy rounds beta * S2 before subtracting: no fused multiply-add here -- on integer samples many voxels sit
+    // EXACTLY on the threshold and the last bit decides)
+    if (a.suppress_fluid) v = v * (double)(__dsub_rn(s1, __dmul_rn(a.beta, s2)) > 0.1 * maxnf);
   } else {
     if (a.suppress_fat) v = v * (double)((float)s1 > 0.15f * (float)max1);
-    if (a.suppress_fluid) v = v * (double)(((float)s1 - (float)a.beta * (float)s2) > 0.1f * (float)maxnf);
+    if (a.suppress_fluid) v = v * (double)(__fsub_rn((float)s1, __fmul_rn((float)a.beta, (float)s2)) > 0.1f * (float)maxnf);
   }
   return v;
 }
@@ -78,7 +80,7 @@ __device__ __forceinline__ float qdess_voxel(const QdessArgs& a, float s1, float
   if (a.has_fill && v != v) v = (float)a.fill;
   if (a.decimals >= 0) v = rintf(v * (float)a.round_scale) / (float)a.round_scale;
   if (a.suppress_fat) v = v * (float)(s1 > 0.15f * max1);
-  if (a.suppress_fluid) v = v * (float)((s1 - (float)a.beta * s2) > 0.1f * maxnf);
+  if (a.suppress_fluid) v = v * (float)(__fsub_rn(s1, __fmul_rn((float)a.beta, s2)) > 0.1f * maxnf);
   return v;
 }
 
@@ -128,11 +130,11 @@ __global__ void __launch_bounds__(256) qdess_max_kernel(const void* e1, const vo
     if (wide) {
       const double s1 = load_as<double>(e1, dtype, v), s2 = load_as<double>(e2, dtype, v);
       m1 = fmax(m1, s1);  // (fmax ignores NaN like np.max would not; volumes are finite by construction)
-      m2 = fmax(m2, s1 - beta * s2);
+      m2 = fmax(m2, __dsub_rn(s1, __dmul_rn(beta, s2)));  // (product rounded first, like numpy: see qdess_voxel)
     } else {
       const float s1 = load_as<float>(e1, dtype, v), s2 = load_as<float>(e2, dtype, v);
       m1 = fmax(m1, (double)s1);
-      m2 = fmax(m2, (double)(s1 - (float)beta * s2));
+      m2 = fmax(m2, (double)__fsub_rn(s1, __fmul_rn((float)beta, s2)));
     }
   }
   for (int o = 16; o > 0; o >>= 1) {
