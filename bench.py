@@ -65,22 +65,56 @@ def synth_numpy(n, seed, echoes=ECHOES):
 # ------------------------------------------------------------------------------------------------
 # CPU legs (the only places bench.py touches oracle/)
 # ------------------------------------------------------------------------------------------------
-def cpu_port_rate(n_sample, workers, seed=1234):
-    from oracle import dosma_oracle as O
+_REF = {}
 
+
+def reference_impl():
+    """The CPU implementation the CPU legs time: the UNMODIFIED reference `dosma.core.fitting` from `baseline/_ref`
+    (installed there by `pip install --no-deps --target baseline/_ref /root/reference`; loaded
+    through tests/golden/ref_loader.py, which stands in for the third-party imports the image lacks) -- kind
+    "reference" -- or, where that directory did not travel, the oracle port of the same code -- kind "port"."""
+    if not _REF:
+        ref_root = os.path.join(ROOT, "baseline", "_ref")
+        try:
+            if not os.path.isdir(os.path.join(ref_root, "dosma", "core")):
+                raise FileNotFoundError(ref_root)
+            os.environ["DOSMA_REFERENCE_ROOT"] = ref_root
+            import importlib
+
+            R = importlib.import_module("tests.golden.ref_loader")
+            R.REFERENCE_ROOT = ref_root
+            F, _ = R.load_reference_fitting()
+            _REF.update(kind="reference", curve_fit=F.curve_fit, model=F.monoexponential,
+                        what="dosma.core.fitting.curve_fit of the unmodified reference (baseline/_ref)")
+        except Exception as e:  # noqa: BLE001
+            from oracle import dosma_oracle as O
+
+            _REF.update(kind="port", curve_fit=O.curve_fit, model=O.monoexponential,
+                        what=f"oracle/dosma_oracle.py (baseline/_ref unavailable: {type(e).__name__})")
+    return _REF
+
+
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:  # pragma: no cover
+        return os.cpu_count() or 1
+
+
+def cpu_port_rate(n_sample, workers, seed=1234):
+    impl = reference_impl()
     x, y = synth_numpy(n_sample, seed)
     t0 = time.perf_counter()
-    popt, r2 = O.curve_fit(O.monoexponential, x, y, p0=P0, num_workers=workers if workers > 1 else 0,
-                           chunksize=max(64, min(1000, n_sample // (4 * max(workers, 1)))))
+    popt, r2 = impl["curve_fit"](impl["model"], x, y, p0=P0, num_workers=workers if workers > 1 else 0,
+                                 chunksize=max(64, min(1000, n_sample // (4 * max(workers, 1)))))
     dt = time.perf_counter() - t0
     assert popt.shape == (n_sample, 2)
     return n_sample / dt, dt
 
 
 def cpu_baseline(target_seconds=12.0):
-    from oracle import dosma_oracle as O
-
-    cores = O.host_cores()
+    cores = host_cores()
+    impl = reference_impl()
     rate, _ = cpu_port_rate(256 * cores, cores)  # calibration (dominated by pool start-up: a lower bound)
     n = int(min(max(rate * target_seconds, 1024), 2_000_000))
     rate, dt = cpu_port_rate(n, cores)
@@ -90,9 +124,9 @@ def cpu_baseline(target_seconds=12.0):
     # BASELINE.json's configs[0] names the reference's num_workers=1 case: time that too (a few seconds)
     n1 = int(min(max(rate / max(cores, 1) * 3.0, 512), 65536))
     rate1, dt1 = cpu_port_rate(n1, 1, seed=4321)
-    return {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
+    return {"value": rate, "unit": UNIT, "cores": cores, "kind": impl["kind"],
             "sample": f"{n} voxels of the same workload (seed 1234), scipy.optimize.curve_fit per voxel via "
-                      f"oracle/dosma_oracle.py with a {cores}-process pool, {dt:.1f} s",
+                      f"{impl['what']} with a {cores}-process pool, {dt:.1f} s",
             "single_core_value": rate1, "single_core_sample": f"{n1} voxels, num_workers=1, {dt1:.1f} s"}
 
 
@@ -100,9 +134,8 @@ def run_reference(args):
     rank = env_int("RANK", 0)
     if rank != 0:
         return
-    from oracle import dosma_oracle as O
-
-    cores = O.host_cores()
+    cores = host_cores()
+    impl = reference_impl()
     rate, _ = cpu_port_rate(256 * cores, cores)  # dominated by pool start-up: a lower bound
     rate, _ = cpu_port_rate(int(min(max(rate * 3.0, 2048), 200_000)), cores)  # second, larger calibration sample
     per_step = int(min(max(rate * 8.0, 1024), 1_000_000))  # ~8 s per step
@@ -114,12 +147,12 @@ def run_reference(args):
     dt = time.perf_counter() - t0
     value = per_step * args.steps / dt
     sample = (f"{per_step} voxels per step of the same workload, scipy.optimize.curve_fit per voxel "
-              f"(oracle/dosma_oracle.py, {cores}-process pool)")
+              f"({impl['what']}, {cores}-process pool)")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(args.gpus),
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": impl["kind"], "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -129,6 +162,35 @@ def run_reference(args):
 # ------------------------------------------------------------------------------------------------
 # clocks
 # ------------------------------------------------------------------------------------------------
+def bind_to_gpu_numa_node(local_rank):
+    """Pin this process (and the threads / page-locked allocations it makes from here on) to the CPUs next to its GPU:
+    with one rank per GPU, host staging and the copy threads of `dfit_fit_host` then stay on the socket the GPU's PCIe
+    root hangs off.  Returns a short description for the JSON line, or None when the topology cannot be read."""
+    try:
+        import torch
+
+        bus = torch.cuda.get_device_properties(local_rank).pci_bus_id
+        dom = getattr(torch.cuda.get_device_properties(local_rank), "pci_domain_id", 0)
+        dev = getattr(torch.cuda.get_device_properties(local_rank), "pci_device_id", 0)
+        path = f"/sys/bus/pci/devices/{dom:04x}:{bus:02x}:{dev:02x}.0/local_cpulist"
+        with open(path) as f:
+            spec = f.read().strip()
+        cpus = set()
+        for part in spec.split(","):
+            if "-" in part:
+                a, b = part.split("-")
+                cpus.update(range(int(a), int(b) + 1))
+            elif part:
+                cpus.add(int(part))
+        allowed = cpus & set(os.sched_getaffinity(0))
+        if not allowed:
+            return None
+        os.sched_setaffinity(0, allowed)
+        return f"{len(allowed)} CPUs local to GPU {local_rank} ({spec})"
+    except Exception:  # noqa: BLE001
+        return None
+
+
 class ClockSampler:
     QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
              "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
@@ -142,7 +204,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits", "-lms", "100", "-i",
+                ["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits", "-lms", "50", "-i",
                  str(self.idx)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -195,16 +257,18 @@ def peak_hbm():
 
 
 def recorded_traffic():
-    """dram bytes per launch of the fit kernel from the committed ncu --set full capture, if any."""
+    """DRAM bytes per voxel of the fit kernel from the committed `ncu --set full` capture of this same command
+    (profiles/traffic.json names the capture), or (None, None).  A profiler cannot run inside a timed bench, so the
+    figure is the committed measurement, not one of this run."""
     path = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(path):
         try:
             with open(path) as f:
                 t = json.load(f)
-            return t.get("dram_bytes_per_voxel")
+            return t.get("dram_bytes_per_voxel"), t.get("source")
         except Exception:
-            return None
-    return None
+            return None, None
+    return None, None
 
 
 def run_gpu(args):
@@ -226,6 +290,7 @@ def run_gpu(args):
         raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}; launch with torch.distributed.run")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    numa = bind_to_gpu_numa_node(local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
@@ -244,15 +309,18 @@ def run_gpu(args):
     r2 = torch.empty((n,), dtype=torch.float32, device=dev)
     counts = [n] * world
 
-    # N > 1: the reassembly of the parameter map is fused into the fit kernel's epilogue -- each voxel's
-    # [a, b, r2] row is stored straight into every rank's map over NVLink (dosma_b200.sharding.PeerMaps).
-    # If peer mapping is unavailable the same result is produced by a plain NCCL all-gather.
+    # N > 1: the reassembly of the T2 map is fused into the fit kernel's epilogue -- each voxel's [b, r2] row (what a
+    # T2 map needs of the fit: 8 bytes) is stored straight into every rank's map, by one NVLS multicast store that the
+    # NVSwitch replicates where torch's symmetric memory provides a multicast mapping, else by one peer store per rank
+    # over NVLink (dosma_b200.sharding.PeerMaps).  If neither mapping is available the same map is produced by a plain
+    # NCCL all-gather after the fit.  The local [a, b] / r2 maps are written as at N = 1: same workload per GPU.
+    GATHER_COLS = [1, 2]  # b, r2
     peer = None
     gather_mode = "none"
     if world > 1:
         try:
-            peer = sharding.PeerMaps(n, P + 1, dev)
-            gather_mode = "fused peer stores over NVLink (in-kernel all-gather)"
+            peer = sharding.PeerMaps(n, len(GATHER_COLS), dev, param_mask=0b10)
+            gather_mode = f"fused in-kernel all-gather of [b, r2] rows: {peer.transport}"
         except Exception as e:  # pragma: no cover
             peer = None
             gather_mode = f"nccl all_gather_into_tensor (peer mapping unavailable: {type(e).__name__})"
@@ -263,17 +331,19 @@ def run_gpu(args):
             peer = None
             gather_mode = "nccl all_gather_into_tensor (peer mapping unavailable on some rank)"
 
+    def packed():
+        return torch.cat([popt[:, 1:2], r2[:, None]], dim=1)
+
     def step():
         A.fit_device(opts, P, X_MS, y, popt=popt, r2=r2, handle=handle)
         if world > 1 and peer is None:
-            packed = torch.cat([popt, r2[:, None]], dim=1)
-            return sharding.gather_maps(packed, counts)
+            return sharding.gather_maps(packed(), counts)
         return popt
 
     if peer is not None:  # one-off check of the fused gather against NCCL
         step()
         peer.synchronize()
-        ref = sharding.gather_maps(torch.cat([popt, r2[:, None]], dim=1), counts)
+        ref = sharding.gather_maps(packed(), counts)
         same = torch.equal(peer.local.nan_to_num(-1.0), ref.nan_to_num(-1.0))
         del ref
         if not same:
@@ -284,12 +354,12 @@ def run_gpu(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(args.warmup):
-        step()
-    sync()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+    for _ in range(args.warmup):
+        step()
+    sync()
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
     kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     sync()
@@ -299,13 +369,24 @@ def run_gpu(args):
         A.fit_device(opts, P, X_MS, y, popt=popt, r2=r2, handle=handle)
         kev[k][1].record()
         if world > 1 and peer is None:
-            packed = torch.cat([popt, r2[:, None]], dim=1)
-            sharding.gather_maps(packed, counts)
+            sharding.gather_maps(packed(), counts)
         ev[k + 1].record()
     sync()
     total_ms = ev[0].elapsed_time(ev[-1])
     kernel_ms = float(np.mean([s.elapsed_time(e) for s, e in kev]))
     stats = handle.stats()
+
+    # the same step back to back for >= 1 s: the figure under sustained clocks / power, next to the burst of K steps
+    # above (and long enough for nvidia-smi to see the clocks under load)
+    n_sus = int(min(max(1200.0 / max(total_ms / args.steps, 1e-3), args.steps), 20000))
+    s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sync()
+    s0.record()
+    for _ in range(n_sus):
+        step()
+    s1.record()
+    sync()
+    sustained_ms = s0.elapsed_time(s1)
     clocks = sampler.stop() if rank == 0 else None
     if peer is not None:
         peer.close()
@@ -348,40 +429,74 @@ def run_gpu(args):
         py_s = (time.perf_counter() - t0) / 2
         py_api = {"value": n / py_s, "unit": UNIT, "api": "dosma_b200.curve_fit on pageable numpy arrays, float64 results",
                   "seconds_per_step": py_s}
-        del y_np, p_np, r_np
+        del p_np, r_np
+        # ... and what every DOSMA pipeline calls: MonoExponentialFit.fit on a list of volumes (tc0='polyfit' like
+        # cube_quant.py:172 / mapss.py:172), float64 T2 and r2 maps
+        vols = [D.MedicalVolume(y_np[e].reshape(SHAPE), np.eye(4)) for e in range(ECHOES)]
+        fitter = D.MonoExponentialFit(tc0="polyfit", decimal_precision=1)
+        fitter.fit(xs, vols)
+        t0 = time.perf_counter()
+        for _ in range(2):
+            tc_v, r2_v = fitter.fit(xs, vols)
+        mf_s = (time.perf_counter() - t0) / 2
+        py_api["monoexponentialfit"] = {"value": n / mf_s, "unit": UNIT, "seconds_per_step": mf_s,
+                                        "api": "dosma_b200.MonoExponentialFit(tc0='polyfit').fit on volumes, float64 maps"}
+        del y_np, vols, tc_v, r2_v
 
-    times = torch.tensor([total_ms, e2e_s * 1e3, kernel_ms], dtype=torch.float64, device=dev)
+    times = torch.tensor([total_ms, e2e_s * 1e3, kernel_ms, sustained_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
-    total_ms, e2e_ms, kernel_ms = [float(t) for t in times.tolist()]
+    total_ms, e2e_ms, kernel_ms, sustained_ms = [float(t) for t in times.tolist()]
 
     if rank == 0:
         ms_per_step = total_ms / args.steps
         value = world * n / (ms_per_step * 1e-3)
         peak, peak_src = peak_hbm()
         achieved = n * BYTES_PER_VOXEL / (kernel_ms * 1e-3) / 1e9
-        tpv = recorded_traffic()
+        tpv, traffic_src = recorded_traffic()
+        hbm = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+               "traffic": tpv * n if tpv else None, "traffic_source": traffic_src, "peak_source": peak_src,
+               "kernel": ("dfit::fit_kernel_mono2_tma<MonoExp,8,GATHER=false,float>" if world == 1 else
+                          "dfit::fit_kernel_mono2_tma<MonoExp,8,GATHER=true,float>" if peer is not None else
+                          "dfit::fit_kernel_mono2_tma<MonoExp,8,GATHER=false,float> + ncclAllGather"),
+               "kernel_ms": kernel_ms, "algorithmic_bytes_per_voxel": BYTES_PER_VOXEL,
+               "note": "variable-projection Newton on q = exp(b dx), two voxels per lane, straight-line two-pass fit, "
+                       "tiles staged by TMA; FP32-pipe / issue bound, HBM fraction is the contract figure"}
+        if world == 1:
+            roofline = hbm
+        else:
+            # N > 1: the step is bound by what every GPU must RECEIVE -- (N - 1) ranks' rows of the reassembled map --
+            # against the peer-copy rate measured on this pool (B200_PROFILING.md: 770 GB/s per direction per GPU)
+            ingress = (world - 1) * n * 4 * len(GATHER_COLS)
+            nv = ingress / (ms_per_step * 1e-3) / 1e9
+            roofline = {"bound": "nvlink", "achieved": nv, "peak": 770.0, "unit": "GB/s", "frac": nv / 770.0,
+                        "traffic": None, "peak_source": "measured peer copy per direction per GPU (B200_PROFILING.md)",
+                        "ingress_bytes_per_gpu_per_step": ingress, "row_bytes": 4 * len(GATHER_COLS),
+                        "kernel": hbm["kernel"], "kernel_ms": kernel_ms,
+                        "note": "fused compute + collective: target time = max(fit at the HBM roofline, (N-1) x map bytes / 770 GB/s); "
+                                "the HBM view of the same kernel is in roofline_hbm",
+                        }
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": dict(workload_config(world), gather=gather_mode),
+            "config": workload_config(world),
+            "gather": gather_mode,
             "clocks": clocks,
+            "sustained": {"value": world * n * n_sus / (sustained_ms * 1e-3), "unit": UNIT, "steps": n_sus,
+                          "seconds": sustained_ms * 1e-3, "ms_per_step": sustained_ms / n_sus,
+                          "note": "the same step back to back for >= 1 s (the clock samples cover this region too)"},
             "e2e": {"value": world * n * e2e_steps / (e2e_ms * 1e-3), "unit": UNIT,
                     "h2d_bytes_per_step": 4 * ECHOES * n, "d2h_bytes_per_step": 4 * (P + 1) * n,
-                    "steps": e2e_steps, "launches_per_step": e2e_launches,
+                    "steps": e2e_steps, "launches_per_step": e2e_launches, "host_affinity": numa,
                     "api": "dfit_fit_host (C-ABI), pinned host buffers in and out"},
             "gpu_launches": args.steps * stats["n_launches"],
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": tpv * n if tpv else None, "peak_source": peak_src,
-                         "kernel": ("dfit::fit_kernel_mono2_tma<MonoExp,8>" if world == 1 else
-                                    "dfit::fit_kernel<MonoExp,float,8,true,GATHER>"),
-                         "kernel_ms": kernel_ms, "algorithmic_bytes_per_voxel": BYTES_PER_VOXEL,
-                         "note": "variable-projection Newton on q = exp(b dx), two voxels per lane, tiles staged by "
-                                 "TMA; FP32-pipe / issue bound, HBM fraction is the contract figure"},
+            "roofline": roofline,
             "lm": {"mean_iters": stats["sum_iters"] / max(stats["n_fitted"], 1), "max_iters": stats["max_iters"],
                    "failed_voxels": stats["n_failed"], "fitted_voxels": stats["n_fitted"]},
         }
+        if world > 1:
+            line["roofline_hbm"] = hbm
         if py_api is not None:
             line["e2e_python_api"] = py_api
         if not args.no_cpu and world == 1:

@@ -473,7 +473,9 @@ int dfit_fit_device(dfit_handle* h, const dfit_opts* opts, int n_echo, int64_t n
     return fail(DFIT_ERR_BAD_ARG, "split_list gathers need a mask (of the whole volume) and a scalar initial guess");
   if (gathering && (h->g.cols >> model_nparams(opts->model)) != 0u)
     return fail(DFIT_ERR_BAD_ARG, "gather param_mask names a parameter the model does not have");
-  if (ld < (y_layout == DFIT_PLANAR ? n_vox : (int64_t)n_echo)) return fail(DFIT_ERR_BAD_ARG, "ld too small");
+  // (split-list gathers: y holds only this rank's span of the volume, its pitch is the caller's business)
+  if (!(gathering && h->g.split_list) && ld < (y_layout == DFIT_PLANAR ? n_vox : (int64_t)n_echo))
+    return fail(DFIT_ERR_BAD_ARG, "ld too small");
   CUDA_TRY(cudaSetDevice(h->device));
   cudaStream_t st = (cudaStream_t)stream;  // NULL is the legacy default stream (what torch calls its default stream)
   LaunchDesc d;
