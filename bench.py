@@ -319,7 +319,9 @@ def run_gpu(args):
     gather_mode = "none"
     if world > 1:
         try:
-            peer = sharding.PeerMaps(n, len(GATHER_COLS), dev, param_mask=0b10)
+            # (DFIT_BENCH_MULTICAST=off: peer stores even where a multicast mapping exists -- for A/B runs)
+            peer = sharding.PeerMaps(n, len(GATHER_COLS), dev, param_mask=0b10,
+                                     multicast=os.environ.get("DFIT_BENCH_MULTICAST", "auto"))
             gather_mode = f"fused in-kernel all-gather of [b, r2] rows: {peer.transport}"
         except Exception as e:  # pragma: no cover
             peer = None

@@ -97,6 +97,8 @@ class DfitGatherDesc(ctypes.Structure):
         ("row0", ctypes.c_int64),
         ("param_mask", ctypes.c_uint32),
         ("split_list", ctypes.c_int32),
+        ("fit_lo", ctypes.c_int64),
+        ("fit_hi", ctypes.c_int64),
         ("y_voxel0", ctypes.c_int64),
     ]
 

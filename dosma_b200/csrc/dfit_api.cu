@@ -755,7 +755,12 @@ int dfit_set_gather_ex(dfit_handle* h, const dfit_gather_desc* gd) {
   g.ncols = 0;  // (set per launch: depends on the model)
   g.row0 = gd->row0;
   g.split_list = gd->split_list ? 1 : 0;
+  g.fit_lo = gd->fit_lo;
+  g.fit_hi = gd->fit_hi;
   g.y_voxel0 = gd->y_voxel0;
+  if (g.split_list && !(g.fit_lo >= 0 && g.fit_hi >= g.fit_lo && g.y_voxel0 >= 0 && g.y_voxel0 <= g.fit_lo))
+    return fail(DFIT_ERR_BAD_ARG, "split_list needs 0 <= y_voxel0 <= fit_lo <= fit_hi");
+  if (const char* e = std::getenv("DFIT_MC_WEAK")) g.mc_weak = e[0] == '1';
   h->g = g;
   h->gather_rows = gd->rows;
   return DFIT_OK;

@@ -23,13 +23,15 @@ __global__ void __launch_bounds__(256) mask_compact_kernel(const __grid_constant
   for (int k = 0; k < kCompactPerThread; ++k) {
     const int64_t v = v0 + k * 256 + threadIdx.x;
     const bool in = v < a.n;
-    const bool active = in && a.mask[v] != 0;
+    const bool masked = in && a.mask[v] != 0;
+    // (multi-GPU split mode: masked voxels outside this rank's span are a peer's to fit -- neither listed nor filled)
+    const bool active = masked && (!a.g.split_list || (v >= a.g.fit_lo && v < a.g.fit_hi));
     const unsigned ballot = __ballot_sync(0xffffffffu, active);
     unsigned base = 0;
     if (lane == 0 && ballot) base = atomicAdd(&s_n, (unsigned)__popc(ballot));  // shared-memory atomic
     base = __shfl_sync(0xffffffffu, base, 0);
     if (active) s_list[base + __popc(ballot & ((1u << lane) - 1u))] = (unsigned)v;
-    if (in && !active) {
+    if (in && !masked) {
       T p[P];
       store_voxel<P, T, EMAX>(a, v, p, (T)0, false, ST_SKIPPED, 0);
     }
@@ -72,8 +74,7 @@ __global__ void __launch_bounds__(kBlock, sizeof(T) == 4 ? (EMAX <= 8 ? 8 : 3) :
     return;
   } else {
     // compacted mask path: grid-stride over the index list (its length is only known on the device)
-    unsigned first = 0, count = *a.index_count;
-    if (GATHER && a.g.split_list) list_share(a.g, first, count);  // multi-GPU: this rank's share of the list
+    const unsigned first = 0, count = *a.index_count;
     int it_sum = 0;
     unsigned n_fit = 0, n_fail = 0, n_nf = 0, n_oob = 0;
     for (unsigned i = blockIdx.x * kBlock + threadIdx.x; i < count; i += gridDim.x * kBlock) {

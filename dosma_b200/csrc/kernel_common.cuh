@@ -32,9 +32,11 @@ struct GatherArgs {
   unsigned cols;           // bit i: parameter i is carried in the row (r2 always is, last)
   int ncols;               // floats per row = popcount(cols) + 1
   int64_t row0;            // row of this launch's voxel 0
-  int split_list;          // masked fits: this rank fits entries [count self / world, count (self + 1) / world) of the
-                           // compacted voxel list (every rank compacts the same whole-volume mask)
-  int64_t y_voxel0;        // voxel index of the first sample of `y` (split_list: a rank holds only its span of samples)
+  int split_list;          // masked fits of ONE volume by all ranks: every rank scans the same whole-volume mask, fills
+                           // its own map outside it and fits the masked voxels of its span [fit_lo, fit_hi) only
+  int64_t fit_lo, fit_hi;  // this rank's voxel span (the host balances the spans by masked-voxel count)
+  int64_t y_voxel0;        // voxel index of the first sample of `y` (a rank holds only its span of samples)
+  int mc_weak;             // diagnostic: multicast stores with .weak instead of .relaxed.sys semantics
 };
 
 template <typename T, int EMAX>
@@ -158,6 +160,16 @@ __device__ __forceinline__ void store_vec(TO* __restrict__ dst, const double (&q
 template <int N>
 __device__ __forceinline__ void gather_store(const GatherArgs& g, int64_t off, const float (&w)[N]) {
   static_assert(N == 1 || N == 2 || N == 4, "vector width");
+  if (g.mc != nullptr && g.mc_weak) {
+    float* dst = g.mc + off;
+    if constexpr (N == 4)
+      asm volatile("multimem.st.weak.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(w[0]), "f"(w[1]), "f"(w[2]), "f"(w[3]) : "memory");
+    else if constexpr (N == 2)
+      asm volatile("multimem.st.weak.global.v2.f32 [%0], {%1, %2};" ::"l"(dst), "f"(w[0]), "f"(w[1]) : "memory");
+    else
+      asm volatile("multimem.st.weak.global.f32 [%0], %1;" ::"l"(dst), "f"(w[0]) : "memory");
+    return;
+  }
   if (g.mc != nullptr) {
     float* dst = g.mc + off;
     if constexpr (N == 4)
@@ -177,16 +189,6 @@ __device__ __forceinline__ void gather_store(const GatherArgs& g, int64_t off, c
       else *dst = w[0];
     }
   }
-}
-
-// Split-list mode: this rank's share [first, first + count) of a compacted list of `count` entries (on entry).
-// (The same integer formula as dosma_b200.sharding.voxel_ranges, so that the host knows each rank's voxel span.)
-__device__ __forceinline__ void list_share(const GatherArgs& g, unsigned& first, unsigned& count) {
-  const unsigned long long n = count;
-  const unsigned lo = (unsigned)(n * (unsigned)g.self / (unsigned)g.world);
-  const unsigned hi = (unsigned)(n * ((unsigned)g.self + 1u) / (unsigned)g.world);
-  first = lo;
-  count = hi - lo;
 }
 
 // The row of one voxel: the selected parameters, then r2.  Returns the number of floats.

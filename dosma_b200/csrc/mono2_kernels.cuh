@@ -148,11 +148,10 @@ template <class M, int EMAX, bool GATHER = false>
 __global__ void __launch_bounds__(kBlock, 5) fit_kernel_mono2_list(const __grid_constant__ KernelArgs<float, EMAX> a) {
   typedef float T;
   constexpr int P = 2;
-  // the list entries this launch fits: all of them, or -- multi-GPU split-list mode -- this rank's share
-  unsigned first = 0, count = *a.index_count;
-  if (GATHER && a.g.split_list) list_share(a.g, first, count);
+  // (multi-GPU split mode: the list holds the masked voxels of this rank's span only, see mask_compact_kernel)
+  const unsigned count = *a.index_count;
   const unsigned npairs = (count + 1u) >> 1;
-  const unsigned* __restrict__ list = a.index + first;
+  const unsigned* __restrict__ list = a.index;
   int it_sum = 0, it_max = 0;
   unsigned n_fit = 0, n_fail = 0, n_nf = 0, n_oob = 0;
   for (unsigned i = blockIdx.x * kBlock + threadIdx.x; i < npairs; i += gridDim.x * kBlock) {

@@ -7,7 +7,7 @@ padded to the largest slab so that the reassembly stays a single `all_gather_int
 """
 import numpy as np
 
-__all__ = ["slab_bounds", "voxel_ranges", "list_shares", "gather_maps", "fit_sharded", "PeerMaps"]
+__all__ = ["slab_bounds", "voxel_ranges", "masked_spans", "gather_maps", "fit_sharded", "PeerMaps"]
 
 
 def slab_bounds(n_slices, world_size):
@@ -26,11 +26,22 @@ def voxel_ranges(n_vox, world_size, align=1):
     return np.minimum(b, n_vox)
 
 
-def list_shares(count, world_size):
-    """Boundaries of the ranks' shares of a compacted voxel list of `count` entries: rank r fits entries
-    [b[r], b[r + 1]).  The integer formula of the kernels' split-list mode (`list_share` in csrc/kernel_common.cuh),
-    so that the host can tell which voxel span -- hence which samples -- each rank needs."""
-    return np.asarray([int(count) * r // int(world_size) for r in range(int(world_size) + 1)], dtype=np.int64)
+def masked_spans(mask, world_size, align=4):
+    """Voxel spans [lo_r, hi_r) of the ranks for a masked fit of ONE volume by all ranks (the kernels' split mode,
+    `dfit_gather_desc.split_list`): consecutive, covering the whole volume, cut so that every span holds (nearly) the
+    same number of masked voxels -- the balanced partition of the mask-compacted voxel list, expressed in voxel
+    indices so that each rank knows which samples it needs.  Cuts fall on multiples of `align` voxels.
+    Returns world_size + 1 boundaries."""
+    m = np.asarray(mask).reshape(-1) != 0
+    n = m.shape[0]
+    idx = np.flatnonzero(m)
+    b = [0]
+    for r in range(1, int(world_size)):
+        k = idx.shape[0] * r // int(world_size)
+        cut = int(idx[k]) // align * align if idx.shape[0] else n * r // int(world_size) // align * align
+        b.append(max(cut, b[-1]))
+    b.append(n)
+    return np.asarray(b, dtype=np.int64)
 
 
 def gather_maps(local, counts, group=None):
@@ -90,12 +101,13 @@ class PeerMaps:
     all maps while the fit is running.  `synchronize()` (stream drain + barrier) makes the local map complete.
 
     rows_per_rank, ncols: the dense layout (rank r's voxels are rows [r rows_per_rank, (r + 1) rows_per_rank)).
-    total_rows / row0: any other layout (e.g. the split-list mode: every rank addresses the whole volume, row0 = 0).
+    total_rows / row0: any other layout (e.g. the split mode for masked fits of one volume: every rank addresses the
+    whole volume, row0 = 0, and fits the masked voxels of `fit_span` from samples that start at voxel `y_voxel0`).
     param_mask: parameters carried per row (bit i = parameter i, 0 = all); ncols must equal their number + 1.
     """
 
     def __init__(self, rows_per_rank, ncols, device, group=None, *, total_rows=None, row0=None, param_mask=0,
-                 split_list=False, y_voxel0=0, multicast="auto"):
+                 split_list=False, fit_span=(0, 0), y_voxel0=0, multicast="auto"):
         import ctypes
 
         import torch
@@ -152,6 +164,7 @@ class PeerMaps:
         gd.rows, gd.row0 = rows, row0
         gd.param_mask = int(param_mask)
         gd.split_list = int(bool(split_list))
+        gd.fit_lo, gd.fit_hi = int(fit_span[0]), int(fit_span[1])
         gd.y_voxel0 = int(y_voxel0)
         self._desc = gd
         _cabi.check(lib.dfit_set_gather_ex(self._handle.ptr, ctypes.byref(gd)))

@@ -181,11 +181,11 @@ int dfit_set_gather(dfit_handle* h, int world, int rank, void* const* maps, int6
  * GPU must receive.  `multicast`: an NVLS multicast address bound to the same `world` buffers (e.g. from
  * torch.distributed._symmetric_memory): every row then leaves the GPU once (multimem.st) and the NVSwitch replicates
  * it, instead of `world - 1` peer stores.
- * `split_list` (masked fits, SURVEY.md section 8e: "shard the mask-compacted voxel list"): every rank passes the mask of the WHOLE
- * volume (n_vox = whole volume, the same on all ranks), fills its own map outside the mask and fits only its share
- * [count rank / world, count (rank + 1) / world) of the compacted voxel list -- balanced however the tissue is
- * distributed over the slabs; `y` then holds only the samples of that share's voxel span, y_voxel0 being the voxel
- * index of its first column (dosma_b200.sharding.list_shares computes the spans). */
+ * `split_list` (masked fits of ONE volume by all ranks, SURVEY.md section 8e: "shard the mask-compacted voxel list"): every
+ * rank passes the mask of the WHOLE volume (n_vox = whole volume, the same on all ranks), fills its own map outside
+ * the mask and fits the masked voxels of its voxel span [fit_lo, fit_hi) only -- the host cuts the spans so that each
+ * holds the same number of masked voxels however the tissue is distributed (dosma_b200.sharding.masked_spans); `y`
+ * then holds only the samples of the span, y_voxel0 <= fit_lo being the voxel index of its first column. */
 typedef struct dfit_gather_desc {
   int32_t struct_size; /* sizeof(dfit_gather_desc) */
   int32_t world, rank;
@@ -195,6 +195,7 @@ typedef struct dfit_gather_desc {
   int64_t row0;        /* row of voxel 0 of this rank's dfit_fit_device calls */
   uint32_t param_mask;
   int32_t split_list;
+  int64_t fit_lo, fit_hi;
   int64_t y_voxel0;
 } dfit_gather_desc;
 int dfit_set_gather_ex(dfit_handle* h, const dfit_gather_desc* g); /* g == NULL or g->world == 0 clears */

@@ -87,12 +87,13 @@ def check_split_list(rank, world, dev, mc):
         torch.cuda.synchronize()
         expect = torch.stack([p1[:, 1], r1], dim=1)
         idx = torch.nonzero(mask)[:, 0]
-        b = sharding.list_shares(idx.numel(), world)
-        lo, hi = int(b[rank]), int(b[rank + 1])
-        v_lo = int(idx[lo]) // 4 * 4 if hi > lo else 0  # (span start kept 16-byte aligned)
-        v_hi = int(idx[hi - 1]) + 1 if hi > lo else 0
+        b = sharding.masked_spans(mask.cpu().numpy(), world)
+        v_lo, v_hi = int(b[rank]), int(b[rank + 1])
+        share = int(mask[v_lo:v_hi].sum())
+        lo, hi = int(mask[:v_lo].sum()), int(mask[:v_lo].sum()) + share
         y_span = y_full[:, v_lo:v_hi].contiguous()
-        peer = sharding.PeerMaps(n, 2, dev, total_rows=n, row0=0, param_mask=0b10, split_list=True, y_voxel0=v_lo, multicast=mc)
+        peer = sharding.PeerMaps(n, 2, dev, total_rows=n, row0=0, param_mask=0b10, split_list=True, fit_span=(v_lo, v_hi),
+                                 y_voxel0=v_lo, multicast=mc)
         import ctypes
 
         from dosma_b200 import _cabi
@@ -104,12 +105,20 @@ def check_split_list(rank, world, dev, mc):
                                         None, None, ctypes.c_void_p(stream)))
         peer.synchronize()
         same = torch.equal(peer.local.nan_to_num(-7.0), expect.nan_to_num(-7.0))
+        if not same:  # say where: inside / outside the mask, own share / the peers'
+            bad = (peer.local.nan_to_num(-7.0) != expect.nan_to_num(-7.0)).any(dim=1)
+            inside = mask.bool()
+            own = torch.zeros(n, dtype=torch.bool, device=dev)
+            own[idx[lo:hi]] = True
+            print(f"[rank {rank}] MISMATCH rows: {int(bad.sum())} (inside mask {int((bad & inside).sum())}, own share "
+                  f"{int((bad & own).sum())}, outside mask {int((bad & ~inside).sum())}); first: "
+                  f"{[(int(i), peer.local[i].tolist(), expect[i].tolist()) for i in torch.nonzero(bad)[:4, 0]]}", flush=True)
         fitted = h.stats()["n_fitted"]
         print(f"[rank {rank}] split list post={post is not None} via {peer.transport}: share {hi - lo} of {idx.numel()} voxels "
               f"(fitted {fitted}), span [{v_lo}, {v_hi}); complete map == single-GPU masked fit: {same}", flush=True)
         peer.close()
         dist.barrier()
-        ok = ok and same and fitted <= hi - lo
+        ok = ok and same and fitted <= hi - lo and abs(share - idx.numel() / world) < 8
     return ok
 
 

@@ -134,3 +134,21 @@ def test_partition_helpers():
     assert b.tolist() == [0, 3, 6, 8, 10]
     r = S.voxel_ranges(1000, 3, align=128)
     assert r[0] == 0 and r[-1] == 1000 and all(x % 128 == 0 for x in r[:-1]) and np.all(np.diff(r) >= 0)
+
+
+def test_masked_spans_balance_a_clustered_mask():
+    """`sharding.masked_spans`: consecutive spans covering the volume, each with (nearly) the same number of masked
+    voxels however the tissue is clustered; cuts on aligned voxel indices; degenerate masks."""
+    from dosma_b200 import sharding as S
+
+    rng = np.random.default_rng(0)
+    n = 200_000
+    z = np.arange(n) / n
+    mask = rng.random(n) < 0.3 * np.exp(-((z - 0.7) / 0.05) ** 2)  # all the tissue in a thin slab
+    for world in (1, 2, 3, 8):
+        b = S.masked_spans(mask, world)
+        assert b[0] == 0 and b[-1] == n and len(b) == world + 1 and (np.diff(b) >= 0).all() and (b[1:-1] % 4 == 0).all()
+        counts = [int(mask[b[r]:b[r + 1]].sum()) for r in range(world)]
+        assert sum(counts) == int(mask.sum()) and max(counts) - min(counts) <= 4
+    assert S.masked_spans(np.zeros(100, bool), 4).tolist() == [0, 24, 48, 72, 100]
+    assert S.masked_spans(np.ones(10, bool), 2).tolist() == [0, 4, 10]
