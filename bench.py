@@ -319,9 +319,11 @@ def run_gpu(args):
     gather_mode = "none"
     if world > 1:
         try:
-            # (DFIT_BENCH_MULTICAST=off: peer stores even where a multicast mapping exists -- for A/B runs)
+            # Peer stores by default: a multicast store also delivers the rank's OWN copy through the switch, so every
+            # GPU receives N instead of N - 1 maps -- measured slower (2 GPUs: 1.42 against 0.83 ms per step).
+            # DFIT_BENCH_MULTICAST=auto selects the NVLS multicast path where torch's symmetric memory offers it.
             peer = sharding.PeerMaps(n, len(GATHER_COLS), dev, param_mask=0b10,
-                                     multicast=os.environ.get("DFIT_BENCH_MULTICAST", "auto"))
+                                     multicast=os.environ.get("DFIT_BENCH_MULTICAST", "off"))
             gather_mode = f"fused in-kernel all-gather of [b, r2] rows: {peer.transport}"
         except Exception as e:  # pragma: no cover
             peer = None

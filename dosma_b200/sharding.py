@@ -104,10 +104,13 @@ class PeerMaps:
     total_rows / row0: any other layout (e.g. the split mode for masked fits of one volume: every rank addresses the
     whole volume, row0 = 0, and fits the masked voxels of `fit_span` from samples that start at voxel `y_voxel0`).
     param_mask: parameters carried per row (bit i = parameter i, 0 = all); ncols must equal their number + 1.
+    multicast: "off" (default: one peer store per rank), "auto" (NVLS multicast stores where available) or "require".
+        A multicast store also delivers the rank's own copy through the switch -- N instead of N - 1 maps arrive at every
+        GPU -- and measured slower than peer stores on this pool; it saves SM store instructions.
     """
 
     def __init__(self, rows_per_rank, ncols, device, group=None, *, total_rows=None, row0=None, param_mask=0,
-                 split_list=False, fit_span=(0, 0), y_voxel0=0, multicast="auto"):
+                 split_list=False, fit_span=(0, 0), y_voxel0=0, multicast="off"):
         import ctypes
 
         import torch
@@ -129,6 +132,8 @@ class PeerMaps:
         self.transport = None
         mc_ptr = 0
         ptrs = None
+        if multicast not in ("off", "auto", "require"):
+            raise ValueError("multicast must be 'off', 'auto' or 'require'")
         if multicast != "off":
             ptrs, mc_ptr = self._try_symmetric(shape, device, group)
         if ptrs is None:
