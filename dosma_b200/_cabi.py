@@ -115,6 +115,7 @@ class DfitStats(ctypes.Structure):
         ("n_launches", ctypes.c_int32),
         ("kernel_ms", ctypes.c_float),
         ("total_ms", ctypes.c_float),
+        ("n_deferred", ctypes.c_int64),
     ]
 
     def as_dict(self):

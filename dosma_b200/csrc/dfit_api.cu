@@ -1,7 +1,10 @@
 // C-ABI of libdfit.so (include/dfit.h): handles, streams, chunked host<->device pipeline, dispatch.
 // Device code only -- there is deliberately no host implementation of the fit in this library.
 #include <cuda_runtime.h>
+#include <pthread.h>
+#include <sched.h>
 
+#include <cctype>
 #include <chrono>
 #include <cmath>
 #include <cstdarg>
@@ -42,13 +45,30 @@ int ensure(DevBuf& b, size_t bytes) {
   return DFIT_OK;
 }
 
-int ensure_host(HostBuf& b, size_t bytes) {
+int ensure_host(HostBuf& b, size_t bytes, const cpu_set_t* cpus) {
   if (bytes <= b.cap) return DFIT_OK;
   if (b.p) cudaFreeHost(b.p);
   b.p = nullptr;
   b.cap = 0;
   const size_t want = bytes + (bytes >> 3) + 256;
-  CUDA_TRY(cudaHostAlloc(&b.p, want, cudaHostAllocDefault));
+  if (cpus) {
+    // allocated (and first touched) by a thread on the GPU's NUMA node, so that the pages live next to the PCIe root
+    cudaError_t err = cudaSuccess;
+    int device = 0;
+    cudaGetDevice(&device);
+    void* p = nullptr;
+    std::thread t([&] {
+      pthread_setaffinity_np(pthread_self(), sizeof(cpu_set_t), cpus);
+      cudaSetDevice(device);
+      err = cudaHostAlloc(&p, want, cudaHostAllocDefault);
+      if (err == cudaSuccess) std::memset(p, 0, want);
+    });
+    t.join();
+    CUDA_TRY(err);
+    b.p = p;
+  } else {
+    CUDA_TRY(cudaHostAlloc(&b.p, want, cudaHostAllocDefault));
+  }
   b.cap = want;
   return DFIT_OK;
 }
@@ -65,7 +85,15 @@ struct CopySeg {
   size_t bytes;
 };
 
+// Worker threads of the host-side copies run on the CPUs next to the GPU (set per call by the entry points).
+thread_local const cpu_set_t* g_worker_cpus = nullptr;
+
+inline void bind_worker(const cpu_set_t* cpus) {
+  if (cpus) pthread_setaffinity_np(pthread_self(), sizeof(cpu_set_t), cpus);
+}
+
 void par_copy(const CopySeg* segs, int count) {
+  const cpu_set_t* cpus = g_worker_cpus;
   constexpr size_t kBlk = (size_t)1 << 20;
   size_t total_blocks = 0;
   for (int i = 0; i < count; ++i) total_blocks += (segs[i].bytes + kBlk - 1) / kBlk;
@@ -89,7 +117,11 @@ void par_copy(const CopySeg* segs, int count) {
   }
   std::vector<std::thread> th;
   th.reserve(nt - 1);
-  for (int t = 1; t < nt; ++t) th.emplace_back(work, t);
+  for (int t = 1; t < nt; ++t)
+    th.emplace_back([&work, cpus, t] {
+      bind_worker(cpus);
+      work(t);
+    });
   work(0);
   for (auto& x : th) x.join();
 }
@@ -97,6 +129,7 @@ void par_copy(const CopySeg* segs, int count) {
 // Generic static partition of [0, n) over a few host threads.
 template <class F>
 void par_for(int64_t n, int64_t grain, F fn) {
+  const cpu_set_t* cpus = g_worker_cpus;
   unsigned hw = std::thread::hardware_concurrency();
   int nt = (int)(hw == 0 ? 4 : (hw > 16 ? 16 : hw));
   const int64_t nb = (n + grain - 1) / grain;
@@ -112,7 +145,11 @@ void par_for(int64_t n, int64_t grain, F fn) {
   };
   std::vector<std::thread> th;
   th.reserve(nt - 1);
-  for (int t = 1; t < nt; ++t) th.emplace_back(work, t);
+  for (int t = 1; t < nt; ++t)
+    th.emplace_back([&work, cpus, t] {
+      bind_worker(cpus);
+      work(t);
+    });
   work(0);
   for (auto& x : th) x.join();
 }
@@ -415,6 +452,40 @@ int dfit_create(int device, dfit_handle** out) {
                 prop.major, prop.minor);
   }
   h->sm_count = prop.multiProcessorCount;
+  {
+    const char* off = std::getenv("DFIT_HOST_AFFINITY");
+    char bus[32] = "";
+    if (!(off && off[0] == '0') && cudaDeviceGetPCIBusId(bus, sizeof(bus), device) == cudaSuccess) {
+      for (char* c = bus; *c; ++c) *c = (char)std::tolower((unsigned char)*c);
+      char path[128];
+      std::snprintf(path, sizeof(path), "/sys/bus/pci/devices/%s/local_cpulist", bus);
+      if (FILE* f = std::fopen(path, "r")) {
+        char line[4096];
+        if (std::fgets(line, sizeof(line), f)) {
+          CPU_ZERO(&h->local_cpus);
+          int n_set = 0;
+          for (char* tok = std::strtok(line, ",\n"); tok; tok = std::strtok(nullptr, ",\n")) {
+            int a = 0, b = 0;
+            const int k = std::sscanf(tok, "%d-%d", &a, &b);
+            if (k == 1) b = a;
+            if (k >= 1)
+              for (int c = a; c <= b && c < CPU_SETSIZE; ++c) {
+                CPU_SET(c, &h->local_cpus);
+                ++n_set;
+              }
+          }
+          // only CPUs this process may run on; none left (cgroup elsewhere): no binding
+          cpu_set_t allowed;
+          if (n_set > 0 && sched_getaffinity(0, sizeof(allowed), &allowed) == 0) {
+            CPU_AND(&h->local_cpus, &h->local_cpus, &allowed);
+            h->have_local_cpus = CPU_COUNT(&h->local_cpus) > 0;
+          }
+        }
+        std::fclose(f);
+      }
+    }
+    cudaGetLastError();
+  }
   CUDA_TRY(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
   for (int s = 0; s < kSlots; ++s) {
     CUDA_TRY(cudaStreamCreateWithFlags(&h->slots[s].stream, cudaStreamNonBlocking));
@@ -570,6 +641,8 @@ static int fit_host_impl(dfit_handle* h, const dfit_opts* opts, int n_echo, int6
     if (!y_planes[e]) return fail(DFIT_ERR_BAD_ARG, "y_planes[%d] is NULL", e);
   CUDA_TRY(cudaSetDevice(h->device));
   const auto t0 = std::chrono::steady_clock::now();
+  const cpu_set_t* cpus = h->have_local_cpus ? &h->local_cpus : nullptr;
+  g_worker_cpus = cpus;
   const int P = model_nparams(opts->model);
   const int PW = opts->out_param >= 0 ? 1 : P;  // parameters written per voxel
   // fp32 arithmetic with float64 result maps (the reference's dtype, fitting.py:870): the maps cross PCIe as float32 --
@@ -652,7 +725,7 @@ static int fit_host_impl(dfit_handle* h, const dfit_opts* opts, int n_echo, int6
     if (niter && (rc = ensure(sl.niter, (size_t)chunk)) != DFIT_OK) return rc;
     cudaStream_t st = sl.stream;
     if (in_pageable) {
-      if ((rc = ensure_host(sl.hin, (size_t)n_echo * chunk * ysz)) != DFIT_OK) return rc;
+      if ((rc = ensure_host(sl.hin, (size_t)n_echo * chunk * ysz, cpus)) != DFIT_OK) return rc;
       if (idx >= kSlots) CUDA_TRY(cudaEventSynchronize(sl.ev_in));  // the DMA that last read this staging block is done
       CopySeg segs[DFIT_MAX_ECHOES];
       for (int e = 0; e < n_echo; ++e)
@@ -698,8 +771,8 @@ static int fit_host_impl(dfit_handle* h, const dfit_opts* opts, int n_echo, int6
     CUDA_TRY(dispatch(d));
     h->last_launches += mask && d.tmap == nullptr ? 2 : 1;
     if (out_pageable) {
-      if ((rc = ensure_host(sl.hpopt, (size_t)chunk * PW * osz)) != DFIT_OK) return rc;
-      if ((rc = ensure_host(sl.hr2, (size_t)chunk * osz)) != DFIT_OK) return rc;
+      if ((rc = ensure_host(sl.hpopt, (size_t)chunk * PW * osz, cpus)) != DFIT_OK) return rc;
+      if ((rc = ensure_host(sl.hr2, (size_t)chunk * osz, cpus)) != DFIT_OK) return rc;
       CUDA_TRY(cudaMemcpyAsync(sl.hpopt.p, sl.popt.p, (size_t)n * PW * osz, cudaMemcpyDeviceToHost, st));
       CUDA_TRY(cudaMemcpyAsync(sl.hr2.p, sl.r2.p, (size_t)n * osz, cudaMemcpyDeviceToHost, st));
       CUDA_TRY(cudaEventRecord(sl.ev_out, st));
@@ -854,6 +927,7 @@ int dfit_get_stats(dfit_handle* h, dfit_stats* out) {
   out->n_oob = (int64_t)c[CNT_OOB];
   out->sum_iters = (int64_t)c[CNT_ITERS];
   out->max_iters = (int32_t)c[CNT_MAXITER];
+  out->n_deferred = (int64_t)c[CNT_DEFERRED];
   out->n_launches = h->last_launches;
   out->kernel_ms = kms;
   out->total_ms = h->last_total_ms;

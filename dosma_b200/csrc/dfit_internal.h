@@ -3,6 +3,7 @@
 #pragma once
 
 #include <cuda_runtime.h>
+#include <sched.h>
 
 #include <cstdarg>
 #include <cstdio>
@@ -39,7 +40,7 @@ struct HostBuf {
   size_t cap = 0;
 };
 
-int ensure_host(HostBuf& b, size_t bytes);
+int ensure_host(HostBuf& b, size_t bytes, const cpu_set_t* cpus = nullptr);
 
 struct Slot {
   cudaStream_t stream = nullptr;
@@ -65,6 +66,10 @@ struct dfit_handle {
   float host_kernel_ms = -1.f;
   dfit::GatherArgs g = {};     // fused all-gather (dfit_set_gather / dfit_set_gather_ex); g.world == 0: off
   int64_t gather_rows = 0;     // rows in every map
+  // CPUs on the NUMA node the GPU's PCIe root hangs off (sysfs local_cpulist): the host threads that fill / drain /
+  // widen the staging blocks run there, and the page-locked staging is allocated from there (DFIT_HOST_AFFINITY=0: off)
+  cpu_set_t local_cpus;
+  bool have_local_cpus = false;
   dfit::DevBuf scratch;    // small device scratch (qDESS maxima, metrics partials)
   dfit::DevBuf index_buf;  // compacted voxel list of the masked device path
 };

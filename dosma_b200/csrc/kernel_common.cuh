@@ -17,7 +17,7 @@ constexpr int kBlock = 128;
 
 enum DType : int { DT_F32 = 0, DT_F64 = 1, DT_I16 = 2, DT_U16 = 3, DT_I32 = 4, DT_U8 = 5 };
 enum Layout : int { LAYOUT_PLANAR = 0, LAYOUT_ECHO_FASTEST = 1 };
-enum Counter : int { CNT_FITTED = 0, CNT_FAILED, CNT_NONFINITE, CNT_OOB, CNT_ITERS, CNT_MAXITER, CNT_COUNT };
+enum Counter : int { CNT_FITTED = 0, CNT_FAILED, CNT_NONFINITE, CNT_OOB, CNT_ITERS, CNT_MAXITER, CNT_DEFERRED, CNT_COUNT };
 constexpr int kStatSlots = 1024;  // power of two
 constexpr int kMaxPeers = 8;
 
@@ -180,9 +180,13 @@ __device__ __forceinline__ void gather_store(const GatherArgs& g, int64_t off, c
       asm volatile("multimem.st.relaxed.sys.global.f32 [%0], %1;" ::"l"(dst), "f"(w[0]) : "memory");
     return;
   }
+  // (each rank starts with its own map and goes round the ring from there: at any moment the ranks address
+  // different destinations instead of all converging on the same GPU)
 #pragma unroll
-  for (int r = 0; r < kMaxPeers; ++r) {
-    if (r < g.world) {
+  for (int k = 0; k < kMaxPeers; ++k) {
+    if (k < g.world) {
+      int r = g.self + k;
+      if (r >= g.world) r -= g.world;
       float* dst = g.maps[r] + off;
       if constexpr (N == 4) *reinterpret_cast<float4*>(dst) = make_float4(w[0], w[1], w[2], w[3]);
       else if constexpr (N == 2) *reinterpret_cast<float2*>(dst) = make_float2(w[0], w[1]);
@@ -301,8 +305,10 @@ __device__ __forceinline__ void store_voxel(const KernelArgs<T, EMAX>& a, int64_
       }
       const int64_t block0 = (a.g.row0 + (v - lane)) * C;
 #pragma unroll
-      for (int r = 0; r < kMaxPeers; ++r) {
-        if (r < a.g.world) {
+      for (int k2 = 0; k2 < kMaxPeers; ++k2) {
+        if (k2 < a.g.world) {
+          int r = a.g.self + k2;  // (own map first, then round the ring: see gather_store)
+          if (r >= a.g.world) r -= a.g.world;
           float* dst = a.g.maps[r] + block0 + lane;  // local HBM for r == own rank, a peer's over NVLink otherwise
 #pragma unroll
           for (int k = 0; k < C; ++k) dst[k * 32] = word[k];

@@ -295,7 +295,7 @@ __global__ void __launch_bounds__(kM2Warps * 32, m2_min_ctas(EMAX))
   }
   __syncwarp();
 
-  unsigned n_fast = 0, n_fit = 0, n_fail = 0, n_nf = 0, n_oob = 0, it_sum = 0, it_max = 0;
+  unsigned n_fast = 0, n_fit = 0, n_fail = 0, n_nf = 0, n_oob = 0, it_sum = 0, it_max = 0, n_deferred = 0;
   int n_def = 0;  // entries in this warp's queue (warp-uniform)
   // fp32 maps (raw parameters or the fp32 form of the fused epilogue) and nothing else to write: two vector stores per lane
   const bool plain = a.out_dtype == DT_F32 && a.popt != nullptr && a.status == nullptr && a.niter == nullptr;
@@ -418,6 +418,7 @@ __global__ void __launch_bounds__(kM2Warps * 32, m2_min_ctas(EMAX))
       if (defA) defer_q[warp][n_def + __popc(mA & below)] = (unsigned)v0;
       if (defB) defer_q[warp][n_def + nA + __popc(mB & below)] = (unsigned)(v0 + 1);
       n_def += nA + __popc(mB);
+      if (lane == 0) n_deferred += (unsigned)(nA + __popc(mB));
       __syncwarp();
       if (n_def >= 32) {
         do {
@@ -447,6 +448,7 @@ __global__ void __launch_bounds__(kM2Warps * 32, m2_min_ctas(EMAX))
       if (c_oob) atomicAdd(stat_slot + CNT_OOB, (unsigned long long)c_oob);
       if (its) atomicAdd(stat_slot + CNT_ITERS, its);
       if (c_max) atomicMax(stat_slot + CNT_MAXITER, (unsigned long long)c_max);
+      if (n_deferred) atomicAdd(stat_slot + CNT_DEFERRED, (unsigned long long)n_deferred);
     }
   }
 }

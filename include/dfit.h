@@ -138,6 +138,8 @@ typedef struct dfit_stats {
   int32_t n_launches;   /* kernels launched by the call */
   float kernel_ms;      /* device time of the fit kernel(s), CUDA events on the engine's stream */
   float total_ms;       /* device time of the whole call incl. copies (host entry point only) */
+  int64_t n_deferred;   /* dense two-voxel TMA kernel: voxels the straight-line fast path turned down (they are queued per
+                           warp and fitted 32 at a time by the one-voxel path: Newton loop, then LM from p0) */
 } dfit_stats;
 
 typedef struct dfit_handle dfit_handle;

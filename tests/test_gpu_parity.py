@@ -125,7 +125,10 @@ def test_low_snr_failure_rate(D):
     fail = np.isnan(popt[:, 0])
     ref_fail = np.isnan(c["popt"][:, 0])
     assert np.isnan(popt[fail]).all() and (r2[fail] == 0).all()
-    assert abs(fail.mean() - ref_fail.mean()) < 0.05, (fail.mean(), ref_fail.mean())
+    # measured on this fixture (SNR 5, 2048 voxels): reference 1.4 % failures, engine 2.0 % (2.2 % with the LM only),
+    # symmetric difference of the two sets 1.0 % -- bounded at a few voxels above that, not at percentage points
+    assert abs(fail.mean() - ref_fail.mean()) < 0.012, (fail.mean(), ref_fail.mean())
+    assert (fail ^ ref_fail).mean() < 0.02, (fail ^ ref_fail).mean()
 
 
 @pytest.mark.parametrize("name", ["curvefit_biexp16_clean_f32"])
