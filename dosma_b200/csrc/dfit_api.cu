@@ -1,6 +1,9 @@
 // C-ABI of libdfit.so (include/dfit.h): handles, streams, chunked host<->device pipeline, dispatch.
 // Device code only -- there is deliberately no host implementation of the fit in this library.
 #include <cuda_runtime.h>
+#if defined(__SSE2__)
+#include <emmintrin.h>
+#endif
 #include <pthread.h>
 #include <sched.h>
 
@@ -92,6 +95,40 @@ inline void bind_worker(const cpu_set_t* cpus) {
   if (cpus) pthread_setaffinity_np(pthread_self(), sizeof(cpu_set_t), cpus);
 }
 
+// memcpy with streaming (non-temporal) stores: the destination -- a staging block about to be DMA'd, or a result array
+// the caller reads later -- is not wanted in the cache, and a regular store would first READ every destination line
+// (read for ownership): a third of the memory traffic of these copies, which are bandwidth-bound.
+inline void stream_copy(void* dst, const void* src, size_t bytes) {
+#if defined(__SSE2__)
+  char* d = static_cast<char*>(dst);
+  const char* s = static_cast<const char*>(src);
+  const size_t head = (16 - (reinterpret_cast<uintptr_t>(d) & 15)) & 15;
+  if (bytes < 256 + head) {
+    std::memcpy(d, s, bytes);
+    return;
+  }
+  std::memcpy(d, s, head);
+  d += head;
+  s += head;
+  bytes -= head;
+  const size_t blocks = bytes / 64;
+  for (size_t i = 0; i < blocks; ++i, d += 64, s += 64) {
+    const __m128i a = _mm_loadu_si128(reinterpret_cast<const __m128i*>(s));
+    const __m128i b = _mm_loadu_si128(reinterpret_cast<const __m128i*>(s + 16));
+    const __m128i c = _mm_loadu_si128(reinterpret_cast<const __m128i*>(s + 32));
+    const __m128i e = _mm_loadu_si128(reinterpret_cast<const __m128i*>(s + 48));
+    _mm_stream_si128(reinterpret_cast<__m128i*>(d), a);
+    _mm_stream_si128(reinterpret_cast<__m128i*>(d + 16), b);
+    _mm_stream_si128(reinterpret_cast<__m128i*>(d + 32), c);
+    _mm_stream_si128(reinterpret_cast<__m128i*>(d + 48), e);
+  }
+  std::memcpy(d, s, bytes - blocks * 64);
+  _mm_sfence();
+#else
+  std::memcpy(dst, src, bytes);
+#endif
+}
+
 void par_copy(const CopySeg* segs, int count) {
   const cpu_set_t* cpus = g_worker_cpus;
   constexpr size_t kBlk = (size_t)1 << 20;
@@ -107,7 +144,7 @@ void par_copy(const CopySeg* segs, int count) {
       for (size_t k = 0; k < nb; ++k, ++b) {
         if ((int)(b % (size_t)nt) != t) continue;
         const size_t off = k * kBlk, len = segs[i].bytes - off < kBlk ? segs[i].bytes - off : kBlk;
-        std::memcpy((char*)segs[i].dst + off, (const char*)segs[i].src + off, len);
+        stream_copy((char*)segs[i].dst + off, (const char*)segs[i].src + off, len);
       }
     }
   };
@@ -158,18 +195,34 @@ void par_for(int64_t n, int64_t grain, F fn) {
 // device (v = fl32(m / scale), m an integer below 2^22): it is put back onto the float64 grid with numpy.around's own
 // formula, rint(v scale) / scale, which recovers m exactly; other columns (and NaN / inf) are widened as they are.
 void par_widen(double* dst, const float* src, int64_t n, int ncols, const double* scale) {
-  par_for(n, (int64_t)1 << 17, [&](int64_t lo, int64_t hi) {
-    if (ncols == 1) {
-      const double s = scale[0];
-      if (s > 0) for (int64_t i = lo; i < hi; ++i) dst[i] = std::nearbyint((double)src[i] * s) / s;
-      else for (int64_t i = lo; i < hi; ++i) dst[i] = (double)src[i];
-      return;
+  // flat element range [lo, hi) of the (n, ncols) map; element k belongs to column k % ncols
+  par_for(n * ncols, (int64_t)1 << 18, [&](int64_t lo, int64_t hi) {
+    auto one = [&](int64_t k) {
+      const double v = (double)src[k], s = scale[ncols == 1 ? 0 : k % ncols];
+      return s > 0 ? std::nearbyint(v * s) / s : v;
+    };
+#if defined(__SSE2__)
+    // streaming stores, two doubles at a time (see stream_copy); the pair (k, k + 1) starts on a 16-byte boundary
+    int64_t k = lo;
+    while (k < hi && (reinterpret_cast<uintptr_t>(dst + k) & 15)) {
+      dst[k] = one(k);
+      ++k;
     }
-    for (int64_t i = lo; i < hi; ++i)
-      for (int c = 0; c < ncols; ++c) {
-        const double v = (double)src[i * ncols + c], s = scale[c];
-        dst[i * ncols + c] = s > 0 ? std::nearbyint(v * s) / s : v;
+    bool any_scale = false;
+    for (int c = 0; c < ncols; ++c) any_scale = any_scale || scale[c] > 0;
+    if (!any_scale) {
+      for (; k + 4 <= hi; k += 4) {
+        const __m128 f = _mm_loadu_ps(src + k);
+        _mm_stream_pd(dst + k, _mm_cvtps_pd(f));
+        _mm_stream_pd(dst + k + 2, _mm_cvtps_pd(_mm_movehl_ps(f, f)));
       }
+    }
+    for (; k + 2 <= hi; k += 2) _mm_stream_pd(dst + k, _mm_set_pd(one(k + 1), one(k)));
+    for (; k < hi; ++k) dst[k] = one(k);
+    _mm_sfence();
+#else
+    for (int64_t k = lo; k < hi; ++k) dst[k] = one(k);
+#endif
   });
 }
 

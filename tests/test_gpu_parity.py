@@ -681,6 +681,43 @@ def test_patch_dosma_swaps_the_engine_in(D):
                 sys.modules[n] = m
 
 
+def test_host_widening_equals_device_float64_maps(D, monkeypatch):
+    """fp32 arithmetic with float64 result maps: by default the maps cross PCIe as float32 and the host threads widen
+    them (rounded parameters back onto numpy's decimal grid); DFIT_HOST_WIDEN=0 has the device write float64.  Raw
+    parameters, r2 and rounded time constants must be bit-identical either way; an unrounded 1/|b| carries the float32
+    rounding of the epilogue's result (1e-7 relative)."""
+    rng = np.random.default_rng(12)
+    x = np.arange(1, 9) * 10.0
+    n = 300_001
+    t2 = rng.uniform(5, 130, n)
+    y = (rng.uniform(500, 1500, n) * np.exp(-x[:, None] / t2) + rng.normal(0, 10, (8, n))).astype(np.float32)
+    shape = (n, 1, 1)
+    vols = [D.MedicalVolume(y[e].reshape(shape), np.eye(4)) for e in range(8)]
+    mask = rng.random(shape) > 0.2
+
+    def run():
+        out = [D.curve_fit(D.monoexponential, x, y, p0=(1.0, -1 / 30))]
+        out.append(tuple(v.volume for v in D.MonoExponentialFit(tc0="polyfit", decimal_precision=1).fit(x, vols)))
+        out.append(tuple(v.volume for v in D.MonoExponentialFit(decimal_precision=3, bounds=(0, 60)).fit(x, vols, mask=mask)))
+        f = D.CurveFitter(D.monoexponential, p0=(1.0, -1 / 30), out_ufuncs=(None, lambda v: 1 / np.abs(v)), out_bounds=((0, 2000), (0, 100)),
+                          r2_threshold=0.9, nan_to_num=None)
+        out.append(tuple(v.volume for v in f.fit(x, vols, mask=mask)))
+        return out
+
+    wide = run()
+    monkeypatch.setenv("DFIT_HOST_WIDEN", "0")
+    dev64 = run()
+    for k, (a, b) in enumerate(zip(wide, dev64)):
+        for u, v in zip(a, b):
+            assert u.dtype == np.float64 and v.dtype == np.float64 and u.shape == v.shape
+            if k == 3:  # unrounded ufunc output
+                assert np.array_equal(np.isnan(u), np.isnan(v)) and np.allclose(u, v, rtol=1.2e-7, atol=0, equal_nan=True)
+            else:
+                assert np.array_equal(u, v, equal_nan=True), k
+    tc = wide[1][0]
+    assert np.array_equal(np.around(tc, 1), tc) and (tc > 0).mean() > 0.5  # on numpy's float64 decimal grid
+
+
 def test_nonfinite_input_raises(D):
     x = np.arange(1, 5) * 10.0
     y = np.ones((4, 100), dtype=np.float32)
