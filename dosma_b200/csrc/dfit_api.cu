@@ -9,6 +9,9 @@
 
 #include <cctype>
 #include <chrono>
+#include <condition_variable>
+#include <functional>
+#include <mutex>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -95,6 +98,74 @@ inline void bind_worker(const cpu_set_t* cpus) {
   if (cpus) pthread_setaffinity_np(pthread_self(), sizeof(cpu_set_t), cpus);
 }
 
+// A few persistent host threads for the staging copies (a chunk is filled / drained in ~1 ms: spawning 15 threads
+// per copy would cost as much again).  run(nt, cpus, work) executes work(0) on the caller and work(1..nt-1) on the
+// pool's threads, bound to `cpus`, and returns when all are done.  One job at a time (concurrent callers queue up).
+class HostPool {
+ public:
+  static HostPool& get() {
+    static HostPool* p = new HostPool();  // (never destroyed: its threads may outlive static destruction order)
+    return *p;
+  }
+  int size() const { return (int)threads_.size() + 1; }
+  void run(int nt, const cpu_set_t* cpus, const std::function<void(int)>& work) {
+    if (nt <= 1) {
+      work(0);
+      return;
+    }
+    std::lock_guard<std::mutex> job(job_mu_);
+    {
+      std::lock_guard<std::mutex> lk(mu_);
+      work_ = &work;
+      cpus_ = cpus;
+      nt_ = nt;
+      pending_ = nt - 1;
+      ++epoch_;
+    }
+    cv_.notify_all();
+    work(0);
+    std::unique_lock<std::mutex> lk(mu_);
+    done_.wait(lk, [&] { return pending_ == 0; });
+    work_ = nullptr;
+  }
+
+ private:
+  HostPool() {
+    unsigned hw = std::thread::hardware_concurrency();
+    const int n = (int)(hw == 0 ? 4 : (hw > 16 ? 16 : hw));
+    for (int t = 1; t < n; ++t) threads_.emplace_back([this, t] { loop(t); });
+    for (auto& th : threads_) th.detach();
+  }
+  void loop(int t) {
+    unsigned long long seen = 0;
+    for (;;) {
+      const std::function<void(int)>* work = nullptr;
+      const cpu_set_t* cpus = nullptr;
+      {
+        std::unique_lock<std::mutex> lk(mu_);
+        cv_.wait(lk, [&] { return epoch_ != seen; });
+        seen = epoch_;
+        if (t >= nt_) continue;  // not part of this job
+        work = work_;
+        cpus = cpus_;
+      }
+      bind_worker(cpus);
+      (*work)(t);
+      {
+        std::lock_guard<std::mutex> lk(mu_);
+        if (--pending_ == 0) done_.notify_one();
+      }
+    }
+  }
+  std::vector<std::thread> threads_;
+  std::mutex mu_, job_mu_;
+  std::condition_variable cv_, done_;
+  const std::function<void(int)>* work_ = nullptr;
+  const cpu_set_t* cpus_ = nullptr;
+  int nt_ = 0, pending_ = 0;
+  unsigned long long epoch_ = 0;
+};
+
 // memcpy with streaming (non-temporal) stores: the destination -- a staging block about to be DMA'd, or a result array
 // the caller reads later -- is not wanted in the cache, and a regular store would first READ every destination line
 // (read for ownership): a third of the memory traffic of these copies, which are bandwidth-bound.
@@ -134,8 +205,7 @@ void par_copy(const CopySeg* segs, int count) {
   constexpr size_t kBlk = (size_t)1 << 20;
   size_t total_blocks = 0;
   for (int i = 0; i < count; ++i) total_blocks += (segs[i].bytes + kBlk - 1) / kBlk;
-  unsigned hw = std::thread::hardware_concurrency();
-  int nt = (int)(hw == 0 ? 4 : (hw > 16 ? 16 : hw));
+  int nt = HostPool::get().size();
   if ((size_t)nt > total_blocks) nt = (int)total_blocks;
   auto work = [&](int t) {
     size_t b = 0;  // global block counter; thread t takes blocks with b % nt == t
@@ -148,47 +218,24 @@ void par_copy(const CopySeg* segs, int count) {
       }
     }
   };
-  if (nt <= 1) {
-    if (total_blocks) work(0);
-    return;
-  }
-  std::vector<std::thread> th;
-  th.reserve(nt - 1);
-  for (int t = 1; t < nt; ++t)
-    th.emplace_back([&work, cpus, t] {
-      bind_worker(cpus);
-      work(t);
-    });
-  work(0);
-  for (auto& x : th) x.join();
+  if (total_blocks == 0) return;
+  HostPool::get().run(nt, cpus, work);
 }
 
 // Generic static partition of [0, n) over a few host threads.
 template <class F>
 void par_for(int64_t n, int64_t grain, F fn) {
   const cpu_set_t* cpus = g_worker_cpus;
-  unsigned hw = std::thread::hardware_concurrency();
-  int nt = (int)(hw == 0 ? 4 : (hw > 16 ? 16 : hw));
+  int nt = HostPool::get().size();
   const int64_t nb = (n + grain - 1) / grain;
   if (nt > nb) nt = (int)nb;
-  if (nt <= 1) {
-    if (n > 0) fn(0, n);
-    return;
-  }
+  if (n <= 0) return;
   auto work = [&](int t) {
     const int64_t b0 = nb * t / nt, b1 = nb * (t + 1) / nt;
     const int64_t lo = b0 * grain, hi = b1 * grain < n ? b1 * grain : n;
     if (lo < hi) fn(lo, hi);
   };
-  std::vector<std::thread> th;
-  th.reserve(nt - 1);
-  for (int t = 1; t < nt; ++t)
-    th.emplace_back([&work, cpus, t] {
-      bind_worker(cpus);
-      work(t);
-    });
-  work(0);
-  for (auto& x : th) x.join();
+  HostPool::get().run(nt < 1 ? 1 : nt, cpus, work);
 }
 
 // float32 staging [n, ncols] -> the caller's float64 map.  scale[c] > 0: column c was rounded to a decimal grid on the
