@@ -97,6 +97,19 @@ inline cudaError_t launch_one(const LaunchDesc& d) {
     }
     return cudaGetLastError();
   }
+  // dense fits that go straight to the LM: persistent warps whose lanes start the next voxel as soon as theirs is done
+  if (d.g.world == 0 && d.use_tma != 1 && (!M::MONO || d.fast_path == 0 || a.vo.has_bounds)) {
+    int per_sm = 0;
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fit_kernel_stream<M, T, EMAX, EXACT>, kStreamBlock, 0);
+    if (e != cudaSuccess) return e;
+    if (per_sm < 1) per_sm = 1;
+    int64_t g = (int64_t)d.sm_count * per_sm;
+    const int64_t cap = (d.n_vox + 2 * kStreamBlock - 1) / (2 * kStreamBlock);  // at least ~64 voxels per warp
+    if (g > cap) g = cap;
+    if (g < 1) g = 1;
+    fit_kernel_stream<M, T, EMAX, EXACT><<<(unsigned)g, kStreamBlock, 0, d.stream>>>(a);
+    return cudaGetLastError();
+  }
   // the fused all-gather epilogue is a separate instance so that single-GPU launches do not pay its registers
   if (d.g.world > 0) {
     if constexpr (sizeof(T) == 4) fit_kernel<M, T, EMAX, EXACT, true><<<(unsigned)blocks, kBlock, 0, d.stream>>>(a);
