@@ -12,6 +12,8 @@
 // log-linear initial guess (:701-718), `_process_params` (:109-146) and rounding (:734-737).
 #pragma once
 
+#include <cstdlib>
+
 #include "fit_kernels1.cuh"
 #include "kernel_common.cuh"
 #include "mono2_kernels.cuh"
@@ -98,7 +100,14 @@ inline cudaError_t launch_one(const LaunchDesc& d) {
     return cudaGetLastError();
   }
   // dense fits that go straight to the LM: persistent warps whose lanes start the next voxel as soon as theirs is done
-  if (d.g.world == 0 && d.use_tma != 1 && (!M::MONO || d.fast_path == 0 || a.vo.has_bounds)) {
+  // (DFIT_LM_STREAM=0/1 overrides the choice: for A/B runs)
+  static const int stream_env = [] {
+    const char* e = std::getenv("DFIT_LM_STREAM");
+    return e ? (e[0] == '1' ? 1 : 0) : -1;
+  }();
+  const bool stream_default = M::P >= 4;  // measured: pays where the pass count varies widely (bi-exponential)
+  if (d.g.world == 0 && d.use_tma != 1 && (!M::MONO || d.fast_path == 0 || a.vo.has_bounds) &&
+      (stream_env < 0 ? stream_default : stream_env == 1)) {
     int per_sm = 0;
     cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fit_kernel_stream<M, T, EMAX, EXACT>, kStreamBlock, 0);
     if (e != cudaSuccess) return e;

@@ -110,19 +110,29 @@ __global__ void __launch_bounds__(kBlock, sizeof(T) == 4 ? (EMAX <= 8 ? 8 : 3) :
 // the arithmetic is lm_solve's, bit for bit.
 constexpr int kStreamBlock = 128;
 constexpr int stream_min_ctas(int tsize, int E) { return tsize == 4 ? (E <= 8 ? 4 : 3) : (E <= 8 ? 2 : 1); }
+constexpr int stream_tile(int tsize) { return tsize == 4 ? 64 : 32; }  // voxels per staged tile (<= 32 KB per CTA)
 
 template <class M, typename T, int EMAX, bool EXACT>
 __global__ void __launch_bounds__(kStreamBlock, stream_min_ctas(sizeof(T), EMAX))
     fit_kernel_stream(const __grid_constant__ KernelArgs<T, EMAX> a) {
   constexpr int P = M::P;
   constexpr int NA = P * (P + 1) / 2;
+  constexpr int TILE = stream_tile(sizeof(T));
+  // Samples reach the lanes through a per-warp tile in shared memory: the warp loads the next TILE voxels of its
+  // range with coalesced loads (converting to the arithmetic type), and a lane that needs a new voxel copies that
+  // voxel's column into registers -- lanes start voxels at different times, and column-wise global loads would
+  // fetch a 32-byte sector for every 4-byte sample.
+  __shared__ T tile[kStreamBlock / 32][EMAX][TILE];
   const unsigned full = 0xffffffffu;
-  const int lane = threadIdx.x & 31;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const unsigned below = (1u << lane) - 1u;
   const int64_t n_warps = (int64_t)gridDim.x * (kStreamBlock / 32);
-  const int64_t warp_global = (int64_t)blockIdx.x * (kStreamBlock / 32) + (threadIdx.x >> 5);
+  const int64_t warp_global = (int64_t)blockIdx.x * (kStreamBlock / 32) + warp;
   const int64_t w1 = a.n * (warp_global + 1) / n_warps;
   int64_t next = a.n * warp_global / n_warps;  // first voxel of the range nobody has taken yet (warp-uniform)
+  int64_t tile_hi = next;                      // end of the staged tile (warp-uniform); [next, tile_hi) is in shared memory
+  int64_t tile_lo = next;
+  const int E = EXACT ? EMAX : a.E;
 
   LmStream<M, T, T, EMAX, EXACT> ls;
   T y[EMAX], ysum = 0;
@@ -157,11 +167,30 @@ __global__ void __launch_bounds__(kStreamBlock, stream_min_ctas(sizeof(T), EMAX)
     for (;;) {
       const unsigned m = __ballot_sync(full, !busy);
       if (m == 0u || next >= w1) break;
-      const int64_t cand = next + __popc(m & below);
-      next += __popc(m);
-      if (!busy && cand < w1) {
-        v = cand;
-        load_samples<T, EMAX, EXACT>(a, v, y);
+      if (next >= tile_hi) {  // stage the next tile (all lanes, coalesced)
+        tile_lo = next;
+        tile_hi = next + TILE < w1 ? next + TILE : w1;
+        const int nv = (int)(tile_hi - tile_lo);
+        __syncwarp();
+        if (a.layout == LAYOUT_PLANAR) {
+          for (int e = 0; e < E; ++e)
+            for (int k = lane; k < nv; k += 32) tile[warp][e][k] = load_as<T>(a.y, a.y_dtype, (int64_t)e * a.ld + tile_lo + k);
+        } else {
+          for (int i = lane; i < nv * E; i += 32) {
+            const int k = i / E, e = i - k * E;
+            tile[warp][e][k] = load_as<T>(a.y, a.y_dtype, (tile_lo + k) * a.ld + e);
+          }
+        }
+        __syncwarp();
+      }
+      const int avail = (int)(tile_hi - next), asked = __popc(m);
+      const int take = asked < avail ? asked : avail;
+      const int rank = __popc(m & below);
+      if (!busy && rank < take) {
+        v = next + rank;
+        const int k = (int)(v - tile_lo);
+#pragma unroll
+        for (int e = 0; e < EMAX; ++e) y[e] = (EXACT || e < E) ? tile[warp][e][k] : (T)0;
         T p[P];
         load_p0<P, T, EMAX>(a, v, p);
         unsigned flags = 0;
@@ -174,6 +203,7 @@ __global__ void __launch_bounds__(kStreamBlock, stream_min_ctas(sizeof(T), EMAX)
           wants = ls.want(pe);
         }
       }
+      next += take;
     }
     if (!__any_sync(full, wants)) break;  // the range is exhausted and every lane has stored its last voxel
     if (wants) {
