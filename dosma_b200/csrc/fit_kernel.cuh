@@ -12,8 +12,6 @@
 // log-linear initial guess (:701-718), `_process_params` (:109-146) and rounding (:734-737).
 #pragma once
 
-#include <cstdlib>
-
 #include "fit_kernels1.cuh"
 #include "kernel_common.cuh"
 #include "mono2_kernels.cuh"
@@ -97,26 +95,6 @@ inline cudaError_t launch_one(const LaunchDesc& d) {
     } else {
       fit_kernel<M, T, EMAX, EXACT, false><<<(unsigned)g, kBlock, 0, d.stream>>>(a);
     }
-    return cudaGetLastError();
-  }
-  // dense fits that go straight to the LM: persistent warps whose lanes start the next voxel as soon as theirs is done
-  // (DFIT_LM_STREAM=0/1 overrides the choice: for A/B runs)
-  static const int stream_env = [] {
-    const char* e = std::getenv("DFIT_LM_STREAM");
-    return e ? (e[0] == '1' ? 1 : 0) : -1;
-  }();
-  const bool stream_default = M::P >= 4;  // measured: pays where the pass count varies widely (bi-exponential)
-  if (d.g.world == 0 && d.use_tma != 1 && (!M::MONO || d.fast_path == 0 || a.vo.has_bounds) &&
-      (stream_env < 0 ? stream_default : stream_env == 1)) {
-    int per_sm = 0;
-    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fit_kernel_stream<M, T, EMAX, EXACT>, kStreamBlock, 0);
-    if (e != cudaSuccess) return e;
-    if (per_sm < 1) per_sm = 1;
-    int64_t g = (int64_t)d.sm_count * per_sm;
-    const int64_t cap = (d.n_vox + 2 * kStreamBlock - 1) / (2 * kStreamBlock);  // at least ~64 voxels per warp
-    if (g > cap) g = cap;
-    if (g < 1) g = 1;
-    fit_kernel_stream<M, T, EMAX, EXACT><<<(unsigned)g, kStreamBlock, 0, d.stream>>>(a);
     return cudaGetLastError();
   }
   // the fused all-gather epilogue is a separate instance so that single-GPU launches do not pay its registers

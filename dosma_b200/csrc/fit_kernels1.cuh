@@ -101,121 +101,6 @@ __global__ void __launch_bounds__(kBlock, sizeof(T) == 4 ? (EMAX <= 8 ? 8 : 3) :
 }
 
 // ------------------------------------------------------------------------------------------------
-// Lane-refill LM kernel (dense fits that go straight to the LM: bi-exponential, linear, mono-exponential with
-// fast_path = 0 or y_bounds).  The LM's pass count varies widely from voxel to voxel -- bi-exponential benchmark volume:
-// 4 .. 32 passes, mean 7.5 -- and with one voxel per lane for the lifetime of a warp (fit_kernel) the warp runs as long
-// as its slowest voxel: ncu showed 12.5 of 32 lanes active on average.  Here the warps are persistent, each owns a
-// contiguous range of voxels, and the solver is the resumable LmStream: every trip all lanes run ONE model evaluation
-// together, and a lane whose voxel has finished stores it and starts the next voxel of the range at once.  Per voxel
-// the arithmetic is lm_solve's, bit for bit.
-constexpr int kStreamBlock = 128;
-constexpr int stream_min_ctas(int tsize, int E) { return tsize == 4 ? (E <= 8 ? 4 : 3) : (E <= 8 ? 2 : 1); }
-constexpr int stream_tile(int tsize) { return tsize == 4 ? 64 : 32; }  // voxels per staged tile (<= 32 KB per CTA)
-
-template <class M, typename T, int EMAX, bool EXACT>
-__global__ void __launch_bounds__(kStreamBlock, stream_min_ctas(sizeof(T), EMAX))
-    fit_kernel_stream(const __grid_constant__ KernelArgs<T, EMAX> a) {
-  constexpr int P = M::P;
-  constexpr int NA = P * (P + 1) / 2;
-  constexpr int TILE = stream_tile(sizeof(T));
-  // Samples reach the lanes through a per-warp tile in shared memory: the warp loads the next TILE voxels of its
-  // range with coalesced loads (converting to the arithmetic type), and a lane that needs a new voxel copies that
-  // voxel's column into registers -- lanes start voxels at different times, and column-wise global loads would
-  // fetch a 32-byte sector for every 4-byte sample.
-  __shared__ T tile[kStreamBlock / 32][EMAX][TILE];
-  const unsigned full = 0xffffffffu;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const unsigned below = (1u << lane) - 1u;
-  const int64_t n_warps = (int64_t)gridDim.x * (kStreamBlock / 32);
-  const int64_t warp_global = (int64_t)blockIdx.x * (kStreamBlock / 32) + warp;
-  const int64_t w1 = a.n * (warp_global + 1) / n_warps;
-  int64_t next = a.n * warp_global / n_warps;  // first voxel of the range nobody has taken yet (warp-uniform)
-  int64_t tile_hi = next;                      // end of the staged tile (warp-uniform); [next, tile_hi) is in shared memory
-  int64_t tile_lo = next;
-  const int E = EXACT ? EMAX : a.E;
-
-  LmStream<M, T, T, EMAX, EXACT> ls;
-  T y[EMAX], ysum = 0;
-  int64_t v = 0;
-  bool busy = false;
-  int it_sum = 0, it_max = 0;
-  unsigned n_fit = 0, n_fail = 0, n_nf = 0, n_oob = 0;
-
-  auto finalize = [&](int status, T F, int iters, unsigned flags, T (&p)[P]) {
-    T r2;
-    voxel_finish<M, T, EMAX, EXACT>(status, y, a.E, a.vo, ysum, F, p, r2);
-    store_voxel<P, T, EMAX, false>(a, v, p, r2, true, status, iters);
-    it_sum += iters;
-    it_max = iters > it_max ? iters : it_max;
-    n_fit += (unsigned)(status >= ST_CONV_F);
-    n_fail += (unsigned)(status >= ST_MAXITER);
-    n_nf += (unsigned)((flags & FLAG_NONFINITE) != 0);
-    n_oob += (unsigned)((flags & FLAG_OOB) != 0);
-  };
-
-  for (;;) {
-    T pe[P];
-    bool wants = false;
-    if (busy) {
-      wants = ls.want(pe);
-      if (!wants) {  // finished (converged, failed, or the step was below the tolerance): store, free the lane
-        finalize(ls.status, (T)ls.F, ls.iters, 0u, ls.p);
-        busy = false;
-      }
-    }
-    // refill: lanes without a voxel take the next ones of the range, in order
-    for (;;) {
-      const unsigned m = __ballot_sync(full, !busy);
-      if (m == 0u || next >= w1) break;
-      if (next >= tile_hi) {  // stage the next tile (all lanes, coalesced)
-        tile_lo = next;
-        tile_hi = next + TILE < w1 ? next + TILE : w1;
-        const int nv = (int)(tile_hi - tile_lo);
-        __syncwarp();
-        if (a.layout == LAYOUT_PLANAR) {
-          for (int e = 0; e < E; ++e)
-            for (int k = lane; k < nv; k += 32) tile[warp][e][k] = load_as<T>(a.y, a.y_dtype, (int64_t)e * a.ld + tile_lo + k);
-        } else {
-          for (int i = lane; i < nv * E; i += 32) {
-            const int k = i / E, e = i - k * E;
-            tile[warp][e][k] = load_as<T>(a.y, a.y_dtype, (tile_lo + k) * a.ld + e);
-          }
-        }
-        __syncwarp();
-      }
-      const int avail = (int)(tile_hi - next), asked = __popc(m);
-      const int take = asked < avail ? asked : avail;
-      const int rank = __popc(m & below);
-      if (!busy && rank < take) {
-        v = next + rank;
-        const int k = (int)(v - tile_lo);
-#pragma unroll
-        for (int e = 0; e < EMAX; ++e) y[e] = (EXACT || e < E) ? tile[warp][e][k] : (T)0;
-        T p[P];
-        load_p0<P, T, EMAX>(a, v, p);
-        unsigned flags = 0;
-        const int st = voxel_prepare<M, T, EMAX, EXACT>(y, a.xt, a.E, a.vo, p, ysum, flags);
-        if (st >= 0) {  // skipped / non-finite: nothing to solve
-          finalize(st, (T)0, 0, flags, p);
-        } else {
-          ls.begin(p, y, a.E, a.vo.s);
-          busy = true;
-          wants = ls.want(pe);
-        }
-      }
-      next += take;
-    }
-    if (!__any_sync(full, wants)) break;  // the range is exhausted and every lane has stored its last voxel
-    if (wants) {
-      T Fn, An[NA], gn[P];
-      eval_all<M, T, T, EMAX, EXACT>(pe, y, a.xt.x, a.xt.xs, a.E, Fn, An, gn);
-      ls.absorb(Fn, An, gn);
-    }
-  }
-  block_stats_counts(a.counters, n_fit, n_fail, n_nf, n_oob, it_sum, it_max);
-}
-
-// ------------------------------------------------------------------------------------------------
 // TMA-staged variant.  Persistent warps: every warp owns a 2-stage shared-memory ring of
 // [E][32-voxel] sample tiles that the Tensor Memory Accelerator fills (cp.async.bulk.tensor.2d over a
 // 2-D tensor map of the planar (E, ld) array, box = 32 voxels x E echoes) while the warp is busy

@@ -680,183 +680,6 @@ DFIT_HD int lm_solve(T (&p)[M::P], const T (&y)[EMAX], const T* __restrict__ x, 
   return status;
 }
 
-// ------------------------------------------------------------------------------------ resumable LM
-// lm_solve cut at its evaluations: the same arithmetic in the same order, but as a state machine that asks for ONE
-// model evaluation (eval_all) at a time.  A kernel can then keep every lane of a warp busy: whenever a lane's voxel is
-// finished it starts the next one, and all lanes run the expensive evaluation together each trip -- the per-voxel
-// pass count of the LM varies widely (4 .. 32 on the bi-exponential benchmark volume, mean 7.5), and with one voxel
-// per lane for the lifetime of the warp two thirds of the lanes idle.
-//
-//   LmStream s;  s.begin(p0, y, E, o);
-//   while (s.want(pe)) { eval_all(pe, ...) -> F, A, g;  s.absorb(F, A, g); }     // s.status, s.p, s.F, s.iters
-//
-// Bit-identical to lm_solve (tests: the host build runs every LM fixture through both).
-template <class M, typename T, typename TA, int EMAX, bool EXACT>
-struct LmStream {
-  static constexpr int P = M::P;
-  static constexpr int NA = P * (P + 1) / 2;
-  static constexpr unsigned ALL = (1u << P) - 1u;
-  enum Phase : int { PH_PROJ = 0, PH_START = 1, PH_START_PLAIN = 2, PH_ITER = 3, PH_DONE = 4 };
-  T p[P], pt[P], plin[P];
-  TA F, A[NA], g[P], D2[P], lam, nu, zz, pnorm2, pred, ysq, floorF, ftol, xtol2, eps16;
-  int fev, iters, status, phase, maxfev;
-
-  DFIT_HD void begin(const T (&p0)[P], const T (&y)[EMAX], int E, const SolverOpts<T>& o) {
-    iters = 0;
-    fev = 0;
-    maxfev = o.maxfev;
-    ysq = 0;
-#pragma unroll
-    for (int e = 0; e < EMAX; ++e)
-      if (EXACT || e < E) ysq = num<TA>::fma_((TA)y[e], (TA)y[e], ysq);
-    floorF = (TA)o.floor_rel * ysq;
-    ftol = (TA)o.ftol;
-    xtol2 = (TA)o.xtol * (TA)o.xtol;
-    eps16 = (TA)16 * (TA)num<T>::eps();
-    F = 0;
-    zz = pnorm2 = pred = 0;
-    lam = (TA)o.lambda0;
-    nu = 2;
-    status = ST_MAXITER;
-#pragma unroll
-    for (int i = 0; i < P; ++i) {
-      D2[i] = 0;
-      p[i] = plin[i] = pt[i] = p0[i];
-    }
-    if (o.init_linear != 0) {
-#pragma unroll
-      for (int i = 0; i < P; ++i)
-        if ((M::LIN >> i) & 1u) pt[i] = (T)0;
-      phase = PH_PROJ;
-    } else {
-      phase = PH_START_PLAIN;
-    }
-  }
-
-  // Where the next evaluation is wanted (pe), or false: finished -- status, p, F and iters are final.
-  DFIT_HD bool want(T (&pe)[P]) {
-    if (phase == PH_ITER) {
-      // the head of lm_solve's loop: budget, exact fit, step, step-below-tolerance shortcut
-      if (!(fev < maxfev)) {
-        finish();
-        return false;
-      }
-      if (F <= floorF) {
-        status = ST_EXACT;
-        finish();
-        return false;
-      }
-      bool solved = lm_step<P, T, TA>(p, A, g, D2, lam, ALL, pt, zz, pnorm2, pred);
-      for (int tries = 0; tries < 12 && !solved; ++tries) {
-        lam = num<TA>::max_(lam * (TA)10, (TA)1e-3);
-        solved = lm_step<P, T, TA>(p, A, g, D2, lam, ALL, pt, zz, pnorm2, pred);
-      }
-      if (!solved) {
-        finish();
-        return false;
-      }
-      if (pred <= ftol * F && lam <= (TA)1) {
-#pragma unroll
-        for (int i = 0; i < P; ++i) p[i] = pt[i];
-        status = zz <= xtol2 * pnorm2 ? ST_CONV_FX : ST_CONV_F;
-        finish();
-        return false;
-      }
-    }
-    if (phase == PH_DONE) return false;
-#pragma unroll
-    for (int i = 0; i < P; ++i) pe[i] = pt[i];
-    return true;
-  }
-
-  DFIT_HD void finish() {
-    if (status == ST_MAXITER && F <= floorF) status = ST_EXACT;
-    phase = PH_DONE;
-  }
-
-  // The evaluation at the point want() returned: cost Fn, normal matrix An, gradient gn.
-  DFIT_HD void absorb(TA Fn, const TA (&An)[NA], const TA (&gn)[P]) {
-    ++iters;
-    if (phase == PH_PROJ) {
-      // projection pass: only the linear block of (An, gn) is used -- its unregularised solution is the least-squares
-      // optimum of the linear parameters for the given non-linear ones
-      fev += 1;
-      TA D2p[P];
-#pragma unroll
-      for (int i = 0; i < P; ++i) D2p[i] = 0;
-      T pp[P];
-      bool projected = lm_step<P, T, TA>(pt, An, gn, D2p, (TA)0, M::LIN, pp, zz, pnorm2, pred);
-#pragma unroll
-      for (int i = 0; i < P; ++i) {
-        projected = projected && num<T>::finite(pp[i]);
-        pt[i] = pp[i];
-      }
-      if (!projected) {
-#pragma unroll
-        for (int i = 0; i < P; ++i) pt[i] = plin[i];
-      }
-      phase = projected ? PH_START : PH_START_PLAIN;
-      return;
-    }
-    if (phase == PH_START || phase == PH_START_PLAIN) {
-      fev += 1 + P;
-      const bool good = num<TA>::finite(Fn);
-      if (phase == PH_START && !(good && Fn <= ysq)) {  // degenerate linear sub-problem: start from p0 as given
-#pragma unroll
-        for (int i = 0; i < P; ++i) pt[i] = plin[i];
-        phase = PH_START_PLAIN;
-        return;
-      }
-      F = Fn;
-#pragma unroll
-      for (int k = 0; k < NA; ++k) A[k] = An[k];
-#pragma unroll
-      for (int i = 0; i < P; ++i) g[i] = gn[i];
-      if (!good) {
-        status = ST_NUMERIC;
-        phase = PH_DONE;
-        return;
-      }
-#pragma unroll
-      for (int i = 0; i < P; ++i) p[i] = pt[i];
-      phase = PH_ITER;
-      return;
-    }
-    // a trial point of the LM loop
-    ++fev;
-    const bool good = num<TA>::finite(Fn);
-    const TA act = F - Fn;
-    const TA tau2 = eps16 * eps16 * ysq * F;
-    const bool reliable = pred * pred > tau2;
-    const bool accept = good && (reliable ? act > (TA)1e-4 * pred : act * num<TA>::abs_(act) > -tau2);
-    const TA rho = reliable ? act * num<TA>::rcp_(pred) : (TA)1;
-    const bool small_f =
-        good && pred <= ftol * F && (!reliable || (num<TA>::abs_(act) <= ftol * F && act <= (TA)2 * pred));
-    const bool conv_x = accept && zz <= xtol2 * pnorm2;
-    if (accept) {
-#pragma unroll
-      for (int i = 0; i < P; ++i) {
-        p[i] = pt[i];
-        g[i] = gn[i];
-      }
-#pragma unroll
-      for (int k = 0; k < NA; ++k) A[k] = An[k];
-      F = Fn;
-      const TA t = (TA)2 * rho - (TA)1;
-      lam = num<TA>::max_(lam * num<TA>::max_((TA)(1.0 / 3.0), (TA)1 - t * t * t), (TA)1e-9);
-      nu = 2;
-      fev += P;
-    } else {
-      lam *= nu;
-      nu *= 2;
-    }
-    if (small_f || conv_x) {
-      status = small_f ? (conv_x ? ST_CONV_FX : ST_CONV_F) : ST_CONV_X;
-      finish();
-    }
-  }
-};
-
 // ------------------------------------------------------------------------------------ echo table
 // Echo-time table shared by all voxels of a launch (lives in the kernel parameter / constant bank).
 template <typename T, int EMAX>
@@ -933,17 +756,13 @@ struct VoxelOpts {
 };
 
 // Everything the reference does for one voxel (`_curve_fit`, fitting.py:1026-1073), on samples that
-// are already in registers, in three steps so that kernels can put their own solver loop in the middle:
-//   voxel_prepare  skip rules (:1065-1067), optional log-linear initial guess, non-finite check
-//                  -> a final Status, or -1: run the solver from p
-//   (solver)       lm_solve, or the resumable LmStream
-//   voxel_finish   r2 (:1032-1035) on success, NaN parameters and r2 = 0 otherwise (:1067, :1072)
-template <class M, typename T, int EMAX, bool EXACT>
-DFIT_HD int voxel_prepare(const T (&y)[EMAX], const XTab<T, EMAX>& xt, int E, const VoxelOpts<T>& vo, T (&p)[M::P],
-                          T& ysum, unsigned& flags) {
+// are already in registers.  p: in = initial guess, out = fitted parameters (NaN on skip/failure).
+template <class M, typename T, typename TA, int EMAX, bool EXACT>
+DFIT_HD int fit_voxel(const T (&y)[EMAX], const XTab<T, EMAX>& xt, int E, const VoxelOpts<T>& vo, T (&p)[M::P],
+                      T& r2, int& iters, unsigned& flags) {
   constexpr int P = M::P;
   bool all_zero = true, oob = false, nonfinite = false;
-  ysum = 0;
+  T ysum = 0;
 #pragma unroll
   for (int e = 0; e < EMAX; ++e) {
     if (EXACT || e < E) {
@@ -954,29 +773,29 @@ DFIT_HD int voxel_prepare(const T (&y)[EMAX], const XTab<T, EMAX>& xt, int E, co
       ysum += v;
     }
   }
+  iters = 0;
   flags = 0;
+  int status;
+  T F = 0;
   if (oob || all_zero) {
+    status = ST_SKIPPED;
     if (oob) flags |= FLAG_OOB;
-    return ST_SKIPPED;
-  }
-  if (vo.init_mode == INIT_LOGLINEAR && P == 2) {
-    T q[2];
-    loglinear_init<T, EMAX, EXACT>(y, xt.xc, xt.xbar, xt.inv_sxx, E, q);
-    p[0] = q[0];
-    p[P - 1] = q[1];
-  }
+  } else {
+    if (vo.init_mode == INIT_LOGLINEAR && P == 2) {
+      T q[2];
+      loglinear_init<T, EMAX, EXACT>(y, xt.xc, xt.xbar, xt.inv_sxx, E, q);
+      p[0] = q[0];
+      p[P - 1] = q[1];
+    }
 #pragma unroll
-  for (int i = 0; i < P; ++i) nonfinite = nonfinite || !num<T>::finite(p[i]);
-  if (nonfinite) {
-    flags |= FLAG_NONFINITE;
-    return ST_NONFINITE;
+    for (int i = 0; i < P; ++i) nonfinite = nonfinite || !num<T>::finite(p[i]);
+    if (nonfinite) {
+      status = ST_NONFINITE;
+      flags |= FLAG_NONFINITE;
+    } else {
+      status = lm_solve<M, T, TA, EMAX, EXACT>(p, y, xt.x, xt.xs, E, vo.s, F, iters);
+    }
   }
-  return -1;
-}
-
-template <class M, typename T, int EMAX, bool EXACT>
-DFIT_HD void voxel_finish(int status, const T (&y)[EMAX], int E, const VoxelOpts<T>& vo, T ysum, T F, T (&p)[M::P], T& r2) {
-  constexpr int P = M::P;
   if (status >= ST_CONV_F && status <= ST_EXACT) {
     const T mean = ysum / (T)E;
     T ss_tot = 0;
@@ -989,18 +808,6 @@ DFIT_HD void voxel_finish(int status, const T (&y)[EMAX], int E, const VoxelOpts
     for (int i = 0; i < P; ++i) p[i] = (T)NAN;
     r2 = (T)0;  // fitting.py:1067, 1072
   }
-}
-
-// p: in = initial guess, out = fitted parameters (NaN on skip/failure).
-template <class M, typename T, typename TA, int EMAX, bool EXACT>
-DFIT_HD int fit_voxel(const T (&y)[EMAX], const XTab<T, EMAX>& xt, int E, const VoxelOpts<T>& vo, T (&p)[M::P],
-                      T& r2, int& iters, unsigned& flags) {
-  T ysum;
-  iters = 0;
-  T F = 0;
-  int status = voxel_prepare<M, T, EMAX, EXACT>(y, xt, E, vo, p, ysum, flags);
-  if (status < 0) status = lm_solve<M, T, TA, EMAX, EXACT>(p, y, xt.x, xt.xs, E, vo.s, F, iters);
-  voxel_finish<M, T, EMAX, EXACT>(status, y, E, vo, ysum, F, p, r2);
   return status;
 }
 

@@ -79,31 +79,6 @@ static void run(int E, int64_t N, const double* x, const double* y, const double
     unsigned flags;
     int st = -1;
     flags = 0;
-    if (fast == 3) {  // the LM through its resumable form (what the lane-refill kernel runs): must equal fast == 0 bit for bit
-      T ysum, F = 0;
-      it = 0;
-      st = voxel_prepare<M, T, EMAX, EXACT>(yy, xt, E, vo, p, ysum, flags);
-      if (st < 0) {
-        LmStream<M, T, TA, EMAX, EXACT> ls;
-        ls.begin(p, yy, E, vo.s);
-        T pe[P];
-        while (ls.want(pe)) {
-          TA Fn, An[P * (P + 1) / 2], gn[P];
-          eval_all<M, T, TA, EMAX, EXACT>(pe, yy, xt.x, xt.xs, E, Fn, An, gn);
-          ls.absorb(Fn, An, gn);
-        }
-        st = ls.status;
-        it = ls.iters;
-        F = (T)ls.F;
-        for (int i = 0; i < P; ++i) p[i] = ls.p[i];
-      }
-      voxel_finish<M, T, EMAX, EXACT>(st, yy, E, vo, ysum, F, p, r2v);
-      for (int i = 0; i < P; ++i) popt[(size_t)v * P + i] = (double)p[i];
-      r2[v] = (double)r2v;
-      status[v] = st;
-      iters[v] = it;
-      continue;
-    }
     if constexpr (sizeof(T) == sizeof(TA)) st = fit_voxel_fast<M, T, EMAX, EXACT>(yy, xt, vo, p, r2v, it);
     if (st < 0) {
       for (int i = 0; i < P; ++i) p[i] = (T)pv[i];

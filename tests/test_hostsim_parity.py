@@ -231,22 +231,3 @@ def test_monoexpfit_chain_on_the_host_build(name, fast):
     assert close.mean() > need, close.mean()
     kept = (tc != 0) & (ref_tc != 0)
     assert np.quantile(np.abs(r2 - ref_r2)[kept], 0.99) < 1e-4
-
-
-@pytest.mark.parametrize("name", [n for n in G.names("curvefit_")])
-@pytest.mark.parametrize("dtype", ["f32", "f64"])
-def test_resumable_lm_equals_lm_solve(name, dtype):
-    """LmStream -- the LM cut at its evaluations, what the lane-refill kernel (fit_kernel_stream) runs -- must equal
-    lm_solve bit for bit (parameters, r2, status, pass count), with and without the variable-projection start."""
-    c = G.load(name)
-    func = c["meta"]["func"]
-    model = {"_linear": "linear"}.get(func, func)
-    p0 = G.p0_of(c)
-    if isinstance(p0, dict):
-        p0 = [p0.get(k, 1.0) for k in ("a", "b")]
-    yb = c["meta"]["kwargs"].get("y_bounds")
-    for il in (0, 1):
-        a = H.fit(model, c["x"], c["y"], p0=p0, dtype=dtype, fast=0, init_linear=il, y_bounds=yb)
-        b = H.fit(model, c["x"], c["y"], p0=p0, dtype=dtype, fast=3, init_linear=il, y_bounds=yb)
-        for u, v in zip(a, b):
-            assert np.array_equal(u, v, equal_nan=True)
