@@ -31,10 +31,7 @@ __global__ void __launch_bounds__(256) mask_compact_kernel(const __grid_constant
     if (lane == 0 && ballot) base = atomicAdd(&s_n, (unsigned)__popc(ballot));  // shared-memory atomic
     base = __shfl_sync(0xffffffffu, base, 0);
     if (active) s_list[base + __popc(ballot & ((1u << lane) - 1u))] = (unsigned)v;
-    if (in && !masked) {
-      T p[P];
-      store_voxel<P, T, EMAX>(a, v, p, (T)0, false, ST_SKIPPED, 0);
-    }
+    if (in && !masked) fill_voxel<P, T, EMAX>(a, v);
   }
   __syncthreads();
   const unsigned n = s_n;

@@ -62,6 +62,7 @@ struct KernelArgs {
   uint8_t* status;
   uint8_t* niter;
   double mask_fill;  // value written outside the mask: NaN or nan_to_num (fitting.py:207-212)
+  double fill_q[4];  // the same per parameter, after the epilogue's rounding (what a voxel outside the mask reads)
   unsigned long long* counters;
   GatherArgs g;
 };
@@ -332,6 +333,50 @@ __device__ __forceinline__ void store_voxel(const KernelArgs<T, EMAX>& a, int64_
   if (a.niter) a.niter[v] = (uint8_t)(iters > 255 ? 255 : iters);
 }
 
+// A voxel outside the mask: the fill value into every output (fitting.py:205-215).  The single-GPU case is a few
+// streaming stores; with a fused all-gather the general store_voxel decides where the row goes.
+template <int P, typename T, int EMAX>
+__device__ __forceinline__ void fill_voxel(const KernelArgs<T, EMAX>& a, int64_t v) {
+  if (a.g.world > 0) {
+    T p[P];
+    store_voxel<P, T, EMAX>(a, v, p, (T)0, false, ST_SKIPPED, 0);
+    return;
+  }
+  if (a.popt != nullptr) {
+    if (a.out_dtype == DT_F32) {
+      if (a.sel >= 0) {
+        float qs = (float)a.fill_q[0];
+#pragma unroll
+        for (int i = 1; i < P; ++i)
+          if (i == a.sel) qs = (float)a.fill_q[i];
+        __stcs(reinterpret_cast<float*>(a.popt) + v, qs);
+      } else {
+        double q[P];
+#pragma unroll
+        for (int i = 0; i < P; ++i) q[i] = a.fill_q[i];
+        store_vec<P, float>(reinterpret_cast<float*>(a.popt) + v * P, q);
+      }
+      __stcs(reinterpret_cast<float*>(a.r2) + v, (float)a.mask_fill);
+    } else {
+      if (a.sel >= 0) {
+        double qs = a.fill_q[0];
+#pragma unroll
+        for (int i = 1; i < P; ++i)
+          if (i == a.sel) qs = a.fill_q[i];
+        __stcs(reinterpret_cast<double*>(a.popt) + v, qs);
+      } else {
+        double q[P];
+#pragma unroll
+        for (int i = 0; i < P; ++i) q[i] = a.fill_q[i];
+        store_vec<P, double>(reinterpret_cast<double*>(a.popt) + v * P, q);
+      }
+      __stcs(reinterpret_cast<double*>(a.r2) + v, a.mask_fill);
+    }
+  }
+  if (a.status) a.status[v] = (uint8_t)ST_SKIPPED;
+  if (a.niter) a.niter[v] = 0;
+}
+
 // Statistics are reduced per warp (dense path) or per CTA (grid-stride paths) and added to one of
 // kStatSlots slots of global counters (same-address atomics serialise in the L2 atomic unit; 1.8 M warps
 // hammering six addresses cost more than the fit itself).  The host sums the slots in dfit_get_stats.
@@ -504,6 +549,11 @@ inline void fill_args(const LaunchDesc& d, KernelArgs<T, EMAX>& a) {
   a.status = d.status;
   a.niter = d.niter;
   a.mask_fill = d.mask_fill;
+  for (int i = 0; i < 4; ++i) {
+    double q = d.mask_fill;
+    if (d.po.enabled && d.po.decimals[i] >= 0) q = nearbyint(q * d.po.scale[i]) / d.po.scale[i];  // np.around of the fill
+    a.fill_q[i] = q;
+  }
   a.counters = d.counters;
   a.g = d.g;
 }
