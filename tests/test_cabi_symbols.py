@@ -74,3 +74,31 @@ def test_product_does_not_touch_oracle():
                 src = open(os.path.join(base, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+(oracle|tests)\b", src, flags=re.M), f
                 assert "liboracle" not in src and "hostsim" not in src.replace("tests/hostsim", ""), f
+
+
+def test_ctypes_structs_have_the_header_layout(tmp_path):
+    """The ctypes mirrors in dosma_b200/_cabi.py against include/dfit.h as gcc lays it out: sizes and the offsets of the
+    fields most recently added (an ABI guard for the binding a DOSMA maintainer would copy from INTEGRATION.md)."""
+    import subprocess
+    import textwrap
+
+    from dosma_b200 import _cabi
+
+    src = tmp_path / "layout.c"
+    src.write_text(textwrap.dedent('''
+        #include <stddef.h>
+        #include <stdio.h>
+        #include "dfit.h"
+        int main(void) {
+          printf("%zu %zu %zu %zu %zu %zu %zu %zu\\n", sizeof(dfit_opts), sizeof(dfit_stats), sizeof(dfit_gather_desc),
+                 sizeof(dfit_qdess_opts), offsetof(dfit_opts, out_param), offsetof(dfit_opts, decimals),
+                 offsetof(dfit_stats, n_deferred), offsetof(dfit_gather_desc, y_voxel0));
+          return 0;
+        }'''))
+    exe = tmp_path / "layout"
+    subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
+    got = [int(v) for v in subprocess.check_output([str(exe)]).split()]
+    want = [ctypes.sizeof(_cabi.DfitOpts), ctypes.sizeof(_cabi.DfitStats), ctypes.sizeof(_cabi.DfitGatherDesc),
+            ctypes.sizeof(_cabi.DfitQdessOpts), _cabi.DfitOpts.out_param.offset, _cabi.DfitOpts.decimals.offset,
+            _cabi.DfitStats.n_deferred.offset, _cabi.DfitGatherDesc.y_voxel0.offset]
+    assert got == want, (got, want)
