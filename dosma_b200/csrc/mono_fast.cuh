@@ -1,7 +1,8 @@
-// Mono-exponential fast path: variable-projection Newton iteration on the projected cost, one voxel per lane
-// (mono_uniform_newton) and two voxels per lane (mono_uniform_newton2 for uniformly spaced echoes,
-// mono_general_newton2 for arbitrary echo times), with the per-voxel entry points fit_voxel_fast /
-// fit_voxel_fast2 that the kernels call before the general LM of lm_core.cuh.  See DESIGN.md section 3.
+// Mono-exponential fast path: variable-projection Newton iteration on the projected cost.  Two voxels per lane,
+// straight line, exactly two passes (mono_uniform_fast2 for uniformly spaced echoes, mono_general_fast2 for arbitrary
+// echo times; entry point fit_voxel_fast2s) is what the dense kernels run; the loop forms (mono_uniform_newton, one
+// voxel per lane; mono_general_newton2; entry point fit_voxel_fast) take the voxels those turn down, before the
+// general LM of lm_core.cuh.  See DESIGN.md section 3.
 //
 // Like lm_core.cuh this header compiles for the device and, through the same portability shim, for the
 // test-only host build (tests/hostsim).
@@ -67,7 +68,7 @@ DFIT_HD int mono_uniform_newton(const T (&y)[E], const XTab<T, E>& xt, const Sol
 #pragma unroll
   for (int k = 1; k + 1 < E; ++k) nd = p2_fma<T>(p2_bcast<T>(y[k]), p2_make<T>(y[k + 1], y[k]), nd);
   const T ysq = nm::fma_(y[E - 1], y[E - 1], nd.hi);
-  const T pdb = nm::fma_(-y[0], y[0], ysq);  // descending echo times: predicted backwards (see mono_uniform_newton2)
+  const T pdb = nm::fma_(-y[0], y[0], ysq);  // descending echo times: predicted backwards (a per-launch choice: with descending echo times a decaying signal grows with the echo index, and the large samples should carry the estimate)
   T q = xt.backward != 0 ? pdb * nm::rcp_(nd.lo) : nd.lo * nm::rcp_(nd.hi);
   // no admissible start (also catches NaN and all-zero voxels): this lane declines, but keeps in step
   bool active = q > xt.q_lo && q < xt.q_hi && nm::finite(ysq);
@@ -237,125 +238,6 @@ DFIT_HD void newton_lane_step(NewtonLane<T>& L, int k, T h, T pred2, T tol2, T d
   L.af = (act && conv) ? nm::fma_(ap, dq, a) : L.af;
   L.npass = act ? k + 1 : L.npass;
   L.dprev2 = act ? (conv ? (T)kLaneDone : (convex ? step2 : (T)kLaneDeclined)) : L.dprev2;
-}
-
-// Y[e] = (sample e of voxel A, sample e of voxel B); Y is an array of pair2<T> or any object whose operator[]
-// returns one (the TMA kernel reads the samples from its shared-memory tile on every use instead of holding
-// them in 2 E registers).  Outputs per voxel: status (-1 = declined), passes,
-// a, b, cost F at the returned point and sum of squares about the mean.
-template <typename T, int E, class YS>
-DFIT_HD void mono_uniform_newton2(const YS& Y, const XTab<T, E>& xt, const SolverOpts<T>& o, pair2<T>& pa,
-                                  pair2<T>& pb, pair2<T>& F_out, int (&status)[2], int (&iters)[2]) {
-  static_assert(E >= 3, "needs at least three echoes");
-  typedef num<T> nm;
-  typedef pair2<T> V;
-  const unsigned lanes = DFIT_LANES();
-  (void)lanes;
-  const V one = p2_bcast<T>((T)1);
-  // Prony start q0 = sum y_k y_k+1 / sum y_k^2; sum y^2 falls out of the same recurrence
-  V pn = p2_mul<T>(Y[0], Y[1]), pd = p2_mul<T>(Y[0], Y[0]);
-#pragma unroll
-  for (int k = 1; k + 1 < E; ++k) {
-    pn = p2_fma<T>(Y[k], Y[k + 1], pn);
-    pd = p2_fma<T>(Y[k], Y[k], pd);
-  }
-  const V ysq = p2_fma<T>(Y[E - 1], Y[E - 1], pd);
-  // with descending echo times a decaying signal grows with the echo index: predict backwards,
-  // q0 = sum y_k+1^2 / sum y_k y_k+1, so that the large samples carry the estimate (a per-launch choice)
-  const V pdb = p2_fma<T>(p2_mul<T>(Y[0], p2_bcast<T>((T)-1)), Y[0], ysq);
-  NewtonLane<T> A, B;
-  {
-    T qa, qb;
-    if (xt.backward != 0) {
-      qa = pdb.lo * nm::rcp_(pn.lo);
-      qb = pdb.hi * nm::rcp_(pn.hi);
-    } else {
-      qa = pn.lo * nm::rcp_(pd.lo);
-      qb = pn.hi * nm::rcp_(pd.hi);
-    }
-    // no admissible start (also catches NaN and all-zero voxels): the lane declines but keeps in step
-    A.start(qa, qa > xt.q_lo && qa < xt.q_hi && nm::finite(ysq.lo), (T)0.5);
-    B.start(qb, qb > xt.q_lo && qb < xt.q_hi && nm::finite(ysq.hi), (T)0.5);
-  }
-  // tolerance on twice the Newton decrement: 2 (ftol F + floor_rel sum y^2)
-  const V floor2 = p2_mul<T>(ysq, p2_bcast<T>((T)2 * o.floor_rel));
-  const V ftol2 = p2_bcast<T>((T)2 * o.ftol);
-  // one pass; the first one is a separate instance (first-step gate, no contraction estimate yet)
-  auto pass = [&](auto first_tag, int k) {
-    constexpr bool FIRST = decltype(first_tag)::value;
-    const V q = p2_make<T>(A.q, B.q);
-    const V s = p2_mul<T>(q, q);
-    // Horner with first and (half) second derivative: N(q) over the samples, D(s) over ones
-    V N0 = Y[E - 1], N1 = N0, N2, D0 = one, D1 = one, D2;
-    N0 = p2_fma<T>(N0, q, Y[E - 2]);
-    D0 = p2_add<T>(s, one);
-    N2 = N1;
-    D2 = D1;
-    N1 = p2_fma<T>(N1, q, N0);
-    D1 = p2_add<T>(s, D0);
-    N0 = p2_fma<T>(N0, q, Y[E - 3]);
-    D0 = p2_fma<T>(D0, s, one);
-#pragma unroll
-    for (int j = E - 4; j >= 0; --j) {
-      N2 = p2_fma<T>(N2, q, N1);
-      D2 = p2_fma<T>(D2, s, D1);
-      N1 = p2_fma<T>(N1, q, N0);
-      D1 = p2_fma<T>(D1, s, D0);
-      N0 = p2_fma<T>(N0, q, Y[j]);
-      D0 = p2_fma<T>(D0, s, one);
-    }
-    // N0 = N, N1 = dN/dq, N2 = (d2N/dq2)/2;  D0 = D(s), D1 = dD/ds, D2 = (d2D/ds2)/2
-    const V nDq = p2_mul<T>(p2_mul<T>(q, p2_bcast<T>((T)-2)), D1);                     // -dD/dq
-    const V Dqq = p2_fma<T>(p2_mul<T>(s, p2_bcast<T>((T)8)), D2, p2_add<T>(D1, D1));  // d2D/dq2
-    const V rD = p2_make<T>(nm::rcp_(D0.lo), nm::rcp_(D0.hi));
-    const V a = p2_mul<T>(N0, rD);           // projected amplitude a'(q)
-    const V w = p2_fma<T>(a, nDq, N1);       // = D da'/dq
-    const V ap = p2_mul<T>(w, rD);           // da'/dq
-    const V mg = p2_mul<T>(a, p2_add<T>(w, N1));  // -dphi/dq
-    const V t2 = p2_fma<T>(N2, p2_bcast<T>((T)-4), p2_mul<T>(a, Dqq));
-    const V h = p2_fma<T>(a, t2, p2_mul<T>(p2_mul<T>(w, ap), p2_bcast<T>((T)-2)));  // d2phi/dq2
-    const V dq = p2_mul<T>(mg, p2_make<T>(nm::rcp_(h.lo), nm::rcp_(h.hi)));
-    const V pred2 = p2_mul<T>(mg, dq);       // twice the Newton decrement
-    // projected cost estimate sum y^2 - N a (clamped at 0 per voxel below) -> tolerance
-    const V Fe = p2_fma<T>(p2_mul<T>(N0, p2_bcast<T>((T)-1)), a, ysq);
-    const V tol2 = p2_fma<T>(ftol2, p2_make<T>(nm::max_(Fe.lo, (T)0), nm::max_(Fe.hi, (T)0)), floor2);
-    newton_lane_step<FIRST, T>(A, k, h.lo, pred2.lo, tol2.lo, dq.lo, a.lo, ap.lo, (T)-0.5 * A.q, A.q, kFirstStepCap * A.q);
-    newton_lane_step<FIRST, T>(B, k, h.hi, pred2.hi, tol2.hi, dq.hi, a.hi, ap.hi, (T)-0.5 * B.q, B.q, kFirstStepCap * B.q);
-  };
-  if (DFIT_ANY(lanes, A.active() || B.active())) pass(FirstPass<true>(), 0);
-#pragma unroll 1
-  for (int k = 1; k < kMonoFastPasses; ++k) {
-    if (!DFIT_ANY(lanes, A.active() || B.active())) break;
-    pass(FirstPass<false>(), k);
-  }
-  iters[0] = A.npass;
-  iters[1] = B.npass;
-  const bool okA = A.done() && A.q > xt.q_lo && A.q < xt.q_hi && nm::finite(A.af);
-  const bool okB = B.done() && B.q > xt.q_lo && B.q < xt.q_hi && nm::finite(B.af);
-  // a declined voxel rides along on harmless values
-  const V qf = p2_make<T>(okA ? A.q : (T)0.5, okB ? B.q : (T)0.5);
-  const V af = p2_make<T>(okA ? A.af : (T)0, okB ? B.af : (T)0);
-  // cost at the returned point: r_k = y_k - a' q^k
-  V ee = qf, F = p2_bcast<T>((T)0);
-  const V naf = p2_mul<T>(af, p2_bcast<T>((T)-1));
-  {
-    const V r0 = p2_add<T>(Y[0], naf);
-    F = p2_mul<T>(r0, r0);
-  }
-#pragma unroll
-  for (int e = 1; e < E; ++e) {
-    const V r = p2_fma<T>(naf, ee, Y[e]);
-    F = p2_fma<T>(r, r, F);
-    if (e + 1 < E) ee = p2_mul<T>(ee, qf);
-  }
-  // back to the reference's parameters: b = ln(q) / dx, a = a' exp(-b x0)
-  const V b = p2_mul<T>(p2_log_pos<T>(qf), p2_bcast<T>(xt.inv_dx));
-  pb = b;
-  pa = af;
-  if (xt.x0 != (T)0) pa = p2_mul<T>(af, p2_make<T>(nm::expbx(-b.lo, xt.x0, xt.x0s), nm::expbx(-b.hi, xt.x0, xt.x0s)));
-  F_out = F;
-  status[0] = okA ? (F.lo <= o.floor_rel * ysq.lo ? ST_EXACT : ST_CONV_F) : -1;
-  status[1] = okB ? (F.hi <= o.floor_rel * ysq.hi ? ST_EXACT : ST_CONV_F) : -1;
 }
 
 // ---- general echo times ------------------------------------------------------------------------------
@@ -549,7 +431,7 @@ DFIT_HD void mono_uniform_fast2(const YS& Y, const XTab<T, E>& xt, const SolverO
   }
   const V ysq = p2_fma<T>(Y[E - 1], Y[E - 1], pd);
   V q;
-  if (xt.backward != 0) {  // descending echo times: predicted backwards (see mono_uniform_newton2)
+  if (xt.backward != 0) {  // descending echo times: predicted backwards (a per-launch choice: with descending echo times a decaying signal grows with the echo index, and the large samples should carry the estimate)
     const V pdb = p2_fma<T>(p2_mul<T>(Y[0], p2_bcast<T>((T)-1)), Y[0], ysq);
     q = p2_mul<T>(pdb, p2_make<T>(nm::rcp_(pn.lo), nm::rcp_(pn.hi)));
   } else {
@@ -795,14 +677,15 @@ DFIT_HD T ss_total(const T (&y)[E]) {
 }
 
 
-// Fast-path attempt for two voxels: status[i] = -1 where voxel i has to take the general path.
+// Loop-form fast-path attempt for two voxels on ARBITRARY echo times (the one-voxel path below runs its voxel through
+// it; uniformly spaced echoes have their own one-voxel solver, mono_uniform_newton): status[i] = -1 where voxel i has
+// to take the general path.
 template <class M, typename T, int EMAX, class YS>
 DFIT_HD void fit_voxel_fast2(const YS& Y, const XTab<T, EMAX>& xt, const VoxelOpts<T>& vo, pair2<T>& pa,
                              pair2<T>& pb, pair2<T>& r2, int (&status)[2], int (&iters)[2]) {
   static_assert(M::MONO && EMAX >= 3, "mono-exponential model only");
   pair2<T> F;
-  if (xt.uniform != 0) mono_uniform_newton2<T, EMAX, YS>(Y, xt, vo.s, pa, pb, F, status, iters);
-  else mono_general_newton2<T, EMAX, YS>(Y, xt, vo.s, pa, pb, F, status, iters);
+  mono_general_newton2<T, EMAX, YS>(Y, xt, vo.s, pa, pb, F, status, iters);
   const pair2<T> den = p2_add<T>(ss_total2<T, EMAX, YS>(Y), p2_bcast<T>(vo.r2_eps));
   const pair2<T> nr = p2_make<T>(-num<T>::rcp_(den.lo), -num<T>::rcp_(den.hi));
   r2 = p2_fma<T>(F, nr, p2_bcast<T>((T)1));  // fitting.py:1032-1035
