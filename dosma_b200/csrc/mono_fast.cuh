@@ -68,7 +68,9 @@ DFIT_HD int mono_uniform_newton(const T (&y)[E], const XTab<T, E>& xt, const Sol
 #pragma unroll
   for (int k = 1; k + 1 < E; ++k) nd = p2_fma<T>(p2_bcast<T>(y[k]), p2_make<T>(y[k + 1], y[k]), nd);
   const T ysq = nm::fma_(y[E - 1], y[E - 1], nd.hi);
-  const T pdb = nm::fma_(-y[0], y[0], ysq);  // descending echo times: predicted backwards (a per-launch choice: with descending echo times a decaying signal grows with the echo index, and the large samples should carry the estimate)
+  // descending echo times: a decaying signal grows with the echo index; it is predicted backwards so that the large
+  // samples carry the estimate (a per-launch choice)
+  const T pdb = nm::fma_(-y[0], y[0], ysq);
   T q = xt.backward != 0 ? pdb * nm::rcp_(nd.lo) : nd.lo * nm::rcp_(nd.hi);
   // no admissible start (also catches NaN and all-zero voxels): this lane declines, but keeps in step
   bool active = q > xt.q_lo && q < xt.q_hi && nm::finite(ysq);
@@ -431,7 +433,7 @@ DFIT_HD void mono_uniform_fast2(const YS& Y, const XTab<T, E>& xt, const SolverO
   }
   const V ysq = p2_fma<T>(Y[E - 1], Y[E - 1], pd);
   V q;
-  if (xt.backward != 0) {  // descending echo times: predicted backwards (a per-launch choice: with descending echo times a decaying signal grows with the echo index, and the large samples should carry the estimate)
+  if (xt.backward != 0) {  // descending echo times: predicted backwards (see mono_uniform_newton)
     const V pdb = p2_fma<T>(p2_mul<T>(Y[0], p2_bcast<T>((T)-1)), Y[0], ysq);
     q = p2_mul<T>(pdb, p2_make<T>(nm::rcp_(pn.lo), nm::rcp_(pn.hi)));
   } else {
