@@ -5,6 +5,8 @@
 //                         path in front for the mono-exponential model), fit_kernel_tma
 //   mono2_kernels.cuh  -- two voxels per lane, mono-exponential fast path: fit_kernel_mono2 (plain loads),
 //                         fit_kernel_mono2_list (mask path), fit_kernel_mono2_tma (persistent, TMA-staged: the headline)
+//   lmq_kernel.cuh     -- the LM in rounds with a per-warp stack of suspended fits (fit_kernel_lmq): every fp32 fit that
+//                         goes straight to the LM (bi-exponential, linear, mono-exponential with fast_path = 0)
 //   this file          -- launch_one: which kernel a launch description gets, and the per-echo-count instances
 //
 // Together they replace the N-voxel loop of dosma/core/fitting.py:855-868 and fuse what the reference does
@@ -14,6 +16,7 @@
 
 #include "fit_kernels1.cuh"
 #include "kernel_common.cuh"
+#include "lmq_kernel.cuh"
 #include "mono2_kernels.cuh"
 
 namespace dfit {
@@ -72,6 +75,9 @@ inline cudaError_t launch_one(const LaunchDesc& d) {
     }
   }
   const int64_t blocks = (d.n_vox + kBlock - 1) / kBlock;
+  // fits that go straight to the LM (no fast path in front), fp32, one GPU: the LM in rounds (lmq_kernel.cuh)
+  [[maybe_unused]] const bool lmq = EXACT && sizeof(T) == 4 && d.g.world == 0 && lmq_config().enabled &&
+                                    (!M::MONO || d.fast_path == 0 || a.vo.has_bounds) && d.n_vox < ((int64_t)1 << 32);
   if (d.mask != nullptr && d.index != nullptr) {
     // mask path: compact + fill, then fit the list with a grid sized for the SMs (grid-stride)
     cudaError_t e = cudaMemsetAsync(d.index_count, 0, sizeof(unsigned), d.stream);
@@ -89,6 +95,9 @@ inline cudaError_t launch_one(const LaunchDesc& d) {
         return cudaGetLastError();
       }
     }
+    if constexpr (EXACT && sizeof(T) == 4) {
+      if (lmq) return launch_lmq<M, EMAX>(d, a);
+    }
     if (d.g.world > 0) {
       if constexpr (sizeof(T) == 4) fit_kernel<M, T, EMAX, EXACT, true><<<(unsigned)g, kBlock, 0, d.stream>>>(a);
       else return cudaErrorNotSupported;
@@ -96,6 +105,9 @@ inline cudaError_t launch_one(const LaunchDesc& d) {
       fit_kernel<M, T, EMAX, EXACT, false><<<(unsigned)g, kBlock, 0, d.stream>>>(a);
     }
     return cudaGetLastError();
+  }
+  if constexpr (EXACT && sizeof(T) == 4) {
+    if (lmq) return launch_lmq<M, EMAX>(d, a);
   }
   // the fused all-gather epilogue is a separate instance so that single-GPU launches do not pay its registers
   if (d.g.world > 0) {

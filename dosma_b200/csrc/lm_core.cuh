@@ -526,157 +526,193 @@ DFIT_HD bool lm_step(const T (&p)[P], const TA (&A)[P * (P + 1) / 2], const TA (
   return true;
 }
 
-// The solver.  On entry p holds the initial guess; on exit the accepted parameters.
-// Returns a Status; F_out is the sum of squared residuals at the returned point, iters the number
-// of passes over the echoes (model + Jacobian evaluations) spent.
+// The solver, in two pieces so that a kernel can run it in ROUNDS (fit_kernel_lmq): lm_begin evaluates the start
+// point, lm_iterate runs the Levenberg-Marquardt trips and can stop -- right before a model evaluation, with the step
+// to evaluate already computed -- once it has spent `budget` evaluations; called again with resume = true it carries on
+// exactly where it stopped.  Everything the iteration carries from one trip to the next lives in LmState, so a
+// suspended fit can be parked in shared memory and picked up by any lane; per voxel the arithmetic is the same, in
+// the same order, however the trips are cut into rounds.  lm_solve is the two run back to back.
 //
 // Every pass (eval_all) yields the cost for the gain ratio AND the normal equations for the next
 // step.  Two passes are saved relative to a textbook LM:
 //   * the variable-projection start is a first step restricted to the linear parameters with zero
 //     damping, taken from the linear parameters set to zero (its trial pass IS the first pass);
 //   * a step whose predicted reduction is already below ftol*F is taken without evaluating it.
+constexpr int ST_PENDING = -1;  // lm_iterate: the budget of this round is spent, the fit is not finished
+
+template <int P, typename T, typename TA>
+struct LmState {
+  static constexpr int NA = P * (P + 1) / 2;
+  TA F, A[NA], g[P], D2[P];  // cost, normal equations and running column scales at the accepted point
+  TA lam, nu, ysq;           // damping, its growth factor, sum y^2
+  T pt[P];                   // the trial point the next evaluation is wanted at ...
+  TA zz, pnorm2, pred;       // ... its squared scaled step, squared scaled norm and predicted reduction
+  int fev, iters;            // MINPACK-style budget spent, passes over the echoes spent
+};
+
+// Start: returns ST_PENDING (iterate from p) or a final status.
 template <class M, typename T, typename TA, int EMAX, bool EXACT>
-DFIT_HD int lm_solve(T (&p)[M::P], const T (&y)[EMAX], const T* __restrict__ x, const T* __restrict__ xs, int E,
-                     const SolverOpts<T>& o, T& F_out, int& iters) {
+DFIT_HD int lm_begin(T (&p)[M::P], const T (&y)[EMAX], const T* __restrict__ x, const T* __restrict__ xs, int E,
+                     const SolverOpts<T>& o, LmState<M::P, T, TA>& s) {
   constexpr int P = M::P;
   constexpr int NA = P * (P + 1) / 2;
-  constexpr unsigned ALL = (1u << P) - 1u;
-  iters = 0;
-
+  s.iters = 0;
+  s.fev = 0;
   TA ysq = 0;
 #pragma unroll
   for (int e = 0; e < EMAX; ++e)
     if (EXACT || e < E) ysq = num<TA>::fma_((TA)y[e], (TA)y[e], ysq);
-  const TA floorF = (TA)o.floor_rel * ysq;
-  const TA ftol = (TA)o.ftol, xtol2 = (TA)o.xtol * (TA)o.xtol;
-  const TA eps16 = (TA)16 * (TA)num<T>::eps();
-
-  TA F = 0, A[NA], g[P], D2[P];
+  s.ysq = ysq;
+  s.F = 0;
 #pragma unroll
-  for (int i = 0; i < P; ++i) D2[i] = 0;
-  TA zz = 0, pnorm2 = 0, pred = 0;
-  int fev = 0;
+  for (int i = 0; i < P; ++i) s.D2[i] = 0;
+  s.zz = s.pnorm2 = s.pred = 0;
+  s.lam = (TA)o.lambda0;
+  s.nu = 2;
 
-  // ---- start ---------------------------------------------------------------------------------------
   // Projection: with the linear parameters at zero the residual is -y and only the linear block of
   // the normal equations is needed (a cheap pass); its unregularised solution is the least-squares
   // optimum of the linear parameters for the given non-linear ones.  The projected point is then
   // evaluated in full; if that is not an improvement over sum y^2 (degenerate linear sub-problem),
   // or projection is off, the fit starts from p0 exactly as given.
-  {
-    T plin[P], pt[P];
-    bool projected = false;
+  T plin[P], pt[P];
+  bool projected = false;
 #pragma unroll
-    for (int i = 0; i < P; ++i) plin[i] = pt[i] = p[i];
-    if (o.init_linear != 0) {
+  for (int i = 0; i < P; ++i) plin[i] = pt[i] = p[i];
+  if (o.init_linear != 0) {
 #pragma unroll
-      for (int i = 0; i < P; ++i)
-        if ((M::LIN >> i) & 1u) pt[i] = (T)0;
-      TA F0, A0[NA], g0[P], D2p[P];
+    for (int i = 0; i < P; ++i)
+      if ((M::LIN >> i) & 1u) pt[i] = (T)0;
+    TA F0, A0[NA], g0[P], D2p[P];
 #pragma unroll
-      for (int k = 0; k < NA; ++k) A0[k] = 0;
+    for (int k = 0; k < NA; ++k) A0[k] = 0;
 #pragma unroll
-      for (int i = 0; i < P; ++i) {
-        g0[i] = 0;
-        D2p[i] = 0;
-      }
-      eval_all<M, T, TA, EMAX, EXACT, M::LIN>(pt, y, x, xs, E, F0, A0, g0);
-      ++iters;
-      fev += 1;
-      T pp[P];
-      projected = lm_step<P, T, TA>(pt, A0, g0, D2p, (TA)0, M::LIN, pp, zz, pnorm2, pred);
-#pragma unroll
-      for (int i = 0; i < P; ++i) {
-        projected = projected && num<T>::finite(pp[i]);
-        pt[i] = pp[i];
-      }
+    for (int i = 0; i < P; ++i) {
+      g0[i] = 0;
+      D2p[i] = 0;
     }
-    for (int trip = 0; trip < 2; ++trip) {
-      if (!projected) {
+    eval_all<M, T, TA, EMAX, EXACT, M::LIN>(pt, y, x, xs, E, F0, A0, g0);
+    ++s.iters;
+    s.fev += 1;
+    T pp[P];
+    projected = lm_step<P, T, TA>(pt, A0, g0, D2p, (TA)0, M::LIN, pp, s.zz, s.pnorm2, s.pred);
 #pragma unroll
-        for (int i = 0; i < P; ++i) pt[i] = plin[i];
-      }
-      eval_all<M, T, TA, EMAX, EXACT>(pt, y, x, xs, E, F, A, g);
-      ++iters;
-      fev += 1 + P;
-      const bool good = num<TA>::finite(F);
-      if (projected && !(good && F <= ysq)) {
-        projected = false;
-        continue;
-      }
-      if (!good) {
-        F_out = (T)F;
-        return ST_NUMERIC;
-      }
-      break;
+    for (int i = 0; i < P; ++i) {
+      projected = projected && num<T>::finite(pp[i]);
+      pt[i] = pp[i];
     }
-#pragma unroll
-    for (int i = 0; i < P; ++i) p[i] = pt[i];
   }
-
-  // ---- Levenberg-Marquardt iterations -----------------------------------------------------------
-  TA lam = (TA)o.lambda0, nu = 2;
-  int status = ST_MAXITER;
-  while (fev < o.maxfev) {
-    if (F <= floorF) {
-      status = ST_EXACT;
-      break;
-    }
-    T pt[P];
-    bool solved = lm_step<P, T, TA>(p, A, g, D2, lam, ALL, pt, zz, pnorm2, pred);
-    for (int tries = 0; tries < 12 && !solved; ++tries) {
-      lam = num<TA>::max_(lam * (TA)10, (TA)1e-3);
-      solved = lm_step<P, T, TA>(p, A, g, D2, lam, ALL, pt, zz, pnorm2, pred);
-    }
-    if (!solved) break;
-    if (pred <= ftol * F && lam <= (TA)1) {
-      // the step is below the tolerance before it is even evaluated: take it and stop
+  for (int trip = 0; trip < 2; ++trip) {
+    if (!projected) {
 #pragma unroll
-      for (int i = 0; i < P; ++i) p[i] = pt[i];
-      status = zz <= xtol2 * pnorm2 ? ST_CONV_FX : ST_CONV_F;
-      break;
+      for (int i = 0; i < P; ++i) pt[i] = plin[i];
     }
+    eval_all<M, T, TA, EMAX, EXACT>(pt, y, x, xs, E, s.F, s.A, s.g);
+    ++s.iters;
+    s.fev += 1 + P;
+    const bool good = num<TA>::finite(s.F);
+    if (projected && !(good && s.F <= ysq)) {
+      projected = false;
+      continue;
+    }
+    if (!good) return ST_NUMERIC;
+    break;
+  }
+#pragma unroll
+  for (int i = 0; i < P; ++i) p[i] = pt[i];
+  return ST_PENDING;
+}
+
+// Levenberg-Marquardt trips from the state lm_begin (or an earlier, suspended lm_iterate: resume = true) left.
+// Returns the final status, or ST_PENDING after `budget` evaluations with the fit still going.
+template <class M, typename T, typename TA, int EMAX, bool EXACT>
+DFIT_HD int lm_iterate(T (&p)[M::P], const T (&y)[EMAX], const T* __restrict__ x, const T* __restrict__ xs, int E,
+                       const SolverOpts<T>& o, LmState<M::P, T, TA>& s, int budget, bool resume) {
+  constexpr int P = M::P;
+  constexpr int NA = P * (P + 1) / 2;
+  constexpr unsigned ALL = (1u << P) - 1u;
+  const TA floorF = (TA)o.floor_rel * s.ysq;
+  const TA ftol = (TA)o.ftol, xtol2 = (TA)o.xtol * (TA)o.xtol;
+  const TA eps16 = (TA)16 * (TA)num<T>::eps();
+  int status = ST_MAXITER;
+  for (;;) {
+    if (!resume) {
+      if (!(s.fev < o.maxfev)) break;
+      if (s.F <= floorF) {
+        status = ST_EXACT;
+        break;
+      }
+      bool solved = lm_step<P, T, TA>(p, s.A, s.g, s.D2, s.lam, ALL, s.pt, s.zz, s.pnorm2, s.pred);
+      for (int tries = 0; tries < 12 && !solved; ++tries) {
+        s.lam = num<TA>::max_(s.lam * (TA)10, (TA)1e-3);
+        solved = lm_step<P, T, TA>(p, s.A, s.g, s.D2, s.lam, ALL, s.pt, s.zz, s.pnorm2, s.pred);
+      }
+      if (!solved) break;
+      if (s.pred <= ftol * s.F && s.lam <= (TA)1) {
+        // the step is below the tolerance before it is even evaluated: take it and stop
+#pragma unroll
+        for (int i = 0; i < P; ++i) p[i] = s.pt[i];
+        status = s.zz <= xtol2 * s.pnorm2 ? ST_CONV_FX : ST_CONV_F;
+        break;
+      }
+      if (budget <= 0) return ST_PENDING;  // suspended with the step computed: the next call evaluates it first
+    }
+    resume = false;
+    --budget;
     TA Fn, An[NA], gn[P];
-    eval_all<M, T, TA, EMAX, EXACT>(pt, y, x, xs, E, Fn, An, gn);
-    ++iters;
-    ++fev;
+    eval_all<M, T, TA, EMAX, EXACT>(s.pt, y, x, xs, E, Fn, An, gn);
+    ++s.iters;
+    ++s.fev;
     const bool good = num<TA>::finite(Fn);
-    const TA act = F - Fn;
+    const TA act = s.F - Fn;
     // F and Fn are sums of squares of model evaluations that each carry ~eps*|y| of rounding, so
     // their difference cannot resolve reductions below tau ~ eps*sqrt(sum y^2 * F).  Below that
     // level the gain ratio is noise: trust the (accurately computed) predicted reduction instead
     // of rejecting at random.  (Compared squared to avoid the square root.)
-    const TA tau2 = eps16 * eps16 * ysq * F;
-    const bool reliable = pred * pred > tau2;
-    const bool accept = good && (reliable ? act > (TA)1e-4 * pred : act * num<TA>::abs_(act) > -tau2);
-    const TA rho = reliable ? act * num<TA>::rcp_(pred) : (TA)1;
+    const TA tau2 = eps16 * eps16 * s.ysq * s.F;
+    const bool reliable = s.pred * s.pred > tau2;
+    const bool accept = good && (reliable ? act > (TA)1e-4 * s.pred : act * num<TA>::abs_(act) > -tau2);
+    const TA rho = reliable ? act * num<TA>::rcp_(s.pred) : (TA)1;
     const bool small_f =
-        good && pred <= ftol * F && (!reliable || (num<TA>::abs_(act) <= ftol * F && act <= (TA)2 * pred));
-    const bool conv_x = accept && zz <= xtol2 * pnorm2;
+        good && s.pred <= ftol * s.F && (!reliable || (num<TA>::abs_(act) <= ftol * s.F && act <= (TA)2 * s.pred));
+    const bool conv_x = accept && s.zz <= xtol2 * s.pnorm2;
     if (accept) {
 #pragma unroll
       for (int i = 0; i < P; ++i) {
-        p[i] = pt[i];
-        g[i] = gn[i];
+        p[i] = s.pt[i];
+        s.g[i] = gn[i];
       }
 #pragma unroll
-      for (int k = 0; k < NA; ++k) A[k] = An[k];
-      F = Fn;
+      for (int k = 0; k < NA; ++k) s.A[k] = An[k];
+      s.F = Fn;
       const TA t = (TA)2 * rho - (TA)1;
-      lam = num<TA>::max_(lam * num<TA>::max_((TA)(1.0 / 3.0), (TA)1 - t * t * t), (TA)1e-9);
-      nu = 2;
-      fev += P;  // MINPACK re-differences its Jacobian here: P more evaluations of its budget
+      s.lam = num<TA>::max_(s.lam * num<TA>::max_((TA)(1.0 / 3.0), (TA)1 - t * t * t), (TA)1e-9);
+      s.nu = 2;
+      s.fev += P;  // MINPACK re-differences its Jacobian here: P more evaluations of its budget
     } else {
-      lam *= nu;
-      nu *= 2;
+      s.lam *= s.nu;
+      s.nu *= 2;
     }
     if (small_f || conv_x) {
       status = small_f ? (conv_x ? ST_CONV_FX : ST_CONV_F) : ST_CONV_X;
       break;
     }
   }
-  if (status == ST_MAXITER && F <= floorF) status = ST_EXACT;
-  F_out = (T)F;
+  if (status == ST_MAXITER && s.F <= floorF) status = ST_EXACT;
+  return status;
+}
+
+// On entry p holds the initial guess; on exit the accepted parameters.  Returns a Status; F_out is the sum of
+// squared residuals at the returned point, iters the number of passes over the echoes (model + Jacobian
+// evaluations) spent.
+template <class M, typename T, typename TA, int EMAX, bool EXACT>
+DFIT_HD int lm_solve(T (&p)[M::P], const T (&y)[EMAX], const T* __restrict__ x, const T* __restrict__ xs, int E,
+                     const SolverOpts<T>& o, T& F_out, int& iters) {
+  LmState<M::P, T, TA> s;
+  int status = lm_begin<M, T, TA, EMAX, EXACT>(p, y, x, xs, E, o, s);
+  if (status == ST_PENDING) status = lm_iterate<M, T, TA, EMAX, EXACT>(p, y, x, xs, E, o, s, 0x7fffffff, false);
+  F_out = (T)s.F;
+  iters = s.iters;
   return status;
 }
 
@@ -756,13 +792,16 @@ struct VoxelOpts {
 };
 
 // Everything the reference does for one voxel (`_curve_fit`, fitting.py:1026-1073), on samples that
-// are already in registers.  p: in = initial guess, out = fitted parameters (NaN on skip/failure).
-template <class M, typename T, typename TA, int EMAX, bool EXACT>
-DFIT_HD int fit_voxel(const T (&y)[EMAX], const XTab<T, EMAX>& xt, int E, const VoxelOpts<T>& vo, T (&p)[M::P],
-                      T& r2, int& iters, unsigned& flags) {
+// are already in registers, in three steps so that kernels can put their own solver loop in the middle:
+//   voxel_prepare  skip rules (:1065-1067), optional log-linear initial guess, non-finite check
+//                  -> a final Status, or ST_PENDING: run the solver from p
+//   (solver)       lm_solve, or lm_begin + rounds of lm_iterate
+//   voxel_finish   r2 (:1032-1035) on success, NaN parameters and r2 = 0 otherwise (:1067, :1072)
+template <class M, typename T, int EMAX, bool EXACT>
+DFIT_HD int voxel_prepare(const T (&y)[EMAX], const XTab<T, EMAX>& xt, int E, const VoxelOpts<T>& vo, T (&p)[M::P],
+                          unsigned& flags) {
   constexpr int P = M::P;
   bool all_zero = true, oob = false, nonfinite = false;
-  T ysum = 0;
 #pragma unroll
   for (int e = 0; e < EMAX; ++e) {
     if (EXACT || e < E) {
@@ -770,33 +809,36 @@ DFIT_HD int fit_voxel(const T (&y)[EMAX], const XTab<T, EMAX>& xt, int E, const 
       all_zero = all_zero && (v == (T)0);
       oob = oob || (v < vo.y_lo) || (v > vo.y_hi);
       nonfinite = nonfinite || !num<T>::finite(v);
-      ysum += v;
     }
   }
-  iters = 0;
   flags = 0;
-  int status;
-  T F = 0;
   if (oob || all_zero) {
-    status = ST_SKIPPED;
     if (oob) flags |= FLAG_OOB;
-  } else {
-    if (vo.init_mode == INIT_LOGLINEAR && P == 2) {
-      T q[2];
-      loglinear_init<T, EMAX, EXACT>(y, xt.xc, xt.xbar, xt.inv_sxx, E, q);
-      p[0] = q[0];
-      p[P - 1] = q[1];
-    }
-#pragma unroll
-    for (int i = 0; i < P; ++i) nonfinite = nonfinite || !num<T>::finite(p[i]);
-    if (nonfinite) {
-      status = ST_NONFINITE;
-      flags |= FLAG_NONFINITE;
-    } else {
-      status = lm_solve<M, T, TA, EMAX, EXACT>(p, y, xt.x, xt.xs, E, vo.s, F, iters);
-    }
+    return ST_SKIPPED;
   }
+  if (vo.init_mode == INIT_LOGLINEAR && P == 2) {
+    T q[2];
+    loglinear_init<T, EMAX, EXACT>(y, xt.xc, xt.xbar, xt.inv_sxx, E, q);
+    p[0] = q[0];
+    p[P - 1] = q[1];
+  }
+#pragma unroll
+  for (int i = 0; i < P; ++i) nonfinite = nonfinite || !num<T>::finite(p[i]);
+  if (nonfinite) {
+    flags |= FLAG_NONFINITE;
+    return ST_NONFINITE;
+  }
+  return ST_PENDING;
+}
+
+template <class M, typename T, int EMAX, bool EXACT>
+DFIT_HD void voxel_finish(int status, const T (&y)[EMAX], int E, const VoxelOpts<T>& vo, T F, T (&p)[M::P], T& r2) {
+  constexpr int P = M::P;
   if (status >= ST_CONV_F && status <= ST_EXACT) {
+    T ysum = 0;
+#pragma unroll
+    for (int e = 0; e < EMAX; ++e)
+      if (EXACT || e < E) ysum += y[e];
     const T mean = ysum / (T)E;
     T ss_tot = 0;
 #pragma unroll
@@ -808,6 +850,17 @@ DFIT_HD int fit_voxel(const T (&y)[EMAX], const XTab<T, EMAX>& xt, int E, const 
     for (int i = 0; i < P; ++i) p[i] = (T)NAN;
     r2 = (T)0;  // fitting.py:1067, 1072
   }
+}
+
+// p: in = initial guess, out = fitted parameters (NaN on skip/failure).
+template <class M, typename T, typename TA, int EMAX, bool EXACT>
+DFIT_HD int fit_voxel(const T (&y)[EMAX], const XTab<T, EMAX>& xt, int E, const VoxelOpts<T>& vo, T (&p)[M::P],
+                      T& r2, int& iters, unsigned& flags) {
+  iters = 0;
+  T F = 0;
+  int status = voxel_prepare<M, T, EMAX, EXACT>(y, xt, E, vo, p, flags);
+  if (status == ST_PENDING) status = lm_solve<M, T, TA, EMAX, EXACT>(p, y, xt.x, xt.xs, E, vo.s, F, iters);
+  voxel_finish<M, T, EMAX, EXACT>(status, y, E, vo, F, p, r2);
   return status;
 }
 

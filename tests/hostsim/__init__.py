@@ -56,6 +56,12 @@ def fit(model, x, y, p0=None, dtype="f32", acc64=False, init_mode=0, init_linear
     return popt, r2, status, iters
 
 
+def set_rounds(k_first, k_next=None):
+    """LM in rounds (what fit_kernel_lmq does): lm_begin, then lm_iterate with `k_first` / `k_next` evaluations per round,
+    the solver state parked in between.  0 switches back to lm_solve."""
+    _load().hostsim_set_rounds(ctypes.c_int(int(k_first)), ctypes.c_int(int(k_first if k_next is None else k_next)))
+
+
 def engine_fit(model_id, nparams, x, planes, mask, p0_cols, *, init_mode=0, y_bounds=None, maxfev=100, ftol=1e-5,
                eps=1e-8, post=None, engine=None, out_param=None):
     """TEST-ONLY stand-in for `dosma_b200.fitting._engine_fit` with the same signature and return values: the device

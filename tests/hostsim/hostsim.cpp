@@ -10,6 +10,45 @@
 
 using namespace dfit;
 
+// fit_kernel_lmq's way through the LM: lm_begin, then rounds of lm_iterate with a budget of evaluations, the solver
+// state parked (copied away and back) between rounds.  0 = off: fit_voxel / lm_solve.
+static int g_round_first = 0, g_round_next = 0;
+extern "C" void hostsim_set_rounds(int k_first, int k_next) {
+  g_round_first = k_first;
+  g_round_next = k_next;
+}
+
+template <class M, typename T, typename TA, int EMAX, bool EXACT>
+static int fit_voxel_any(const T (&y)[EMAX], const XTab<T, EMAX>& xt, int E, const VoxelOpts<T>& vo, T (&p)[M::P], T& r2,
+                         int& iters, unsigned& flags) {
+  if (g_round_first <= 0) return fit_voxel<M, T, TA, EMAX, EXACT>(y, xt, E, vo, p, r2, iters, flags);
+  constexpr int P = M::P;
+  LmState<P, T, TA> s;
+  s.F = 0;
+  s.iters = 0;
+  int st = voxel_prepare<M, T, EMAX, EXACT>(y, xt, E, vo, p, flags);
+  if (st == ST_PENDING) st = lm_begin<M, T, TA, EMAX, EXACT>(p, y, xt.x, xt.xs, E, vo.s, s);
+  bool resume = false;
+  int budget = g_round_first;
+  while (st == ST_PENDING) {
+    st = lm_iterate<M, T, TA, EMAX, EXACT>(p, y, xt.x, xt.xs, E, vo.s, s, budget, resume);
+    if (st == ST_PENDING) {  // park: the state and the parameters survive as plain bytes, nothing else does
+      unsigned char park[sizeof(s) + sizeof(p)];
+      memcpy(park, &s, sizeof(s));
+      memcpy(park + sizeof(s), p, sizeof(p));
+      memset(&s, 0xff, sizeof(s));
+      memset(p, 0xff, sizeof(p));
+      memcpy(&s, park, sizeof(s));
+      memcpy(p, park + sizeof(s), sizeof(p));
+      resume = true;
+      budget = g_round_next;
+    }
+  }
+  voxel_finish<M, T, EMAX, EXACT>(st, y, E, vo, (T)s.F, p, r2);
+  iters = s.iters;
+  return st;
+}
+
 template <class M, typename T, typename TA, int EMAX, bool EXACT>
 static void run(int E, int64_t N, const double* x, const double* y, const double* p0, int64_t n_p0, int init_mode,
                 int init_linear, int fast, double ftol, double xtol, double lambda0, double floor_rel, int max_iter,
@@ -56,7 +95,7 @@ static void run(int E, int64_t N, const double* x, const double* y, const double
             if (st < 0) {
               const double* pv = p0 + (n_p0 > 1 ? (size_t)(v + hsel) * P : 0);
               for (int i = 0; i < P; ++i) p[i] = (T)pv[i];
-              st = fit_voxel<M, T, TA, EMAX, EXACT>(yy, xt, E, vo, p, r2v, it, flags);
+              st = fit_voxel_any<M, T, TA, EMAX, EXACT>(yy, xt, E, vo, p, r2v, it, flags);
             }
           }
           for (int i = 0; i < P; ++i) popt[(size_t)(v + hsel) * P + i] = (double)p[i];
@@ -82,7 +121,7 @@ static void run(int E, int64_t N, const double* x, const double* y, const double
     if constexpr (sizeof(T) == sizeof(TA)) st = fit_voxel_fast<M, T, EMAX, EXACT>(yy, xt, vo, p, r2v, it);
     if (st < 0) {
       for (int i = 0; i < P; ++i) p[i] = (T)pv[i];
-      st = fit_voxel<M, T, TA, EMAX, EXACT>(yy, xt, E, vo, p, r2v, it, flags);
+      st = fit_voxel_any<M, T, TA, EMAX, EXACT>(yy, xt, E, vo, p, r2v, it, flags);
     }
     for (int i = 0; i < P; ++i) popt[(size_t)v * P + i] = (double)p[i];
     r2[v] = (double)r2v;

@@ -154,6 +154,69 @@ def test_biexp_fp32_golden(D, name):
     G.check_biexp_f32(name, popt, r2)
 
 
+@pytest.mark.parametrize("case", ["biexp16", "biexp16_mask", "biexp9_ragged", "mono8_lm", "mono8_ybounds", "linear4"])
+def test_lm_in_rounds_kernel_equals_plain_kernel(D, case, monkeypatch):
+    """fit_kernel_lmq (LM in rounds, suspended fits parked on a per-warp stack in shared memory) against the plain
+    one-voxel-per-lane kernel (DFIT_LMQ=0) on the same inputs: popt, r2, status and pass counts bit for bit, for dense
+    and masked launches, ragged sizes, several round budgets."""
+    import torch
+
+    from dosma_b200 import _cabi, device_api as A
+
+    dev = torch.device("cuda", 0)
+    g = torch.Generator(device=dev).manual_seed(11)
+    kw, mask = {}, None
+    if case.startswith("biexp"):
+        E = 16 if "16" in case else 9
+        n = 40000 if "ragged" not in case else 32 * 77 + 13
+        x = [5.0 * i for i in range(1, E + 1)]
+        xt = torch.tensor(x, device=dev)[:, None]
+        amp = 500 + 1000 * torch.rand(n, device=dev, generator=g)
+        fs = 0.3 + 0.4 * torch.rand(n, device=dev, generator=g)
+        y = amp * fs * torch.exp(-xt / (8 + 12 * torch.rand(n, device=dev, generator=g))) + \
+            amp * (1 - fs) * torch.exp(-xt / (50 + 50 * torch.rand(n, device=dev, generator=g))) + \
+            10 * torch.randn(E, n, device=dev, generator=g)
+        model, p0 = D.biexponential, (500.0, -1 / 10, 500.0, -1 / 60)
+        if "mask" in case:
+            mask = (torch.rand(n, device=dev, generator=g) < 0.3).to(torch.uint8)
+    elif case.startswith("mono8"):
+        n = 50001
+        x = [10.0 * i for i in range(1, 9)]
+        xt = torch.tensor(x, device=dev)[:, None]
+        y = 1000 * torch.exp(-xt / (10 + 70 * torch.rand(n, device=dev, generator=g))) + 100 * torch.randn(8, n, device=dev, generator=g)
+        y[:, ::97] = 0  # skipped voxels
+        model, p0 = D.monoexponential, (1.0, -1 / 30)
+        kw = dict(fast_path=0) if case == "mono8_lm" else dict(y_bounds=(-150.0, 1100.0))
+    else:
+        n = 5000
+        x = [1.0, 2.0, 3.0, 4.0]
+        xt = torch.tensor(x, device=dev)[:, None]
+        y = xt * (1 + torch.rand(n, device=dev, generator=g)) + 0.1 * torch.randn(4, n, device=dev, generator=g)
+        model, p0 = D.linear, (1.0,)
+    o, P = A.make_opts(model, p0=p0, compute_dtype="f32", **kw)
+
+    def run():
+        popt = torch.full((n, P), -7.0, device=dev)
+        r2 = torch.full((n,), -7.0, device=dev)
+        st = torch.full((n,), 99, device=dev, dtype=torch.uint8)
+        it = torch.full((n,), 99, device=dev, dtype=torch.uint8)
+        A.fit_device(o, P, x, y, mask=mask, popt=popt, r2=r2, status=st, niter=it)
+        torch.cuda.synchronize()
+        return popt, r2, st, it, _cabi.get_handle(0).stats()
+
+    monkeypatch.setenv("DFIT_LMQ", "0")
+    ref = run()
+    for budgets in ("4,3", "1,1", "2,9"):
+        monkeypatch.setenv("DFIT_LMQ", budgets)
+        out = run()
+        for a, b in zip(ref[:4], out[:4]):
+            assert torch.equal(a.view(torch.uint8 if a.dtype == torch.uint8 else torch.int32),
+                               b.view(torch.uint8 if b.dtype == torch.uint8 else torch.int32)), (case, budgets)
+        for k in ("n_fitted", "n_failed", "sum_iters", "max_iters", "n_oob"):
+            assert ref[4][k] == out[4][k], (k, ref[4], out[4])
+    assert ref[4]["max_iters"] > 5
+
+
 def test_config4_sample_against_c_oracle(D):
     """A config-4-shaped volume (16 echoes x 5 ms, bi-exponential, SNR 100, fp32) fitted on the GPU in fp32; a seeded
     sample of voxels is compared with the MINPACK restatement (oracle/minpack_lmdif.c, pinned to SciPy on the

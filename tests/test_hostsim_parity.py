@@ -62,6 +62,36 @@ def test_biexp_fp32_golden(name):
     G.check_biexp_f32(name, popt, r2)
 
 
+@pytest.mark.parametrize("rounds", [(1, 1), (4, 3), (2, 7)])
+def test_lm_in_rounds_is_lm_solve_bit_for_bit(rounds):
+    """fit_kernel_lmq runs the LM in rounds -- lm_begin, then lm_iterate with a budget of evaluations, the solver state
+    parked between rounds (csrc/lmq_kernel.cuh).  However the trips are cut, every output must equal lm_solve's bit for
+    bit: bi-exponential (noisy and clean fixture, incl. voxels that run into maxfev), mono-exponential LM with the
+    projection start, the linear model, a tiny maxfev."""
+    cases = []
+    for name in sorted(G.BIEXP_F32_TOL):
+        c = G.load(name)
+        cases.append(("biexponential", c["x"], c["y"], dict(p0=G.p0_of(c), fast=0, init_linear=0)))
+        cases.append(("biexponential", c["x"], c["y"], dict(p0=G.p0_of(c), fast=0, init_linear=1, maxfev=30)))
+    c = G.load("curvefit_mono8_snr5_f32")
+    cases.append(("monoexponential", c["x"], c["y"], dict(p0=(1.0, -1 / 30), fast=0)))
+    cases.append(("monoexponential", c["x"], c["y"], dict(p0=(1.0, -1 / 30), fast=0, maxfev=7)))
+    c = G.load("curvefit_linear4_f64")
+    cases.append(("linear", c["x"], c["y"], dict(p0=G.p0_of(c), fast=0)))
+    try:
+        for model, x, y, kw in cases:
+            for dtype in ("f32", "f64"):
+                H.set_rounds(0)
+                ref = H.fit(model, x, y, dtype=dtype, **kw)
+                H.set_rounds(*rounds)
+                out = H.fit(model, x, y, dtype=dtype, **kw)
+                for a, b in zip(ref, out):
+                    assert np.array_equal(a, b, equal_nan=True), (model, dtype, kw)
+                assert ref[3].max() > rounds[0] + 1  # (the budget did cut some fits)
+    finally:
+        H.set_rounds(0)
+
+
 def test_degenerate_and_bounds():
     c = G.load("curvefit_mono8_degenerate_f32")
     popt, r2, st, it = H.fit("monoexponential", c["x"], c["y"], p0=(1.0, -1 / 30))
