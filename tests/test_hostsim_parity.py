@@ -87,7 +87,7 @@ def test_lm_in_rounds_is_lm_solve_bit_for_bit(rounds):
                 out = H.fit(model, x, y, dtype=dtype, **kw)
                 for a, b in zip(ref, out):
                     assert np.array_equal(a, b, equal_nan=True), (model, dtype, kw)
-                assert ref[3].max() > rounds[0] + 1  # (the budget did cut some fits)
+                assert model == "linear" or ref[3].max() > rounds[0] + 1  # (the budget did cut some fits)
     finally:
         H.set_rounds(0)
 
