@@ -214,6 +214,70 @@ __device__ __forceinline__ pair2<float> p2_expbx<float>(float b, pair2<float> /*
 }
 #endif
 
+// ------------------------------------------------------------------------------------ echo table
+// Echo-time table shared by all voxels of a launch (lives in the kernel parameter / constant bank).
+template <typename T, int EMAX>
+struct XTab {
+  T x[EMAX];   // echo / spin-lock times
+  T xs[EMAX];  // x * log2(e), so exp(b x) = ex2(b * xs)
+  T xc[EMAX];  // x - mean(x), for the log-linear initial guess
+  T xbar, inv_sxx;
+  // Uniform spacing x_k = x0 + k dx (multi-echo spin echo, cones, ...): exp(b x_k) = e0 q^k with
+  // q = exp(b dx), so the mono-exponential model is a POLYNOMIAL in q (mono_uniform_newton).
+  int uniform;   // 1: spacing is uniform to within the arithmetic's resolution (host decides)
+  int backward;  // 1: dx < 0 (descending echo times): the Prony start is taken backwards
+  T x0, x0s;     // first echo time and x0 * log2(e)
+  T inv_dx;      // 1 / dx
+  T dx2, dxs2;   // 2 dx and 2 dx * log2(e): exp(b x_k+2) = exp(b x_k) * exp(b * dx2)
+  T q_lo, q_hi;  // admissible range of q: q^(2E-2) must stay finite
+  T xx[EMAX];    // x^2, for the second derivatives of the general (non-uniform) fast path
+  T inv_xmax;    // 1 / max |x|: the largest step in b the general fast path takes at once
+  T span2;       // (max x - min x)^2
+};
+
+// Host-side fill of the echo table (shared by the C-ABI layer and the test-only host build).
+template <typename T, int EMAX>
+inline void fill_xtab(XTab<T, EMAX>& xt, const double* x, int n_echo) {
+  double xbar = 0, sxx = 0;
+  for (int e = 0; e < n_echo; ++e) xbar += x[e];
+  xbar /= n_echo;
+  for (int e = 0; e < EMAX; ++e) {
+    const double xe = e < n_echo ? x[e] : 0.0;
+    xt.x[e] = (T)xe;
+    xt.xs[e] = (T)(xe * 1.4426950408889634074);
+    xt.xc[e] = (T)(e < n_echo ? xe - xbar : 0.0);
+    if (e < n_echo) sxx += (xe - xbar) * (xe - xbar);
+  }
+  xt.xbar = (T)xbar;
+  xt.inv_sxx = (T)(sxx > 0 ? 1.0 / sxx : 0.0);
+  const double dx = n_echo >= 2 ? (x[n_echo - 1] - x[0]) / (n_echo - 1) : 0.0;
+  bool uni = n_echo >= 3 && dx != 0.0 && dx == dx;
+  double xmax = 0;
+  for (int e = 0; e < n_echo; ++e) xmax = fmax(xmax, fabs(x[e]));
+  // "uniform" must not change the model: deviations from the grid have to be below what the
+  // arithmetic type resolves in b * x (one ulp of the largest echo time)
+  const double tol = (double)num<T>::eps() * xmax;
+  for (int e = 0; e < n_echo && uni; ++e) uni = fabs(x[e] - (x[0] + e * dx)) <= tol;
+  xt.uniform = uni ? 1 : 0;
+  xt.backward = dx < 0 ? 1 : 0;
+  xt.x0 = (T)(n_echo ? x[0] : 0.0);
+  xt.x0s = (T)(n_echo ? x[0] * 1.4426950408889634074 : 0.0);
+  xt.inv_dx = (T)(uni ? 1.0 / dx : 0.0);
+  xt.dx2 = (T)(2.0 * dx);
+  xt.dxs2 = (T)(2.0 * dx * 1.4426950408889634074);
+  const double decades = sizeof(T) == 4 ? 30.0 : 280.0;
+  xt.q_hi = (T)pow(10.0, decades / (2.0 * (n_echo > 1 ? n_echo : 2) - 2.0));
+  xt.q_lo = (T)(sizeof(T) == 4 ? 1e-30 : 1e-280);
+  for (int e = 0; e < EMAX; ++e) xt.xx[e] = (T)(e < n_echo ? x[e] * x[e] : 0.0);
+  xt.inv_xmax = (T)(xmax > 0 ? 1.0 / xmax : 0.0);
+  double xlo = n_echo ? x[0] : 0.0, xhi = xlo;
+  for (int e = 1; e < n_echo; ++e) {
+    xlo = fmin(xlo, x[e]);
+    xhi = fmax(xhi, x[e]);
+  }
+  xt.span2 = (T)((xhi - xlo) * (xhi - xlo));
+}
+
 // ------------------------------------------------------------------------------------ models
 // Each model provides, for one sample, the value f and an UNSCALED Jacobian row Jh[P]; the true
 // Jacobian is J_i = cs_i * Jh_i with per-parameter column scales cs (colscale()) that do not depend
@@ -244,6 +308,33 @@ struct MonoExp {
   static DFIT_HD void colscale(const T (&p)[2], T (&cs)[2]) {
     cs[0] = (T)1;
     cs[1] = p[0];
+  }
+  // Uniformly spaced echoes: exp(b x_k+2) = exp(b x_k) * exp(2 b dx), so after the first echo pair every further pair
+  // costs ONE packed multiply instead of a packed multiply and two MUFU.EX2 -- the evaluation loop of eval_all is
+  // bound by the MUFU pipe otherwise (4 per SM sub-partition and clock).  The rounding of the multiplier acts like a
+  // relative perturbation of b by ~3e-7; see eval_all.
+  static constexpr bool HAS_REC = true;
+  template <typename T>
+  struct Rec {
+    pair2<T> e, m;
+  };
+  template <typename T, int EMAX>
+  static DFIT_HD void rec_init(const T (&p)[2], const XTab<T, EMAX>& xt, Rec<T>& rc) {
+    rc.e = p2_expbx<T>(p[1], p2_make<T>(xt.x[0], xt.x[EMAX > 1 ? 1 : 0]), p2_make<T>(xt.xs[0], xt.xs[EMAX > 1 ? 1 : 0]));
+    rc.m = p2_bcast<T>(num<T>::expbx(p[1], xt.dx2, xt.dxs2));
+  }
+  template <typename T>
+  static DFIT_HD void eval2u(const T (&p)[2], Rec<T>& rc, pair2<T> x, pair2<T> yneg, pair2<T>& r, pair2<T> (&Jh)[2]) {
+    Jh[0] = rc.e;
+    Jh[1] = p2_mul<T>(x, rc.e);
+    r = p2_fma<T>(p2_bcast<T>(p[0]), rc.e, yneg);
+    rc.e = p2_mul<T>(rc.e, rc.m);
+  }
+  template <typename T>
+  static DFIT_HD void eval1u(const T (&p)[2], const Rec<T>& rc, T x, T& f, T (&Jh)[2]) {  // the odd last echo
+    Jh[0] = rc.e.lo;
+    Jh[1] = x * rc.e.lo;
+    f = p[0] * rc.e.lo;
   }
 };
 
@@ -279,6 +370,37 @@ struct BiExp {
     cs[2] = (T)1;
     cs[3] = p[2];
   }
+  static constexpr bool HAS_REC = true;  // (see MonoExp)
+  template <typename T>
+  struct Rec {
+    pair2<T> e1, e2, m1, m2;
+  };
+  template <typename T, int EMAX>
+  static DFIT_HD void rec_init(const T (&p)[4], const XTab<T, EMAX>& xt, Rec<T>& rc) {
+    const pair2<T> x01 = p2_make<T>(xt.x[0], xt.x[EMAX > 1 ? 1 : 0]), xs01 = p2_make<T>(xt.xs[0], xt.xs[EMAX > 1 ? 1 : 0]);
+    rc.e1 = p2_expbx<T>(p[1], x01, xs01);
+    rc.e2 = p2_expbx<T>(p[3], x01, xs01);
+    rc.m1 = p2_bcast<T>(num<T>::expbx(p[1], xt.dx2, xt.dxs2));
+    rc.m2 = p2_bcast<T>(num<T>::expbx(p[3], xt.dx2, xt.dxs2));
+  }
+  template <typename T>
+  static DFIT_HD void eval2u(const T (&p)[4], Rec<T>& rc, pair2<T> x, pair2<T> yneg, pair2<T>& r, pair2<T> (&Jh)[4]) {
+    Jh[0] = rc.e1;
+    Jh[1] = p2_mul<T>(x, rc.e1);
+    Jh[2] = rc.e2;
+    Jh[3] = p2_mul<T>(x, rc.e2);
+    r = p2_fma<T>(p2_bcast<T>(p[0]), rc.e1, p2_fma<T>(p2_bcast<T>(p[2]), rc.e2, yneg));
+    rc.e1 = p2_mul<T>(rc.e1, rc.m1);
+    rc.e2 = p2_mul<T>(rc.e2, rc.m2);
+  }
+  template <typename T>
+  static DFIT_HD void eval1u(const T (&p)[4], const Rec<T>& rc, T x, T& f, T (&Jh)[4]) {
+    Jh[0] = rc.e1.lo;
+    Jh[1] = x * rc.e1.lo;
+    Jh[2] = rc.e2.lo;
+    Jh[3] = x * rc.e2.lo;
+    f = num<T>::fma_(p[0], rc.e1.lo, p[2] * rc.e2.lo);
+  }
 };
 
 // f = a x : the 1-parameter custom model of the reference's tests (tests/core/test_fitting.py:52-53)
@@ -300,6 +422,7 @@ struct Linear1 {
   static DFIT_HD void colscale(const T (&)[1], T (&cs)[1]) {
     cs[0] = (T)1;
   }
+  static constexpr bool HAS_REC = false;  // no exponentials
 };
 
 // ------------------------------------------------------------------------------------ options
@@ -317,17 +440,30 @@ struct SolverOpts {
 // Packed lower-triangular index, i >= j.
 DFIT_HD constexpr int tri(int i, int j) { return i * (i + 1) / 2 + j; }
 
+template <class M, typename T, bool ON>
+struct RecOf {
+  typedef int type;
+};
+template <class M, typename T>
+struct RecOf<M, T, true> {
+  typedef typename M::template Rec<T> type;
+};
+
 // One pass over the echoes: cost F = sum (f - y)^2, A = J^T J (packed lower), g = J^T r.
 // With an exact echo count and matching accumulator type the echoes are processed two at a time
 // (pair2 -> packed FP32 instructions on sm_100a); partial sums of even and odd echoes are kept in
 // the two halves and added at the end.
 // MASK selects the parameters whose rows/columns are accumulated (all of them for an LM pass, only
 // the linear ones for the projection pass, where the rest of the system is never read).
-template <class M, typename T, typename TA, int EMAX, bool EXACT, unsigned MASK = 0xffu>
-DFIT_HD void eval_all(const T (&p)[M::P], const T (&y)[EMAX], const T* __restrict__ x,
-                      const T* __restrict__ xs, int E, TA& F, TA (&A)[M::P * (M::P + 1) / 2], TA (&g)[M::P]) {
+// UNI (models with exponentials, uniformly spaced echoes -- the caller checks xt.uniform): the exponentials come from
+// the model's two-echo recurrence (M::Rec) instead of one MUFU.EX2 per echo and exponential.
+template <class M, typename T, typename TA, int EMAX, bool EXACT, unsigned MASK = 0xffu, bool UNI = false>
+DFIT_HD void eval_all(const T (&p)[M::P], const T (&y)[EMAX], const XTab<T, EMAX>& xt, int E, TA& F,
+                      TA (&A)[M::P * (M::P + 1) / 2], TA (&g)[M::P]) {
   constexpr int P = M::P;
   constexpr int NA = P * (P + 1) / 2;
+  const T* __restrict__ x = xt.x;
+  const T* __restrict__ xs = xt.xs;
 #define DFIT_ON(i) (((MASK) >> (i)) & 1u)
   constexpr bool PAIRED = EXACT && sizeof(T) == sizeof(TA) && EMAX >= 2;
   if constexpr (PAIRED) {
@@ -336,11 +472,16 @@ DFIT_HD void eval_all(const T (&p)[M::P], const T (&y)[EMAX], const T* __restric
     for (int k = 0; k < NA; ++k) A2[k] = p2_bcast<T>((T)0);
 #pragma unroll
     for (int k = 0; k < P; ++k) g2[k] = p2_bcast<T>((T)0);
+    [[maybe_unused]] typename RecOf<M, T, UNI && M::HAS_REC>::type rc;
+    if constexpr (UNI && M::HAS_REC) M::template rec_init<T, EMAX>(p, xt, rc);
 #pragma unroll
     for (int e = 0; e + 1 < EMAX; e += 2) {
       pair2<T> r, J[P];
-      M::template eval2<T>(p, p2_make<T>(x[e], x[e + 1]), p2_make<T>(xs[e], xs[e + 1]), p2_make<T>(-y[e], -y[e + 1]), r,
-                           J);
+      if constexpr (UNI && M::HAS_REC)
+        M::template eval2u<T>(p, rc, p2_make<T>(x[e], x[e + 1]), p2_make<T>(-y[e], -y[e + 1]), r, J);
+      else
+        M::template eval2<T>(p, p2_make<T>(x[e], x[e + 1]), p2_make<T>(xs[e], xs[e + 1]), p2_make<T>(-y[e], -y[e + 1]), r,
+                             J);
       F2 = p2_fma<T>(r, r, F2);
 #pragma unroll
       for (int i = 0; i < P; ++i) {
@@ -357,7 +498,8 @@ DFIT_HD void eval_all(const T (&p)[M::P], const T (&y)[EMAX], const T* __restric
     for (int k = 0; k < P; ++k) g[k] = (TA)(g2[k].lo + g2[k].hi);
     if constexpr (EMAX & 1) {
       T f, J[P];
-      M::template eval<T>(p, x[EMAX - 1], xs[EMAX - 1], f, J);
+      if constexpr (UNI && M::HAS_REC) M::template eval1u<T>(p, rc, x[EMAX - 1], f, J);
+      else M::template eval<T>(p, x[EMAX - 1], xs[EMAX - 1], f, J);
       const T re = f - y[EMAX - 1];
       F = num<TA>::fma_((TA)re, (TA)re, F);
 #pragma unroll
@@ -425,13 +567,16 @@ DFIT_HD bool chol_solve(const TA (&C)[P * (P + 1) / 2], TA lam, const TA (&gs)[P
     return det > tiny * d0 * d1 && d0 > tiny && d1 > tiny;
   } else {
     TA L[P * (P + 1) / 2], Dinv[P];
+    bool pd = true;
 #pragma unroll
     for (int j = 0; j < P; ++j) {
       const bool aj = (active >> j) & 1u;
       TA s = aj ? C[tri(j, j)] + lam : (TA)1;
 #pragma unroll
       for (int k = 0; k < j; ++k) s -= L[tri(j, k)] * L[tri(j, k)];
-      if (!(s > tiny)) return false;
+      // (no early exit: a pivot that is not positive poisons what follows, and the caller discards z when told so --
+      // straight-line code instead of a branch per column)
+      pd = pd && (s > tiny);
       const TA inv = num<TA>::rsqrt_(s);
       Dinv[j] = inv;
 #pragma unroll
@@ -458,7 +603,7 @@ DFIT_HD bool chol_solve(const TA (&C)[P * (P + 1) / 2], TA lam, const TA (&gs)[P
       for (int k = i + 1; k < P; ++k) t -= L[tri(k, i)] * z[k];
       z[i] = t * Dinv[i];
     }
-    return true;
+    return pd;
   }
 }
 
@@ -512,17 +657,18 @@ DFIT_HD bool lm_step(const T (&p)[P], const TA (&A)[P * (P + 1) / 2], const TA (
   if (!chol_solve<P, TA>(C, lam, gs, active, z)) return false;
   zz = 0;
   pnorm2 = 0;
-  TA zCz = 0;
+  // z solves (C + lam I) z = -gs, so z^T C z = -z^T gs - lam z^T z and the predicted reduction
+  // z^T C z + 2 lam z^T z is -z^T gs + lam z^T z: P multiply-adds instead of the P (P + 1) / 2 terms of the quadratic
+  // form (both forms cancel to the same extent: by the condition number of C)
+  TA zg = 0;
 #pragma unroll
   for (int i = 0; i < P; ++i) {
     pt[i] = p[i] + (T)(z[i] * Di[i]);
     zz = num<TA>::fma_(z[i], z[i], zz);
-    zCz = num<TA>::fma_(C[tri(i, i)] * z[i], z[i], zCz);
-#pragma unroll
-    for (int j = 0; j < i; ++j) zCz = num<TA>::fma_((TA)2 * C[tri(i, j)] * z[i], z[j], zCz);
+    zg = num<TA>::fma_(z[i], gs[i], zg);
     pnorm2 = num<TA>::fma_(D2[i] * (TA)pt[i], (TA)pt[i], pnorm2);
   }
-  pred = zCz + (TA)2 * lam * zz;
+  pred = lam * zz - zg;
   return true;
 }
 
@@ -551,9 +697,9 @@ struct LmState {
 };
 
 // Start: returns ST_PENDING (iterate from p) or a final status.
-template <class M, typename T, typename TA, int EMAX, bool EXACT>
-DFIT_HD int lm_begin(T (&p)[M::P], const T (&y)[EMAX], const T* __restrict__ x, const T* __restrict__ xs, int E,
-                     const SolverOpts<T>& o, LmState<M::P, T, TA>& s) {
+template <class M, typename T, typename TA, int EMAX, bool EXACT, bool UNI = false>
+DFIT_HD int lm_begin(T (&p)[M::P], const T (&y)[EMAX], const XTab<T, EMAX>& xt, int E, const SolverOpts<T>& o,
+                     LmState<M::P, T, TA>& s) {
   constexpr int P = M::P;
   constexpr int NA = P * (P + 1) / 2;
   s.iters = 0;
@@ -591,7 +737,7 @@ DFIT_HD int lm_begin(T (&p)[M::P], const T (&y)[EMAX], const T* __restrict__ x, 
       g0[i] = 0;
       D2p[i] = 0;
     }
-    eval_all<M, T, TA, EMAX, EXACT, M::LIN>(pt, y, x, xs, E, F0, A0, g0);
+    eval_all<M, T, TA, EMAX, EXACT, M::LIN, UNI>(pt, y, xt, E, F0, A0, g0);
     ++s.iters;
     s.fev += 1;
     T pp[P];
@@ -607,7 +753,7 @@ DFIT_HD int lm_begin(T (&p)[M::P], const T (&y)[EMAX], const T* __restrict__ x, 
 #pragma unroll
       for (int i = 0; i < P; ++i) pt[i] = plin[i];
     }
-    eval_all<M, T, TA, EMAX, EXACT>(pt, y, x, xs, E, s.F, s.A, s.g);
+    eval_all<M, T, TA, EMAX, EXACT, 0xffu, UNI>(pt, y, xt, E, s.F, s.A, s.g);
     ++s.iters;
     s.fev += 1 + P;
     const bool good = num<TA>::finite(s.F);
@@ -625,9 +771,9 @@ DFIT_HD int lm_begin(T (&p)[M::P], const T (&y)[EMAX], const T* __restrict__ x, 
 
 // Levenberg-Marquardt trips from the state lm_begin (or an earlier, suspended lm_iterate: resume = true) left.
 // Returns the final status, or ST_PENDING after `budget` evaluations with the fit still going.
-template <class M, typename T, typename TA, int EMAX, bool EXACT>
-DFIT_HD int lm_iterate(T (&p)[M::P], const T (&y)[EMAX], const T* __restrict__ x, const T* __restrict__ xs, int E,
-                       const SolverOpts<T>& o, LmState<M::P, T, TA>& s, int budget, bool resume) {
+template <class M, typename T, typename TA, int EMAX, bool EXACT, bool UNI = false>
+DFIT_HD int lm_iterate(T (&p)[M::P], const T (&y)[EMAX], const XTab<T, EMAX>& xt, int E, const SolverOpts<T>& o,
+                       LmState<M::P, T, TA>& s, int budget, bool resume) {
   constexpr int P = M::P;
   constexpr int NA = P * (P + 1) / 2;
   constexpr unsigned ALL = (1u << P) - 1u;
@@ -660,7 +806,7 @@ DFIT_HD int lm_iterate(T (&p)[M::P], const T (&y)[EMAX], const T* __restrict__ x
     resume = false;
     --budget;
     TA Fn, An[NA], gn[P];
-    eval_all<M, T, TA, EMAX, EXACT>(s.pt, y, x, xs, E, Fn, An, gn);
+    eval_all<M, T, TA, EMAX, EXACT, 0xffu, UNI>(s.pt, y, xt, E, Fn, An, gn);
     ++s.iters;
     ++s.fev;
     const bool good = num<TA>::finite(Fn);
@@ -706,75 +852,14 @@ DFIT_HD int lm_iterate(T (&p)[M::P], const T (&y)[EMAX], const T* __restrict__ x
 // squared residuals at the returned point, iters the number of passes over the echoes (model + Jacobian
 // evaluations) spent.
 template <class M, typename T, typename TA, int EMAX, bool EXACT>
-DFIT_HD int lm_solve(T (&p)[M::P], const T (&y)[EMAX], const T* __restrict__ x, const T* __restrict__ xs, int E,
-                     const SolverOpts<T>& o, T& F_out, int& iters) {
+DFIT_HD int lm_solve(T (&p)[M::P], const T (&y)[EMAX], const XTab<T, EMAX>& xt, int E, const SolverOpts<T>& o, T& F_out,
+                     int& iters) {
   LmState<M::P, T, TA> s;
-  int status = lm_begin<M, T, TA, EMAX, EXACT>(p, y, x, xs, E, o, s);
-  if (status == ST_PENDING) status = lm_iterate<M, T, TA, EMAX, EXACT>(p, y, x, xs, E, o, s, 0x7fffffff, false);
+  int status = lm_begin<M, T, TA, EMAX, EXACT>(p, y, xt, E, o, s);
+  if (status == ST_PENDING) status = lm_iterate<M, T, TA, EMAX, EXACT>(p, y, xt, E, o, s, 0x7fffffff, false);
   F_out = (T)s.F;
   iters = s.iters;
   return status;
-}
-
-// ------------------------------------------------------------------------------------ echo table
-// Echo-time table shared by all voxels of a launch (lives in the kernel parameter / constant bank).
-template <typename T, int EMAX>
-struct XTab {
-  T x[EMAX];   // echo / spin-lock times
-  T xs[EMAX];  // x * log2(e), so exp(b x) = ex2(b * xs)
-  T xc[EMAX];  // x - mean(x), for the log-linear initial guess
-  T xbar, inv_sxx;
-  // Uniform spacing x_k = x0 + k dx (multi-echo spin echo, cones, ...): exp(b x_k) = e0 q^k with
-  // q = exp(b dx), so the mono-exponential model is a POLYNOMIAL in q (mono_uniform_newton).
-  int uniform;   // 1: spacing is uniform to within the arithmetic's resolution (host decides)
-  int backward;  // 1: dx < 0 (descending echo times): the Prony start is taken backwards
-  T x0, x0s;     // first echo time and x0 * log2(e)
-  T inv_dx;      // 1 / dx
-  T q_lo, q_hi;  // admissible range of q: q^(2E-2) must stay finite
-  T xx[EMAX];    // x^2, for the second derivatives of the general (non-uniform) fast path
-  T inv_xmax;    // 1 / max |x|: the largest step in b the general fast path takes at once
-  T span2;       // (max x - min x)^2
-};
-
-// Host-side fill of the echo table (shared by the C-ABI layer and the test-only host build).
-template <typename T, int EMAX>
-inline void fill_xtab(XTab<T, EMAX>& xt, const double* x, int n_echo) {
-  double xbar = 0, sxx = 0;
-  for (int e = 0; e < n_echo; ++e) xbar += x[e];
-  xbar /= n_echo;
-  for (int e = 0; e < EMAX; ++e) {
-    const double xe = e < n_echo ? x[e] : 0.0;
-    xt.x[e] = (T)xe;
-    xt.xs[e] = (T)(xe * 1.4426950408889634074);
-    xt.xc[e] = (T)(e < n_echo ? xe - xbar : 0.0);
-    if (e < n_echo) sxx += (xe - xbar) * (xe - xbar);
-  }
-  xt.xbar = (T)xbar;
-  xt.inv_sxx = (T)(sxx > 0 ? 1.0 / sxx : 0.0);
-  const double dx = n_echo >= 2 ? (x[n_echo - 1] - x[0]) / (n_echo - 1) : 0.0;
-  bool uni = n_echo >= 3 && dx != 0.0 && dx == dx;
-  double xmax = 0;
-  for (int e = 0; e < n_echo; ++e) xmax = fmax(xmax, fabs(x[e]));
-  // "uniform" must not change the model: deviations from the grid have to be below what the
-  // arithmetic type resolves in b * x (one ulp of the largest echo time)
-  const double tol = (double)num<T>::eps() * xmax;
-  for (int e = 0; e < n_echo && uni; ++e) uni = fabs(x[e] - (x[0] + e * dx)) <= tol;
-  xt.uniform = uni ? 1 : 0;
-  xt.backward = dx < 0 ? 1 : 0;
-  xt.x0 = (T)(n_echo ? x[0] : 0.0);
-  xt.x0s = (T)(n_echo ? x[0] * 1.4426950408889634074 : 0.0);
-  xt.inv_dx = (T)(uni ? 1.0 / dx : 0.0);
-  const double decades = sizeof(T) == 4 ? 30.0 : 280.0;
-  xt.q_hi = (T)pow(10.0, decades / (2.0 * (n_echo > 1 ? n_echo : 2) - 2.0));
-  xt.q_lo = (T)(sizeof(T) == 4 ? 1e-30 : 1e-280);
-  for (int e = 0; e < EMAX; ++e) xt.xx[e] = (T)(e < n_echo ? x[e] * x[e] : 0.0);
-  xt.inv_xmax = (T)(xmax > 0 ? 1.0 / xmax : 0.0);
-  double xlo = n_echo ? x[0] : 0.0, xhi = xlo;
-  for (int e = 1; e < n_echo; ++e) {
-    xlo = fmin(xlo, x[e]);
-    xhi = fmax(xhi, x[e]);
-  }
-  xt.span2 = (T)((xhi - xlo) * (xhi - xlo));
 }
 
 // ------------------------------------------------------------------------------------ one voxel
@@ -859,7 +944,7 @@ DFIT_HD int fit_voxel(const T (&y)[EMAX], const XTab<T, EMAX>& xt, int E, const 
   iters = 0;
   T F = 0;
   int status = voxel_prepare<M, T, EMAX, EXACT>(y, xt, E, vo, p, flags);
-  if (status == ST_PENDING) status = lm_solve<M, T, TA, EMAX, EXACT>(p, y, xt.x, xt.xs, E, vo.s, F, iters);
+  if (status == ST_PENDING) status = lm_solve<M, T, TA, EMAX, EXACT>(p, y, xt, E, vo.s, F, iters);
   voxel_finish<M, T, EMAX, EXACT>(status, y, E, vo, F, p, r2);
   return status;
 }

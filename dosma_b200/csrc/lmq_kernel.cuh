@@ -40,9 +40,12 @@ struct LmqLayout {  // word offsets of one suspended fit; slot s of word w lives
 };
 
 // resident CTAs per SM the register allocation is asked to leave room for
-constexpr int lmq_min_ctas(int P, int E) { return P >= 4 ? (E <= 8 ? 4 : 3) : (E <= 8 ? 6 : 4); }
+#ifndef DFIT_LMQ_CTAS4
+#define DFIT_LMQ_CTAS4 4  // 4-parameter models above 8 echoes: 128 registers (measured against 3 CTAs: 1.44 / 1.54 ms on config 4)
+#endif
+constexpr int lmq_min_ctas(int P, int E) { return P >= 4 ? (E <= 8 ? 4 : DFIT_LMQ_CTAS4) : (E <= 8 ? 6 : 4); }
 
-template <class M, int EMAX>
+template <class M, int EMAX, bool UNI>
 __global__ void __launch_bounds__(kLmqWarps * 32, lmq_min_ctas(M::P, EMAX))
     fit_kernel_lmq(const __grid_constant__ KernelArgs<float, EMAX> a, const int k_first, const int k_next) {
   typedef float T;
@@ -84,7 +87,7 @@ __global__ void __launch_bounds__(kLmqWarps * 32, lmq_min_ctas(M::P, EMAX))
         st = voxel_prepare<M, T, EMAX, true>(y, a.xt, a.E, a.vo, p, flags);
         s.F = 0;
         s.iters = 0;
-        if (st == ST_PENDING) st = lm_begin<M, T, T, EMAX, true>(p, y, a.xt.x, a.xt.xs, a.E, a.vo.s, s);
+        if (st == ST_PENDING) st = lm_begin<M, T, T, EMAX, true, UNI>(p, y, a.xt, a.E, a.vo.s, s);
       }
     } else if (n_q > 0) {
       // ---- up to 32 suspended fits off the stack ----
@@ -123,7 +126,7 @@ __global__ void __launch_bounds__(kLmqWarps * 32, lmq_min_ctas(M::P, EMAX))
     }
 
     // ---- one round of the solver ----
-    if (live && st == ST_PENDING) st = lm_iterate<M, T, T, EMAX, true>(p, y, a.xt.x, a.xt.xs, a.E, a.vo.s, s, budget, resume);
+    if (live && st == ST_PENDING) st = lm_iterate<M, T, T, EMAX, true, UNI>(p, y, a.xt, a.E, a.vo.s, s, budget, resume);
 
     // ---- retire: store what is finished, suspend what is not ----
     const bool pending = live && st == ST_PENDING;
@@ -176,7 +179,7 @@ struct LmqConfig {
   int enabled, k_first, k_next;
 };
 inline LmqConfig lmq_config() {  // (read at every launch: a getenv, so that tests can switch within one process)
-  LmqConfig c{1, 4, 3};
+  LmqConfig c{1, 5, 2};
   if (const char* e = std::getenv("DFIT_LMQ")) {
     int a = 0, b = 0;
     const int n = std::sscanf(e, "%d,%d", &a, &b);
@@ -190,7 +193,11 @@ inline LmqConfig lmq_config() {  // (read at every launch: a getenv, so that tes
 template <class M, int EMAX>
 inline cudaError_t launch_lmq(const LaunchDesc& d, const KernelArgs<float, EMAX>& a) {
   const LmqConfig cfg = lmq_config();
-  auto kfn = fit_kernel_lmq<M, EMAX>;
+  // uniformly spaced echoes (the host decided: fill_xtab): the exponentials of the model come from a two-echo
+  // recurrence instead of MUFU.EX2 (DFIT_LMQ_UNI=0 switches that off, for A/B runs)
+  bool uni = M::HAS_REC && EMAX >= 4 && a.xt.uniform != 0;
+  if (const char* e = std::getenv("DFIT_LMQ_UNI")) uni = uni && e[0] != '0';
+  auto kfn = uni ? fit_kernel_lmq<M, EMAX, M::HAS_REC && EMAX >= 4> : fit_kernel_lmq<M, EMAX, false>;
   const size_t smem = LmqLayout<M::P, EMAX>::bytes();
   cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;

@@ -1,0 +1,15 @@
+#!/bin/bash
+# TEST TOOLING: tuvar.sh <name> <translation unit, e.g. inst_biexp_f32_hi> [nvcc -D flags...] builds
+# dosma_b200/libdfit_<name>.so = the main build's objects with that one translation unit recompiled with the given flags.
+# For A/B timing of kernel variants (DOSMA_B200_LIB selects the library).  Needs an up-to-date main build.
+set -e
+name=$1; tu=$2; shift 2
+root=$(cd "$(dirname "$0")/../.." && pwd)
+cs=$root/dosma_b200/csrc
+b=$cs/_build_$name
+mkdir -p $b
+F="-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC,-O2 -Xptxas -v --expt-relaxed-constexpr -I $root/include"
+nvcc $F "$@" -c $cs/$tu.cu -o $b/$tu.o > $b/log.txt 2>&1 || { tail -20 $b/log.txt; exit 1; }
+objs=$(ls $cs/_build/*.o | grep -v "/$tu.o" | grep -v stubs.o)
+nvcc -shared -gencode arch=compute_100a,code=sm_100a -o $root/dosma_b200/libdfit_$name.so $objs $b/$tu.o
+echo "$name: built $(ls -la $root/dosma_b200/libdfit_$name.so | awk '{print $5}') bytes"

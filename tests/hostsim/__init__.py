@@ -62,6 +62,12 @@ def set_rounds(k_first, k_next=None):
     _load().hostsim_set_rounds(ctypes.c_int(int(k_first)), ctypes.c_int(int(k_first if k_next is None else k_next)))
 
 
+def set_uniform_recurrence(on):
+    """With set_rounds(k > 0): take the model's exponentials from the two-echo recurrence on uniformly spaced echoes, as
+    fit_kernel_lmq does (fp32, >= 4 echoes)."""
+    _load().hostsim_set_uniform_recurrence(ctypes.c_int(int(bool(on))))
+
+
 def engine_fit(model_id, nparams, x, planes, mask, p0_cols, *, init_mode=0, y_bounds=None, maxfev=100, ftol=1e-5,
                eps=1e-8, post=None, engine=None, out_param=None):
     """TEST-ONLY stand-in for `dosma_b200.fitting._engine_fit` with the same signature and return values: the device

@@ -12,7 +12,8 @@ using namespace dfit;
 
 // fit_kernel_lmq's way through the LM: lm_begin, then rounds of lm_iterate with a budget of evaluations, the solver
 // state parked (copied away and back) between rounds.  0 = off: fit_voxel / lm_solve.
-static int g_round_first = 0, g_round_next = 0;
+static int g_round_first = 0, g_round_next = 0, g_uni = 0;
+extern "C" void hostsim_set_uniform_recurrence(int on) { g_uni = on; }
 extern "C" void hostsim_set_rounds(int k_first, int k_next) {
   g_round_first = k_first;
   g_round_next = k_next;
@@ -27,11 +28,16 @@ static int fit_voxel_any(const T (&y)[EMAX], const XTab<T, EMAX>& xt, int E, con
   s.F = 0;
   s.iters = 0;
   int st = voxel_prepare<M, T, EMAX, EXACT>(y, xt, E, vo, p, flags);
-  if (st == ST_PENDING) st = lm_begin<M, T, TA, EMAX, EXACT>(p, y, xt.x, xt.xs, E, vo.s, s);
+  // (fit_kernel_lmq's choice: exponentials by recurrence on uniformly spaced echoes, fp32, >= 4 echoes)
+  constexpr bool CAN_UNI = M::HAS_REC && EXACT && EMAX >= 4 && sizeof(T) == 4 && sizeof(TA) == 4;
+  const bool uni = CAN_UNI && g_uni && xt.uniform != 0;
+  if (st == ST_PENDING)
+    st = uni ? lm_begin<M, T, TA, EMAX, EXACT, CAN_UNI>(p, y, xt, E, vo.s, s) : lm_begin<M, T, TA, EMAX, EXACT>(p, y, xt, E, vo.s, s);
   bool resume = false;
   int budget = g_round_first;
   while (st == ST_PENDING) {
-    st = lm_iterate<M, T, TA, EMAX, EXACT>(p, y, xt.x, xt.xs, E, vo.s, s, budget, resume);
+    st = uni ? lm_iterate<M, T, TA, EMAX, EXACT, CAN_UNI>(p, y, xt, E, vo.s, s, budget, resume)
+             : lm_iterate<M, T, TA, EMAX, EXACT>(p, y, xt, E, vo.s, s, budget, resume);
     if (st == ST_PENDING) {  // park: the state and the parameters survive as plain bytes, nothing else does
       unsigned char park[sizeof(s) + sizeof(p)];
       memcpy(park, &s, sizeof(s));

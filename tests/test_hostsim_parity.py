@@ -94,6 +94,44 @@ def test_lm_in_rounds_is_lm_solve_bit_for_bit(rounds):
     assert cut > 10  # (the budgets did cut fits into several rounds)
 
 
+def test_uniform_recurrence_form_of_the_lm():
+    """On uniformly spaced echoes fit_kernel_lmq takes the model's exponentials from a two-echo recurrence
+    (exp(b x_k+2) = exp(b x_k) * exp(2 b dx): MonoExp / BiExp ::Rec in lm_core.cuh) instead of one MUFU.EX2 per echo.
+    That perturbs the model like a relative change of b by a few 1e-7: the bi-exponential fixtures must hold their
+    reference tolerances, and the result must agree with the direct form far inside them."""
+    try:
+        for name in sorted(G.BIEXP_F32_TOL):
+            c = G.load(name)
+            kw = dict(p0=G.p0_of(c), dtype="f32", fast=0, init_linear=0)
+            H.set_rounds(0)
+            ref = H.fit("biexponential", c["x"], c["y"], **kw)
+            H.set_rounds(5, 2)
+            H.set_uniform_recurrence(1)
+            out = H.fit("biexponential", c["x"], c["y"], **kw)
+            H.set_uniform_recurrence(0)
+            G.check_biexp_f32(name, out[0], out[1])
+            ok = ~np.isnan(ref[0][:, 0]) & ~np.isnan(out[0][:, 0])
+            assert (np.isnan(ref[0][:, 0]) ^ np.isnan(out[0][:, 0])).mean() < 5e-3
+            rel = _rel(out[0][ok], ref[0][ok]).max(axis=1)
+            assert np.median(rel) < 5e-6 and np.percentile(rel, 99) < 5e-4, (np.median(rel), np.percentile(rel, 99))
+            assert np.abs(out[1][ok] - ref[1][ok]).max() < 1e-6
+        for name, odd in (("curvefit_mono8_snr100_f32", False), ("curvefit_mono7_t1rho_snr100_f32", True)):
+            c = G.load(name)  # (the 7-echo T1rho protocol is not uniformly spaced: the recurrence must not be taken)
+            H.set_rounds(0)
+            ref = H.fit("monoexponential", c["x"], c["y"], p0=(1.0, -1 / 30), fast=0)
+            H.set_rounds(6, 6)
+            H.set_uniform_recurrence(1)
+            out = H.fit("monoexponential", c["x"], c["y"], p0=(1.0, -1 / 30), fast=0)
+            H.set_uniform_recurrence(0)
+            if odd:
+                assert np.array_equal(ref[0], out[0], equal_nan=True)
+            else:
+                assert np.nanmax(_rel(out[0], ref[0])) < 2e-6 and not np.array_equal(ref[0], out[0])
+    finally:
+        H.set_uniform_recurrence(0)
+        H.set_rounds(0)
+
+
 def test_degenerate_and_bounds():
     c = G.load("curvefit_mono8_degenerate_f32")
     popt, r2, st, it = H.fit("monoexponential", c["x"], c["y"], p0=(1.0, -1 / 30))
