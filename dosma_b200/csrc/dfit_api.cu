@@ -375,7 +375,30 @@ void make_desc(const dfit_opts* o, int n_echo, int64_t n_vox, const double* x, L
   d.sm_count = 148;
   d.index = nullptr;
   d.index_count = nullptr;
+  d.lm_list = nullptr;
+  d.lm_head = nullptr;
+  d.lm_parity = nullptr;
   d.g = GatherArgs{};
+}
+
+// LM tail of the dense two-voxel TMA kernel (see KernelArgs::lm_list): device scratch for the list of voxels that go
+// to the LM and its two alternating counters.  DFIT_LM_TAIL=0 keeps the LM inside the kernel (A/B runs).
+int lm_tail_prepare(DevBuf& buf, int& parity, int64_t n_vox, cudaStream_t st, LaunchDesc& d) {
+  if (const char* e = std::getenv("DFIT_LM_TAIL")) {
+    if (e[0] == '0') return DFIT_OK;
+  }
+  if (d.tmap2 == nullptr || d.g.world != 0 || n_vox >= ((int64_t)1 << 32)) return DFIT_OK;
+  const size_t need = 16 + (size_t)n_vox * sizeof(unsigned);
+  if (need > buf.cap) {
+    const int rc = ensure(buf, need);
+    if (rc != DFIT_OK) return rc;
+    CUDA_TRY(cudaMemsetAsync(buf.p, 0, 16, st));
+    parity = 0;
+  }
+  d.lm_head = reinterpret_cast<unsigned*>(buf.p);
+  d.lm_list = d.lm_head + 4;
+  d.lm_parity = &parity;
+  return DFIT_OK;
 }
 
 // May the result maps of this fit cross PCIe as float32 and be widened on the host?  Yes for fp32 arithmetic into
@@ -606,7 +629,7 @@ int dfit_destroy(dfit_handle* h) {
   cudaDeviceSynchronize();
   for (int s = 0; s < kSlots; ++s) {
     Slot& sl = h->slots[s];
-    DevBuf* bufs[] = {&sl.y, &sl.mask, &sl.p0, &sl.popt, &sl.r2, &sl.status, &sl.niter, &sl.index};
+    DevBuf* bufs[] = {&sl.y, &sl.mask, &sl.p0, &sl.popt, &sl.r2, &sl.status, &sl.niter, &sl.index, &sl.lm};
     for (DevBuf* b : bufs)
       if (b->p) cudaFree(b->p);
     HostBuf* hbufs[] = {&sl.hin, &sl.hpopt, &sl.hr2};
@@ -620,6 +643,7 @@ int dfit_destroy(dfit_handle* h) {
   if (h->counters) cudaFree(h->counters);
   if (h->scratch.p) cudaFree(h->scratch.p);
   if (h->index_buf.p) cudaFree(h->index_buf.p);
+  if (h->lm_buf.p) cudaFree(h->lm_buf.p);
   if (h->ev_start) cudaEventDestroy(h->ev_start);
   if (h->ev_stop) cudaEventDestroy(h->ev_stop);
   delete h;
@@ -694,8 +718,10 @@ int dfit_fit_device(dfit_handle* h, const dfit_opts* opts, int n_echo, int64_t n
                 "base and pitch, fp32 arithmetic and <= 16 echoes");
   }
   if (n_vox > 0) {
+    if ((rc = lm_tail_prepare(h->lm_buf, h->lm_parity, n_vox, st, d)) != DFIT_OK) return rc;
+    const int par0 = h->lm_parity;
     CUDA_TRY(dispatch(d));
-    h->last_launches = mask != nullptr && d.tmap == nullptr ? 2 : 1;
+    h->last_launches = (mask != nullptr && d.tmap == nullptr ? 2 : 1) + (h->lm_parity != par0 ? 1 : 0);
   }
   CUDA_TRY(cudaEventRecord(h->ev_stop, st));
   h->ev_valid = true;
@@ -868,8 +894,11 @@ static int fit_host_impl(dfit_handle* h, const dfit_opts* opts, int n_echo, int6
     CUtensorMap tmap2;
     d.tmap2 = nullptr;
     if (tma2_eligible(d) && make_sample_tmap(&tmap2, d.y, n_echo, n, chunk, kM2Tile, y_dtype)) d.tmap2 = &tmap2;
+    d.lm_list = nullptr;
+    if ((rc = lm_tail_prepare(sl.lm, sl.lm_parity, chunk, st, d)) != DFIT_OK) return rc;
+    const int par0 = sl.lm_parity;
     CUDA_TRY(dispatch(d));
-    h->last_launches += mask && d.tmap == nullptr ? 2 : 1;
+    h->last_launches += (mask && d.tmap == nullptr ? 2 : 1) + (sl.lm_parity != par0 ? 1 : 0);
     if (out_pageable) {
       if ((rc = ensure_host(sl.hpopt, (size_t)chunk * PW * osz, cpus)) != DFIT_OK) return rc;
       if ((rc = ensure_host(sl.hr2, (size_t)chunk * osz, cpus)) != DFIT_OK) return rc;

@@ -45,6 +45,8 @@ int ensure_host(HostBuf& b, size_t bytes, const cpu_set_t* cpus = nullptr);
 struct Slot {
   cudaStream_t stream = nullptr;
   DevBuf y, mask, p0, popt, r2, status, niter, index;
+  DevBuf lm;          // LM tail of the dense fast-path kernel: two alternating counters (16 bytes) + the voxel list
+  int lm_parity = 0;
   HostBuf hin, hpopt, hr2;
   cudaEvent_t ev_in = nullptr, ev_out = nullptr;  // staging consumed by the H2D copy / filled by the D2H copies
 };
@@ -72,4 +74,6 @@ struct dfit_handle {
   bool have_local_cpus = false;
   dfit::DevBuf scratch;    // small device scratch (qDESS maxima, metrics partials)
   dfit::DevBuf index_buf;  // compacted voxel list of the masked device path
+  dfit::DevBuf lm_buf;     // LM tail of the dense fast-path kernel (device path): counters + voxel list
+  int lm_parity = 0;
 };

@@ -51,8 +51,24 @@ inline cudaError_t launch_one(const LaunchDesc& d) {
         int64_t g = (int64_t)d.sm_count * per_sm;
         const int64_t needed = (n_tiles + kM2Warps - 1) / kM2Warps;
         if (g > needed) g = needed;
+        const bool tail = d.lm_list != nullptr && d.g.world == 0 && lmq_config(M::P).enabled;
+        const int par = tail ? (*d.lm_parity & 1) : 0;
+        if (tail) {
+          a.lm_list = d.lm_list;
+          a.lm_count = d.lm_head + par;
+        }
         kfn<<<(unsigned)g, kM2Warps * 32, 0, d.stream>>>(a, *d.tmap2);
-        return cudaGetLastError();
+        e = cudaGetLastError();
+        if (e != cudaSuccess || !tail) return e;
+        // the LM tail: voxels neither the straight-line fit nor the Newton loop settled (a.lm_list), by the LM in rounds
+        KernelArgs<T, EMAX> at = a;
+        at.index = d.lm_list;
+        at.index_count = d.lm_head + par;
+        at.lm_list = nullptr;
+        at.lm_count = nullptr;
+        at.lm_count_next = d.lm_head + (par ^ 1);  // zeroed by the tail kernel: the next launch counts there
+        *d.lm_parity = par ^ 1;
+        return launch_lmq<M, EMAX>(d, at, true);
       }
       const int64_t per_cta = 2 * kBlock2;
       fit_kernel_mono2<M, EMAX><<<(unsigned)((d.n_vox + per_cta - 1) / per_cta), kBlock2, 0, d.stream>>>(a);

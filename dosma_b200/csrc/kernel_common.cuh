@@ -64,6 +64,13 @@ struct KernelArgs {
   double mask_fill;  // value written outside the mask: NaN or nan_to_num (fitting.py:207-212)
   double fill_q[4];  // the same per parameter, after the epilogue's rounding (what a voxel outside the mask reads)
   unsigned long long* counters;
+  // LM tail (dense two-voxel TMA kernel): voxels that neither the straight-line fit nor the one-voxel Newton loop
+  // settle are appended to this list instead of running the LM inside the kernel; the LM-in-rounds kernel
+  // (fit_kernel_lmq) fits the list right after.  Null: the LM runs in place.  `lm_count_next` is the counter of the NEXT
+  // launch, which the tail kernel zeroes (two counters alternate, so no launch pays a memset).
+  unsigned* lm_list;
+  unsigned* lm_count;
+  unsigned* lm_count_next;
   GatherArgs g;
 };
 
@@ -511,6 +518,9 @@ struct LaunchDesc {
   const CUtensorMap* tmap;   // host pointer to an encoded 2-D map of the planar fp32 samples (box 32 x E), or null
   const CUtensorMap* tmap2;  // the same with a 64-voxel box, for the two-voxels-per-lane kernel, or null
   int sm_count;
+  unsigned* lm_list;  // LM tail (see KernelArgs): device list of n_vox entries, or null: the LM runs inside the kernel
+  unsigned* lm_head;  // device, two alternating counters
+  int* lm_parity;     // host: which of the two the next launch counts in (flipped by launch_one when a tail was launched)
 };
 
 template <typename T, int EMAX>
@@ -555,6 +565,9 @@ inline void fill_args(const LaunchDesc& d, KernelArgs<T, EMAX>& a) {
     a.fill_q[i] = q;
   }
   a.counters = d.counters;
+  a.lm_list = nullptr;  // (set by launch_one for the kernel that fills it)
+  a.lm_count = nullptr;
+  a.lm_count_next = nullptr;
   a.g = d.g;
 }
 

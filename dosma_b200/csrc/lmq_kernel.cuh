@@ -57,6 +57,10 @@ __global__ void __launch_bounds__(kLmqWarps * 32, lmq_min_ctas(M::P, EMAX))
   const int warp = __shfl_sync(full, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   const unsigned below = (1u << lane) - 1u;
   float* const q = lmq_smem + (size_t)warp * L::WORDS * kLmqCap;  // this warp's stack: q[w * kLmqCap + slot]
+  // launched as the LM tail of a dense fast-path kernel (programmatic stream serialisation): wait until that grid has
+  // completed and its list is visible; a no-op in a plain launch
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  if (a.lm_count_next != nullptr && blockIdx.x == 0 && threadIdx.x == 0) *a.lm_count_next = 0u;  // the next launch's counter
   const bool listed = a.index != nullptr;
   const int64_t total = listed ? (int64_t)*a.index_count : a.n;
   const int64_t n_batches = (total + 31) >> 5;
@@ -178,8 +182,9 @@ __global__ void __launch_bounds__(kLmqWarps * 32, lmq_min_ctas(M::P, EMAX))
 struct LmqConfig {
   int enabled, k_first, k_next;
 };
-inline LmqConfig lmq_config() {  // (read at every launch: a getenv, so that tests can switch within one process)
-  LmqConfig c{1, 5, 2};
+inline LmqConfig lmq_config(int P = 4) {  // (read at every launch: a getenv, so that tests can switch within one process)
+  LmqConfig c{1, 5, 2};  // measured on config 4 (bi-exponential, 16 echoes): 4,3 1.50 ms / 4,2 1.46 / 5,2 1.44 / 6,2 1.50
+  if (P < 4) c = LmqConfig{1, 6, 4};
   if (const char* e = std::getenv("DFIT_LMQ")) {
     int a = 0, b = 0;
     const int n = std::sscanf(e, "%d,%d", &a, &b);
@@ -190,9 +195,11 @@ inline LmqConfig lmq_config() {  // (read at every launch: a getenv, so that tes
   return c;
 }
 
+// `tail`: launched behind the dense fast-path kernel whose LM list it fits (programmatic stream serialisation: the
+// launch overlaps the end of that kernel; griddepcontrol.wait orders the memory).
 template <class M, int EMAX>
-inline cudaError_t launch_lmq(const LaunchDesc& d, const KernelArgs<float, EMAX>& a) {
-  const LmqConfig cfg = lmq_config();
+inline cudaError_t launch_lmq(const LaunchDesc& d, const KernelArgs<float, EMAX>& a, bool tail = false) {
+  const LmqConfig cfg = lmq_config(M::P);
   // uniformly spaced echoes (the host decided: fill_xtab): the exponentials of the model come from a two-echo
   // recurrence instead of MUFU.EX2 (DFIT_LMQ_UNI=0 switches that off, for A/B runs)
   bool uni = M::HAS_REC && EMAX >= 4 && a.xt.uniform != 0;
@@ -209,8 +216,17 @@ inline cudaError_t launch_lmq(const LaunchDesc& d, const KernelArgs<float, EMAX>
   const int64_t needed = (d.n_vox + kLmqWarps * 32 - 1) / (kLmqWarps * 32);
   if (g > needed) g = needed;
   if (g < 1) g = 1;
-  kfn<<<(unsigned)g, kLmqWarps * 32, smem, d.stream>>>(a, cfg.k_first, cfg.k_next);
-  return cudaGetLastError();
+  cudaLaunchConfig_t lc = {};
+  lc.gridDim = dim3((unsigned)g);
+  lc.blockDim = dim3(kLmqWarps * 32);
+  lc.dynamicSmemBytes = smem;
+  lc.stream = d.stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  lc.attrs = attr;
+  lc.numAttrs = tail ? 1 : 0;
+  return cudaLaunchKernelEx(&lc, kfn, a, cfg.k_first, cfg.k_next);
 }
 
 #endif  // __CUDACC__

@@ -240,17 +240,34 @@ __device__ __forceinline__ void fit_deferred(const KernelArgs<float, EMAX>& a, c
                                              unsigned& it_sum, unsigned& it_max) {
   typedef float T;
   constexpr int P = 2;
-  if (lane < cnt) {
-    const int64_t v = (int64_t)queue[lane];
-    T y[EMAX], p[P], r2 = 0;
-    int it = 0;
-    unsigned fl = 0;
+  const bool active = lane < cnt;
+  int64_t v = 0;
+  T y[EMAX], p[P], r2 = 0;
+  int it = 0, st = -1;
+  unsigned fl = 0;
+  if (active) {
+    v = (int64_t)queue[lane];
     load_samples<T, EMAX, true>(a, v, y);
-    int st = fit_voxel_fast<M, T, EMAX, true>(y, a.xt, a.vo, p, r2, it);
-    if (st < 0) {
-      load_p0<P, T, EMAX>(a, v, p);
-      st = fit_voxel<M, T, T, EMAX, true>(y, a.xt, a.E, a.vo, p, r2, it, fl);
+    st = fit_voxel_fast<M, T, EMAX, true>(y, a.xt, a.vo, p, r2, it);
+  }
+  if (!GATHER && a.lm_list != nullptr) {
+    // LM tail: what the Newton loop turned down as well goes onto the launch's list (one atomic per warp) and is fitted
+    // by the LM-in-rounds kernel that follows this one -- the LM's pass count varies from 5 to 50 on such voxels, and run
+    // here a warp would wait for its slowest lane.  (Warp-uniform branch; every lane of the warp is here.)
+    const bool to_lm = active && st < 0;
+    const unsigned m = __ballot_sync(0xffffffffu, to_lm);
+    if (m != 0u) {
+      unsigned base = 0;
+      if (lane == 0) base = atomicAdd(a.lm_count, (unsigned)__popc(m));
+      base = __shfl_sync(0xffffffffu, base, 0);
+      if (to_lm) a.lm_list[base + __popc(m & ((1u << lane) - 1u))] = (unsigned)v;
     }
+    if (!active || st < 0) return;
+  } else if (active && st < 0) {
+    load_p0<P, T, EMAX>(a, v, p);
+    st = fit_voxel<M, T, T, EMAX, true>(y, a.xt, a.E, a.vo, p, r2, it, fl);
+  }
+  if (active) {
     store_voxel<P, T, EMAX, GATHER>(a, v, p, r2, true, st, it);
     n_fit += (unsigned)(st >= ST_CONV_F);
     n_fail += (unsigned)(st >= ST_MAXITER);
@@ -279,6 +296,9 @@ __global__ void __launch_bounds__(kM2Warps * 32, m2_min_ctas(EMAX))
   const int n_tiles = (n_vox + kM2Tile - 1) / kM2Tile;
   const int warp_global = (int)blockIdx.x * kM2Warps + warp;
   const int warp_stride = (int)gridDim.x * kM2Warps;
+  // (the LM tail kernel is launched with programmatic stream serialisation: its CTAs may take the place of this
+  // grid's CTAs as they retire, and wait there for the whole grid -- the tail's launch latency disappears)
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
   if (lane == 0) {
 #pragma unroll

@@ -131,6 +131,70 @@ def test_low_snr_failure_rate(D):
     assert (fail ^ ref_fail).mean() < 0.02, (fail ^ ref_fail).mean()
 
 
+@pytest.mark.parametrize("post", [False, True])
+def test_lm_tail_of_the_dense_kernel(D, post, monkeypatch):
+    """Dense mono-exponential fit of a volume that is half noise (air): the two-voxel TMA kernel hands the voxels that
+    neither its straight-line fit nor the Newton loop settle to the LM-in-rounds kernel through a device list (the LM
+    tail, csrc/mono2_kernels.cuh::fit_deferred), launched right behind it.  Same results as with the LM run inside
+    the kernel (DFIT_LM_TAIL=0) up to the two kernels' rounding, same counts; repeated launches alternate the list's
+    two counters; every voxel is written exactly once; and the LM voxels equal what the LM alone (fast_path=0) finds."""
+    import torch
+
+    from dosma_b200 import _cabi, device_api as A
+
+    dev = torch.device("cuda", 0)
+    g = torch.Generator(device=dev).manual_seed(21)
+    n = 64 * 4096 + 128  # TMA-aligned pitch
+    x = [10.0 * i for i in range(1, 9)]
+    xt = torch.tensor(x, device=dev)[:, None]
+    air = (torch.rand(n // 1024 + 1, device=dev, generator=g) < 0.5).repeat_interleave(1024)[:n]
+    sig = (500 + 1000 * torch.rand(n, device=dev, generator=g)) * torch.exp(-xt / (10 + 70 * torch.rand(n, device=dev, generator=g)))
+    y = torch.where(air, torch.zeros((), device=dev), sig) + 10 * torch.randn(8, n, device=dev, generator=g)
+    kw = dict(post=dict(ufunc=[0, 1], lb=[-np.inf, 0.0], ub=[np.inf, 100.0], decimals=[-1, 3], r2_threshold=0.9,
+                        nan_to_num=0.0)) if post else {}
+    o, P = A.make_opts(D.monoexponential, p0=(1.0, -1 / 30), **kw)
+
+    def run(opts=o):
+        popt = torch.full((n, 2), -7.0, device=dev)
+        r2 = torch.full((n,), -7.0, device=dev)
+        A.fit_device(opts, P, x, y, popt=popt, r2=r2)
+        torch.cuda.synchronize()
+        return popt, r2, _cabi.get_handle(0).stats()
+
+    monkeypatch.setenv("DFIT_LM_TAIL", "0")
+    ref = run()
+    assert ref[2]["n_launches"] == 1 and ref[2]["n_deferred"] > 0.4 * n
+    monkeypatch.setenv("DFIT_LM_TAIL", "1")
+    outs = [run() for _ in range(3)]  # (three launches: both counters of the list are used, each starts from zero)
+    for out in outs:
+        assert out[2]["n_launches"] == 2
+        assert not (out[0] == -7.0).any() and not (out[1] == -7.0).any()
+        for k in ("n_fitted", "n_deferred"):
+            assert out[2][k] == ref[2][k], (k, out[2], ref[2])
+        assert abs(out[2]["n_failed"] - ref[2]["n_failed"]) <= 2e-3 * n
+        assert torch.equal(out[0].view(torch.int32), outs[0][0].view(torch.int32)) and torch.equal(out[1], outs[0][1])
+        same = (out[0] == ref[0]).all(dim=1) | (torch.isnan(out[0]).all(dim=1) & torch.isnan(ref[0]).all(dim=1))
+        assert same[~air].float().mean() > 0.995  # tissue: the same kernel code fitted it
+        # air: the LM from p0 on pure noise is chaotic -- the two kernels are different compilations of the solver, and
+        # a last-bit difference can end in another local minimum or in maxfev -- so the bulk must agree, not every voxel
+        nan_o, nan_r = torch.isnan(out[0][:, 0]), torch.isnan(ref[0][:, 0])
+        assert (nan_o ^ nan_r).float().mean() < 0.02
+        both = ~nan_o & ~nan_r
+        if not post:
+            assert ((out[1][both] - ref[1][both]).abs() < 1e-4).float().mean() > 0.97
+            rel = ((out[0][both] - ref[0][both]).abs() / ref[0][both].abs()).max(dim=1).values
+            assert (rel < 1e-3).float().mean() > 0.95
+        else:
+            assert ((out[0][both, 1] - ref[0][both, 1]).abs() <= 1.001e-3).float().mean() > 0.99  # one rounding step
+    if not post:
+        o_lm, _ = A.make_opts(D.monoexponential, p0=(1.0, -1 / 30), fast_path=0)
+        lm = run(o_lm)  # the LM alone, through the same rounds kernel: the air voxels' results bit for bit
+        both = air & ~torch.isnan(outs[0][0][:, 0]) & ~torch.isnan(lm[0][:, 0])
+        assert both.float().sum() > 0.3 * n
+        same_lm = (outs[0][0][both] == lm[0][both]).all(dim=1).float().mean()
+        assert same_lm > 0.6, same_lm  # (the rest: air voxels the Newton loop settled before the list)
+
+
 @pytest.mark.parametrize("name", ["curvefit_biexp16_clean_f32"])
 def test_biexp_noise_free(D, name):
     c = G.load(name)
