@@ -227,6 +227,7 @@ __global__ void __launch_bounds__(kBlock, 5) fit_kernel_mono2_list(const __grid_
 constexpr int m2_min_ctas(int E) { return E <= 8 ? DFIT_M2_MIN_CTAS : 4; }
 constexpr int kM2Warps = 4;
 constexpr int kM2Tile = 64;
+constexpr int kLmListMin = 16;  // LM-bound voxels among the 32 of a deferred batch from which they go to the LM tail's list
 constexpr int kDeferCap = 96;  // per-warp queue of deferred voxels: at most 31 left over + 64 from one tile
 constexpr int m2_stages(int E) { return E <= 8 ? DFIT_M2_STAGES : 2; }  // <= 24 KB (32 KB above 8 echoes) of tiles per CTA
 
@@ -250,18 +251,18 @@ __device__ __forceinline__ void fit_deferred(const KernelArgs<float, EMAX>& a, c
     load_samples<T, EMAX, true>(a, v, y);
     st = fit_voxel_fast<M, T, EMAX, true>(y, a.xt, a.vo, p, r2, it);
   }
-  if (!GATHER && a.lm_list != nullptr) {
+  const unsigned m_lm = __ballot_sync(0xffffffffu, active && st < 0);  // (warp-uniform call sites: all 32 lanes are here)
+  if (!GATHER && a.lm_list != nullptr && __popc(m_lm) >= kLmListMin) {
     // LM tail: what the Newton loop turned down as well goes onto the launch's list (one atomic per warp) and is fitted
     // by the LM-in-rounds kernel that follows this one -- the LM's pass count varies from 5 to 50 on such voxels, and run
-    // here a warp would wait for its slowest lane.  (Warp-uniform branch; every lane of the warp is here.)
+    // here a warp would wait for its slowest lane.  Only when at least kLmListMin of the 32 are LM-bound (air, background):
+    // on tissue they are one or two per batch, cheaper to fit right here behind the other warps' work than in a launch
+    // of their own, and the list stays empty.  (A deterministic rule: where a voxel is fitted depends on the data only.)
     const bool to_lm = active && st < 0;
-    const unsigned m = __ballot_sync(0xffffffffu, to_lm);
-    if (m != 0u) {
-      unsigned base = 0;
-      if (lane == 0) base = atomicAdd(a.lm_count, (unsigned)__popc(m));
-      base = __shfl_sync(0xffffffffu, base, 0);
-      if (to_lm) a.lm_list[base + __popc(m & ((1u << lane) - 1u))] = (unsigned)v;
-    }
+    unsigned base = 0;
+    if (lane == 0) base = atomicAdd(a.lm_count, (unsigned)__popc(m_lm));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (to_lm) a.lm_list[base + __popc(m_lm & ((1u << lane) - 1u))] = (unsigned)v;
     if (!active || st < 0) return;
   } else if (active && st < 0) {
     load_p0<P, T, EMAX>(a, v, p);
@@ -296,9 +297,6 @@ __global__ void __launch_bounds__(kM2Warps * 32, m2_min_ctas(EMAX))
   const int n_tiles = (n_vox + kM2Tile - 1) / kM2Tile;
   const int warp_global = (int)blockIdx.x * kM2Warps + warp;
   const int warp_stride = (int)gridDim.x * kM2Warps;
-  // (the LM tail kernel is launched with programmatic stream serialisation: its CTAs may take the place of this
-  // grid's CTAs as they retire, and wait there for the whole grid -- the tail's launch latency disappears)
-  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
   if (lane == 0) {
 #pragma unroll
