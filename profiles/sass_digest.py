@@ -17,6 +17,7 @@ WANT = sys.argv[1:] or [r"fit_kernel_mono2_tma<dfit::MonoExp, 8, false, float>",
                         r"fit_kernel_mono2_tma<dfit::MonoExp, 8, false, short>", r"fit_kernel_mono2_tma<dfit::MonoExp, 7, false, float>",
                         r"fit_kernel_mono2_list<dfit::MonoExp, 7, false>", r"fit_kernel_mono2<dfit::MonoExp, 8>",
                         r"fit_kernel<dfit::MonoExp, float, 8, true, false>", r"fit_kernel<dfit::BiExp, float, 16, true, false>",
+                        r"fit_kernel_lmq<dfit::BiExp, 16, true>", r"fit_kernel_lmq<dfit::BiExp, 16, false>", r"fit_kernel_lmq<dfit::MonoExp, 8, true>",
                         r"mask_compact_kernel<2, float, 8>", r"qdess_kernel<float>", r"qdess_kernel<double>"]
 KEYS = ["FFMA2", "FMUL2", "FADD2", "FFMA", "FMUL", "FADD", "MUFU", "FSETP", "FSEL", "FMNMX", "UTMALDG", "UBLKCP", "SYNCS", "LDS", "LDG",
         "STG", "DFMA", "DMUL", "DADD", "VOTE", "SHFL", "ATOMG", "REDG", "BRA"]

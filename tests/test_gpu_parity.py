@@ -438,7 +438,7 @@ def test_device_layouts_and_determinism(D):
     assert torch.equal(p1.nan_to_num(-1), p2.nan_to_num(-1)) and torch.equal(r1, r2)
 
 
-def test_tma_staged_variant_is_bitwise_identical(D):
+def test_tma_staged_variant_is_bitwise_identical(D, monkeypatch):
     """The TMA-staged persistent kernel (cp.async.bulk.tensor + mbarrier ring, use_tma=1) and the plain
     coalesced-load kernel run the same per-voxel arithmetic: results must be bit-identical, including a
     ragged last tile."""
@@ -457,11 +457,19 @@ def test_tma_staged_variant_is_bitwise_identical(D):
             # the LM (fast_path=0) is the same code in both kernels: bit-identical
             o0, P = A.make_opts(D.monoexponential, p0=(1.0, -1 / 30), init=init, use_tma=0, fast_path=0)
             o1, _ = A.make_opts(D.monoexponential, p0=(1.0, -1 / 30), init=init, use_tma=1, fast_path=0)
+            monkeypatch.setenv("DFIT_LMQ", "0")  # (the plain one-voxel-per-lane kernel; the default is the LM in rounds)
             p0_, r0_ = A.fit_device(o0, P, x, y, mask=mask)
             p1_, r1_ = A.fit_device(o1, P, x, y, mask=mask)
             torch.cuda.synchronize()
             assert torch.equal(p0_.nan_to_num(-1), p1_.nan_to_num(-1))
             assert torch.equal(r0_.nan_to_num(-1), r1_.nan_to_num(-1))
+            monkeypatch.delenv("DFIT_LMQ")
+            # the LM-in-rounds kernel (what use_tma=0 runs by default): the same iteration, exponentials by recurrence
+            p2_, r2_ = A.fit_device(o0, P, x, y, mask=mask)
+            torch.cuda.synchronize()
+            assert torch.equal(torch.isnan(p2_), torch.isnan(p1_))
+            assert ((p2_ - p1_).abs() / p1_.abs()).nan_to_num(0).max() < 1e-5
+            assert (r2_ - r1_).abs().nan_to_num(0).max() < 1e-5
             # with the fast path the masked voxels go through the two-voxel list kernel (use_tma=0) or the
             # one-voxel TMA kernel (use_tma=1): same iteration, different packing -> equal to rounding
             o0, P = A.make_opts(D.monoexponential, p0=(1.0, -1 / 30), init=init, use_tma=0)
