@@ -322,9 +322,11 @@ def run_gpu(args):
             # Peer stores by default: a multicast store also delivers the rank's OWN copy through the switch, so every
             # GPU receives N instead of N - 1 maps -- measured slower (2 GPUs: 1.42 against 0.83 ms per step).
             # DFIT_BENCH_MULTICAST=auto selects the NVLS multicast path where torch's symmetric memory offers it.
-            peer = sharding.PeerMaps(n, len(GATHER_COLS), dev, param_mask=0b10,
+            transport = os.environ.get("DFIT_BENCH_GATHER", "stores")  # "stores" (fused epilogue) | "copies" (copy engines)
+            peer = sharding.PeerMaps(n, len(GATHER_COLS), dev, param_mask=0b10, copy_engine=transport == "copies",
                                      multicast=os.environ.get("DFIT_BENCH_MULTICAST", "off"))
-            gather_mode = f"fused in-kernel all-gather of [b, r2] rows: {peer.transport}"
+            gather_mode = (f"all-gather of [b, r2] rows: {peer.transport}" if peer.copy_engine
+                           else f"fused in-kernel all-gather of [b, r2] rows: {peer.transport}")
         except Exception as e:  # pragma: no cover
             peer = None
             gather_mode = f"nccl all_gather_into_tensor (peer mapping unavailable: {type(e).__name__})"
@@ -338,8 +340,17 @@ def run_gpu(args):
     def packed():
         return torch.cat([popt[:, 1:2], r2[:, None]], dim=1)
 
+    def fit_chunk(lo, hi):
+        A.fit_device(opts, P, X_MS, y[:, lo:hi], popt=popt[lo:hi], r2=r2[lo:hi], handle=handle)
+
+    def fit_once():
+        if peer is not None and peer.copy_engine:
+            peer.fit_pipelined(fit_chunk, n)
+        else:
+            A.fit_device(opts, P, X_MS, y, popt=popt, r2=r2, handle=handle)
+
     def step():
-        A.fit_device(opts, P, X_MS, y, popt=popt, r2=r2, handle=handle)
+        fit_once()
         if world > 1 and peer is None:
             return sharding.gather_maps(packed(), counts)
         return popt
@@ -370,7 +381,7 @@ def run_gpu(args):
     ev[0].record()
     for k in range(args.steps):
         kev[k][0].record()
-        A.fit_device(opts, P, X_MS, y, popt=popt, r2=r2, handle=handle)
+        fit_once()
         kev[k][1].record()
         if world > 1 and peer is None:
             sharding.gather_maps(packed(), counts)
@@ -392,6 +403,7 @@ def run_gpu(args):
     sync()
     sustained_ms = s0.elapsed_time(s1)
     clocks = sampler.stop() if rank == 0 else None
+    peer_chunks = getattr(peer, "last_chunks", None) if peer is not None else None
     if peer is not None:
         peer.close()
 
@@ -494,7 +506,7 @@ def run_gpu(args):
                     "h2d_bytes_per_step": 4 * ECHOES * n, "d2h_bytes_per_step": 4 * (P + 1) * n,
                     "steps": e2e_steps, "launches_per_step": e2e_launches, "host_affinity": numa,
                     "api": "dfit_fit_host (C-ABI), pinned host buffers in and out"},
-            "gpu_launches": args.steps * stats["n_launches"],
+            "gpu_launches": args.steps * stats["n_launches"] * (peer_chunks or 1),
             "roofline": roofline,
             "lm": {"mean_iters": stats["sum_iters"] / max(stats["n_fitted"], 1), "max_iters": stats["max_iters"],
                    "failed_voxels": stats["n_failed"], "fitted_voxels": stats["n_fitted"]},

@@ -107,10 +107,14 @@ class PeerMaps:
     multicast: "off" (default: one peer store per rank), "auto" (NVLS multicast stores where available) or "require".
         A multicast store also delivers the rank's own copy through the switch -- N instead of N - 1 maps arrive at every
         GPU -- and measured slower than peer stores on this pool; it saves SM store instructions.
+    copy_engine: True = the third transport, for dense layouts: the kernel stores its rows into the rank's OWN map only
+        and `fit_pipelined` cuts the fit into chunks whose rows the copy engines push to the peers' maps (peer-to-peer
+        cudaMemcpyAsync over NVLink on a side stream) while the SMs fit the next chunk -- the copy engines move full-size
+        NVLink packets, which the 16-byte-per-lane stores of the fused epilogue do not reach.
     """
 
     def __init__(self, rows_per_rank, ncols, device, group=None, *, total_rows=None, row0=None, param_mask=0,
-                 split_list=False, fit_span=(0, 0), y_voxel0=0, multicast="off"):
+                 split_list=False, fit_span=(0, 0), y_voxel0=0, multicast="off", copy_engine=False):
         import ctypes
 
         import torch
@@ -130,6 +134,10 @@ class PeerMaps:
         shape = (rows, int(ncols))
         self._own, self._peer_ptrs, self._symm = None, [], None
         self.transport = None
+        self.copy_engine = bool(copy_engine)
+        if self.copy_engine and (split_list or multicast != "off"):
+            raise ValueError("copy_engine is for dense layouts and excludes multicast")
+        self._base_row0 = row0
         mc_ptr = 0
         ptrs = None
         if multicast not in ("off", "auto", "require"):
@@ -165,6 +173,13 @@ class PeerMaps:
         gd.struct_size = ctypes.sizeof(gd)
         gd.world, gd.rank = self.world, self.rank
         gd.maps = ctypes.cast(self._ptrs, ctypes.c_void_p)
+        if self.copy_engine:  # the kernel sees a world of one: its own map
+            self._own_ptr = (ctypes.c_void_p * 1)(ptrs[self.rank])
+            gd.world, gd.rank = 1, 0
+            gd.maps = ctypes.cast(self._own_ptr, ctypes.c_void_p)
+            self.transport = "copy-engine peer copies, pipelined with the fit"
+            self._copy_stream = torch.cuda.Stream(device=device)
+            self._events = {}
         gd.multicast = self.multicast_ptr or None
         gd.rows, gd.row0 = rows, row0
         gd.param_mask = int(param_mask)
@@ -211,6 +226,36 @@ class PeerMaps:
         for k, v in kw.items():
             setattr(self._desc, k, int(v))
         _cabi.check(_cabi.load().dfit_set_gather_ex(self._handle.ptr, ctypes.byref(self._desc)))
+
+    def fit_pipelined(self, fit_chunk, n_rows, chunks=8, align=128):
+        """copy_engine transport: `fit_chunk(lo, hi)` launches the fit of this rank's voxels [lo, hi) on the current stream
+        (the gather is already pointed at their rows); the rows of every chunk then travel to the peers' maps on the copy
+        stream while the next chunk is fitted.  Returns immediately (asynchronous); `synchronize()` completes the maps."""
+        import torch
+
+        assert self.copy_engine
+        cur = torch.cuda.current_stream(self.device)
+        step = max(align, (int(n_rows) + chunks - 1) // chunks // align * align)
+        lo, c = 0, 0
+        while lo < n_rows:
+            hi = min(int(n_rows), lo + step)
+            if hi + align > n_rows:
+                hi = int(n_rows)
+            fitted, copied = self._events.setdefault(c, (torch.cuda.Event(), torch.cuda.Event()))
+            cur.wait_event(copied)  # the previous fit's copies of these rows have left before they are overwritten
+            self.reconfigure(row0=self._base_row0 + lo)
+            fit_chunk(lo, hi)
+            fitted.record(cur)
+            self._copy_stream.wait_event(fitted)
+            with torch.cuda.stream(self._copy_stream):
+                r0, r1 = self._base_row0 + lo, self._base_row0 + hi
+                for k in range(1, self.world):  # round the ring, starting behind the own rank
+                    r = (self.rank + k) % self.world
+                    self.maps[r][r0:r1].copy_(self.local[r0:r1], non_blocking=True)
+                copied.record(self._copy_stream)
+            lo, c = hi, c + 1
+        self.last_chunks = c
+        cur.wait_event(copied)  # the fit is complete on the current stream when its last rows have left
 
     def synchronize(self):
         """All ranks' peer stores into this rank's map are complete after this returns."""

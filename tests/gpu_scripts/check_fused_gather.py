@@ -42,6 +42,8 @@ def main():
         for n in sizes:  # odd sizes take the one-voxel kernel, multiples of 4 the two-voxel TMA kernel (ragged or not)
             ok = check_dense(n, rank, world, dev, mc) and ok
         ok = check_split_list(rank, world, dev, mc) and ok
+    for n in sizes:
+        ok = check_copy_engine(n, rank, world, dev) and ok
     dist.barrier()
     dist.destroy_process_group()
     if not ok:
@@ -69,6 +71,32 @@ def check_dense(n, rank, world, dev, mc):
             peer.close()
             dist.barrier()
             ok = ok and same
+    return ok
+
+
+def check_copy_engine(n, rank, world, dev):
+    """The third transport: the kernel stores into the own map only, the copy engines push every chunk's rows to the peers
+    while the next chunk is fitted (PeerMaps.fit_pipelined).  Chunk boundaries must not change a single bit."""
+    if n % 4 != 0:
+        return True  # (chunked views need the TMA-aligned pitch of the two-voxel kernel to take the same kernel)
+    y = synth(n, dev, 100 + rank)
+    ok = True
+    for post in (None, POST):
+        opts, P = A.make_opts(D.monoexponential, p0=(1.0, -1 / 30), post=post)
+        popt, r2 = A.fit_device(opts, P, X, y)
+        torch.cuda.synchronize()
+        ref = sharding.gather_maps(torch.cat([popt, r2[:, None]], dim=1)[:, [1, 2]].contiguous(), [n] * world)
+        peer = sharding.PeerMaps(n, 2, dev, param_mask=0b10, copy_engine=True)
+        p2, q2 = torch.empty_like(popt), torch.empty_like(r2)
+        for _ in range(2):  # twice: the second fit waits for the first one's copies before it overwrites the rows
+            peer.fit_pipelined(lambda lo, hi: A.fit_device(opts, P, X, y[:, lo:hi], popt=p2[lo:hi], r2=q2[lo:hi]), n, chunks=5)
+        peer.synchronize()
+        same = torch.equal(peer.local.nan_to_num(-1.0), ref.nan_to_num(-1.0)) and torch.equal(p2.nan_to_num(-1.0), popt.nan_to_num(-1.0))
+        print(f"[rank {rank}] n={n} post={post is not None} via {peer.transport} ({peer.last_chunks} chunks): "
+              f"pipelined copies == nccl all_gather: {same}", flush=True)
+        peer.close()
+        dist.barrier()
+        ok = ok and same
     return ok
 
 

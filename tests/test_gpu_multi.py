@@ -24,3 +24,5 @@ def test_fused_gather_matches_nccl():
     # 2 transports x 3 sizes x (raw, fused epilogue) x (all columns, 8-byte rows); 2 transports x 2 split-list runs
     assert res.stdout.count("fused gather == nccl all_gather: True") == 2 * 3 * 4 * world, res.stdout[-3000:]
     assert res.stdout.count("complete map == single-GPU masked fit: True") == 2 * 2 * world, res.stdout[-3000:]
+    # the copy-engine transport: the two sizes with a TMA-aligned pitch x (raw, fused epilogue)
+    assert res.stdout.count("pipelined copies == nccl all_gather: True") == 2 * 2 * world, res.stdout[-3000:]
