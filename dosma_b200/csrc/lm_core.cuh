@@ -783,11 +783,7 @@ DFIT_HD int lm_iterate(T (&p)[M::P], const T (&y)[EMAX], const XTab<T, EMAX>& xt
   int status = ST_MAXITER;
   for (;;) {
     if (!resume) {
-      if (!(s.fev < o.maxfev)) break;
-      if (s.F <= floorF) {
-        status = ST_EXACT;
-        break;
-      }
+      if (!(s.fev < o.maxfev) | (s.F <= floorF)) break;  // (an exact fit reads ST_EXACT after the loop either way)
       bool solved = lm_step<P, T, TA>(p, s.A, s.g, s.D2, s.lam, ALL, s.pt, s.zz, s.pnorm2, s.pred);
       for (int tries = 0; tries < 12 && !solved; ++tries) {
         s.lam = num<TA>::max_(s.lam * (TA)10, (TA)1e-3);
@@ -815,31 +811,34 @@ DFIT_HD int lm_iterate(T (&p)[M::P], const T (&y)[EMAX], const XTab<T, EMAX>& xt
     // their difference cannot resolve reductions below tau ~ eps*sqrt(sum y^2 * F).  Below that
     // level the gain ratio is noise: trust the (accurately computed) predicted reduction instead
     // of rejecting at random.  (Compared squared to avoid the square root.)
+    // (Written with selects and non-short-circuit logic: on the device this is straight-line code; lanes of a warp
+    // disagree about accept / reject all the time, and every branch here was a divergence point.)
     const TA tau2 = eps16 * eps16 * s.ysq * s.F;
     const bool reliable = s.pred * s.pred > tau2;
-    const bool accept = good && (reliable ? act > (TA)1e-4 * s.pred : act * num<TA>::abs_(act) > -tau2);
+    const TA lhs = reliable ? act : act * num<TA>::abs_(act);
+    const TA rhs = reliable ? (TA)1e-4 * s.pred : -tau2;
+    const bool accept = good & (lhs > rhs);
     const TA rho = reliable ? act * num<TA>::rcp_(s.pred) : (TA)1;
-    const bool small_f =
-        good && s.pred <= ftol * s.F && (!reliable || (num<TA>::abs_(act) <= ftol * s.F && act <= (TA)2 * s.pred));
-    const bool conv_x = accept && s.zz <= xtol2 * s.pnorm2;
-    if (accept) {
+    const TA ftolF = ftol * s.F;
+    const bool small_f = good & (s.pred <= ftolF) & (!reliable | ((num<TA>::abs_(act) <= ftolF) & (act <= (TA)2 * s.pred)));
+    const bool conv_x = accept & (s.zz <= xtol2 * s.pnorm2);
+    {
+      const TA t = (TA)2 * rho - (TA)1;
+      const TA lam_acc = num<TA>::max_(s.lam * num<TA>::max_((TA)(1.0 / 3.0), (TA)1 - t * t * t), (TA)1e-9);
+      const TA lam_rej = s.lam * s.nu;
+      s.lam = accept ? lam_acc : lam_rej;
+      s.nu = accept ? (TA)2 : s.nu * (TA)2;
+      s.fev += accept ? P : 0;  // MINPACK re-differences its Jacobian after an accepted step: P more evaluations of its budget
+      s.F = accept ? Fn : s.F;
 #pragma unroll
       for (int i = 0; i < P; ++i) {
-        p[i] = s.pt[i];
-        s.g[i] = gn[i];
+        p[i] = accept ? s.pt[i] : p[i];
+        s.g[i] = accept ? gn[i] : s.g[i];
       }
 #pragma unroll
-      for (int k = 0; k < NA; ++k) s.A[k] = An[k];
-      s.F = Fn;
-      const TA t = (TA)2 * rho - (TA)1;
-      s.lam = num<TA>::max_(s.lam * num<TA>::max_((TA)(1.0 / 3.0), (TA)1 - t * t * t), (TA)1e-9);
-      s.nu = 2;
-      s.fev += P;  // MINPACK re-differences its Jacobian here: P more evaluations of its budget
-    } else {
-      s.lam *= s.nu;
-      s.nu *= 2;
+      for (int k = 0; k < NA; ++k) s.A[k] = accept ? An[k] : s.A[k];
     }
-    if (small_f || conv_x) {
+    if (small_f | conv_x) {
       status = small_f ? (conv_x ? ST_CONV_FX : ST_CONV_F) : ST_CONV_X;
       break;
     }

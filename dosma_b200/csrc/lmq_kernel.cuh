@@ -43,7 +43,10 @@ struct LmqLayout {  // word offsets of one suspended fit; slot s of word w lives
 #ifndef DFIT_LMQ_CTAS4
 #define DFIT_LMQ_CTAS4 4  // 4-parameter models above 8 echoes: 128 registers (measured against 3 CTAs: 1.44 / 1.54 ms on config 4)
 #endif
-constexpr int lmq_min_ctas(int P, int E) { return P >= 4 ? (E <= 8 ? 4 : DFIT_LMQ_CTAS4) : (E <= 8 ? 6 : 4); }
+#ifndef DFIT_LMQ_CTAS2
+#define DFIT_LMQ_CTAS2 6  // one / two parameters, up to 8 echoes
+#endif
+constexpr int lmq_min_ctas(int P, int E) { return P >= 4 ? (E <= 8 ? 4 : DFIT_LMQ_CTAS4) : (E <= 8 ? DFIT_LMQ_CTAS2 : 4); }
 
 template <class M, int EMAX, bool UNI>
 __global__ void __launch_bounds__(kLmqWarps * 32, lmq_min_ctas(M::P, EMAX))
@@ -184,7 +187,7 @@ struct LmqConfig {
 };
 inline LmqConfig lmq_config(int P = 4) {  // (read at every launch: a getenv, so that tests can switch within one process)
   LmqConfig c{1, 5, 2};  // measured on config 4 (bi-exponential, 16 echoes): 4,3 1.50 ms / 4,2 1.46 / 5,2 1.44 / 6,2 1.50
-  if (P < 4) c = LmqConfig{1, 6, 4};
+  if (P < 4) c = LmqConfig{1, 6, 6};  // (pure-noise volume: 6,4 6.93 ms / 6,6 6.78 / 8,4 6.88 / 8,8 6.87 / 4,3 7.35)
   if (const char* e = std::getenv("DFIT_LMQ")) {
     int a = 0, b = 0;
     const int n = std::sscanf(e, "%d,%d", &a, &b);

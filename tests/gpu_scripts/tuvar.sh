@@ -9,7 +9,13 @@ cs=$root/dosma_b200/csrc
 b=$cs/_build_$name
 mkdir -p $b
 F="-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC,-O2 -Xptxas -v --expt-relaxed-constexpr -I $root/include"
-nvcc $F "$@" -c $cs/$tu.cu -o $b/$tu.o > $b/log.txt 2>&1 || { tail -20 $b/log.txt; exit 1; }
-objs=$(ls $cs/_build/*.o | grep -v "/$tu.o" | grep -v stubs.o)
-nvcc -shared -gencode arch=compute_100a,code=sm_100a -o $root/dosma_b200/libdfit_$name.so $objs $b/$tu.o
+# (several translation units: comma-separated)
+objs=$(ls $cs/_build/*.o | grep -v stubs.o)
+new=""
+for t in ${tu//,/ }; do
+  nvcc $F "$@" -c $cs/$t.cu -o $b/$t.o > $b/log_$t.txt 2>&1 || { tail -20 $b/log_$t.txt; exit 1; }
+  objs=$(echo "$objs" | grep -v "/$t.o")
+  new="$new $b/$t.o"
+done
+nvcc -shared -gencode arch=compute_100a,code=sm_100a -o $root/dosma_b200/libdfit_$name.so $objs $new
 echo "$name: built $(ls -la $root/dosma_b200/libdfit_$name.so | awk '{print $5}') bytes"
