@@ -288,6 +288,7 @@ inline void fill_xtab(XTab<T, EMAX>& xt, const double* x, int n_echo) {
 // fitting.py:1016-1018  f = a * exp(b x)
 struct MonoExp {
   static constexpr int P = 2;
+  static DFIT_HD constexpr bool dup(int, int) { return false; }  // (see BiExp)
   static constexpr unsigned LIN = 0x1u;
   static constexpr bool MONO = true;  // eligible for the variable-projection Newton fast path
   template <typename T>
@@ -341,6 +342,10 @@ struct MonoExp {
 // fitting.py:1021-1023  f = a1 exp(b1 x) + a2 exp(b2 x)
 struct BiExp {
   static constexpr int P = 4;
+  // Jh = [e1, x e1, e2, x e2]: the products Jh2 Jh1 = e2 (x e1) and Jh3 Jh0 = (x e2) e1 are the same number, so eval_all
+  // accumulates entry (3, 0) of Jh^T Jh only and copies it into (2, 1)
+  static DFIT_HD constexpr bool dup(int i, int j) { return i == 2 && j == 1; }
+  static constexpr int DUP_DST = 2 * 3 / 2 + 1, DUP_SRC = 3 * 4 / 2 + 0;
   static constexpr unsigned LIN = 0x5u;
   static constexpr bool MONO = false;
   template <typename T>
@@ -406,6 +411,7 @@ struct BiExp {
 // f = a x : the 1-parameter custom model of the reference's tests (tests/core/test_fitting.py:52-53)
 struct Linear1 {
   static constexpr int P = 1;
+  static DFIT_HD constexpr bool dup(int, int) { return false; }
   static constexpr unsigned LIN = 0x1u;
   static constexpr bool MONO = false;
   template <typename T>
@@ -488,7 +494,7 @@ DFIT_HD void eval_all(const T (&p)[M::P], const T (&y)[EMAX], const XTab<T, EMAX
         if (DFIT_ON(i)) g2[i] = p2_fma<T>(J[i], r, g2[i]);
 #pragma unroll
         for (int j = 0; j <= i; ++j)
-          if (DFIT_ON(i) && DFIT_ON(j)) A2[tri(i, j)] = p2_fma<T>(J[i], J[j], A2[tri(i, j)]);
+          if (DFIT_ON(i) && DFIT_ON(j) && !M::dup(i, j)) A2[tri(i, j)] = p2_fma<T>(J[i], J[j], A2[tri(i, j)]);
       }
     }
     F = (TA)(F2.lo + F2.hi);
@@ -507,7 +513,7 @@ DFIT_HD void eval_all(const T (&p)[M::P], const T (&y)[EMAX], const XTab<T, EMAX
         if (DFIT_ON(i)) g[i] = num<TA>::fma_((TA)J[i], (TA)re, g[i]);
 #pragma unroll
         for (int j = 0; j <= i; ++j)
-          if (DFIT_ON(i) && DFIT_ON(j)) A[tri(i, j)] = num<TA>::fma_((TA)J[i], (TA)J[j], A[tri(i, j)]);
+          if (DFIT_ON(i) && DFIT_ON(j) && !M::dup(i, j)) A[tri(i, j)] = num<TA>::fma_((TA)J[i], (TA)J[j], A[tri(i, j)]);
       }
     }
   } else {
@@ -528,11 +534,12 @@ DFIT_HD void eval_all(const T (&p)[M::P], const T (&y)[EMAX], const XTab<T, EMAX
           if (DFIT_ON(i)) g[i] = num<TA>::fma_((TA)J[i], (TA)re, g[i]);
 #pragma unroll
           for (int j = 0; j <= i; ++j)
-            if (DFIT_ON(i) && DFIT_ON(j)) A[tri(i, j)] = num<TA>::fma_((TA)J[i], (TA)J[j], A[tri(i, j)]);
+            if (DFIT_ON(i) && DFIT_ON(j) && !M::dup(i, j)) A[tri(i, j)] = num<TA>::fma_((TA)J[i], (TA)J[j], A[tri(i, j)]);
         }
       }
     }
   }
+  if constexpr (M::dup(2, 1)) A[M::DUP_DST] = A[M::DUP_SRC];
   T cs[P];
   M::template colscale<T>(p, cs);
 #pragma unroll
@@ -545,44 +552,49 @@ DFIT_HD void eval_all(const T (&p)[M::P], const T (&y)[EMAX], const XTab<T, EMAX
 #undef DFIT_ON
 }
 
-// Solve (C + lam I) z = -gs for symmetric C (packed lower), all in registers.  Rows/columns whose
-// bit is cleared in `active` are frozen (z_i = 0).  P <= 2 uses the closed form, larger systems an
-// unrolled Cholesky.  Reciprocals are approximate (see num<>::rcp_).
+// Solve (A + lam diag(dd)) z = -g for symmetric A (packed lower), all in registers: the Marquardt-scaled system
+// (D^-1 A D^-1 + lam I)(D z) = -D^-1 g with D = sqrt(dd), solved WITHOUT forming the scaled matrix -- no rsqrt of the
+// scales, no P (P + 1) multiplies to apply them (a Cholesky factorisation is invariant under diagonal scaling up to
+// rounding; the positive-definiteness thresholds are relative to dd for the same reason).  Rows/columns whose bit is
+// cleared in `active` are frozen (z_i = 0).  P <= 2 uses the closed form, larger systems an unrolled Cholesky.
+// Reciprocals are approximate (see num<>::rcp_).
 template <int P, typename TA>
-DFIT_HD bool chol_solve(const TA (&C)[P * (P + 1) / 2], TA lam, const TA (&gs)[P], unsigned active, TA (&z)[P]) {
+DFIT_HD bool chol_solve(const TA (&A)[P * (P + 1) / 2], TA lam, const TA (&dd)[P], const TA (&g)[P], unsigned active,
+                        TA (&z)[P]) {
   const TA tiny = num<TA>::eps() * (TA)4;
   if constexpr (P == 1) {
-    const TA d = C[0] + lam;
-    z[0] = (active & 1u) ? -gs[0] * num<TA>::rcp_(d) : (TA)0;
-    return d > tiny || !(active & 1u);
+    const TA d = num<TA>::fma_(lam, dd[0], A[0]);
+    z[0] = (active & 1u) ? -g[0] * num<TA>::rcp_(d) : (TA)0;
+    return d > tiny * dd[0] || !(active & 1u);
   } else if constexpr (P == 2) {
     const bool a0 = active & 1u, a1 = (active >> 1) & 1u;
-    const TA d0 = a0 ? C[0] + lam : (TA)1, d1 = a1 ? C[2] + lam : (TA)1;
-    const TA c = (a0 && a1) ? C[1] : (TA)0;
-    const TA g0 = a0 ? gs[0] : (TA)0, g1 = a1 ? gs[1] : (TA)0;
+    const TA s0 = a0 ? dd[0] : (TA)1, s1 = a1 ? dd[1] : (TA)1;
+    const TA d0 = a0 ? num<TA>::fma_(lam, dd[0], A[0]) : (TA)1, d1 = a1 ? num<TA>::fma_(lam, dd[1], A[2]) : (TA)1;
+    const TA c = (a0 && a1) ? A[1] : (TA)0;
+    const TA g0 = a0 ? g[0] : (TA)0, g1 = a1 ? g[1] : (TA)0;
     const TA det = d0 * d1 - c * c;
     const TA inv = num<TA>::rcp_(det);
     z[0] = (c * g1 - d1 * g0) * inv;
     z[1] = (c * g0 - d0 * g1) * inv;
-    return det > tiny * d0 * d1 && d0 > tiny && d1 > tiny;
+    return det > tiny * d0 * d1 && d0 > tiny * s0 && d1 > tiny * s1;
   } else {
     TA L[P * (P + 1) / 2], Dinv[P];
     bool pd = true;
 #pragma unroll
     for (int j = 0; j < P; ++j) {
       const bool aj = (active >> j) & 1u;
-      TA s = aj ? C[tri(j, j)] + lam : (TA)1;
+      TA s = aj ? num<TA>::fma_(lam, dd[j], A[tri(j, j)]) : (TA)1;
 #pragma unroll
       for (int k = 0; k < j; ++k) s -= L[tri(j, k)] * L[tri(j, k)];
       // (no early exit: a pivot that is not positive poisons what follows, and the caller discards z when told so --
       // straight-line code instead of a branch per column)
-      pd = pd && (s > tiny);
+      pd = pd && (s > tiny * (aj ? dd[j] : (TA)1));
       const TA inv = num<TA>::rsqrt_(s);
       Dinv[j] = inv;
 #pragma unroll
       for (int i = j + 1; i < P; ++i) {
         const bool ai = (active >> i) & 1u;
-        TA t = (aj && ai) ? C[tri(i, j)] : (TA)0;
+        TA t = (aj && ai) ? A[tri(i, j)] : (TA)0;
 #pragma unroll
         for (int k = 0; k < j; ++k) t -= L[tri(i, k)] * L[tri(j, k)];
         L[tri(i, j)] = t * inv;
@@ -591,7 +603,7 @@ DFIT_HD bool chol_solve(const TA (&C)[P * (P + 1) / 2], TA lam, const TA (&gs)[P
     TA w[P];
 #pragma unroll
     for (int i = 0; i < P; ++i) {
-      TA t = ((active >> i) & 1u) ? -gs[i] : (TA)0;
+      TA t = ((active >> i) & 1u) ? -g[i] : (TA)0;
 #pragma unroll
       for (int k = 0; k < i; ++k) t -= L[tri(i, k)] * w[k];
       w[i] = t * Dinv[i];
@@ -635,37 +647,30 @@ DFIT_HD void loglinear_init(const T (&y)[EMAX], const T* __restrict__ xc, T xbar
   }
 }
 
-// Marquardt-scaled step from the current normal equations.  Returns false if the (restricted)
-// system is not positive definite.  Outputs the trial point pt, |z|^2, the scaled norm of pt and the
-// predicted reduction z^T C z + 2 lam z^T z (all terms >= 0) of the linearised model.
+// Marquardt-scaled step from the current normal equations: (A + lam diag(D2)) dp = -g with D2 the running maxima of
+// diag(A) (MINPACK's diag rule).  Returns false if the (restricted) system is not positive definite.  Outputs the trial
+// point pt, the squared scaled step |D dp|^2, the squared scaled norm of pt and the predicted reduction of the
+// linearised model, dp^T A dp + 2 lam |D dp|^2 = lam |D dp|^2 - dp^T g (dp solves the system above; P multiply-adds
+// instead of the P (P + 1) / 2 terms of the quadratic form, and both forms cancel to the same extent: by the
+// condition number of the scaled matrix).
 template <int P, typename T, typename TA>
 DFIT_HD bool lm_step(const T (&p)[P], const TA (&A)[P * (P + 1) / 2], const TA (&g)[P], TA (&D2)[P], TA lam,
                      unsigned active, T (&pt)[P], TA& zz, TA& pnorm2, TA& pred) {
-  constexpr int NA = P * (P + 1) / 2;
-  TA Di[P], C[NA], gs[P], z[P];
+  TA dd[P], z[P];
 #pragma unroll
   for (int i = 0; i < P; ++i) {
     D2[i] = num<TA>::max_(D2[i], A[tri(i, i)]);  // running maximum: MINPACK's diag rule
-    Di[i] = D2[i] > 0 ? num<TA>::rsqrt_(D2[i]) : (TA)1;
+    dd[i] = D2[i] > 0 ? D2[i] : (TA)1;
   }
-#pragma unroll
-  for (int i = 0; i < P; ++i) {
-    gs[i] = g[i] * Di[i];
-#pragma unroll
-    for (int j = 0; j <= i; ++j) C[tri(i, j)] = A[tri(i, j)] * Di[i] * Di[j];
-  }
-  if (!chol_solve<P, TA>(C, lam, gs, active, z)) return false;
+  if (!chol_solve<P, TA>(A, lam, dd, g, active, z)) return false;
   zz = 0;
   pnorm2 = 0;
-  // z solves (C + lam I) z = -gs, so z^T C z = -z^T gs - lam z^T z and the predicted reduction
-  // z^T C z + 2 lam z^T z is -z^T gs + lam z^T z: P multiply-adds instead of the P (P + 1) / 2 terms of the quadratic
-  // form (both forms cancel to the same extent: by the condition number of C)
   TA zg = 0;
 #pragma unroll
   for (int i = 0; i < P; ++i) {
-    pt[i] = p[i] + (T)(z[i] * Di[i]);
-    zz = num<TA>::fma_(z[i], z[i], zz);
-    zg = num<TA>::fma_(z[i], gs[i], zg);
+    pt[i] = p[i] + (T)z[i];
+    zz = num<TA>::fma_(dd[i] * z[i], z[i], zz);
+    zg = num<TA>::fma_(z[i], g[i], zg);
     pnorm2 = num<TA>::fma_(D2[i] * (TA)pt[i], (TA)pt[i], pnorm2);
   }
   pred = lam * zz - zg;

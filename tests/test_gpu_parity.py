@@ -306,6 +306,61 @@ def test_lm_in_rounds_kernel(D, case, monkeypatch):
     close(ref, run(), "exponentials by MUFU")
 
 
+@pytest.mark.parametrize("variant", ["echo_fastest", "int16", "p0_voxel", "f64_maps_status"])
+def test_lm_in_rounds_kernel_input_forms(D, variant, monkeypatch):
+    """The rounds kernel behind every way samples and initial guesses reach it -- echo-fastest layout, int16 samples,
+    a per-voxel initial guess, float64 result maps with status / pass-count bytes -- against the plain kernel
+    (DFIT_LMQ=0): same fits to rounding, same skipped voxels."""
+    import torch
+
+    from dosma_b200 import device_api as A
+
+    dev = torch.device("cuda", 0)
+    g = torch.Generator(device=dev).manual_seed(17)
+    n, E = 30000 + 7, 12
+    x = [6.0 * i for i in range(1, E + 1)]
+    xt = torch.tensor(x, device=dev)[:, None]
+    amp = 500 + 1000 * torch.rand(n, device=dev, generator=g)
+    fs = 0.3 + 0.4 * torch.rand(n, device=dev, generator=g)
+    ts, tl = 8 + 12 * torch.rand(n, device=dev, generator=g), 50 + 50 * torch.rand(n, device=dev, generator=g)
+    y = amp * fs * torch.exp(-xt / ts) + amp * (1 - fs) * torch.exp(-xt / tl) + 5 * torch.randn(E, n, device=dev, generator=g)
+    y[:, ::211] = 0  # skipped voxels
+    kw_fit, p0 = {}, (500.0, -1 / 10, 500.0, -1 / 60)
+    if variant == "echo_fastest":
+        y = y.t().contiguous()
+        kw_fit["layout"] = "echo_fastest"
+    elif variant == "int16":
+        y = y.round().to(torch.int16)
+    elif variant == "p0_voxel":
+        p0 = (None, -1 / 10, None, -1 / 60)
+        pv = torch.stack([amp * 0.5, torch.zeros_like(amp), amp * 0.5, torch.zeros_like(amp)], dim=1).contiguous()
+        kw_fit["p0_voxel"] = pv
+    o, P = A.make_opts(D.biexponential, p0=p0, compute_dtype="f32")
+
+    def run():
+        od = torch.float64 if variant == "f64_maps_status" else torch.float32
+        popt = torch.full((n, P), -7.0, device=dev, dtype=od)
+        r2 = torch.full((n,), -7.0, device=dev, dtype=od)
+        st = torch.full((n,), 99, device=dev, dtype=torch.uint8)
+        it = torch.full((n,), 99, device=dev, dtype=torch.uint8)
+        A.fit_device(o, P, x, y, popt=popt, r2=r2, status=st, niter=it, **kw_fit)
+        torch.cuda.synchronize()
+        return popt, r2, st, it
+
+    monkeypatch.setenv("DFIT_LMQ", "0")
+    ref = run()
+    monkeypatch.delenv("DFIT_LMQ")
+    out = run()
+    assert not (out[2] == 99).any() and not (out[0] == -7.0).any()
+    assert torch.equal(out[2] == 0, ref[2] == 0) and int((out[2] == 0).sum()) == len(range(0, n, 211))
+    ok = (ref[2] >= 1) & (ref[2] <= 4) & (out[2] >= 1) & (out[2] <= 4)
+    assert ok.float().mean() > 0.95 and ((ref[2] >= 5) != (out[2] >= 5)).float().mean() < 5e-3
+    assert (ref[1][ok] - out[1][ok]).abs().max() < 2e-5
+    rel = ((ref[0][ok] - out[0][ok]).abs() / ref[0][ok].abs()).max(dim=1).values
+    assert float(torch.quantile(rel.float(), 0.5)) < 2e-5 and float(torch.quantile(rel.float(), 0.99)) < 5e-3
+    assert (ref[3][ok].float() - out[3][ok].float()).abs().mean() < 0.05
+
+
 def test_config4_sample_against_c_oracle(D):
     """A config-4-shaped volume (16 echoes x 5 ms, bi-exponential, SNR 100, fp32) fitted on the GPU in fp32; a seeded
     sample of voxels is compared with the MINPACK restatement (oracle/minpack_lmdif.c, pinned to SciPy on the
