@@ -10,6 +10,51 @@ namespace dfit {
 
 constexpr int kCompactPerThread = 8;  // voxels per thread in the compaction pass (2048 per CTA)
 
+// The fill value into every output of a run of voxels outside the mask (single GPU, popt and r2 16-byte aligned), as
+// 16-byte streaming stores -- the pass over a thin tissue mask IS this fill (config 3: 805 MB of it against 1.6 M voxels
+// to fit), and per-voxel 8- and 4-byte stores ran it at 2.7 TB/s.  Two shapes: a thread's own 8 voxels (v a multiple of
+// 8, idx0 = 0, stride = 1), or a whole warp's 256 voxels with the lanes interleaved (v a multiple of 256, idx0 = lane,
+// stride = 32) so that every store instruction writes 512 contiguous bytes -- a thread's own 64 bytes would be written
+// as half sectors by consecutive instructions.
+template <int P, typename T, int EMAX>
+__device__ __forceinline__ void fill_run(const KernelArgs<T, EMAX>& a, int64_t v, int idx0, int stride) {
+  const int pw = a.sel >= 0 ? 1 : P;  // 1, 2 or 4 values per voxel
+  double pat[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    double q = a.fill_q[0];
+#pragma unroll
+    for (int i = 1; i < P; ++i)
+      if (i == (a.sel >= 0 ? a.sel : (k & (pw - 1)))) q = a.fill_q[i];
+    pat[k] = q;
+  }
+  if (a.out_dtype == DT_F32) {
+    const float4 q4 = make_float4((float)pat[0], (float)pat[1], (float)pat[2], (float)pat[3]);
+    float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(a.popt) + v * pw) + idx0;
+    for (int k = 0; k < 2 * pw; ++k) __stcs(dst + k * stride, q4);
+    const float mf = (float)a.mask_fill;
+    float4* dr = reinterpret_cast<float4*>(reinterpret_cast<float*>(a.r2) + v) + idx0;
+    __stcs(dr, make_float4(mf, mf, mf, mf));
+    __stcs(dr + stride, make_float4(mf, mf, mf, mf));
+  } else {
+    // (a double2 holds values 2 i and 2 i + 1 of the run: which parameters depends on the parity of i for pw = 4)
+    const double2 even = make_double2(pat[0], pat[1]), odd = make_double2(pat[2], pat[3]);
+    double2* dst = reinterpret_cast<double2*>(reinterpret_cast<double*>(a.popt) + v * pw) + idx0;
+    for (int k = 0; k < 4 * pw; ++k) __stcs(dst + k * stride, ((idx0 + k * stride) & 1) ? odd : even);
+    double2* dr = reinterpret_cast<double2*>(reinterpret_cast<double*>(a.r2) + v) + idx0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) __stcs(dr + k * stride, make_double2(a.mask_fill, a.mask_fill));
+  }
+  if (a.status) *(reinterpret_cast<uint2*>(a.status + v) + idx0) = make_uint2(0u, 0u);  // ST_SKIPPED
+  if (a.niter) *(reinterpret_cast<uint2*>(a.niter + v) + idx0) = make_uint2(0u, 0u);
+}
+
+// Mask path, step 1: one streaming pass over the mask that (a) appends the voxels to fit to a compact index list and
+// (b) writes the fill value for every voxel outside the mask (fitting.py:205-215).  Step 2 is the fit kernel over the
+// list: all 32 lanes of a warp fit, however thin the tissue mask is.  A thread takes 8 CONSECUTIVE voxels -- one 8-byte
+// load of their mask bytes, 16-byte fill stores -- a warp claims its run of the CTA's list with one shared-memory atomic
+// after a shuffle scan of the lanes' counts (neighbours stay neighbours), the CTA its run of the global list with ONE
+// global atomic per 2048 voxels.
 template <int P, typename T, int EMAX>
 __global__ void __launch_bounds__(256) mask_compact_kernel(const __grid_constant__ KernelArgs<T, EMAX> a, unsigned* index,
                                                            unsigned* count) {
@@ -17,21 +62,64 @@ __global__ void __launch_bounds__(256) mask_compact_kernel(const __grid_constant
   __shared__ unsigned s_n, s_base;
   if (threadIdx.x == 0) s_n = 0;
   __syncthreads();
-  const int64_t v0 = (int64_t)blockIdx.x * (256 * kCompactPerThread);
+  const int64_t v0 = (int64_t)blockIdx.x * (256 * kCompactPerThread) + (int64_t)threadIdx.x * kCompactPerThread;
   const int lane = threadIdx.x & 31;
+  const bool whole = v0 + kCompactPerThread <= a.n;
+  // mask bytes of the thread's 8 voxels: in range (inb), inside the mask (msk), to fit by this rank (act)
+  unsigned inb = 0, msk = 0;
+  if (whole && (reinterpret_cast<uintptr_t>(a.mask) & 7) == 0) {
+    const uint2 w = __ldcs(reinterpret_cast<const uint2*>(a.mask + v0));
+    inb = 0xffu;
 #pragma unroll
-  for (int k = 0; k < kCompactPerThread; ++k) {
-    const int64_t v = v0 + k * 256 + threadIdx.x;
-    const bool in = v < a.n;
-    const bool masked = in && a.mask[v] != 0;
-    // (multi-GPU split mode: masked voxels outside this rank's span are a peer's to fit -- neither listed nor filled)
-    const bool active = masked && (!a.g.split_list || (v >= a.g.fit_lo && v < a.g.fit_hi));
-    const unsigned ballot = __ballot_sync(0xffffffffu, active);
+    for (int k = 0; k < 4; ++k) {
+      msk |= ((w.x >> (8 * k)) & 0xffu) ? (1u << k) : 0u;
+      msk |= ((w.y >> (8 * k)) & 0xffu) ? (16u << k) : 0u;
+    }
+  } else {
+#pragma unroll
+    for (int k = 0; k < kCompactPerThread; ++k) {
+      if (v0 + k < a.n) {
+        inb |= 1u << k;
+        msk |= a.mask[v0 + k] != 0 ? (1u << k) : 0u;
+      }
+    }
+  }
+  unsigned act = msk;
+  if (a.g.split_list) {  // (multi-GPU split mode: masked voxels outside this rank's span are a peer's to fit -- neither listed nor filled)
+#pragma unroll
+    for (int k = 0; k < kCompactPerThread; ++k)
+      if (!(v0 + k >= a.g.fit_lo && v0 + k < a.g.fit_hi)) act &= ~(1u << k);
+  }
+  // the warp's run of the CTA's list
+  const unsigned cnt = (unsigned)__popc(act);
+  if (__any_sync(0xffffffffu, cnt != 0u)) {
+    unsigned incl = cnt;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const unsigned t = __shfl_up_sync(0xffffffffu, incl, d);
+      if (lane >= d) incl += t;
+    }
     unsigned base = 0;
-    if (lane == 0 && ballot) base = atomicAdd(&s_n, (unsigned)__popc(ballot));  // shared-memory atomic
-    base = __shfl_sync(0xffffffffu, base, 0);
-    if (active) s_list[base + __popc(ballot & ((1u << lane) - 1u))] = (unsigned)v;
-    if (in && !masked) fill_voxel<P, T, EMAX>(a, v);
+    if (lane == 31) base = atomicAdd(&s_n, incl);  // shared-memory atomic
+    base = __shfl_sync(0xffffffffu, base, 31);
+    unsigned pos = base + incl - cnt;
+#pragma unroll
+    for (int k = 0; k < kCompactPerThread; ++k)
+      if ((act >> k) & 1u) s_list[pos++] = (unsigned)(v0 + k);
+  }
+  // the fill value outside the mask
+  const unsigned fillm = inb & ~msk;
+  const bool wide = a.g.world == 0 && a.popt != nullptr && ((reinterpret_cast<uintptr_t>(a.popt) | reinterpret_cast<uintptr_t>(a.r2)) & 15) == 0 &&
+                    ((reinterpret_cast<uintptr_t>(a.status) | reinterpret_cast<uintptr_t>(a.niter)) & 7) == 0;
+  const bool run8 = fillm == 0xffu && wide;
+  if (__all_sync(0xffffffffu, run8)) {
+    fill_run<P, T, EMAX>(a, v0 - lane * kCompactPerThread, lane, 32);  // the warp's 256 voxels, lanes interleaved
+  } else if (run8) {
+    fill_run<P, T, EMAX>(a, v0, 0, 1);
+  } else if (fillm != 0u) {
+#pragma unroll 1
+    for (int k = 0; k < kCompactPerThread; ++k)
+      if ((fillm >> k) & 1u) fill_voxel<P, T, EMAX>(a, v0 + k);
   }
   __syncthreads();
   const unsigned n = s_n;

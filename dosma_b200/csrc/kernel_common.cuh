@@ -417,10 +417,8 @@ __device__ __forceinline__ void warp_stats(unsigned long long* cnt, int st, int 
   }
 }
 
-// Mask path, step 1: one streaming pass over the mask that (a) appends the voxels to fit to a compact
-// index list -- each warp claims a contiguous run with one atomic, so neighbours stay neighbours -- and
-// (b) writes the fill value for every voxel outside the mask (fitting.py:205-215).  Step 2 is the fit
-// kernel over the list: all 32 lanes of a warp fit, however thin the tissue mask is.
+// Grid-stride / persistent kernels: per-thread counts -> one reduction per CTA -> one of the counter slots.
+// Must be reached by every thread of the CTA.
 __device__ __forceinline__ void block_stats_counts(unsigned long long* cnt, unsigned n_fit, unsigned n_fail, unsigned n_nf,
                                                    unsigned n_oob, int it_sum, int it_max) {
   __shared__ unsigned s_c[4], s_iters, s_max;

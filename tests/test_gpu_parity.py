@@ -361,6 +361,64 @@ def test_lm_in_rounds_kernel_input_forms(D, variant, monkeypatch):
     assert (ref[3][ok].float() - out[3][ok].float()).abs().mean() < 0.05
 
 
+@pytest.mark.parametrize("n,offset", [(8 * 5000, 0), (8 * 5000 + 3, 0), (4099, 0), (40000, 3), (7, 0), (300000, 8)])
+@pytest.mark.parametrize("form", ["f32", "f64_status", "out_param", "biexp"])
+def test_mask_compaction_and_fill(D, n, offset, form):
+    """The mask pass (mask_compact_kernel: 8 consecutive voxels per thread, 16-byte fill stores, shuffle-scan compaction):
+    inside the mask the masked fit equals the dense fit (to rounding: the two may take different kernels), outside it every output holds the fill value --
+    ragged sizes, a mask that does not start on an 8-byte boundary, float64 maps with status / pass-count bytes, one
+    selected parameter with a nan_to_num fill, a four-parameter model."""
+    import torch
+
+    from dosma_b200 import device_api as A
+
+    dev = torch.device("cuda", 0)
+    g = torch.Generator(device=dev).manual_seed(n + offset)
+    E = 8 if form != "biexp" else 10
+    x = [10.0 * i for i in range(1, E + 1)]
+    xt = torch.tensor(x, device=dev)[:, None]
+    y = (500 + 1000 * torch.rand(n, device=dev, generator=g)) * torch.exp(-xt / (10 + 70 * torch.rand(n, device=dev, generator=g))) \
+        + 10 * torch.randn(E, n, device=dev, generator=g)
+    big = torch.rand(n + offset, device=dev, generator=g) < 0.2
+    big[offset: offset + min(n, 64)] = True   # a solid run and, below, a solid hole
+    if n > 200:
+        big[offset + 100: offset + 164] = False
+    mask = big[offset:]                        # (offset != 0: the mask bytes do not start on an 8-byte boundary)
+    post, kw, P_model = None, {}, D.monoexponential
+    if form == "out_param":
+        post = dict(ufunc=[0, 1], lb=[-np.inf, 0.0], ub=[np.inf, 100.0], decimals=[-1, 2], r2_threshold=0.5, nan_to_num=0.0)
+        kw = dict(out_param=1)
+    p0 = (1.0, -1 / 30)
+    if form == "biexp":
+        P_model, p0 = D.biexponential, (500.0, -1 / 10, 500.0, -1 / 60)
+    o, P = A.make_opts(P_model, p0=p0, post=post, **kw)
+    od = torch.float64 if form == "f64_status" else torch.float32
+    shape = (n,) if form == "out_param" else (n, P)
+
+    def run(m):
+        popt = torch.full(shape, -7.0, device=dev, dtype=od)
+        r2 = torch.full((n,), -7.0, device=dev, dtype=od)
+        st = torch.full((n,), 99, device=dev, dtype=torch.uint8) if form == "f64_status" else None
+        it = torch.full((n,), 99, device=dev, dtype=torch.uint8) if form == "f64_status" else None
+        A.fit_device(o, P, x, y, mask=m, popt=popt, r2=r2, status=st, niter=it)
+        torch.cuda.synchronize()
+        return popt, r2, st, it
+
+    dense, masked = run(None), run(mask)
+    fill = 0.0 if form == "out_param" else float("nan")
+    for d, m in zip(dense[:2], masked[:2]):
+        inside, ref = m[mask].double(), d[mask].double()  # (dense and masked launches may take different kernels: to rounding)
+        assert torch.equal(torch.isnan(inside), torch.isnan(ref))
+        tol = 1e-5 if form != "out_param" else 1.001e-2  # (out_param: rounded to 2 decimals -- one rounding step)
+        err = (inside - ref).abs() / (ref.abs() if form != "out_param" else 1.0)
+        assert float(err.nan_to_num(0.0).max()) <= tol
+        outside = m[~mask]
+        assert bool(torch.isnan(outside).all()) if fill != fill else bool((outside == fill).all())
+    if form == "f64_status":
+        assert bool((masked[2][~mask] == 0).all()) and bool((masked[3][~mask] == 0).all())
+        assert (masked[2][mask] != dense[2][mask]).float().mean() < 1e-3 and (masked[3][mask] != dense[3][mask]).float().mean() < 1e-2
+
+
 def test_config4_sample_against_c_oracle(D):
     """A config-4-shaped volume (16 echoes x 5 ms, bi-exponential, SNR 100, fp32) fitted on the GPU in fp32; a seeded
     sample of voxels is compared with the MINPACK restatement (oracle/minpack_lmdif.c, pinned to SciPy on the
