@@ -49,6 +49,20 @@ __device__ __forceinline__ void fill_run(const KernelArgs<T, EMAX>& a, int64_t v
   if (a.niter) *(reinterpret_cast<uint2*>(a.niter + v) + idx0) = make_uint2(0u, 0u);
 }
 
+// The same for the multi-GPU split mode with 8-byte [parameter, r2] rows: outside the mask every rank fills its OWN
+// reassembled map (nothing of the fill crosses NVLink); rows of a run of voxels are contiguous.
+template <int P, typename T, int EMAX>
+__device__ __forceinline__ void fill_run_map2(const KernelArgs<T, EMAX>& a, int64_t v, int idx0, int stride) {
+  float q = (float)a.fill_q[0];
+#pragma unroll
+  for (int i = 1; i < P; ++i)
+    if ((a.g.cols >> i) & 1u) q = (float)a.fill_q[i];
+  const float mf = (float)a.mask_fill;
+  float4* dst = reinterpret_cast<float4*>(a.g.maps[a.g.self] + (a.g.row0 + v) * 2) + idx0;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) dst[k * stride] = make_float4(q, mf, q, mf);
+}
+
 // Mask path, step 1: one streaming pass over the mask that (a) appends the voxels to fit to a compact index list and
 // (b) writes the fill value for every voxel outside the mask (fitting.py:205-215).  Step 2 is the fit kernel over the
 // list: all 32 lanes of a warp fit, however thin the tissue mask is.  A thread takes 8 CONSECUTIVE voxels -- one 8-byte
@@ -111,11 +125,17 @@ __global__ void __launch_bounds__(256) mask_compact_kernel(const __grid_constant
   const unsigned fillm = inb & ~msk;
   const bool wide = a.g.world == 0 && a.popt != nullptr && ((reinterpret_cast<uintptr_t>(a.popt) | reinterpret_cast<uintptr_t>(a.r2)) & 15) == 0 &&
                     ((reinterpret_cast<uintptr_t>(a.status) | reinterpret_cast<uintptr_t>(a.niter)) & 7) == 0;
-  const bool run8 = fillm == 0xffu && wide;
-  if (__all_sync(0xffffffffu, run8)) {
-    fill_run<P, T, EMAX>(a, v0 - lane * kCompactPerThread, lane, 32);  // the warp's 256 voxels, lanes interleaved
+  // (split mode of a multi-GPU masked fit whose only output is the [parameter, r2] map: the same, into the own map)
+  const bool wide_map = a.g.world > 0 && a.g.split_list && a.popt == nullptr && a.g.ncols == 2 &&
+                        a.status == nullptr && a.niter == nullptr && (a.g.row0 & 1) == 0 &&
+                        (reinterpret_cast<uintptr_t>(a.g.maps[a.g.self]) & 15) == 0;
+  const bool run8 = fillm == 0xffu && (wide || wide_map);
+  if (__all_sync(0xffffffffu, run8)) {  // the warp's 256 voxels, lanes interleaved
+    if (wide) fill_run<P, T, EMAX>(a, v0 - lane * kCompactPerThread, lane, 32);
+    else fill_run_map2<P, T, EMAX>(a, v0 - lane * kCompactPerThread, lane, 32);
   } else if (run8) {
-    fill_run<P, T, EMAX>(a, v0, 0, 1);
+    if (wide) fill_run<P, T, EMAX>(a, v0, 0, 1);
+    else fill_run_map2<P, T, EMAX>(a, v0, 0, 1);
   } else if (fillm != 0u) {
 #pragma unroll 1
     for (int k = 0; k < kCompactPerThread; ++k)

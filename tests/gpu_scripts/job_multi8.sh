@@ -1,5 +1,5 @@
 #!/bin/bash
-# 8-GPU job: bench.py at N = 8 with peer stores (default) and with NVLS multicast stores, configs 3 / 5 at N = 8 and N = 4.
+# 8-GPU job: bench.py at N = 8 and 4 with peer stores (default; `all`: also N = 8 with NVLS multicast stores), configs 3 / 5 at N = 8 and N = 4.
 tag=${1:-x}
 out=gpurun_out
 mkdir -p $out
@@ -15,7 +15,7 @@ except Exception as e:
 PY
 }
 run_bench 8 off
-run_bench 8 auto
+[ "$2" = all ] && run_bench 8 auto
 run_bench 4 off
 for n in 8 4; do
 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 29551 tests/gpu_scripts/configs_multi.py > $out/configs_multi_${tag}_${n}gpu.json 2> $out/configs_multi_${tag}_${n}gpu.err
