@@ -80,6 +80,10 @@ def build(force=False, verbose=False, variant=None, extra_flags=()):
         return obj
 
     if jobs:
+        # longest translation units first (the fp32 mono- / bi-exponential instances carry the two-voxel, TMA and rounds
+        # kernels): with fewer cores than units the wall time is set by what starts last
+        weight = {"inst_mono_f32": 0, "inst_biexp_f32": 1, "inst_mono_f64": 2, "inst_biexp_f64": 3, "inst_linear_f32": 4}
+        jobs.sort(key=lambda j: min([w for k, w in weight.items() if os.path.basename(j[0]).startswith(k)] or [9]))
         with ThreadPoolExecutor(max_workers=min(len(jobs), os.cpu_count() or 4)) as ex:
             list(ex.map(compile_one, jobs))
     if jobs or force or _stale(lib_path, objs):

@@ -147,34 +147,31 @@ inline cudaError_t launch_exact(const LaunchDesc& d) {
   }
 }
 
-// Split in two halves so that each model/dtype compiles as two translation units in parallel.
-template <class M, typename T>
-inline cudaError_t launch_model_lo(const LaunchDesc& d) {  // 1..8 echoes
-  switch (d.n_echo) {
-    case 1: return launch_exact<M, T, 1>(d);
-    case 2: return launch_exact<M, T, 2>(d);
-    case 3: return launch_exact<M, T, 3>(d);
-    case 4: return launch_exact<M, T, 4>(d);
-    case 5: return launch_exact<M, T, 5>(d);
-    case 6: return launch_exact<M, T, 6>(d);
-    case 7: return launch_exact<M, T, 7>(d);
-    default: return launch_exact<M, T, 8>(d);
+// Echo-count ranges: the instances of one model / arithmetic type are spread over several translation units that
+// compile in parallel (the fp32 mono-exponential ones -- two-voxel, TMA and rounds kernels per echo count -- took 8 of
+// the build's 8.5 minutes as two units).  launch_range covers the exact instances LO..HI (HI <= 16);
+// launch_many the predicated 32-register instance above 16 echoes.
+template <class M, typename T, int LO, int HI>
+inline cudaError_t launch_range(const LaunchDesc& d) {
+  if constexpr (LO > HI) {
+    return cudaErrorInvalidValue;
+  } else {
+    if (d.n_echo == LO) return launch_exact<M, T, LO>(d);
+    return launch_range<M, T, LO + 1, HI>(d);
   }
+}
+template <class M, typename T>
+inline cudaError_t launch_many(const LaunchDesc& d) {
+  return launch_one<M, T, 32, false>(d);
 }
 
 template <class M, typename T>
+inline cudaError_t launch_model_lo(const LaunchDesc& d) {  // 1..8 echoes
+  return launch_range<M, T, 1, 8>(d);
+}
+template <class M, typename T>
 inline cudaError_t launch_model_hi(const LaunchDesc& d) {  // 9..32 echoes
-  switch (d.n_echo) {
-    case 9: return launch_exact<M, T, 9>(d);
-    case 10: return launch_exact<M, T, 10>(d);
-    case 11: return launch_exact<M, T, 11>(d);
-    case 12: return launch_exact<M, T, 12>(d);
-    case 13: return launch_exact<M, T, 13>(d);
-    case 14: return launch_exact<M, T, 14>(d);
-    case 15: return launch_exact<M, T, 15>(d);
-    case 16: return launch_exact<M, T, 16>(d);
-    default: return launch_one<M, T, 32, false>(d);
-  }
+  return d.n_echo <= 16 ? launch_range<M, T, 9, 16>(d) : launch_many<M, T>(d);
 }
 #endif
 
@@ -183,12 +180,35 @@ inline cudaError_t launch_model_hi(const LaunchDesc& d) {  // 9..32 echoes
   cudaError_t launch_##name##_lo(const LaunchDesc& d); \
   cudaError_t launch_##name##_hi(const LaunchDesc& d); \
   inline cudaError_t launch_##name(const LaunchDesc& d) { return d.n_echo <= 8 ? launch_##name##_lo(d) : launch_##name##_hi(d); }
-DFIT_DECLARE_LAUNCH(mono_f32)
 DFIT_DECLARE_LAUNCH(mono_f64)
-DFIT_DECLARE_LAUNCH(biexp_f32)
 DFIT_DECLARE_LAUNCH(biexp_f64)
 DFIT_DECLARE_LAUNCH(linear_f32)
 DFIT_DECLARE_LAUNCH(linear_f64)
 #undef DFIT_DECLARE_LAUNCH
+
+// the fp32 mono- and bi-exponential instances: finer parts (inst_mono_f32_*.cu, inst_biexp_f32_*.cu)
+cudaError_t launch_mono_f32_e1_4(const LaunchDesc& d);
+cudaError_t launch_mono_f32_e5_6(const LaunchDesc& d);
+cudaError_t launch_mono_f32_e7_8(const LaunchDesc& d);
+cudaError_t launch_mono_f32_e9_10(const LaunchDesc& d);
+cudaError_t launch_mono_f32_e11_12(const LaunchDesc& d);
+cudaError_t launch_mono_f32_e13_14(const LaunchDesc& d);
+cudaError_t launch_mono_f32_e15_16(const LaunchDesc& d);
+cudaError_t launch_mono_f32_many(const LaunchDesc& d);
+inline cudaError_t launch_mono_f32(const LaunchDesc& d) {
+  const int e = d.n_echo;
+  return e <= 4 ? launch_mono_f32_e1_4(d) : e <= 6 ? launch_mono_f32_e5_6(d) : e <= 8 ? launch_mono_f32_e7_8(d)
+       : e <= 10 ? launch_mono_f32_e9_10(d) : e <= 12 ? launch_mono_f32_e11_12(d) : e <= 14 ? launch_mono_f32_e13_14(d)
+       : e <= 16 ? launch_mono_f32_e15_16(d) : launch_mono_f32_many(d);
+}
+cudaError_t launch_biexp_f32_e1_8(const LaunchDesc& d);
+cudaError_t launch_biexp_f32_e9_12(const LaunchDesc& d);
+cudaError_t launch_biexp_f32_e13_16(const LaunchDesc& d);
+cudaError_t launch_biexp_f32_many(const LaunchDesc& d);
+inline cudaError_t launch_biexp_f32(const LaunchDesc& d) {
+  const int e = d.n_echo;
+  return e <= 8 ? launch_biexp_f32_e1_8(d) : e <= 12 ? launch_biexp_f32_e9_12(d) : e <= 16 ? launch_biexp_f32_e13_16(d)
+                                                                                           : launch_biexp_f32_many(d);
+}
 
 }  // namespace dfit

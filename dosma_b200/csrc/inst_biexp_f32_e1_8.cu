@@ -2,5 +2,5 @@
 #include "fit_kernel.cuh"
 
 namespace dfit {
-cudaError_t launch_biexp_f32_lo(const LaunchDesc& d) { return launch_model_lo<BiExp, float>(d); }
+cudaError_t launch_biexp_f32_e1_8(const LaunchDesc& d) { return launch_range<BiExp, float, 1, 8>(d); }
 }  // namespace dfit

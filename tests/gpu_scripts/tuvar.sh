@@ -1,5 +1,5 @@
 #!/bin/bash
-# TEST TOOLING: tuvar.sh <name> <translation unit, e.g. inst_biexp_f32_hi> [nvcc -D flags...] builds
+# TEST TOOLING: tuvar.sh <name> <translation unit, e.g. inst_biexp_f32_e13_16> [nvcc -D flags...] builds
 # dosma_b200/libdfit_<name>.so = the main build's objects with that one translation unit recompiled with the given flags.
 # For A/B timing of kernel variants (DOSMA_B200_LIB selects the library).  Needs an up-to-date main build.
 set -e
