@@ -387,7 +387,9 @@ int lm_tail_prepare(DevBuf& buf, int& parity, int64_t n_vox, cudaStream_t st, La
   if (const char* e = std::getenv("DFIT_LM_TAIL")) {
     if (e[0] == '0') return DFIT_OK;
   }
-  if (d.tmap2 == nullptr || d.g.world != 0 || n_vox >= ((int64_t)1 << 32)) return DFIT_OK;
+  // (small launches keep the LM inside the kernel: a second launch costs them a few microseconds -- 10 % of the 64 x 64 x 16
+  // volume's 0.04 ms -- and at that size a divergent warp costs nothing)
+  if (d.tmap2 == nullptr || d.g.world != 0 || n_vox >= ((int64_t)1 << 32) || n_vox < ((int64_t)1 << 20)) return DFIT_OK;
   const size_t need = 16 + (size_t)n_vox * sizeof(unsigned);
   if (need > buf.cap) {
     const int rc = ensure(buf, need);

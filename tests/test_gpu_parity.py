@@ -144,7 +144,7 @@ def test_lm_tail_of_the_dense_kernel(D, post, monkeypatch):
 
     dev = torch.device("cuda", 0)
     g = torch.Generator(device=dev).manual_seed(21)
-    n = 64 * 4096 + 128  # TMA-aligned pitch
+    n = 288 * 4096 + 128  # TMA-aligned pitch; above the 2^20 voxels from which a launch uses the LM tail
     x = [10.0 * i for i in range(1, 9)]
     xt = torch.tensor(x, device=dev)[:, None]
     air = (torch.rand(n // 1024 + 1, device=dev, generator=g) < 0.5).repeat_interleave(1024)[:n]
