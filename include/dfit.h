@@ -139,7 +139,9 @@ typedef struct dfit_stats {
   float kernel_ms;      /* device time of the fit kernel(s), CUDA events on the engine's stream */
   float total_ms;       /* device time of the whole call incl. copies (host entry point only) */
   int64_t n_deferred;   /* dense two-voxel TMA kernel: voxels the straight-line fast path turned down (they are queued per
-                           warp and fitted 32 at a time by the one-voxel path: Newton loop, then LM from p0) */
+                           warp and fitted 32 at a time by the one-voxel path: Newton loop, then LM from p0 -- inside the
+                           kernel, or, where most of a batch is LM-bound (air, background), by the LM-in-rounds kernel
+                           launched right behind it: n_launches then counts two) */
 } dfit_stats;
 
 typedef struct dfit_handle dfit_handle;
