@@ -30,13 +30,27 @@ namespace dfit {
 constexpr int kLmqWarps = 4;
 constexpr int kLmqCap = 64;  // stack slots per warp: at most 31 left waiting + 32 pushed by one round
 
+// integers ride in the state words bit for bit
+template <typename T>
+struct LmqWord;
+template <>
+struct LmqWord<float> {
+  static __device__ __forceinline__ float from_int(int v) { return __int_as_float(v); }
+  static __device__ __forceinline__ int to_int(float w) { return __float_as_int(w); }
+};
+template <>
+struct LmqWord<double> {
+  static __device__ __forceinline__ double from_int(int v) { return __longlong_as_double((long long)v); }
+  static __device__ __forceinline__ int to_int(double w) { return (int)__double_as_longlong(w); }
+};
+
 template <int P, int EMAX>
 struct LmqLayout {  // word offsets of one suspended fit; slot s of word w lives at [w][s] (lanes -> consecutive banks)
   static constexpr int NA = P * (P + 1) / 2;
   static constexpr int Y = 0, PAR = Y + EMAX, PT = PAR + P, A = PT + P, G = A + NA, D2 = G + P, F = D2 + P, LAM = F + 1,
                        NU = LAM + 1, YSQ = NU + 1, ZZ = YSQ + 1, PN = ZZ + 1, PRED = PN + 1, FEV = PRED + 1, ITERS = FEV + 1,
                        VOX = ITERS + 1, WORDS = VOX + 1;
-  static constexpr size_t bytes() { return (size_t)kLmqWarps * WORDS * kLmqCap * sizeof(float); }
+  static constexpr size_t bytes(size_t word) { return (size_t)kLmqWarps * WORDS * kLmqCap * word; }
 };
 
 // resident CTAs per SM the register allocation is asked to leave room for
@@ -46,20 +60,23 @@ struct LmqLayout {  // word offsets of one suspended fit; slot s of word w lives
 #ifndef DFIT_LMQ_CTAS2
 #define DFIT_LMQ_CTAS2 6  // one / two parameters, up to 8 echoes
 #endif
-constexpr int lmq_min_ctas(int P, int E) { return P >= 4 ? (E <= 8 ? 4 : DFIT_LMQ_CTAS4) : (E <= 8 ? DFIT_LMQ_CTAS2 : 4); }
+constexpr int lmq_min_ctas(int P, int E, int word = 4) {
+  return word == 8 ? (P >= 4 || E > 8 ? 2 : 3)  // fp64: twice the registers and twice the stack
+                   : P >= 4 ? (E <= 8 ? 4 : DFIT_LMQ_CTAS4) : (E <= 8 ? DFIT_LMQ_CTAS2 : 4);
+}
 
-template <class M, int EMAX, bool UNI>
-__global__ void __launch_bounds__(kLmqWarps * 32, lmq_min_ctas(M::P, EMAX))
-    fit_kernel_lmq(const __grid_constant__ KernelArgs<float, EMAX> a, const int k_first, const int k_next) {
-  typedef float T;
+template <class M, typename T, int EMAX, bool UNI>
+__global__ void __launch_bounds__(kLmqWarps * 32, lmq_min_ctas(M::P, EMAX, sizeof(T)))
+    fit_kernel_lmq(const __grid_constant__ KernelArgs<T, EMAX> a, const int k_first, const int k_next) {
   constexpr int P = M::P;
   constexpr int NA = P * (P + 1) / 2;
   typedef LmqLayout<P, EMAX> L;
-  extern __shared__ __align__(16) float lmq_smem[];
+  extern __shared__ __align__(16) unsigned char lmq_smem_raw[];
+  T* const lmq_smem = reinterpret_cast<T*>(lmq_smem_raw);
   const unsigned full = 0xffffffffu;
   const int warp = __shfl_sync(full, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   const unsigned below = (1u << lane) - 1u;
-  float* const q = lmq_smem + (size_t)warp * L::WORDS * kLmqCap;  // this warp's stack: q[w * kLmqCap + slot]
+  T* const q = lmq_smem + (size_t)warp * L::WORDS * kLmqCap;  // this warp's stack: q[w * kLmqCap + slot]
   // launched as the LM tail of a dense fast-path kernel (programmatic stream serialisation): wait until that grid has
   // completed and its list is visible; a no-op in a plain launch
   asm volatile("griddepcontrol.wait;" ::: "memory");
@@ -104,7 +121,7 @@ __global__ void __launch_bounds__(kLmqWarps * 32, lmq_min_ctas(M::P, EMAX))
       budget = k_next;
       if (lane < cnt) {
         live = true;
-        const float* __restrict__ src = q + n_q + lane;
+        const T* __restrict__ src = q + n_q + lane;
 #pragma unroll
         for (int e = 0; e < EMAX; ++e) y[e] = src[(L::Y + e) * kLmqCap];
 #pragma unroll
@@ -123,9 +140,9 @@ __global__ void __launch_bounds__(kLmqWarps * 32, lmq_min_ctas(M::P, EMAX))
         s.zz = src[L::ZZ * kLmqCap];
         s.pnorm2 = src[L::PN * kLmqCap];
         s.pred = src[L::PRED * kLmqCap];
-        s.fev = __float_as_int(src[L::FEV * kLmqCap]);
-        s.iters = __float_as_int(src[L::ITERS * kLmqCap]);
-        v = (int64_t)__float_as_uint(src[L::VOX * kLmqCap]);
+        s.fev = LmqWord<T>::to_int(src[L::FEV * kLmqCap]);
+        s.iters = LmqWord<T>::to_int(src[L::ITERS * kLmqCap]);
+        v = (int64_t)(unsigned)LmqWord<T>::to_int(src[L::VOX * kLmqCap]);
       }
       __syncwarp();  // every slot has been read before this round's pushes may overwrite it
     } else {
@@ -150,7 +167,7 @@ __global__ void __launch_bounds__(kLmqWarps * 32, lmq_min_ctas(M::P, EMAX))
     }
     const unsigned m = __ballot_sync(full, pending);
     if (pending) {
-      float* __restrict__ dst = q + n_q + __popc(m & below);
+      T* __restrict__ dst = q + n_q + __popc(m & below);
 #pragma unroll
       for (int e = 0; e < EMAX; ++e) dst[(L::Y + e) * kLmqCap] = y[e];
 #pragma unroll
@@ -169,9 +186,9 @@ __global__ void __launch_bounds__(kLmqWarps * 32, lmq_min_ctas(M::P, EMAX))
       dst[L::ZZ * kLmqCap] = s.zz;
       dst[L::PN * kLmqCap] = s.pnorm2;
       dst[L::PRED * kLmqCap] = s.pred;
-      dst[L::FEV * kLmqCap] = __int_as_float(s.fev);
-      dst[L::ITERS * kLmqCap] = __int_as_float(s.iters);
-      dst[L::VOX * kLmqCap] = __uint_as_float((unsigned)v);
+      dst[L::FEV * kLmqCap] = LmqWord<T>::from_int(s.fev);
+      dst[L::ITERS * kLmqCap] = LmqWord<T>::from_int(s.iters);
+      dst[L::VOX * kLmqCap] = LmqWord<T>::from_int((int)(unsigned)v);
     }
     n_q += __popc(m);
     __syncwarp();
@@ -203,15 +220,16 @@ inline LmqConfig lmq_config(int P = 4) {  // (read at every launch: a getenv, so
 // releases its dependents early (no griddepcontrol.launch_dependents): measured on a pure-noise volume, tail CTAs that
 // become resident while the dense grid is still running cost 1.5 ms (7.07 against 5.51 ms); on the benchmark volume the
 // (empty) tail then costs 0.7 us per launch.
-template <class M, int EMAX>
-inline cudaError_t launch_lmq(const LaunchDesc& d, const KernelArgs<float, EMAX>& a, bool tail = false) {
+template <class M, typename T, int EMAX>
+inline cudaError_t launch_lmq(const LaunchDesc& d, const KernelArgs<T, EMAX>& a, bool tail = false) {
   const LmqConfig cfg = lmq_config(M::P);
   // uniformly spaced echoes (the host decided: fill_xtab): the exponentials of the model come from a two-echo
   // recurrence instead of MUFU.EX2 (DFIT_LMQ_UNI=0 switches that off, for A/B runs)
-  bool uni = M::HAS_REC && EMAX >= 4 && a.xt.uniform != 0;
+  constexpr bool CAN_UNI = M::HAS_REC && EMAX >= 4 && sizeof(T) == 4;
+  bool uni = CAN_UNI && a.xt.uniform != 0;
   if (const char* e = std::getenv("DFIT_LMQ_UNI")) uni = uni && e[0] != '0';
-  auto kfn = uni ? fit_kernel_lmq<M, EMAX, M::HAS_REC && EMAX >= 4> : fit_kernel_lmq<M, EMAX, false>;
-  const size_t smem = LmqLayout<M::P, EMAX>::bytes();
+  auto kfn = uni ? fit_kernel_lmq<M, T, EMAX, CAN_UNI> : fit_kernel_lmq<M, T, EMAX, false>;
+  const size_t smem = LmqLayout<M::P, EMAX>::bytes(sizeof(T));
   cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   int per_sm = 0;
