@@ -27,7 +27,6 @@ namespace dfit {
 
 #if defined(__CUDACC__)
 
-constexpr int kLmqWarps = 4;
 constexpr int kLmqCap = 64;  // stack slots per warp: at most 31 left waiting + 32 pushed by one round
 
 // integers ride in the state words bit for bit
@@ -50,25 +49,29 @@ struct LmqLayout {  // word offsets of one suspended fit; slot s of word w lives
   static constexpr int Y = 0, PAR = Y + EMAX, PT = PAR + P, A = PT + P, G = A + NA, D2 = G + P, F = D2 + P, LAM = F + 1,
                        NU = LAM + 1, YSQ = NU + 1, ZZ = YSQ + 1, PN = ZZ + 1, PRED = PN + 1, FEV = PRED + 1, ITERS = FEV + 1,
                        VOX = ITERS + 1, WORDS = VOX + 1;
-  static constexpr size_t bytes(size_t word) { return (size_t)kLmqWarps * WORDS * kLmqCap * word; }
+  static constexpr size_t bytes(size_t word, int warps) { return (size_t)warps * WORDS * kLmqCap * word; }
 };
 
-// resident CTAs per SM the register allocation is asked to leave room for
-#ifndef DFIT_LMQ_CTAS4
-#define DFIT_LMQ_CTAS4 4  // 4-parameter models above 8 echoes: 128 registers (measured against 3 CTAs: 1.44 / 1.54 ms on config 4)
+// Warps per SM the register allocation is asked to leave room for (128 registers per thread at 16, 80 at 24) -- in ONE
+// CTA per SM: with the same number of warps, larger CTAs measured faster throughout (bi-exponential, config 4: 4 CTAs of
+// 4 warps 1.31 ms / 2 x 8 1.28 / 1 x 16 1.21; two-parameter LM on pure noise: 6 x 4 4.33 ms / 3 x 8 4.17 / 2 x 12 4.05 /
+// 1 x 24 3.81).
+#ifndef DFIT_LMQ_WARPS_SM4
+#define DFIT_LMQ_WARPS_SM4 16  // 4-parameter models above 8 echoes: measured 12 warps (158 registers) 1.54 ms / 16 (128) 1.44 / 20 (96, spills) slower
 #endif
-#ifndef DFIT_LMQ_CTAS2
-#define DFIT_LMQ_CTAS2 6  // one / two parameters, up to 8 echoes
+#ifndef DFIT_LMQ_WARPS_SM2
+#define DFIT_LMQ_WARPS_SM2 24  // one / two parameters, up to 8 echoes (28: 72 registers with spills, slower)
 #endif
-constexpr int lmq_min_ctas(int P, int E, int word = 4) {
-  return word == 8 ? (P >= 4 || E > 8 ? 2 : 3)  // fp64: twice the registers and twice the stack
-                   : P >= 4 ? (E <= 8 ? 4 : DFIT_LMQ_CTAS4) : (E <= 8 ? DFIT_LMQ_CTAS2 : 4);
+constexpr int lmq_cta_warps(int P, int E, int word) {
+  return word == 8 ? (P >= 4 || E > 8 ? 8 : 12)  // fp64: twice the registers and twice the stack
+                   : P >= 4 ? (E <= 8 ? 16 : DFIT_LMQ_WARPS_SM4) : (E <= 8 ? DFIT_LMQ_WARPS_SM2 : 16);
 }
 
 template <class M, typename T, int EMAX, bool UNI>
-__global__ void __launch_bounds__(kLmqWarps * 32, lmq_min_ctas(M::P, EMAX, sizeof(T)))
+__global__ void __launch_bounds__(lmq_cta_warps(M::P, EMAX, sizeof(T)) * 32, 1)
     fit_kernel_lmq(const __grid_constant__ KernelArgs<T, EMAX> a, const int k_first, const int k_next) {
   constexpr int P = M::P;
+  constexpr int kLmqWarps = lmq_cta_warps(P, EMAX, sizeof(T));
   constexpr int NA = P * (P + 1) / 2;
   typedef LmqLayout<P, EMAX> L;
   extern __shared__ __align__(16) unsigned char lmq_smem_raw[];
@@ -229,7 +232,8 @@ inline cudaError_t launch_lmq(const LaunchDesc& d, const KernelArgs<T, EMAX>& a,
   bool uni = CAN_UNI && a.xt.uniform != 0;
   if (const char* e = std::getenv("DFIT_LMQ_UNI")) uni = uni && e[0] != '0';
   auto kfn = uni ? fit_kernel_lmq<M, T, EMAX, CAN_UNI> : fit_kernel_lmq<M, T, EMAX, false>;
-  const size_t smem = LmqLayout<M::P, EMAX>::bytes(sizeof(T));
+  constexpr int kLmqWarps = lmq_cta_warps(M::P, EMAX, sizeof(T));
+  const size_t smem = LmqLayout<M::P, EMAX>::bytes(sizeof(T), kLmqWarps);
   cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   int per_sm = 0;
